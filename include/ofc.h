@@ -1,0 +1,117 @@
+/* libofc -- C-ABI of the B200 (sm_100a) flow -> grid -> k-means -> cosine hot path.
+ *
+ * The reference (menmitsu/opticalFlowClustering, k-means-color-clustering/) has
+ * no FFI of its own: its hot path is Python calling cv2 / scikit-learn.  Each
+ * entry point below replaces one of those library calls (cited per function);
+ * the Python package opticalflowclustering_b200 binds them with ctypes and
+ * re-exports the reference's own function/class names on top.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer
+ *     owned by the caller (the Python side allocates with torch);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
+ *     work is stream-ordered, no call synchronises the device;
+ *   - return 0 on success, a negative OFC_ERR_* otherwise; ofc_last_error()
+ *     gives the message (thread-local).
+ */
+#ifndef OFC_H_
+#define OFC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFC_OK 0
+#define OFC_ERR_INVALID (-1)
+#define OFC_ERR_UNSUPPORTED (-2)
+#define OFC_ERR_CUDA (-3)
+#define OFC_ERR_WORKSPACE (-4)
+
+int ofc_version(void);
+const char* ofc_last_error(void);
+
+/* ---- optional per-kernel timing (benchmark / profiling aid) ----------------
+ * Between begin and end every kernel launch is bracketed by cudaEvents on its
+ * launch stream; end() synchronises on them and returns, per kernel kind, the
+ * summed device time (ms) and the launch count.  Kinds: 0 bgr2gray, 1 prefilter,
+ * 2 polyexp, 3 minmax_init, 4 flow_encode, 5 grid_cells, 6 flow_minmax,
+ * 7 draw_grid, 8 kmeans, 9 cosine, 12+l flow_iter at pyramid level l (0 = full
+ * resolution).  n_kinds must be >= 20.  Not thread-safe. */
+int ofc_profile_begin(void);
+int ofc_profile_end(float* ms_by_kind, int* launches_by_kind, int n_kinds);
+
+/* ---- Farneback dense optical flow --------------------------------------
+ * Replaces cv.calcOpticalFlowFarneback(prev, next, None, pyr_scale, levels,
+ * winsize, iterations, poly_n, poly_sigma, flags)
+ *   reference: computeOpticalFlowModule.py:20-22, computeOpticalFlow.py:99-101.
+ * A plan fixes the frame size and parameters (pyramid geometry, filter taps,
+ * workspace layout) for up to `max_frames` frames per call.  flags must be 0
+ * (box window, no initial flow) -> OFC_ERR_UNSUPPORTED otherwise. */
+typedef struct ofc_flow_plan ofc_flow_plan;
+
+int ofc_flow_plan_create(ofc_flow_plan** plan, int width, int height, int max_frames,
+                         double pyr_scale, int levels, int winsize, int iterations,
+                         int poly_n, double poly_sigma, int flags);
+void ofc_flow_plan_destroy(ofc_flow_plan* plan);
+size_t ofc_flow_plan_workspace_bytes(const ofc_flow_plan* plan);
+int ofc_flow_plan_num_levels(const ofc_flow_plan* plan);
+/* level 0 = coarsest ... num_levels-1 = full resolution */
+int ofc_flow_plan_level_size(const ofc_flow_plan* plan, int level, int* w, int* h);
+/* byte offset inside the workspace of a level's buffer (for parity tests of
+ * the intermediates): kind 0 = I f32[h][w], 1 = RA f32x4[h][w], 2 = RB f32[h][w],
+ * 3 / 4 = flow ping/pong f32x2[h][w]; *frame_stride_bytes = distance between
+ * consecutive frames (or pairs). */
+int ofc_flow_plan_buffer(const ofc_flow_plan* plan, int level, int kind,
+                         size_t* offset_bytes, size_t* frame_stride_bytes);
+
+/* n_frames consecutive gray frames u8[n_frames][H][W] -> n_frames-1 flow fields
+ * f32[n_frames-1][H][W][2]; pair t is (frame t, frame t+1) and the pre-filter
+ * and polynomial expansion of each frame are computed once (streaming reuse).
+ * minmax (nullable) receives per pair the IEEE bits of min and max |flow|
+ * (u32[n_frames-1][2]) for ofc_flow_to_bgr. */
+int ofc_farneback_sequence(const ofc_flow_plan* plan, const uint8_t* gray, int n_frames,
+                           float* flow, uint32_t* minmax,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* one independent pair, the literal cv2 call */
+int ofc_farneback_pair(const ofc_flow_plan* plan, const uint8_t* prev, const uint8_t* next,
+                       float* flow, uint32_t* minmax,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- 8-bit colour ---------------------------------------------------------
+ * cv.cvtColor(frame, COLOR_BGR2GRAY)        computeOpticalFlowModule.py:16,19 */
+int ofc_bgr2gray(const uint8_t* bgr, uint8_t* gray, int64_t n_pixels, void* stream);
+/* min / max of |flow| per frame (IEEE bits), for flows that did not come from
+ * ofc_farneback_*; first step of cv.normalize(..., NORM_MINMAX)  :31 */
+int ofc_flow_minmax(const float* flow, int n_frames, int64_t n_pixels, uint32_t* minmax, void* stream);
+/* cv.cartToPolar + hue byte + cv.normalize + cv.cvtColor(HSV2BGR)  :25-33.
+ * mag_sum (nullable, f64[n_frames]) receives the sum of |flow| per frame for
+ * the "Average Magnitude" series of computeOpticalFlow.py:114-117,146-149.
+ * The row width matters: cv2's HSV2BGR truncates in its 32-pixel SIMD body and
+ * rounds in the scalar tail (last width % 32 pixels of each row). */
+int ofc_flow_to_bgr(const float* flow, int n_frames, int height, int width, const uint32_t* minmax,
+                    uint8_t* bgr, double* mag_sum, void* stream);
+
+/* ---- grid-cell aggregation ------------------------------------------------
+ * overlayGridAndComputeAvgColor (KmeanGrids.py:52-113,
+ * drawGridsAndOutputCSV.py:47-135) and, for n_clusters = 1, the per-cell
+ * preprocess_image + KMeans(1) + rint + BGR2HSV of KmeanGrids.py:269-339 /
+ * color_kmeans.py:35-135.  cells = rows*cols in the reference's row-major
+ * order; any output pointer may be NULL.
+ *   draw_lines  reproduce the state of the white 1-px rectangles the reference
+ *               draws between the mean and the k-means stage
+ *   threshold   preprocess_image's "channel < 30 -> 0" (0 disables)         */
+int ofc_grid_cells(const uint8_t* bgr, int n_frames, int height, int width, int rows, int cols,
+                   int draw_lines, int threshold,
+                   uint8_t* avg_bgr /* [n][cells][3] */, uint8_t* avg_hue /* [n][cells] */,
+                   uint8_t* km_centre /* [n][cells][4] */, uint8_t* km_hue /* [n][cells] */,
+                   uint32_t* km_sums /* [n][cells][4] */, void* stream);
+/* cv2.rectangle(frame,(x1,y1),(x2,y2),(255,255,255),1) for every cell  KmeanGrids.py:108 */
+int ofc_draw_grid(uint8_t* bgr, int n_frames, int height, int width, int rows, int cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFC_H_ */

@@ -1,0 +1,48 @@
+"""Drop-in for the reference's k-means-color-clustering/computeOpticalFlowModule.py.
+
+Same class name (typo included), constructor, attributes and ``compute``
+contract (computeOpticalFlowModule.py:6-36): stateful per video, keeps
+``prev_gray``; ``compute(frame)`` returns a *new* uint8 BGR visualisation.
+numpy in -> numpy out; CUDA torch tensors in -> CUDA torch tensors out.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import flow as _flow
+
+
+class ComputeOpticalFLow:
+    def __init__(self, firstframe):
+        self.firstframe = firstframe
+        self.width = int(firstframe.shape[1])
+        self.height = int(firstframe.shape[0])
+        self._numpy = not isinstance(firstframe, torch.Tensor)
+        if self._numpy:
+            self.outputImg = np.zeros([self.height, 2 * self.width, 3], dtype=firstframe.dtype)
+            self.mask = np.zeros_like(firstframe)
+            self.mask[..., 1] = 255
+        else:
+            self.outputImg = None
+            self.mask = None
+        dev_frame = _flow.to_device_u8(firstframe)
+        self._plan = _flow.FarnebackPlan(self.width, self.height, 2, 0.5, 3, 15, 3, 5, 1.2, 0, device=dev_frame.device)
+        self._prev_gray = _flow.bgr2gray(dev_frame)
+        self._minmax = torch.empty((1, 2), dtype=torch.int32, device=dev_frame.device)
+        self.last_flow = None            # CUDA float32 [H,W,2] of the latest pair
+
+    @property
+    def prev_gray(self):
+        return self._prev_gray.cpu().numpy() if self._numpy else self._prev_gray
+
+    def compute(self, frame):
+        dev_frame = _flow.to_device_u8(frame, self._prev_gray.device)
+        gray = _flow.bgr2gray(dev_frame)
+        fl = self._plan.pair(self._prev_gray, gray, minmax=self._minmax)
+        bgr = _flow.flow_to_bgr(fl.unsqueeze(0), self._minmax)[0]
+        self._prev_gray = gray
+        self.last_flow = fl
+        if self._numpy:
+            return bgr.cpu().numpy()
+        return bgr

@@ -1,0 +1,480 @@
+// Farneback dense optical flow for sm_100a: Gaussian pre-filter + resample,
+// separable polynomial expansion, and the fused
+// update-matrices -> box blur -> 2x2 solve iteration.
+//
+// Replaces the arithmetic behind the reference's call
+//   cv.calcOpticalFlowFarneback(prev, next, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+// (reference k-means-color-clustering/computeOpticalFlowModule.py:20-22,
+// computeOpticalFlow.py:99-101).  Algorithm: SURVEY.md Appendix A.1/A.2.
+//
+// Layout in HBM (per pyramid level, per frame):
+//   I   float  [h][w]      pre-filtered, resampled image
+//   RA  float4 [h][w]      polynomial coefficients R0..R3
+//   RB  float  [h][w]      polynomial coefficient  R4
+// and per frame pair: flow float2 [h][w] (two ping-pong buffers per level).
+// R is split float4 + float so the bilinear gather of the warped frame is one
+// 128-bit and one 32-bit load per tap instead of five scalar loads.
+#include "ofc_common.cuh"
+#include "flow_kernels.cuh"
+
+namespace ofc {
+
+// ---------------------------------------------------------------------------
+// INTER_LINEAR source coordinate (cv::resize): index + fraction, clamped
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void src_coord(int d, double scale, int n_src, int& i, float& fr) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int ii = (int)floorf(f);
+    fr = f - (float)ii;
+    if (ii < 0) { ii = 0; fr = 0.f; }
+    if (ii >= n_src - 1) { ii = n_src - 1; fr = 0.f; }
+    i = ii;
+}
+
+// ---------------------------------------------------------------------------
+// K2: Gaussian pre-filter at full resolution fused with the bilinear
+// down-sample to this level.  Only the blurred samples the resize reads are
+// computed: a block stages the u8 source window in shared memory, runs the
+// horizontal taps for the two source columns of every output column, then the
+// vertical taps for the two source rows of every output row, then the lerp.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prefilter_kernel(PrefilterParams p) {
+    OFC_DYN_SMEM(unsigned char, smem);
+    float* taps = reinterpret_cast<float*>(smem);
+    float* hbuf = taps + p.taps_pad;                                   // [in_rows][tx][2]
+    unsigned char* tile = reinterpret_cast<unsigned char*>(hbuf + (size_t)p.in_rows * p.tx * 2);  // [in_rows][in_pitch]
+
+    const int tid = threadIdx.x;
+    const int r = p.ksz >> 1;
+    const int x0 = blockIdx.x * p.tx, y0 = blockIdx.y * p.ty;
+    const int x_last = min(x0 + p.tx, p.w) - 1, y_last = min(y0 + p.ty, p.h) - 1;
+    const unsigned char* src = p.gray + (int64_t)blockIdx.z * p.gray_stride;
+
+    int c_first, c_last, r_first, r_last;
+    float fr_unused;
+    src_coord(x0, p.sx, p.W, c_first, fr_unused);
+    src_coord(x_last, p.sx, p.W, c_last, fr_unused);
+    src_coord(y0, p.sy, p.H, r_first, fr_unused);
+    src_coord(y_last, p.sy, p.H, r_last, fr_unused);
+    const int c_lo = c_first - r, r_lo = r_first - r;
+    const int ncols = min(c_last + 1, p.W - 1) + r - c_lo + 1;
+    const int nrows = min(r_last + 1, p.H - 1) + r - r_lo + 1;
+
+    for (int i = tid; i < p.ksz; i += blockDim.x) taps[i] = p.taps[i];
+    for (int i = tid; i < nrows * ncols; i += blockDim.x) {
+        int rr = i / ncols, cc = i - rr * ncols;
+        int sy = reflect101(r_lo + rr, p.H), sx = reflect101(c_lo + cc, p.W);
+        tile[rr * p.in_pitch + cc] = src[(int64_t)sy * p.W + sx];
+    }
+    __syncthreads();
+
+    // horizontal taps at the two sample columns of each output column
+    const int nx = x_last - x0 + 1;
+    for (int i = tid; i < nrows * nx * 2; i += blockDim.x) {
+        int c = i & 1;
+        int xx = (i >> 1) % nx;
+        int rr = (i >> 1) / nx;
+        int ci; float fr;
+        src_coord(x0 + xx, p.sx, p.W, ci, fr);
+        ci = min(ci + c, p.W - 1);
+        const unsigned char* t = tile + rr * p.in_pitch + (ci - r - c_lo);
+        float s = 0.f;
+        for (int j = 0; j < p.ksz; ++j) s = fmaf(taps[j], (float)t[j], s);
+        hbuf[(rr * p.tx + xx) * 2 + c] = s;
+    }
+    __syncthreads();
+
+    float* out = p.out + (int64_t)blockIdx.z * p.out_stride;
+    const int ny = y_last - y0 + 1;
+    for (int i = tid; i < ny * nx; i += blockDim.x) {
+        int yy = i / nx, xx = i - yy * nx;
+        int ci, ri; float fx, fy;
+        src_coord(x0 + xx, p.sx, p.W, ci, fx);
+        src_coord(y0 + yy, p.sy, p.H, ri, fy);
+        int ra = ri - r - r_lo, rb = min(ri + 1, p.H - 1) - r - r_lo;
+        float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+        for (int j = 0; j < p.ksz; ++j) {
+            float t = taps[j];
+            const float* ha = hbuf + ((ra + j) * p.tx + xx) * 2;
+            const float* hb = hbuf + ((rb + j) * p.tx + xx) * 2;
+            b00 = fmaf(t, ha[0], b00); b01 = fmaf(t, ha[1], b01);
+            b10 = fmaf(t, hb[0], b10); b11 = fmaf(t, hb[1], b11);
+        }
+        float top = b00 * (1.f - fx) + b01 * fx;
+        float bot = b10 * (1.f - fx) + b11 * fx;
+        out[(int64_t)(y0 + yy) * p.w + x0 + xx] = top * (1.f - fy) + bot * fy;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: separable polynomial expansion (FarnebackPolyExp), I -> (RA, RB).
+// 64x32 output tile per 256-thread block; the vertical pass keeps 4 rows per
+// thread in registers, the horizontal pass 4 columns per thread fed by 128-bit
+// shared-memory loads.
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256) polyexp_kernel(PolyParams p) {
+    constexpr int TW = 64, TH = 32;
+    constexpr int IW = TW + 2 * N, IH = TH + 2 * N;
+    constexpr int PITCH = (IW + 3) / 4 * 4;
+    __shared__ __align__(16) float s_in[IH * PITCH];
+    __shared__ __align__(16) float s_v[3][TH * PITCH];
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const float* I = p.I + (int64_t)blockIdx.z * p.in_stride;
+
+    for (int i = tid; i < IH * IW; i += 256) {
+        int rr = i / IW, cc = i - rr * IW;
+        int sy = clampi(y0 - N + rr, 0, p.h - 1), sx = clampi(x0 - N + cc, 0, p.w - 1);
+        s_in[rr * PITCH + cc] = I[(int64_t)sy * p.w + sx];
+    }
+    __syncthreads();
+
+    // vertical pass: r0 = sum g*I, r1 = sum xg*(I+ - I-), r2 = sum xxg*(I+ + I-)
+    for (int t = tid; t < IW * (TH / 4); t += 256) {
+        int cc = t % IW, seg = t / IW;
+        float v[4 + 2 * N];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; ++j) v[j] = s_in[(seg * 4 + j) * PITCH + cc];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float c = v[o + N];
+            float r0 = c * p.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                float up = v[o + N - k], dn = v[o + N + k];
+                float s = dn + up;
+                r0 = fmaf(p.g[k], s, r0);
+                r1 = fmaf(p.xg[k], dn - up, r1);
+                r2 = fmaf(p.xxg[k], s, r2);
+            }
+            int row = seg * 4 + o;
+            s_v[0][row * PITCH + cc] = r0;
+            s_v[1][row * PITCH + cc] = r1;
+            s_v[2][row * PITCH + cc] = r2;
+        }
+    }
+    __syncthreads();
+
+    float4* RA = p.RA + (int64_t)blockIdx.z * p.out_stride;
+    float* RB = p.RB + (int64_t)blockIdx.z * p.out_stride;
+    for (int t = tid; t < TH * (TW / 4); t += 256) {
+        int seg = t % (TW / 4), row = t / (TW / 4);
+        int gy = y0 + row, gx = x0 + seg * 4;
+        if (gy >= p.h || gx >= p.w) continue;
+        constexpr int NV = (4 + 2 * N + 3) / 4 * 4;
+        float a0[NV], a1[NV], a2[NV];
+#pragma unroll
+        for (int j = 0; j < NV / 4; ++j) {
+            float4 q0 = *reinterpret_cast<const float4*>(&s_v[0][row * PITCH + seg * 4 + j * 4]);
+            float4 q1 = *reinterpret_cast<const float4*>(&s_v[1][row * PITCH + seg * 4 + j * 4]);
+            float4 q2 = *reinterpret_cast<const float4*>(&s_v[2][row * PITCH + seg * 4 + j * 4]);
+            a0[j * 4 + 0] = q0.x; a0[j * 4 + 1] = q0.y; a0[j * 4 + 2] = q0.z; a0[j * 4 + 3] = q0.w;
+            a1[j * 4 + 0] = q1.x; a1[j * 4 + 1] = q1.y; a1[j * 4 + 2] = q1.z; a1[j * 4 + 3] = q1.w;
+            a2[j * 4 + 0] = q2.x; a2[j * 4 + 1] = q2.y; a2[j * 4 + 2] = q2.z; a2[j * 4 + 3] = q2.w;
+        }
+        float4 ra[4];
+        float rb[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int c = o + N;
+            float b1 = a0[c] * p.g[0], b3 = a1[c] * p.g[0], b5 = a2[c] * p.g[0];
+            float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                float tg = a0[c + k] + a0[c - k];
+                b1 = fmaf(tg, p.g[k], b1);
+                b4 = fmaf(tg, p.xxg[k], b4);
+                b2 = fmaf(a0[c + k] - a0[c - k], p.xg[k], b2);
+                b3 = fmaf(a1[c + k] + a1[c - k], p.g[k], b3);
+                b6 = fmaf(a1[c + k] - a1[c - k], p.xg[k], b6);
+                b5 = fmaf(a2[c + k] + a2[c - k], p.g[k], b5);
+            }
+            ra[o].x = b3 * p.ig11;
+            ra[o].y = b2 * p.ig11;
+            ra[o].z = fmaf(b1, p.ig03, b5 * p.ig33);
+            ra[o].w = fmaf(b1, p.ig03, b4 * p.ig33);
+            rb[o] = b6 * p.ig55;
+        }
+        int64_t base = (int64_t)gy * p.w + gx;
+        if (gx + 3 < p.w) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) RA[base + o] = ra[o];
+            if ((p.w & 3) == 0) {
+                *reinterpret_cast<float4*>(RB + base) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+            } else {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) RB[base + o] = rb[o];
+            }
+        } else {
+            for (int o = 0; o < 4 && gx + o < p.w; ++o) { RA[base + o] = ra[o]; RB[base + o] = rb[o]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4+K5+K6 fused: one Farneback iteration.
+//   phase 1  M(y,x) for the tile + box-filter halo, straight from R0, warped R1
+//            and the current flow (optionally the x2 up-sampled coarse flow):
+//            M never goes to HBM;
+//   phase 2  vertical (2R+1)-row sliding sums, in place, one column per thread;
+//   phase 3  horizontal sliding sums for 8 pixels per thread (128-bit shared
+//            loads), the 2x2 solve, the flow store, and -- on the last
+//            iteration of level 0 -- the magnitude min/max the visualisation
+//            needs (warp-shuffle reduce + one atomic pair per warp).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float2 load_flow(const IterParams& p, const float2* fin, int gx, int gy) {
+    if (fin == nullptr) return make_float2(0.f, 0.f);
+    if (!p.upsample) return fin[(int64_t)gy * p.w + gx];
+    int xi, yi; float fx, fy;
+    src_coord(gx, p.usx, p.wc, xi, fx);
+    src_coord(gy, p.usy, p.hc, yi, fy);
+    int xj = min(xi + 1, p.wc - 1), yj = min(yi + 1, p.hc - 1);
+    float2 q00 = fin[(int64_t)yi * p.wc + xi], q01 = fin[(int64_t)yi * p.wc + xj];
+    float2 q10 = fin[(int64_t)yj * p.wc + xi], q11 = fin[(int64_t)yj * p.wc + xj];
+    float ax = 1.f - fx, ay = 1.f - fy;
+    float tx0 = q00.x * ax + q01.x * fx, tx1 = q10.x * ax + q11.x * fx;
+    float ty0 = q00.y * ax + q01.y * fx, ty1 = q10.y * ax + q11.y * fx;
+    float u = tx0 * ay + tx1 * fy, v = ty0 * ay + ty1 * fy;
+    return make_float2((float)((double)u * p.flow_mul), (float)((double)v * p.flow_mul));
+}
+
+template <int R, int TH, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) flow_iter_kernel(IterParams p) {
+    constexpr int TW = 64;
+    static_assert(NT >= 8 * TH, "one phase-3 task per thread");
+    constexpr int MW = TW + 2 * R, MH = TH + 2 * R;
+    constexpr int P0 = (MW + 2 + 3) / 4 * 4;                 // room for the 128-bit over-read
+    constexpr int PITCH = ((P0 / 4) % 2 == 0) ? P0 + 4 : P0; // pitch/4 odd: conflict-free LDS.128
+    constexpr int CH = MH * PITCH;
+    OFC_DYN_SMEM(float, sm);                                 // [5][MH][PITCH]
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int pair = blockIdx.z;
+    const int w = p.w, h = p.h;
+    const float4* RA0 = p.RA + (int64_t)pair * p.r_stride;
+    const float* RB0 = p.RB + (int64_t)pair * p.r_stride;
+    const float4* RA1 = RA0 + p.r_next;
+    const float* RB1 = RB0 + p.r_next;
+    const float2* fin = p.flow_in ? p.flow_in + (int64_t)pair * p.flow_in_stride : nullptr;
+
+    // ---- phase 1: update matrices on the haloed tile -----------------------
+    for (int i = tid; i < MH * MW; i += NT) {
+        int my = i / MW, mx = i - my * MW;
+        int gy = clampi(y0 - R + my, 0, h - 1), gx = clampi(x0 - R + mx, 0, w - 1);
+        float2 fl = load_flow(p, fin, gx, gy);
+        float dx = fl.x, dy = fl.y;
+        float fx = (float)gx + dx, fy = (float)gy + dy;
+        int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+        fx -= (float)x1; fy -= (float)y1;
+        int64_t o0 = (int64_t)gy * w + gx;
+        float4 a = RA0[o0];
+        float b = RB0[o0];
+        float r2, r3, r4, r5, r6;
+        if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+            float a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy, a00 = (1.f - fx) * (1.f - fy);
+            int64_t o1 = (int64_t)y1 * w + x1;
+            float4 q00 = RA1[o1], q01 = RA1[o1 + 1], q10 = RA1[o1 + w], q11 = RA1[o1 + w + 1];
+            float s00 = RB1[o1], s01 = RB1[o1 + 1], s10 = RB1[o1 + w], s11 = RB1[o1 + w + 1];
+            r2 = a00 * q00.x + a01 * q01.x + a10 * q10.x + a11 * q11.x;
+            r3 = a00 * q00.y + a01 * q01.y + a10 * q10.y + a11 * q11.y;
+            r4 = a00 * q00.z + a01 * q01.z + a10 * q10.z + a11 * q11.z;
+            r5 = a00 * q00.w + a01 * q01.w + a10 * q10.w + a11 * q11.w;
+            r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
+            r4 = (a.z + r4) * 0.5f;
+            r5 = (a.w + r5) * 0.5f;
+            r6 = (b + r6) * 0.25f;
+        } else {
+            r2 = r3 = 0.f;
+            r4 = a.z; r5 = a.w; r6 = b * 0.5f;
+        }
+        r2 = (a.x - r2) * 0.5f;
+        r3 = (a.y - r3) * 0.5f;
+        r2 += r4 * dy + r6 * dx;
+        r3 += r6 * dy + r5 * dx;
+        if ((unsigned)(gx - 5) >= (unsigned)(w - 10) || (unsigned)(gy - 5) >= (unsigned)(h - 10)) {
+            float sc = (gx < 5 ? p.border[gx] : 1.f) * (gx >= w - 5 ? p.border[w - gx - 1] : 1.f) *
+                       (gy < 5 ? p.border[gy] : 1.f) * (gy >= h - 5 ? p.border[h - gy - 1] : 1.f);
+            r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+        }
+        float* d = sm + my * PITCH + mx;
+        d[0 * CH] = r4 * r4 + r6 * r6;
+        d[1 * CH] = (r4 + r5) * r6;
+        d[2 * CH] = r5 * r5 + r6 * r6;
+        d[3 * CH] = r4 * r2 + r6 * r3;
+        d[4 * CH] = r6 * r2 + r5 * r3;
+    }
+    __syncthreads();
+
+    // ---- phase 2: vertical sliding sums, in place --------------------------
+    for (int t = tid; t < 5 * MW; t += NT) {
+        int ch = t / MW, mx = t - ch * MW;
+        float* col = sm + ch * CH + mx;
+        float ring[2 * R + 1];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MH; ++i) {
+            float v = col[i * PITCH];
+            if (i >= 2 * R + 1) s -= ring[i % (2 * R + 1)];
+            ring[i % (2 * R + 1)] = v;
+            s += v;
+            if (i >= 2 * R) col[(i - 2 * R) * PITCH] = s;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: horizontal sums (8 px / thread) + solve ------------------
+    const int row = tid % TH, seg = tid / TH;
+    const int gy = y0 + row, gx0 = x0 + seg * 8;
+    float lmin = 3.402823466e38f, lmax = 0.f;
+    if (seg < 8 && gy < h && gx0 < w) {
+        constexpr int NV = (8 + 2 * R + 3) / 4 * 4;
+        float S[5][8];
+#pragma unroll
+        for (int ch = 0; ch < 5; ++ch) {
+            const float* src = sm + ch * CH + row * PITCH + seg * 8;
+            float v[NV];
+#pragma unroll
+            for (int j = 0; j < NV / 4; ++j) {
+                float4 q = *reinterpret_cast<const float4*>(src + j * 4);
+                v[j * 4 + 0] = q.x; v[j * 4 + 1] = q.y; v[j * 4 + 2] = q.z; v[j * 4 + 3] = q.w;
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 2 * R + 1; ++j) s += v[j];
+            S[ch][0] = s;
+#pragma unroll
+            for (int j = 1; j < 8; ++j) {
+                s += v[j + 2 * R] - v[j - 1];
+                S[ch][j] = s;
+            }
+        }
+        float2 res[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double g11 = (double)S[0][j] * p.blur_scale, g12 = (double)S[1][j] * p.blur_scale;
+            double g22 = (double)S[2][j] * p.blur_scale;
+            double h1 = (double)S[3][j] * p.blur_scale, h2 = (double)S[4][j] * p.blur_scale;
+            double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+            res[j].x = (float)((g11 * h2 - g12 * h1) * idet);
+            res[j].y = (float)((g22 * h1 - g12 * h2) * idet);
+        }
+        float2* out = p.flow_out + (int64_t)pair * p.flow_out_stride + (int64_t)gy * w + gx0;
+        if (gx0 + 7 < w && (w & 1) == 0) {
+            float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o4[j] = make_float4(res[2 * j].x, res[2 * j].y, res[2 * j + 1].x, res[2 * j + 1].y);
+        } else {
+            for (int j = 0; j < 8 && gx0 + j < w; ++j) out[j] = res[j];
+        }
+        if (p.minmax) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (gx0 + j < w) {
+                    float m = sqrtf(__fmaf_rn(res[j].x, res[j].x, __fmul_rn(res[j].y, res[j].y)));
+                    lmin = fminf(lmin, m);
+                    lmax = fmaxf(lmax, m);
+                }
+            }
+        }
+    }
+    if (p.minmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        }
+        if ((tid & 31) == 0) {
+            // magnitudes are >= 0, so the IEEE bit patterns order like unsigned ints
+            atomicMin(p.minmax + 2 * pair, __float_as_uint(lmin));
+            atomicMax(p.minmax + 2 * pair + 1, __float_as_uint(lmax));
+        }
+    }
+}
+
+__global__ void minmax_init_kernel(unsigned* mm, int n_pairs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pairs) {
+        mm[2 * i] = 0x7f7fffffu;   // FLT_MAX
+        mm[2 * i + 1] = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* stream) {
+    dim3 grid(cdiv(p.w, p.tx), cdiv(p.h, p.ty), n_frames);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        OFC_CUDA(cudaFuncSetAttribute(prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    ProfScope prof(PK_PREFILTER, stream);
+    OFC_LAUNCH(prefilter_kernel, grid, dim3(256), smem, stream, p);
+    OFC_CHECK_LAUNCH("prefilter");
+    return OFC_OK;
+}
+
+int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, void* stream) {
+    dim3 grid(cdiv(p.w, 64), cdiv(p.h, 32), n_frames);
+    ProfScope prof(PK_POLYEXP, stream);
+    if (poly_n == 5) {
+        OFC_LAUNCH(polyexp_kernel<5>, grid, dim3(256), 0, stream, p);
+    } else if (poly_n == 7) {
+        OFC_LAUNCH(polyexp_kernel<7>, grid, dim3(256), 0, stream, p);
+    } else {
+        set_error("poly_n=%d unsupported (5 or 7)", poly_n);
+        return OFC_ERR_UNSUPPORTED;
+    }
+    OFC_CHECK_LAUNCH("polyexp");
+    return OFC_OK;
+}
+
+template <int R, int TH, int NT, int MINB>
+static int launch_iter_r(const IterParams& p, int n_pairs, void* stream) {
+    constexpr int MW = 64 + 2 * R, MH = TH + 2 * R;
+    constexpr int P0 = (MW + 2 + 3) / 4 * 4;
+    constexpr int PITCH = ((P0 / 4) % 2 == 0) ? P0 + 4 : P0;
+    constexpr size_t smem = (size_t)5 * MH * PITCH * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        OFC_CUDA(cudaFuncSetAttribute(flow_iter_kernel<R, TH, NT, MINB>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(cdiv(p.w, 64), cdiv(p.h, TH), n_pairs);
+    ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
+    OFC_LAUNCH((flow_iter_kernel<R, TH, NT, MINB>), grid, dim3(NT), smem, stream, p);
+    OFC_CHECK_LAUNCH("flow_iter");
+    return OFC_OK;
+}
+
+int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, void* stream) {
+    switch (winsize / 2) {
+        case 2: return launch_iter_r<2, 32, 256, 3>(p, n_pairs, stream);
+        case 3: return launch_iter_r<3, 32, 256, 3>(p, n_pairs, stream);
+        case 4: return launch_iter_r<4, 32, 256, 3>(p, n_pairs, stream);
+        case 5: return launch_iter_r<5, 32, 256, 3>(p, n_pairs, stream);
+        case 6: return launch_iter_r<6, 32, 256, 3>(p, n_pairs, stream);
+        case 7:
+            // winsize 15 (the reference's value): 64x30 tile = 73.9 KB -> 3 CTAs/SM
+            return launch_iter_r<7, 30, 256, 3>(p, n_pairs, stream);
+        case 10: return launch_iter_r<10, 32, 256, 2>(p, n_pairs, stream);
+        case 12: return launch_iter_r<12, 32, 256, 2>(p, n_pairs, stream);
+        default:
+            set_error("winsize=%d unsupported (odd 5..15, 21, 25)", winsize);
+            return OFC_ERR_UNSUPPORTED;
+    }
+}
+
+int launch_minmax_init(unsigned* mm, int n_pairs, void* stream) {
+    ProfScope prof(PK_MINMAX_INIT, stream);
+    OFC_LAUNCH(minmax_init_kernel, dim3(cdiv(n_pairs, 128)), dim3(128), 0, stream, mm, n_pairs);
+    OFC_CHECK_LAUNCH("minmax_init");
+    return OFC_OK;
+}
+
+}  // namespace ofc

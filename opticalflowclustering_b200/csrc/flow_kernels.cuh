@@ -1,0 +1,55 @@
+// Kernel parameter blocks and launchers of flow_kernels.cu (internal header).
+#pragma once
+#include "ofc_common.cuh"
+
+namespace ofc {
+
+struct PrefilterParams {
+    const unsigned char* gray;   // [n_frames][H][W]
+    int64_t gray_stride;         // bytes between frames
+    float* out;                  // [n_frames][h][w]
+    int64_t out_stride;          // floats between frames
+    int W, H, w, h;              // source / level size
+    int ksz;                     // Gaussian taps (odd)
+    double sx, sy;               // source/level ratio used by cv::resize
+    const float* taps;           // device, ksz floats
+    int tx, ty;                  // output tile
+    int in_rows, in_pitch;       // staged source window (max over tiles)
+    int taps_pad;
+};
+
+struct PolyParams {
+    const float* I;
+    int64_t in_stride;
+    float4* RA;
+    float* RB;
+    int64_t out_stride;          // pixels between frames
+    int w, h;
+    float g[8], xg[8], xxg[8];
+    float ig11, ig03, ig33, ig55;
+};
+
+struct IterParams {
+    const float4* RA;            // level's R for frame 0 of the batch
+    const float* RB;
+    int64_t r_stride;            // pixels between the "prev" frames of consecutive pairs
+    int64_t r_next;              // pixels from a pair's "prev" frame to its "next" frame
+    const float2* flow_in;       // null -> zero flow
+    int64_t flow_in_stride;      // float2 between pairs
+    int upsample;                // flow_in is the coarser level: bilinear resize * flow_mul
+    int wc, hc;
+    double usx, usy, flow_mul;
+    float2* flow_out;
+    int64_t flow_out_stride;
+    int w, h;
+    unsigned* minmax;            // [n_pairs][2] float bits (min, max) of |flow|, or null
+    float border[5];
+    double blur_scale;           // 1 / winsize^2
+};
+
+int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* stream);
+int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, void* stream);
+int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, void* stream);
+int launch_minmax_init(unsigned* mm, int n_pairs, void* stream);
+
+}  // namespace ofc

@@ -1,0 +1,450 @@
+// C-ABI entry points of libofc (declared in include/ofc.h) and the host-side
+// Farneback driver: pyramid plan, workspace layout, per-level launch sequence.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/ofc.h"
+#include "ofc_common.cuh"
+#include "flow_kernels.cuh"
+#include "grid_kernels.cuh"
+#include "viz_kernels.cuh"
+
+namespace ofc {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return OFC_OK;
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return OFC_ERR_CUDA;
+}
+
+// ---- optional per-kernel event timing --------------------------------------
+struct ProfRec { int kind; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+int g_prof_level = 0;
+
+ProfScope::ProfScope(int kind_, void* stream_) : kind(kind_), stream(stream_), on(g_prof_on) {
+    if (!on) return;
+    ProfRec r;
+    r.kind = kind;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { on = false; return; }
+    cudaEventRecord(r.a, (cudaStream_t)stream);
+    g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (on) cudaEventRecord(g_prof.back().b, (cudaStream_t)stream);
+}
+
+// cvRound: round half to even
+static int cv_round(double v) { return (int)nearbyint(v); }
+
+struct Level {
+    int k;                 // pyramid index (0 = full resolution)
+    int w, h;
+    int ksz;
+    double sigma;
+    double sx, sy;         // cv::resize source/destination ratio
+    int tx, ty, in_rows, in_pitch, taps_pad;
+    size_t prefilter_smem;
+    size_t off_I, off_RA, off_RB, off_flow[2];
+    size_t taps_off;       // floats into the device tap table
+};
+
+}  // namespace ofc
+
+struct ofc_flow_plan {
+    int W, H, max_frames;
+    double pyr_scale;
+    int levels, winsize, iterations, poly_n;
+    double poly_sigma;
+    std::vector<ofc::Level> lv;      // coarsest first
+    size_t workspace_bytes;
+    float* d_taps;
+    ofc::PolyParams poly;            // taps / inverse-Gram constants filled in
+};
+
+namespace ofc {
+
+static void gaussian_taps(int ksize, double sigma, std::vector<float>& out) {
+    out.resize(ksize);
+    if (sigma <= 0 && ksize == 3) { out[0] = 0.25f; out[1] = 0.5f; out[2] = 0.25f; return; }
+    if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+    std::vector<double> g(ksize);
+    double c = (ksize - 1) * 0.5, sum = 0;
+    for (int i = 0; i < ksize; ++i) { double x = i - c; g[i] = exp(-(x * x) / (2.0 * sigma * sigma)); sum += g[i]; }
+    for (int i = 0; i < ksize; ++i) out[i] = (float)(g[i] / sum);
+}
+
+// FarnebackPrepareGaussian: taps and the four inverse-Gram entries
+static int prepare_poly(int n, double sigma, PolyParams& pp) {
+    if (n > 7) { set_error("poly_n=%d unsupported", n); return OFC_ERR_UNSUPPORTED; }
+    float g[15], xg[15], xxg[15];
+    double s = 0;
+    for (int x = -n; x <= n; ++x) { g[x + n] = (float)exp(-x * x / (2.0 * sigma * sigma)); s += g[x + n]; }
+    s = 1.0 / s;
+    for (int x = -n; x <= n; ++x) {
+        g[x + n] = (float)(g[x + n] * s);
+        xg[x + n] = (float)(x * g[x + n]);
+        xxg[x + n] = (float)(x * x * g[x + n]);
+    }
+    double G[6][6];
+    memset(G, 0, sizeof(G));
+    for (int y = -n; y <= n; ++y)
+        for (int x = -n; x <= n; ++x) {
+            double w = (double)g[y + n] * g[x + n];
+            G[0][0] += w;
+            G[1][1] += w * x * x;
+            G[3][3] += w * x * x * x * x;
+            G[5][5] += w * x * x * y * y;
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    // Gauss-Jordan inverse (6x6, symmetric positive definite)
+    double A[6][12];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 12; ++j) A[i][j] = j < 6 ? G[i][j] : (j - 6 == i ? 1.0 : 0.0);
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+        if (fabs(A[piv][c]) < 1e-300) { set_error("singular Gram matrix"); return OFC_ERR_INVALID; }
+        if (piv != c) for (int j = 0; j < 12; ++j) { double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+        double d = 1.0 / A[c][c];
+        for (int j = 0; j < 12; ++j) A[c][j] *= d;
+        for (int r = 0; r < 6; ++r) if (r != c) {
+            double f = A[r][c];
+            if (f != 0) for (int j = 0; j < 12; ++j) A[r][j] -= f * A[c][j];
+        }
+    }
+    for (int k = 0; k <= n; ++k) { pp.g[k] = g[n + k]; pp.xg[k] = xg[n + k]; pp.xxg[k] = xxg[n + k]; }
+    pp.ig11 = (float)A[1][6 + 1];
+    pp.ig03 = (float)A[0][6 + 3];
+    pp.ig33 = (float)A[3][6 + 3];
+    pp.ig55 = (float)A[5][6 + 5];
+    return OFC_OK;
+}
+
+static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t gray_stride, int n_frames,
+                         float* flow, uint32_t* minmax, void* workspace, size_t workspace_bytes, void* stream) {
+    OFC_REQUIRE(pl != nullptr, "null plan");
+    OFC_REQUIRE(n_frames >= 2 && n_frames <= pl->max_frames, "n_frames=%d outside [2, %d]", n_frames, pl->max_frames);
+    OFC_REQUIRE(gray && flow && workspace, "null buffer");
+    if (workspace_bytes < pl->workspace_bytes) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, pl->workspace_bytes);
+        return OFC_ERR_WORKSPACE;
+    }
+    OFC_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    char* ws = (char*)workspace;
+    const int n_pairs = n_frames - 1;
+    const int F = pl->max_frames;
+    const int nl = (int)pl->lv.size();
+
+    // stage 1: pre-filter + polynomial expansion of every frame at every level
+    for (int l = 0; l < nl; ++l) {
+        const Level& L = pl->lv[l];
+        PrefilterParams pf;
+        pf.gray = gray; pf.gray_stride = gray_stride;
+        pf.out = (float*)(ws + L.off_I); pf.out_stride = (int64_t)L.w * L.h;
+        pf.W = pl->W; pf.H = pl->H; pf.w = L.w; pf.h = L.h;
+        pf.ksz = L.ksz; pf.sx = L.sx; pf.sy = L.sy;
+        pf.taps = pl->d_taps + L.taps_off;
+        pf.tx = L.tx; pf.ty = L.ty; pf.in_rows = L.in_rows; pf.in_pitch = L.in_pitch; pf.taps_pad = L.taps_pad;
+        int rc = launch_prefilter(pf, n_frames, L.prefilter_smem, stream);
+        if (rc != OFC_OK) return rc;
+        PolyParams pp = pl->poly;
+        pp.I = pf.out; pp.in_stride = pf.out_stride;
+        pp.RA = (float4*)(ws + L.off_RA); pp.RB = (float*)(ws + L.off_RB);
+        pp.out_stride = (int64_t)L.w * L.h; pp.w = L.w; pp.h = L.h;
+        rc = launch_polyexp(pp, pl->poly_n, n_frames, stream);
+        if (rc != OFC_OK) return rc;
+    }
+    if (minmax) {
+        int rc = launch_minmax_init(minmax, n_pairs, stream);
+        if (rc != OFC_OK) return rc;
+    }
+    // stage 2: coarse-to-fine iterations, all pairs of the batch per launch
+    const float2* prev_flow = nullptr;
+    int prev_w = 0, prev_h = 0;
+    (void)F;
+    for (int l = 0; l < nl; ++l) {
+        const Level& L = pl->lv[l];
+        const int64_t npx = (int64_t)L.w * L.h;
+        for (int it = 0; it < pl->iterations; ++it) {
+            IterParams ip;
+            ip.RA = (const float4*)(ws + L.off_RA); ip.RB = (const float*)(ws + L.off_RB);
+            ip.r_stride = npx; ip.r_next = npx;
+            ip.w = L.w; ip.h = L.h;
+            ip.border[0] = 0.14f; ip.border[1] = 0.14f; ip.border[2] = 0.4472f; ip.border[3] = 0.4472f; ip.border[4] = 0.4472f;
+            ip.blur_scale = 1.0 / ((double)pl->winsize * pl->winsize);
+            ip.upsample = 0; ip.wc = ip.hc = 0; ip.usx = ip.usy = 1.0; ip.flow_mul = 1.0;
+            if (it == 0) {
+                ip.flow_in = prev_flow;
+                ip.flow_in_stride = (int64_t)prev_w * prev_h;
+                if (prev_flow) {
+                    ip.upsample = 1; ip.wc = prev_w; ip.hc = prev_h;
+                    ip.usx = 1.0 / ((double)L.w / prev_w);
+                    ip.usy = 1.0 / ((double)L.h / prev_h);
+                    ip.flow_mul = 1.0 / pl->pyr_scale;
+                }
+            } else {
+                ip.flow_in = (const float2*)(ws + L.off_flow[(it - 1) & 1]);
+                ip.flow_in_stride = npx;
+            }
+            const bool last = (l == nl - 1) && (it == pl->iterations - 1);
+            ip.flow_out = last ? (float2*)flow : (float2*)(ws + L.off_flow[it & 1]);
+            ip.flow_out_stride = npx;
+            ip.minmax = last ? minmax : nullptr;
+            g_prof_level = nl - 1 - l;
+            int rc = launch_flow_iter(ip, pl->winsize, n_pairs, stream);
+            if (rc != OFC_OK) return rc;
+        }
+        prev_flow = (const float2*)(ws + L.off_flow[(pl->iterations - 1) & 1]);
+        prev_w = L.w; prev_h = L.h;
+    }
+    return OFC_OK;
+}
+
+}  // namespace ofc
+
+using namespace ofc;
+
+extern "C" {
+
+int ofc_version(void) { return 100; }
+
+int ofc_profile_begin(void) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+    return OFC_OK;
+}
+
+int ofc_profile_end(float* ms_by_kind, int* launches_by_kind, int n_kinds) {
+    g_prof_on = false;
+    OFC_REQUIRE(ms_by_kind && launches_by_kind && n_kinds >= PK_COUNT, "need %d slots", (int)PK_COUNT);
+    for (int i = 0; i < n_kinds; ++i) { ms_by_kind[i] = 0.f; launches_by_kind[i] = 0; }
+    int rc = OFC_OK;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (rc == OFC_OK) rc = check_cuda(cudaEventSynchronize(r.b), "cudaEventSynchronize");
+        if (rc == OFC_OK) rc = check_cuda(cudaEventElapsedTime(&ms, r.a, r.b), "cudaEventElapsedTime");
+        if (rc == OFC_OK && r.kind >= 0 && r.kind < n_kinds) { ms_by_kind[r.kind] += ms; launches_by_kind[r.kind] += 1; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return rc;
+}
+
+const char* ofc_last_error(void) { return g_error; }
+
+int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_frames,
+                         double pyr_scale, int levels, int winsize, int iterations,
+                         int poly_n, double poly_sigma, int flags) {
+    OFC_REQUIRE(out != nullptr, "null plan pointer");
+    *out = nullptr;
+    if (flags != 0) {
+        set_error("flags=%d unsupported: only 0 (box window, no initial flow); there is no CPU fallback", flags);
+        return OFC_ERR_UNSUPPORTED;
+    }
+    OFC_REQUIRE(width >= 16 && height >= 16, "frame %dx%d too small", width, height);
+    OFC_REQUIRE(max_frames >= 2, "max_frames must be >= 2");
+    OFC_REQUIRE(pyr_scale > 0 && pyr_scale < 1, "pyr_scale must be in (0,1)");
+    OFC_REQUIRE(levels >= 0 && iterations >= 1, "levels >= 0 and iterations >= 1 required");
+    OFC_REQUIRE(winsize >= 5 && (winsize & 1), "winsize must be odd and >= 5");
+    OFC_REQUIRE(poly_sigma > 0, "poly_sigma must be > 0");
+    ofc_flow_plan* pl = new ofc_flow_plan();
+    pl->W = width; pl->H = height; pl->max_frames = max_frames;
+    pl->pyr_scale = pyr_scale; pl->levels = levels; pl->winsize = winsize;
+    pl->iterations = iterations; pl->poly_n = poly_n; pl->poly_sigma = poly_sigma;
+    pl->d_taps = nullptr;
+    memset(&pl->poly, 0, sizeof(pl->poly));
+    int rc = prepare_poly(poly_n, poly_sigma, pl->poly);
+    if (rc != OFC_OK) { delete pl; return rc; }
+    if (poly_n != 5 && poly_n != 7) { set_error("poly_n=%d unsupported (5 or 7)", poly_n); delete pl; return OFC_ERR_UNSUPPORTED; }
+    {   // winsize instantiations (see launch_flow_iter)
+        int r = winsize / 2;
+        if (!((r >= 2 && r <= 7) || r == 10 || r == 12)) {
+            set_error("winsize=%d unsupported (odd 5..15, 21, 25)", winsize);
+            delete pl; return OFC_ERR_UNSUPPORTED;
+        }
+    }
+    // pyramid: levels+1 scales, cropped while the coarse side stays >= 32
+    int eff = 0;
+    {
+        double scale = 1.0;
+        for (int k = 0; k < levels; ++k) {
+            scale *= pyr_scale;
+            if (width * scale < 32 || height * scale < 32) break;
+            ++eff;
+        }
+    }
+    std::vector<float> all_taps;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    for (int k = eff; k >= 0; --k) {
+        Level L;
+        L.k = k;
+        double scale = 1.0;
+        for (int i = 0; i < k; ++i) scale *= pyr_scale;
+        L.sigma = (1.0 / scale - 1.0) * 0.5;
+        int ksz = cv_round(L.sigma * 5) | 1;
+        L.ksz = ksz < 3 ? 3 : ksz;
+        L.w = cv_round(width * scale);
+        L.h = cv_round(height * scale);
+        L.sx = 1.0 / ((double)L.w / width);
+        L.sy = 1.0 / ((double)L.h / height);
+        if (L.ksz / 2 >= width || L.ksz / 2 >= height) {
+            set_error("Gaussian radius %d exceeds the frame", L.ksz / 2);
+            delete pl; return OFC_ERR_UNSUPPORTED;
+        }
+        std::vector<float> taps;
+        gaussian_taps(L.ksz, L.sigma, taps);
+        L.taps_off = all_taps.size();
+        all_taps.insert(all_taps.end(), taps.begin(), taps.end());
+        // prefilter tile: shrink until the staged window fits in shared memory
+        L.tx = 32; L.ty = 8;
+        for (;;) {
+            int in_cols = (int)ceil((L.tx - 1) * L.sx) + L.ksz + 3;
+            L.in_rows = (int)ceil((L.ty - 1) * L.sy) + L.ksz + 3;
+            L.in_pitch = (in_cols + 3) / 4 * 4;
+            L.taps_pad = (L.ksz + 3) / 4 * 4;
+            L.prefilter_smem = (size_t)L.taps_pad * 4 + (size_t)L.in_rows * L.tx * 2 * 4 + (size_t)L.in_rows * L.in_pitch;
+            if (L.prefilter_smem <= 200 * 1024) break;
+            if (L.tx == 1 && L.ty == 1) { set_error("pyramid level %d needs too much shared memory", k); delete pl; return OFC_ERR_UNSUPPORTED; }
+            if (L.tx >= 2 * L.ty && L.tx > 1) L.tx /= 2; else if (L.ty > 1) L.ty /= 2; else L.tx /= 2;
+        }
+        size_t npx = (size_t)L.w * L.h;
+        L.off_I = take(npx * 4 * max_frames);
+        L.off_RA = take(npx * 16 * max_frames);
+        L.off_RB = take(npx * 4 * max_frames);
+        L.off_flow[0] = take(npx * 8 * (max_frames - 1));
+        L.off_flow[1] = take(npx * 8 * (max_frames - 1));
+        pl->lv.push_back(L);
+    }
+    pl->workspace_bytes = off;
+    void* d = nullptr;
+    rc = check_cuda(cudaMalloc(&d, all_taps.size() * sizeof(float)), "cudaMalloc(taps)");
+    if (rc != OFC_OK) { delete pl; return rc; }
+    pl->d_taps = (float*)d;
+    rc = check_cuda(cudaMemcpy(pl->d_taps, all_taps.data(), all_taps.size() * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy(taps)");
+    if (rc != OFC_OK) { cudaFree(d); delete pl; return rc; }
+    *out = pl;
+    return OFC_OK;
+}
+
+void ofc_flow_plan_destroy(ofc_flow_plan* pl) {
+    if (!pl) return;
+    if (pl->d_taps) cudaFree(pl->d_taps);
+    delete pl;
+}
+
+size_t ofc_flow_plan_workspace_bytes(const ofc_flow_plan* pl) { return pl ? pl->workspace_bytes : 0; }
+
+int ofc_flow_plan_num_levels(const ofc_flow_plan* pl) { return pl ? (int)pl->lv.size() : 0; }
+
+int ofc_flow_plan_level_size(const ofc_flow_plan* pl, int level, int* w, int* h) {
+    OFC_REQUIRE(pl && level >= 0 && level < (int)pl->lv.size(), "bad level %d", level);
+    if (w) *w = pl->lv[level].w;
+    if (h) *h = pl->lv[level].h;
+    return OFC_OK;
+}
+
+int ofc_flow_plan_buffer(const ofc_flow_plan* pl, int level, int kind, size_t* offset_bytes, size_t* frame_stride_bytes) {
+    OFC_REQUIRE(pl && level >= 0 && level < (int)pl->lv.size(), "bad level %d", level);
+    const Level& L = pl->lv[level];
+    size_t npx = (size_t)L.w * L.h, o, s;
+    switch (kind) {
+        case 0: o = L.off_I; s = npx * 4; break;
+        case 1: o = L.off_RA; s = npx * 16; break;
+        case 2: o = L.off_RB; s = npx * 4; break;
+        case 3: o = L.off_flow[0]; s = npx * 8; break;
+        case 4: o = L.off_flow[1]; s = npx * 8; break;
+        default: set_error("bad buffer kind %d", kind); return OFC_ERR_INVALID;
+    }
+    if (offset_bytes) *offset_bytes = o;
+    if (frame_stride_bytes) *frame_stride_bytes = s;
+    return OFC_OK;
+}
+
+int ofc_farneback_sequence(const ofc_flow_plan* plan, const uint8_t* gray, int n_frames, float* flow,
+                           uint32_t* minmax, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!plan) { set_error("null plan"); return OFC_ERR_INVALID; }
+    return run_farneback(plan, gray, (int64_t)plan->W * plan->H, n_frames, flow, minmax, workspace, workspace_bytes, stream);
+}
+
+int ofc_farneback_pair(const ofc_flow_plan* plan, const uint8_t* prev, const uint8_t* next, float* flow,
+                       uint32_t* minmax, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!plan) { set_error("null plan"); return OFC_ERR_INVALID; }
+    OFC_REQUIRE(prev && next, "null frame");
+    return run_farneback(plan, prev, (int64_t)(next - prev), 2, flow, minmax, workspace, workspace_bytes, stream);
+}
+
+int ofc_bgr2gray(const uint8_t* bgr, uint8_t* gray, int64_t n_pixels, void* stream) {
+    OFC_REQUIRE(n_pixels >= 0 && (n_pixels == 0 || (bgr && gray)), "bad arguments");
+    OFC_REQUIRE(((uintptr_t)bgr & 3) == 0 && ((uintptr_t)gray & 3) == 0, "buffers must be 4-byte aligned");
+    return launch_bgr2gray(bgr, gray, n_pixels, stream);
+}
+
+int ofc_flow_minmax(const float* flow, int n_frames, int64_t n_pixels, uint32_t* minmax, void* stream) {
+    OFC_REQUIRE(n_frames >= 0 && n_pixels >= 0, "bad sizes");
+    if (n_frames == 0) return OFC_OK;
+    OFC_REQUIRE(flow && minmax, "null buffer");
+    int rc = launch_minmax_init(minmax, n_frames, stream);
+    if (rc != OFC_OK) return rc;
+    return launch_flow_minmax((const float2*)flow, n_pixels, n_frames, minmax, stream);
+}
+
+int ofc_flow_to_bgr(const float* flow, int n_frames, int height, int width, const uint32_t* minmax,
+                    uint8_t* bgr, double* mag_sum, void* stream) {
+    OFC_REQUIRE(n_frames >= 0 && height >= 0 && width >= 0, "bad sizes");
+    const int64_t n_pixels = (int64_t)height * width;
+    if (n_frames == 0 || n_pixels == 0) return OFC_OK;
+    OFC_REQUIRE(flow && minmax && bgr, "null buffer");
+    OFC_REQUIRE(((uintptr_t)flow & 15) == 0 && ((uintptr_t)bgr & 3) == 0, "flow must be 16-byte and bgr 4-byte aligned");
+    if (mag_sum) OFC_CUDA(cudaMemsetAsync(mag_sum, 0, sizeof(double) * n_frames, (cudaStream_t)stream));
+    VizParams p;
+    p.flow = (const float2*)flow; p.n_px = n_pixels; p.width = width; p.minmax = minmax; p.bgr = bgr; p.mag_sum = mag_sum;
+    return launch_flow_encode(p, n_frames, stream);
+}
+
+int ofc_grid_cells(const uint8_t* bgr, int n_frames, int height, int width, int rows, int cols,
+                   int draw_lines, int threshold, uint8_t* avg_bgr, uint8_t* avg_hue,
+                   uint8_t* km_centre, uint8_t* km_hue, uint32_t* km_sums, void* stream) {
+    OFC_REQUIRE(n_frames >= 0 && height > 0 && width > 0, "bad sizes");
+    OFC_REQUIRE(rows > 0 && cols > 0 && rows <= height && cols <= width, "grid %dx%d does not fit %dx%d", rows, cols, height, width);
+    OFC_REQUIRE(threshold >= 0 && threshold <= 255, "bad threshold");
+    if (n_frames == 0) return OFC_OK;
+    OFC_REQUIRE(bgr != nullptr, "null frame buffer");
+    GridParams p;
+    p.bgr = bgr; p.frame_stride = (int64_t)height * width * 3;
+    p.W = width; p.H = height; p.rows = rows; p.cols = cols;
+    p.x_step = width / cols; p.y_step = height / rows;       // int(width / cols)
+    OFC_REQUIRE((int64_t)p.x_step * p.y_step * 255 < (int64_t)1 << 32, "cell too large for 32-bit sums");
+    p.draw_lines = draw_lines; p.threshold = threshold;
+    p.avg_bgr = avg_bgr; p.avg_hue = avg_hue; p.km_centre = km_centre; p.km_hue = km_hue; p.km_sums = km_sums;
+    return launch_grid_cells(p, n_frames, stream);
+}
+
+int ofc_draw_grid(uint8_t* bgr, int n_frames, int height, int width, int rows, int cols, void* stream) {
+    OFC_REQUIRE(n_frames >= 0 && height > 0 && width > 0 && rows > 0 && cols > 0, "bad sizes");
+    OFC_REQUIRE(rows <= height && cols <= width, "grid does not fit the frame");
+    if (n_frames == 0) return OFC_OK;
+    OFC_REQUIRE(bgr != nullptr, "null frame buffer");
+    return launch_draw_grid(bgr, (int64_t)height * width * 3, width, height, rows, cols,
+                            width / cols, height / rows, n_frames, stream);
+}
+
+}  // extern "C"

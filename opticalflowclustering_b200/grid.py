@@ -1,0 +1,60 @@
+"""Host side of the grid stage (per-cell means, hues and the k = 1 colour cluster).
+
+Mirrors overlayGridAndComputeAvgColor of the reference
+(k-means-color-clustering/KmeanGrids.py:52-113, drawGridsAndOutputCSV.py:47-135)
+and the per-cell preprocess_image + KMeans(n_clusters=1) of
+KmeanGrids.py:269-339.  All arithmetic is integer and runs in libofc.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .flow import _ptr, _stream_ptr
+
+DEFAULT_GRID = {'rows': 14, 'cols': 25, 'cell_width': 50, 'cell_height': 50}   # KmeanGrids.py:177
+
+
+def grid_cells(bgr: torch.Tensor, rows: int = 14, cols: int = 25, draw_lines: bool = True, threshold: int = 30,
+               want=("avg_bgr", "avg_hue", "km_centre", "km_hue")) -> dict:
+    """One CTA per (cell, frame) over CUDA uint8 frames ``[n, H, W, 3]``.
+
+    Returns a dict of CUDA uint8 tensors (cells = rows*cols, reference order):
+      avg_bgr [n,cells,3]  floor(mean) per channel   (np.mean(...).astype(uint8))
+      avg_hue [n,cells]    cv2 BGR2HSV hue of avg_bgr
+      km_centre [n,cells,4] np.rint of the KMeans(1) centre of (c0,c1,c2,alpha)
+      km_hue  [n,cells]    hue of km_centre[:3]
+      km_sums [n,cells,4]  uint32 channel sums of the k-means input (optional)
+    """
+    if bgr.dim() == 3:
+        bgr = bgr.unsqueeze(0)
+    bgr = bgr.contiguous()
+    if bgr.dim() != 4 or bgr.shape[-1] != 3 or bgr.dtype != torch.uint8 or not bgr.is_cuda:
+        raise ValueError("bgr must be a CUDA uint8 tensor [n,H,W,3]")
+    n, H, W = int(bgr.shape[0]), int(bgr.shape[1]), int(bgr.shape[2])
+    cells = rows * cols
+    dev = bgr.device
+    shapes = {"avg_bgr": ((n, cells, 3), torch.uint8), "avg_hue": ((n, cells), torch.uint8),
+              "km_centre": ((n, cells, 4), torch.uint8), "km_hue": ((n, cells), torch.uint8),
+              "km_sums": ((n, cells, 4), torch.int32)}
+    out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in want}
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ofc_grid_cells(_ptr(bgr), n, H, W, rows, cols, int(bool(draw_lines)), int(threshold),
+                                             _ptr(out.get("avg_bgr")), _ptr(out.get("avg_hue")),
+                                             _ptr(out.get("km_centre")), _ptr(out.get("km_hue")),
+                                             _ptr(out.get("km_sums")), _stream_ptr()))
+    return out
+
+
+def draw_grid(bgr: torch.Tensor, rows: int = 14, cols: int = 25) -> torch.Tensor:
+    """In place: the white 1-px rectangles of KmeanGrids.py:108 on CUDA uint8 [n,H,W,3]."""
+    if bgr.dim() == 3:
+        view = bgr.unsqueeze(0)
+    else:
+        view = bgr
+    if not view.is_contiguous() or view.dtype != torch.uint8 or not view.is_cuda or view.shape[-1] != 3:
+        raise ValueError("bgr must be a contiguous CUDA uint8 tensor [n,H,W,3]")
+    n, H, W = int(view.shape[0]), int(view.shape[1]), int(view.shape[2])
+    with torch.cuda.device(view.device):
+        _lib.check(_lib.lib().ofc_draw_grid(_ptr(view), n, H, W, rows, cols, _stream_ptr()))
+    return bgr

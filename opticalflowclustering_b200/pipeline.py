@@ -1,0 +1,98 @@
+"""Batched clip pipeline: the hot path end to end on one GPU.
+
+    BGR frames -> gray -> Farneback flow -> HSV visualisation -> 14x25 grid
+    -> per-cell mean hue + per-cell k-means(1) hue
+
+i.e. what the reference's KmeanGrids.py main loop (:180-231, :376-399) does
+frame by frame in Python, run for a chunk of consecutive frames per launch
+sequence.  Frame pairs are independent given both frames, so a chunk of n
+frames yields n-1 pairs in one set of kernel launches (grid.z = pair); the
+pre-filter and polynomial expansion of every frame are computed once and used
+by both pairs it belongs to.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .flow import FarnebackPlan, _ptr, _stream_ptr
+
+
+class ClipPipeline:
+    def __init__(self, width: int, height: int, chunk_frames: int = 9, rows: int = 14, cols: int = 25,
+                 draw_lines: bool = True, threshold: int = 30, device=None, keep_viz: bool = False,
+                 pyr_scale: float = 0.5, levels: int = 3, winsize: int = 15, iterations: int = 3,
+                 poly_n: int = 5, poly_sigma: float = 1.2):
+        self.W, self.H, self.F = int(width), int(height), int(chunk_frames)
+        if self.F < 2:
+            raise ValueError("chunk_frames must be >= 2")
+        self.rows, self.cols = int(rows), int(cols)
+        self.cells = self.rows * self.cols
+        self.draw_lines, self.threshold = int(bool(draw_lines)), int(threshold)
+        self.plan = FarnebackPlan(width, height, self.F, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma,
+                                  0, device=device)
+        dev = self.device = self.plan.device
+        P = self.F - 1
+        self.gray = torch.empty((self.F, self.H, self.W), dtype=torch.uint8, device=dev)
+        self.flow = torch.empty((P, self.H, self.W, 2), dtype=torch.float32, device=dev)
+        self.minmax = torch.empty((P, 2), dtype=torch.int32, device=dev)
+        self.viz = torch.empty((P, self.H, self.W, 3), dtype=torch.uint8, device=dev)
+        self.mag_sum = torch.empty(P, dtype=torch.float64, device=dev)
+        self.avg_bgr = torch.empty((P, self.cells, 3), dtype=torch.uint8, device=dev)
+        self.avg_hue = torch.empty((P, self.cells), dtype=torch.uint8, device=dev)
+        self.km_centre = torch.empty((P, self.cells, 4), dtype=torch.uint8, device=dev)
+        self.km_hue = torch.empty((P, self.cells), dtype=torch.uint8, device=dev)
+        self.keep_viz = keep_viz
+        #: kernels launched by one full-chunk call of :meth:`run_chunk`
+        self.launches_per_chunk = 1 + 2 * self.plan.num_levels + 1 + self.plan.num_levels * iterations + 1 + 1
+
+    def run_chunk(self, frames: torch.Tensor, n_frames: int | None = None):
+        """frames: CUDA uint8 [n,H,W,3] (n <= chunk_frames).  Results stay in the
+        pipeline's buffers (``avg_hue``, ``km_hue``, ``km_centre``, ``mag_sum``, ``viz``,
+        ``flow``) for pairs 0..n-2; returns n-1."""
+        n = int(frames.shape[0]) if n_frames is None else int(n_frames)
+        if n < 2 or n > self.F:
+            raise ValueError(f"n_frames={n} outside [2, {self.F}]")
+        if tuple(frames.shape[1:]) != (self.H, self.W, 3) or frames.dtype != torch.uint8 or not frames.is_cuda:
+            raise ValueError("frames must be CUDA uint8 [n,H,W,3] of the pipeline's size")
+        if not frames.is_contiguous():
+            frames = frames.contiguous()
+        L = _lib.lib()
+        s = _stream_ptr()
+        P = n - 1
+        with torch.cuda.device(self.device):
+            _lib.check(L.ofc_bgr2gray(_ptr(frames), _ptr(self.gray), n * self.H * self.W, s))
+            _lib.check(L.ofc_farneback_sequence(self.plan._ptr, _ptr(self.gray), n, _ptr(self.flow), _ptr(self.minmax),
+                                                _ptr(self.plan.workspace), self.plan.workspace_bytes, s))
+            _lib.check(L.ofc_flow_to_bgr(_ptr(self.flow), P, self.H, self.W, _ptr(self.minmax), _ptr(self.viz),
+                                         _ptr(self.mag_sum), s))
+            _lib.check(L.ofc_grid_cells(_ptr(self.viz), P, self.H, self.W, self.rows, self.cols, self.draw_lines,
+                                        self.threshold, _ptr(self.avg_bgr), _ptr(self.avg_hue), _ptr(self.km_centre),
+                                        _ptr(self.km_hue), C.c_void_p(0), s))
+        return P
+
+    def process_clip(self, frames, pinned_out: torch.Tensor | None = None):
+        """Whole clip ``[T,H,W,3]`` uint8 (host numpy / pinned torch / CUDA) ->
+        dict of host tensors: ``avg_hue`` ``[T-1,cells]``, ``km_hue`` ``[T-1,cells]``,
+        ``mean_magnitude`` ``[T-1]``.  Chunks overlap by one frame (the halo)."""
+        import numpy as np
+        if isinstance(frames, np.ndarray):
+            frames = torch.from_numpy(frames)
+        T = int(frames.shape[0])
+        avg = torch.empty((T - 1, self.cells), dtype=torch.uint8)
+        km = torch.empty((T - 1, self.cells), dtype=torch.uint8)
+        mag = torch.empty(T - 1, dtype=torch.float64)
+        t = 0
+        while t < T - 1:
+            n = min(self.F, T - t)
+            chunk = frames[t:t + n]
+            if not chunk.is_cuda:
+                chunk = chunk.to(self.device, non_blocking=True)
+            P = self.run_chunk(chunk)
+            avg[t:t + P] = self.avg_hue[:P].cpu()
+            km[t:t + P] = self.km_hue[:P].cpu()
+            mag[t:t + P] = (self.mag_sum[:P] / float(self.H * self.W)).cpu()
+            t += P
+        return {"avg_hue": avg, "km_hue": km, "mean_magnitude": mag}

@@ -1,0 +1,70 @@
+"""Kernel logic on CPU: the .cu sources compiled with g++ against a fiber-based
+CUDA emulation (tests/emu), compared with the oracle.  Debug tooling for a
+container without a GPU; the real parity tests are the `-m gpu` ones."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import farneback_np as FB
+from oracle import grid_np as G
+from oracle import viz_np as V
+from tests.conftest import GOLDEN
+
+E = pytest.importorskip("tests.emu.emu_lib")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    E.build()
+
+
+def test_emu_farneback_golden_96x128():
+    z = np.load(os.path.join(GOLDEN, "flow_96x128.npz"))
+    H, W = z["gray"].shape[1:]
+    pl = E.Plan(W, H, max_frames=3)
+    flow, mm = pl.sequence(z["gray"], want_minmax=True)
+    ref, inter = FB.calc_optical_flow_farneback(z["gray"][0], z["gray"][1], return_intermediates=True)
+    for l, it in enumerate(inter):
+        assert np.abs(pl.buffer(l, 0, 0)[..., 0] - it["I0"]).max() < 1e-4
+        assert np.abs(pl.buffer(l, 1, 0) - it["R0"][..., :4]).max() < 1e-4
+        assert np.abs(pl.buffer(l, 2, 0)[..., 0] - it["R0"][..., 4]).max() < 1e-4
+    for p in range(2):
+        epe = np.linalg.norm(flow[p] - z["flow"][p], axis=-1)
+        assert epe.mean() < 2e-6 and epe.max() < 1e-4
+    mag = V.cart_to_polar(flow[..., 0], flow[..., 1])[0].reshape(2, -1)
+    assert (mm.view(np.float32)[:, 0] == mag.min(1)).all() and (mm.view(np.float32)[:, 1] == mag.max(1)).all()
+
+
+def test_emu_odd_size_and_params():
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    clip = synthetic_clip(2, 101, 150, seed=9).numpy()
+    g = E.bgr2gray(clip)
+    assert (g == np.stack([V.bgr2gray(f) for f in clip])).all()
+    for kw in [dict(), dict(pyr_scale=0.6, levels=2, winsize=11, iterations=2, poly_n=7, poly_sigma=1.5)]:
+        pl = E.Plan(150, 101, max_frames=2, **kw)
+        f = pl.sequence(g)[0]
+        ref = FB.calc_optical_flow_farneback(g[0], g[1], **kw)
+        epe = np.linalg.norm(f - ref, axis=-1)
+        assert epe.mean() < 2e-6 and epe.max() < 2e-4, (kw, epe.mean(), epe.max())
+
+
+def test_emu_viz_and_grid_exact():
+    z = np.load(os.path.join(GOLDEN, "flow_135x240.npz"))
+    bgr, mag, _ = E.flow_to_bgr(z["flow"])
+    assert (bgr == z["viz"]).all()                       # the reference's own compute() output
+    out = E.grid_cells(z["viz"], 14, 25)
+    for i in range(2):
+        fr = z["viz"][i].copy()
+        avg, hue, rois = G.grid_mean_hues(fr, 14, 25)
+        assert (avg == out["avg_bgr"][i]).all() and (hue == out["avg_hue"][i]).all()
+        kc = np.array([G.cluster_colors_k1(G.preprocess_image(r))[0] for r in rois])
+        assert (kc == out["km_centre"][i]).all()
+        lined = z["viz"][i].copy()                      # fr itself was thresholded in place (Q4)
+        G.grid_mean_hues(lined, 14, 25)
+        assert (E.draw_grid(z["viz"][i:i + 1], 14, 25)[0] == lined).all()
+
+
+def test_emu_unsupported_flags():
+    with pytest.raises(RuntimeError, match="flags"):
+        E.Plan(64, 64, flags=256)
