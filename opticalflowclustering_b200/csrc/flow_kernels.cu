@@ -14,6 +14,8 @@
 // and per frame pair: flow float2 [h][w] (two ping-pong buffers per level).
 // R is split float4 + float so the bilinear gather of the warped frame is one
 // 128-bit and one 32-bit load per tap instead of five scalar loads.
+#include <stdlib.h>
+
 #include "ofc_common.cuh"
 #include "flow_kernels.cuh"
 
@@ -43,66 +45,100 @@ __global__ void __launch_bounds__(256) prefilter_kernel(PrefilterParams p) {
     float* taps = reinterpret_cast<float*>(smem);
     float* hbuf = taps + p.taps_pad;                                   // [in_rows][tx][2]
     unsigned char* tile = reinterpret_cast<unsigned char*>(hbuf + (size_t)p.in_rows * p.tx * 2);  // [in_rows][in_pitch]
+    __shared__ int s_ci[32], s_ri[32];        // per output column / row: source index
+    __shared__ float s_fx[32], s_fy[32];      //                           and lerp fraction
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int r = p.ksz >> 1;
     const int x0 = blockIdx.x * p.tx, y0 = blockIdx.y * p.ty;
-    const int x_last = min(x0 + p.tx, p.w) - 1, y_last = min(y0 + p.ty, p.h) - 1;
+    const int nx = min(p.tx, p.w - x0), ny = min(p.ty, p.h - y0);
     const unsigned char* src = p.gray + (int64_t)blockIdx.z * p.gray_stride;
 
-    int c_first, c_last, r_first, r_last;
-    float fr_unused;
-    src_coord(x0, p.sx, p.W, c_first, fr_unused);
-    src_coord(x_last, p.sx, p.W, c_last, fr_unused);
-    src_coord(y0, p.sy, p.H, r_first, fr_unused);
-    src_coord(y_last, p.sy, p.H, r_last, fr_unused);
-    const int c_lo = c_first - r, r_lo = r_first - r;
-    const int ncols = min(c_last + 1, p.W - 1) + r - c_lo + 1;
-    const int nrows = min(r_last + 1, p.H - 1) + r - r_lo + 1;
-
+    if (tid < nx) src_coord(x0 + tid, p.sx, p.W, s_ci[tid], s_fx[tid]);
+    if (tid >= 32 && tid - 32 < ny) src_coord(y0 + tid - 32, p.sy, p.H, s_ri[tid - 32], s_fy[tid - 32]);
     for (int i = tid; i < p.ksz; i += blockDim.x) taps[i] = p.taps[i];
-    for (int i = tid; i < nrows * ncols; i += blockDim.x) {
-        int rr = i / ncols, cc = i - rr * ncols;
-        int sy = reflect101(r_lo + rr, p.H), sx = reflect101(c_lo + cc, p.W);
-        tile[rr * p.in_pitch + cc] = src[(int64_t)sy * p.W + sx];
+    __syncthreads();
+    const int c_lo = s_ci[0] - r, r_lo = s_ri[0] - r;
+    const int ncols = min(s_ci[nx - 1] + 1, p.W - 1) + r - c_lo + 1;
+    const int nrows = min(s_ri[ny - 1] + 1, p.H - 1) + r - r_lo + 1;
+
+    for (int rr = warp; rr < nrows; rr += nwarps) {
+        const unsigned char* row = src + (int64_t)reflect101(r_lo + rr, p.H) * p.W;
+        for (int cc = lane; cc < ncols; cc += 32) tile[rr * p.in_pitch + cc] = row[reflect101(c_lo + cc, p.W)];
     }
     __syncthreads();
 
     // horizontal taps at the two sample columns of each output column
-    const int nx = x_last - x0 + 1;
-    for (int i = tid; i < nrows * nx * 2; i += blockDim.x) {
-        int c = i & 1;
-        int xx = (i >> 1) % nx;
-        int rr = (i >> 1) / nx;
-        int ci; float fr;
-        src_coord(x0 + xx, p.sx, p.W, ci, fr);
-        ci = min(ci + c, p.W - 1);
-        const unsigned char* t = tile + rr * p.in_pitch + (ci - r - c_lo);
-        float s = 0.f;
-        for (int j = 0; j < p.ksz; ++j) s = fmaf(taps[j], (float)t[j], s);
-        hbuf[(rr * p.tx + xx) * 2 + c] = s;
+    for (int rr = warp; rr < nrows; rr += nwarps) {
+        for (int j2 = lane; j2 < nx * 2; j2 += 32) {
+            int xx = j2 >> 1, c = j2 & 1;
+            int ci = min(s_ci[xx] + c, p.W - 1);
+            const unsigned char* t = tile + rr * p.in_pitch + (ci - r - c_lo);
+            float s = 0.f;
+            for (int j = 0; j < p.ksz; ++j) s = fmaf(taps[j], (float)t[j], s);
+            hbuf[(rr * p.tx + xx) * 2 + c] = s;
+        }
     }
     __syncthreads();
 
     float* out = p.out + (int64_t)blockIdx.z * p.out_stride;
-    const int ny = y_last - y0 + 1;
-    for (int i = tid; i < ny * nx; i += blockDim.x) {
-        int yy = i / nx, xx = i - yy * nx;
-        int ci, ri; float fx, fy;
-        src_coord(x0 + xx, p.sx, p.W, ci, fx);
-        src_coord(y0 + yy, p.sy, p.H, ri, fy);
-        int ra = ri - r - r_lo, rb = min(ri + 1, p.H - 1) - r - r_lo;
-        float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
-        for (int j = 0; j < p.ksz; ++j) {
-            float t = taps[j];
-            const float* ha = hbuf + ((ra + j) * p.tx + xx) * 2;
-            const float* hb = hbuf + ((rb + j) * p.tx + xx) * 2;
-            b00 = fmaf(t, ha[0], b00); b01 = fmaf(t, ha[1], b01);
-            b10 = fmaf(t, hb[0], b10); b11 = fmaf(t, hb[1], b11);
+    for (int yy = warp; yy < ny; yy += nwarps) {
+        const int ri = s_ri[yy];
+        const float fy = s_fy[yy];
+        const int ra = ri - r - r_lo, rb = min(ri + 1, p.H - 1) - r - r_lo;
+        for (int xx = lane; xx < nx; xx += 32) {
+            const float fx = s_fx[xx];
+            float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+            for (int j = 0; j < p.ksz; ++j) {
+                float t = taps[j];
+                const float2 ha = *reinterpret_cast<const float2*>(hbuf + ((ra + j) * p.tx + xx) * 2);
+                const float2 hb = *reinterpret_cast<const float2*>(hbuf + ((rb + j) * p.tx + xx) * 2);
+                b00 = fmaf(t, ha.x, b00); b01 = fmaf(t, ha.y, b01);
+                b10 = fmaf(t, hb.x, b10); b11 = fmaf(t, hb.y, b11);
+            }
+            float top = b00 * (1.f - fx) + b01 * fx;
+            float bot = b10 * (1.f - fx) + b11 * fx;
+            out[(int64_t)(y0 + yy) * p.w + x0 + xx] = top * (1.f - fy) + bot * fy;
         }
-        float top = b00 * (1.f - fx) + b01 * fx;
-        float bot = b10 * (1.f - fx) + b11 * fx;
-        out[(int64_t)(y0 + yy) * p.w + x0 + xx] = top * (1.f - fy) + bot * fy;
+    }
+}
+
+// Level 0 of the pyramid is never resampled and always uses the fixed 3-tap
+// kernel [1/4, 1/2, 1/4] (sigma = 0).  Its products and sums are exact in
+// float32 for 8-bit input, so any evaluation order gives the reference's bits.
+// One thread = 4 consecutive output pixels of one row; 3 rows x 6 bytes in.
+__global__ void __launch_bounds__(256) prefilter_identity3_kernel(PrefilterParams p) {
+    const int gx = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+    const int gy = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (gx >= p.W || gy >= p.H) return;
+    const unsigned char* src = p.gray + (int64_t)blockIdx.z * p.gray_stride;
+    float h[3][4];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const unsigned char* row = src + (int64_t)reflect101(gy + dy, p.H) * p.W;
+        float v[6];
+        if (gx >= 4 && gx + 8 <= p.W && (p.W & 3) == 0) {
+            unsigned a = *reinterpret_cast<const unsigned*>(row + gx - 4);
+            unsigned b = *reinterpret_cast<const unsigned*>(row + gx);
+            unsigned c = *reinterpret_cast<const unsigned*>(row + gx + 4);
+            v[0] = (float)(a >> 24);
+            v[1] = (float)(b & 255); v[2] = (float)((b >> 8) & 255); v[3] = (float)((b >> 16) & 255); v[4] = (float)(b >> 24);
+            v[5] = (float)(c & 255);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) v[i] = (float)row[reflect101(gx - 1 + i, p.W)];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[dy + 1][i] = 0.25f * v[i] + 0.5f * v[i + 1] + 0.25f * v[i + 2];
+    }
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = 0.25f * h[0][i] + 0.5f * h[1][i] + 0.25f * h[2][i];
+    float* out = p.out + (int64_t)blockIdx.z * p.out_stride + (int64_t)gy * p.W + gx;
+    if (gx + 4 <= p.W && (p.W & 3) == 0) {
+        *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int i = 0; i < 4 && gx + i < p.W; ++i) out[i] = o[i];
     }
 }
 
@@ -406,6 +442,13 @@ __global__ void minmax_init_kernel(unsigned* mm, int n_pairs) {
 // host-side launchers
 // ---------------------------------------------------------------------------
 int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* stream) {
+    if (p.w == p.W && p.h == p.H && p.ksz == 3 && p.identity3) {
+        dim3 g(cdiv(p.W, 256), cdiv(p.H, 4), n_frames);
+        ProfScope prof(PK_PREFILTER, stream);
+        OFC_LAUNCH(prefilter_identity3_kernel, g, dim3(256), 0, stream, p);
+        OFC_CHECK_LAUNCH("prefilter_identity3");
+        return OFC_OK;
+    }
     dim3 grid(cdiv(p.w, p.tx), cdiv(p.h, p.ty), n_frames);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -459,9 +502,14 @@ int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, void* stream
         case 4: return launch_iter_r<4, 32, 256, 3>(p, n_pairs, stream);
         case 5: return launch_iter_r<5, 32, 256, 3>(p, n_pairs, stream);
         case 6: return launch_iter_r<6, 32, 256, 3>(p, n_pairs, stream);
-        case 7:
+        case 7: {
             // winsize 15 (the reference's value): 64x30 tile = 73.9 KB -> 3 CTAs/SM
+            static int variant = -1;
+            if (variant < 0) { const char* e = getenv("OFC_ITER_VARIANT"); variant = e ? atoi(e) : 0; }
+            if (variant == 1) return launch_iter_r<7, 48, 384, 2>(p, n_pairs, stream);
+            if (variant == 2) return launch_iter_r<7, 32, 256, 2>(p, n_pairs, stream);
             return launch_iter_r<7, 30, 256, 3>(p, n_pairs, stream);
+        }
         case 10: return launch_iter_r<10, 32, 256, 2>(p, n_pairs, stream);
         case 12: return launch_iter_r<12, 32, 256, 2>(p, n_pairs, stream);
         default:

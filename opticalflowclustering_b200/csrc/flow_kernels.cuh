@@ -16,6 +16,7 @@ struct PrefilterParams {
     int tx, ty;                  // output tile
     int in_rows, in_pitch;       // staged source window (max over tiles)
     int taps_pad;
+    int identity3;               // level is full resolution with the fixed [1/4,1/2,1/4] taps
 };
 
 struct PolyParams {

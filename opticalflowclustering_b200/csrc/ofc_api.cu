@@ -161,6 +161,7 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         pf.W = pl->W; pf.H = pl->H; pf.w = L.w; pf.h = L.h;
         pf.ksz = L.ksz; pf.sx = L.sx; pf.sy = L.sy;
         pf.taps = pl->d_taps + L.taps_off;
+        pf.identity3 = (L.sigma <= 0 && L.ksz == 3 && L.w == pl->W && L.h == pl->H) ? 1 : 0;
         pf.tx = L.tx; pf.ty = L.ty; pf.in_rows = L.in_rows; pf.in_pitch = L.in_pitch; pf.taps_pad = L.taps_pad;
         int rc = launch_prefilter(pf, n_frames, L.prefilter_smem, stream);
         if (rc != OFC_OK) return rc;

@@ -1,0 +1,16 @@
+"""Short, fixed launch sequence for ncu: 2 warm steps + 1 step of the 1080p pipeline (chunk of 9 frames)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from opticalflowclustering_b200.pipeline import ClipPipeline
+from opticalflowclustering_b200.synthetic import synthetic_clip
+
+H, W, F = 1080, 1920, int(os.environ.get("OFC_CHUNK", "9"))
+clip = synthetic_clip(F, H, W, seed=0, device="cuda")
+pipe = ClipPipeline(W, H, chunk_frames=F)
+for _ in range(3):
+    pipe.run_chunk(clip)
+torch.cuda.synchronize()
+print("ok", pipe.km_hue[0, :8].tolist())
