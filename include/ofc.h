@@ -83,6 +83,9 @@ int ofc_farneback_pair(const ofc_flow_plan* plan, const uint8_t* prev, const uin
 /* ---- 8-bit colour ---------------------------------------------------------
  * cv.cvtColor(frame, COLOR_BGR2GRAY)        computeOpticalFlowModule.py:16,19 */
 int ofc_bgr2gray(const uint8_t* bgr, uint8_t* gray, int64_t n_pixels, void* stream);
+/* cv2.cvtColor(x, COLOR_BGR2HSV) on n 8-bit pixels (H 0..179): KmeanGrids.py:92,336,
+ * color_kmeans.py:121 (applied there to cell means / cluster centres). */
+int ofc_bgr2hsv(const uint8_t* bgr, uint8_t* hsv, int64_t n_pixels, void* stream);
 /* min / max of |flow| per frame (IEEE bits), for flows that did not come from
  * ofc_farneback_*; first step of cv.normalize(..., NORM_MINMAX)  :31 */
 int ofc_flow_minmax(const float* flow, int n_frames, int64_t n_pixels, uint32_t* minmax, void* stream);
@@ -110,6 +113,81 @@ int ofc_grid_cells(const uint8_t* bgr, int n_frames, int height, int width, int 
                    uint32_t* km_sums /* [n][cells][4] */, void* stream);
 /* cv2.rectangle(frame,(x1,y1),(x2,y2),(255,255,255),1) for every cell  KmeanGrids.py:108 */
 int ofc_draw_grid(uint8_t* bgr, int n_frames, int height, int width, int rows, int cols, void* stream);
+
+/* ---- k-means (Lloyd) --------------------------------------------------------
+ * Replaces sklearn.cluster.KMeans(n_clusters=k).fit(X) / .predict(X) as called at
+ *   reference: KmeanGrids.py:299-304, color_kmeans.py:65-78
+ * (scikit-learn 1.9.0 dense Lloyd).  The host loop (stopping rule,
+ * optional cross-GPU all-reduce of `sums`/`counts` between ofc_kmeans_sums and
+ * ofc_kmeans_centres) lives in opticalflowclustering_b200/kmeans.py.
+ * All calls are batched over `batch` independent problems of equal shape
+ * (X is [batch][n][d], row-major); the reference runs one fit per grid cell.
+ * dtype: OFC_U8 (worked in float64 like sklearn), OFC_F32 (float32), OFC_F64.
+ * `active` (nullable, u8 [batch]) selects the problems a call touches: problems
+ * that already met the stopping rule are frozen while the rest keep iterating. */
+#define OFC_U8 0
+#define OFC_F32 1
+#define OFC_F64 2
+
+size_t ofc_kmeans_workspace_bytes(int batch, int64_t n, int d, int k);
+
+/* E-step: labels[i] = first strict minimum over j of ||c_j||^2 - 2 (x_i - mean).c_j
+ * (_k_means_lloyd.pyx:160-213).  mean [batch][d] (nullable) is subtracted from every
+ * row on the fly (KMeans.fit centres X, _kmeans.py:1487-1493; predict does not).
+ * prev_labels/n_changed (nullable): n_changed[b] = #{i: labels[i] != prev_labels[i]}.
+ * inertia (nullable, [batch]) = sum of squared distances to the
+ * chosen centres; min_dist (nullable, [batch][n]) the per-point values. */
+int ofc_kmeans_assign(const void* X, int dtype, int batch, int64_t n, int d, int k,
+                      const double* mean, const double* centres /* [batch][k][d] */,
+                      int32_t* labels, const int32_t* prev_labels, uint64_t* n_changed,
+                      double* inertia, double* min_dist, const uint8_t* active,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* M-step sums: sums[b][j][:] = sum over members of (x - mean) (or its square when
+ * `square`), counts[b][j] = members; labels NULL = one cluster holding everything
+ * (column statistics for KMeans' tolerance, _kmeans.py:285-293).  Deterministic:
+ * private accumulators folded in a fixed order, no floating-point atomics. */
+int ofc_kmeans_sums(const void* X, int dtype, int batch, int64_t n, int d, int k,
+                    const double* mean, const int32_t* labels, int square,
+                    double* sums /* [batch][k][d] */, int64_t* counts /* [batch][k] */, const uint8_t* active,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* centres[b][j] = sums/counts (use_reciprocal: sums * (1/count) as sklearn's _average_centers)
+ * minus mean_sub (nullable); empty clusters copy the heaviest cluster; shift_tot[b] =
+ * sum_j ||new_j - old_j||^2 (_k_means_common.pyx:274-311).  centres: old in, new out. */
+int ofc_kmeans_centres(int batch, int d, int k, const double* sums, const int64_t* counts,
+                       const double* mean_sub, int use_reciprocal, double* centres, double* shift_tot,
+                       const uint8_t* active, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Empty-cluster relocation on the sums/counts (_k_means_common.pyx:167-211): every empty
+ * cluster, in index order, takes the point farthest from the (old) centre of its label.
+ * Distances use (x - mean) against centres_old; raw_sums says whether `sums` holds sums of
+ * the raw rows (uint8 path) or of the centred rows.  Returns immediately on the device for
+ * problems without an empty cluster, so it can be launched every iteration; call it
+ * between ofc_kmeans_sums and ofc_kmeans_centres. */
+int ofc_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
+                        const int32_t* labels, const double* centres_old, double* sums, int64_t* counts,
+                        int raw_sums, const uint8_t* active, void* stream);
+
+/* image_dict ROIs (KmeanGrids.py:85,113) + preprocess_image (:269-286) for every cell:
+ * out u8 [n_frames][rows*cols][ (H/rows)*(W/cols) ][4] = (c0, c1, c2, alpha).  draw_lines:
+ * white row 0 / column 0 as at the reference's k-means stage; swap_rb:
+ * read_image's BGR->RGB (color_kmeans.py:32-33). */
+int ofc_grid_extract_cells(const uint8_t* bgr, int n_frames, int height, int width, int rows, int cols,
+                           int draw_lines, int threshold, int swap_rb, uint8_t* out, void* stream);
+
+/* ---- cosine similarity ------------------------------------------------------
+ * findCosineDifferentVectors.py:5-66: sims[i] = cos(a, b[i:i+n]) for i in 0..m-n
+ * (0 when a norm is 0), *best = max, *best_idx = LAST i attaining it. */
+int ofc_sliding_cosine(const double* a, int n, const double* b, int64_t m,
+                       double* sims /* [m-n+1] */, double* best, int64_t* best_idx, void* stream);
+/* out[i] = cos(X[i,:], q) for the n rows of X [n][d] (the 1M-row sweep; same formula). */
+int ofc_row_cosine(const void* X, int dtype, int64_t n, int d, const double* q, double* out, void* stream);
+/* computeVectorDistance.py:22-43 on two length-n columns: *cos = sklearn cosine_similarity of
+ * the flattened vectors, quirk_row[j] = a[0]*b[j] / (|a[j]|*|b[j]|) (the script's printed
+ * "Cosine similarity" row, :25,29), *l1 = sum |a-b|.  Any output may be NULL. */
+int ofc_vector_distance(const double* a, const double* b, int64_t n, double* cos, double* quirk_row,
+                        double* l1, void* stream);
 
 #ifdef __cplusplus
 }

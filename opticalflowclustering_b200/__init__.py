@@ -5,4 +5,5 @@ grid-cell aggregation -> k-means -> cosine similarity.
 The operators need the in-tree CUDA library ``libofc.so`` (built by
 ``__graft_entry__.build()``); there is no CPU fallback.
 """
-__all__ = ["flow", "grid", "pipeline", "synthetic", "computeOpticalFlowModule"]
+__all__ = ["flow", "grid", "pipeline", "synthetic", "kmeans", "cosine", "computeOpticalFlowModule", "computeOpticalFlow",
+           "KmeanGrids", "drawGridsAndOutputCSV", "color_kmeans", "findCosineDifferentVectors", "computeVectorDistance"]

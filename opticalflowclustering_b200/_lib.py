@@ -30,10 +30,20 @@ SIGNATURES = {
     "ofc_farneback_sequence": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "ofc_farneback_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_bgr2gray": (_i, [_vp, _vp, _i64, _vp]),
+    "ofc_bgr2hsv": (_i, [_vp, _vp, _i64, _vp]),
     "ofc_flow_minmax": (_i, [_vp, _i, _i64, _vp, _vp]),
     "ofc_flow_to_bgr": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ofc_grid_cells": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ofc_draw_grid": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
+    "ofc_kmeans_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
+    "ofc_kmeans_assign": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_sums": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_centres": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_relocate": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "ofc_grid_extract_cells": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ofc_sliding_cosine": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ofc_row_cosine": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),
+    "ofc_vector_distance": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -114,6 +114,33 @@ __global__ void __launch_bounds__(256) draw_grid_kernel(unsigned char* bgr, int6
     }
 }
 
+// cv2.cvtColor(..., COLOR_BGR2HSV) on 8-bit pixels (H in 0..179): the integer table formula
+// of SURVEY.md A.3 (hdiv/sdiv tables, +2048 >> 12).  Used on cell means and cluster centres
+// (KmeanGrids.py:92,336, color_kmeans.py:121).
+__global__ void __launch_bounds__(256) bgr2hsv_kernel(const unsigned char* bgr, unsigned char* hsv, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = bgr[i * 3], g = bgr[i * 3 + 1], r = bgr[i * 3 + 2];
+    const int v = max(max(b, g), r), mn = min(min(b, g), r);
+    const int d = v - mn;
+    int s = 0;
+    if (v > 0) {
+        const int sdiv = (int)rint((double)(255 << 12) / (double)v);
+        s = (d * sdiv + (1 << 11)) >> 12;
+    }
+    hsv[i * 3] = (unsigned char)hue_of_bgr(b, g, r);
+    hsv[i * 3 + 1] = (unsigned char)s;
+    hsv[i * 3 + 2] = (unsigned char)v;
+}
+
+int launch_bgr2hsv(const unsigned char* bgr, unsigned char* hsv, int64_t n, void* stream) {
+    if (n <= 0) return OFC_OK;
+    ProfScope prof(PK_GRID, stream);
+    OFC_LAUNCH(bgr2hsv_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, bgr, hsv, n);
+    OFC_CHECK_LAUNCH("bgr2hsv");
+    return OFC_OK;
+}
+
 int launch_grid_cells(const GridParams& p, int n_frames, void* stream) {
     if (n_frames <= 0) return OFC_OK;
     ProfScope prof(PK_GRID, stream);

@@ -18,6 +18,7 @@ struct GridParams {
 };
 
 int launch_grid_cells(const GridParams& p, int n_frames, void* stream);
+int launch_bgr2hsv(const unsigned char* bgr, unsigned char* hsv, int64_t n, void* stream);
 int launch_draw_grid(unsigned char* bgr, int64_t frame_stride, int W, int H, int rows, int cols,
                      int x_step, int y_step, int n_frames, void* stream);
 

@@ -1,0 +1,556 @@
+// Lloyd k-means for sm_100a: E-step (assign) and M-step (deterministic partial sums).
+//
+// Replaces the arithmetic behind the reference's
+//   clt = KMeans(n_clusters = k); clt.fit(X); clt.predict(X)
+// (reference k-means-color-clustering/KmeanGrids.py:299-304, color_kmeans.py:65-78),
+// i.e. scikit-learn 1.9.0's dense Lloyd iteration:
+//   E-step  label = first strict minimum over j of  ||c_j||^2 - 2 x.c_j   (ties -> lowest j)
+//   M-step  c_j = sum of the members / count; empty clusters take the farthest points.
+//
+// uint8 input (the reference's pixels and hues) is promoted to float64 exactly as
+// sklearn does; float32 input is worked in float32.  The M-step never uses
+// floating-point atomics: every lane group owns a private accumulator in shared
+// memory, the copies are folded in a fixed order, and so are the per-CTA partials.
+// For uint8 data the sums are integers held exactly in float64, so any reduction
+// order (including the cross-GPU all-reduce) gives the same bits.
+//
+// All kernels take a batch dimension (independent problems of equal shape): the
+// reference runs one fit per grid cell per frame (350 per frame).
+#include "ofc_common.cuh"
+#include "kmeans_kernels.cuh"
+
+namespace ofc {
+
+template <typename W> __device__ __forceinline__ W fma_w(W a, W b, W c);
+template <> __device__ __forceinline__ double fma_w<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> __device__ __forceinline__ float fma_w<float>(float a, float b, float c) { return fmaf(a, b, c); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum in a fixed order (xor tree inside a warp, warps 0..7 in sequence)
+__device__ __forceinline__ double block_sum_256(double v, double* s_red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+    __syncthreads();
+    return t;      // valid in thread 0
+}
+
+// ---------------------------------------------------------------------------
+// E-step, one thread per point: the row lives in registers (d <= DP), the
+// centres and their squared norms in shared memory.
+// ---------------------------------------------------------------------------
+template <typename T, typename W, int DP>
+__global__ void __launch_bounds__(256) kmeans_assign_small_kernel(KmAssignParams p) {
+    OFC_DYN_SMEM(unsigned char, raw);
+    W* sc = reinterpret_cast<W*>(raw);               // [k][d]
+    W* sc2 = sc + (size_t)p.k * p.d;                  // [k]
+    W* smean = sc2 + p.k;                             // [d]
+    __shared__ double s_red[8];
+    const int b = blockIdx.y, tid = threadIdx.x, d = p.d, k = p.k;
+    if (p.active && !p.active[b]) return;
+    const double* cen = p.centres + (int64_t)b * k * d;
+    for (int i = tid; i < k * d; i += 256) sc[i] = (W)cen[i];
+    for (int i = tid; i < d; i += 256) smean[i] = p.mean ? (W)p.mean[(int64_t)b * d + i] : (W)0;
+    __syncthreads();
+    for (int j = tid; j < k; j += 256) {
+        W s = (W)0;
+        for (int t = 0; t < d; ++t) s = fma_w<W>(sc[j * d + t], sc[j * d + t], s);
+        sc2[j] = s;
+    }
+    __syncthreads();
+
+    const T* X = reinterpret_cast<const T*>(p.X) + (int64_t)b * p.n * d;
+    int32_t* labels = p.labels + (int64_t)b * p.n;
+    const int32_t* prev = p.prev_labels ? p.prev_labels + (int64_t)b * p.n : nullptr;
+    double inert = 0.0;
+    unsigned changed = 0;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < p.n; base += (int64_t)gridDim.x * 256) {
+        const int64_t i = base + tid;
+        if (i < p.n) {
+            W x[DP];
+            const T* row = X + i * d;
+            if (sizeof(T) == 1 && DP == 4 && d == 4) {
+                const uchar4 q = *reinterpret_cast<const uchar4*>(row);
+                x[0] = (W)q.x - smean[0]; x[1] = (W)q.y - smean[1];
+                x[2] = (W)q.z - smean[2]; x[3] = (W)q.w - smean[3];
+#pragma unroll
+                for (int t = 4; t < DP; ++t) x[t] = (W)0;
+            } else {
+#pragma unroll
+                for (int t = 0; t < DP; ++t) x[t] = t < d ? (W)row[t] - smean[t] : (W)0;
+            }
+            W best = (W)0;
+            int label = 0;
+            for (int j = 0; j < k; ++j) {
+                const W* c = sc + j * d;
+                W dot = (W)0;
+#pragma unroll
+                for (int t = 0; t < DP; ++t)
+                    if (t < d) dot = fma_w<W>(x[t], c[t], dot);
+                const W dist = fma_w<W>((W)-2, dot, sc2[j]);
+                if (j == 0 || dist < best) { best = dist; label = j; }
+            }
+            labels[i] = label;
+            if (prev && prev[i] != label) ++changed;
+            if (p.inertia_partial || p.min_dist) {
+                const W* c = sc + label * d;
+                W sq = (W)0;
+#pragma unroll
+                for (int t = 0; t < DP; ++t)
+                    if (t < d) { W df = x[t] - c[t]; sq = fma_w<W>(df, df, sq); }
+                inert += (double)sq;
+                if (p.min_dist) p.min_dist[(int64_t)b * p.n + i] = (double)sq;
+            }
+        }
+    }
+    if (p.inertia_partial) {
+        double t = block_sum_256(inert, s_red);
+        if (tid == 0) p.inertia_partial[(int64_t)b * gridDim.x + blockIdx.x] = t;
+    }
+    if (p.n_changed && prev) {
+        // integer counts: any order gives the same total
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+        if ((tid & 31) == 0 && changed) atomicAdd(p.n_changed + b, (unsigned long long)changed);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// E-step, generic shape (large d, or k*d beyond shared memory): one warp per
+// point, lanes stride over the features, centres read through L1/L2.
+// ---------------------------------------------------------------------------
+template <typename T, typename W>
+__global__ void __launch_bounds__(256) kmeans_assign_generic_kernel(KmAssignParams p) {
+    __shared__ double s_red[8];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, d = p.d, k = p.k;
+    if (p.active && !p.active[b]) return;
+    const double* cen = p.centres + (int64_t)b * k * d;
+    const double* c2 = p.c2 + (int64_t)b * k;
+    const double* mean = p.mean ? p.mean + (int64_t)b * d : nullptr;
+    const T* X = reinterpret_cast<const T*>(p.X) + (int64_t)b * p.n * d;
+    int32_t* labels = p.labels + (int64_t)b * p.n;
+    const int32_t* prev = p.prev_labels ? p.prev_labels + (int64_t)b * p.n : nullptr;
+    double inert = 0.0;
+    unsigned changed = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + warp; i < p.n; i += (int64_t)gridDim.x * 8) {
+        const T* row = X + i * d;
+        W best = (W)0;
+        int label = 0;
+        for (int j = 0; j < k; ++j) {
+            const double* c = cen + (int64_t)j * d;
+            W part = (W)0;
+            for (int t = lane; t < d; t += 32) {
+                W xv = (W)row[t] - (mean ? (W)mean[t] : (W)0);
+                part = fma_w<W>(xv, (W)c[t], part);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            const W dist = fma_w<W>((W)-2, part, (W)c2[j]);
+            if (j == 0 || dist < best) { best = dist; label = j; }
+        }
+        if (lane == 0) {
+            labels[i] = label;
+            if (prev && prev[i] != label) ++changed;
+        }
+        if (p.inertia_partial || p.min_dist) {
+            const double* c = cen + (int64_t)label * d;
+            W sq = (W)0;
+            for (int t = lane; t < d; t += 32) {
+                W df = ((W)row[t] - (mean ? (W)mean[t] : (W)0)) - (W)c[t];
+                sq = fma_w<W>(df, df, sq);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) {
+                inert += (double)sq;
+                if (p.min_dist) p.min_dist[(int64_t)b * p.n + i] = (double)sq;
+            }
+        }
+    }
+    if (p.inertia_partial) {
+        double t = block_sum_256(inert, s_red);
+        if (tid == 0) p.inertia_partial[(int64_t)b * gridDim.x + blockIdx.x] = t;
+    }
+    if (p.n_changed && prev && lane == 0 && changed) atomicAdd(p.n_changed + b, (unsigned long long)changed);
+}
+
+__global__ void kmeans_c2_kernel(const double* centres, double* c2, int d, int k, int as_float) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (j >= k) return;
+    const double* c = centres + ((int64_t)b * k + j) * d;
+    if (as_float) {
+        float s = 0.f;
+        for (int t = 0; t < d; ++t) s = fmaf((float)c[t], (float)c[t], s);
+        c2[(int64_t)b * k + j] = (double)s;
+    } else {
+        double s = 0.0;
+        for (int t = 0; t < d; ++t) s = fma(c[t], c[t], s);
+        c2[(int64_t)b * k + j] = s;
+    }
+}
+
+// inertia[b] = sum of the per-CTA partials in CTA order
+__global__ void inertia_reduce_kernel(const double* partial, int parts, double* inertia, const unsigned char* active) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < parts; ++i) s += partial[(int64_t)b * parts + i];
+        inertia[b] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// M-step partial sums.  grid = (splits, feature tiles, batch); a warp is cut
+// into G = 32/dt lane groups, group g of warp w owns accumulator copy (w, g) of
+// [kt][dt] doubles and walks its own subsequence of the split's points, so no
+// two lanes ever touch the same word.  Copies are folded in index order.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) kmeans_sums_kernel(KmSumsParams p) {
+    OFC_DYN_SMEM(double, acc);                         // [8*G][kt][dt]
+    const int dt = p.dt, G = 32 / dt, kt = p.kt, d = p.d, k = p.k;
+    int* cnt = reinterpret_cast<int*>(acc + (size_t)8 * G * kt * dt);   // [8*G][kt]
+    const int split = blockIdx.x, dtile = blockIdx.y, b = blockIdx.z;
+    if (p.active && !p.active[b]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane / dt, t = lane - g * dt, dim = dtile * dt + t;
+    const bool dim_ok = dim < d;
+    const int64_t chunk = (p.n + p.splits - 1) / p.splits;
+    const int64_t lo = (int64_t)split * chunk, hi = lo + chunk < p.n ? lo + chunk : p.n;
+    const int copy = warp * G + g;
+    double* my = acc + (size_t)copy * kt * dt + t;
+    int* mycnt = cnt + copy * kt;
+    const double m = (p.mean && dim_ok) ? p.mean[(int64_t)b * d + dim] : 0.0;
+    const T* X = reinterpret_cast<const T*>(p.X) + (int64_t)b * p.n * d;
+    const int32_t* labels = p.labels ? p.labels + (int64_t)b * p.n : nullptr;
+
+    for (int k0 = 0; k0 < k; k0 += kt) {
+        const int kk = k - k0 < kt ? k - k0 : kt;
+        for (int j = 0; j < kk; ++j) {
+            my[j * dt] = 0.0;
+            if (t == 0) mycnt[j] = 0;
+        }
+        __syncwarp();
+        for (int64_t i = lo + copy; i < hi; i += 8 * G) {
+            const int j = (labels ? labels[i] : 0) - k0;
+            if ((unsigned)j < (unsigned)kk) {
+                if (dim_ok) {
+                    double v = (double)X[i * d + dim] - m;
+                    if (p.square) v *= v;
+                    my[j * dt] += v;
+                }
+                if (t == 0) mycnt[j] += 1;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < kk * dt; e += 256) {
+            const int j = e / dt, tt = e - j * dt;
+            double s = 0.0;
+            for (int c = 0; c < 8 * G; ++c) s += acc[((size_t)c * kt + j) * dt + tt];
+            if (dtile * dt + tt < d)
+                p.partial[(((int64_t)b * p.splits + split) * k + k0 + j) * d + dtile * dt + tt] = s;
+        }
+        if (dtile == 0) {
+            for (int j = tid; j < kk; j += 256) {
+                long long c = 0;
+                for (int q = 0; q < 8 * G; ++q) c += cnt[q * kt + j];
+                p.cnt_partial[((int64_t)b * p.splits + split) * k + k0 + j] = c;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// sums[b][j][t] = sum over splits (in split order) of the partials; counts likewise
+__global__ void kmeans_fold_kernel(const double* partial, const long long* cnt_partial, int splits, int k, int d,
+                                   double* sums, long long* counts, const unsigned char* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t kd = (int64_t)k * d;
+    if (e < kd) {
+        double s = 0.0;
+        for (int sp = 0; sp < splits; ++sp) s += partial[((int64_t)b * splits + sp) * kd + e];
+        sums[(int64_t)b * kd + e] = s;
+    }
+    if (e < k && counts) {
+        long long c = 0;
+        for (int sp = 0; sp < splits; ++sp) c += cnt_partial[((int64_t)b * splits + sp) * k + e];
+        counts[(int64_t)b * k + e] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// centres from (all-reduced) sums and counts; empty clusters copy the heaviest
+// cluster's new centre (_k_means_common.pyx:274-295); shift_tot = sum_j ||new-old||^2
+// taken as (sqrt(.))^2 like sklearn's center_shift (:298-311, _kmeans.py:733).
+// One CTA per problem.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kmeans_centres_kernel(int d, int k, const double* sums, const long long* counts,
+                                                             const double* mean_sub, int use_reciprocal,
+                                                             double* centres, double* shift_tot, double* shift_ws,
+                                                             const unsigned char* active) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (active && !active[b]) return;
+    const double* S = sums + (int64_t)b * k * d;
+    const long long* Cn = counts + (int64_t)b * k;
+    double* C = centres + (int64_t)b * k * d;
+    double* sh = shift_ws + (int64_t)b * k;
+    __shared__ int s_heavy;
+    if (tid == 0) {
+        int best = 0;
+        for (int j = 1; j < k; ++j) if (Cn[j] > Cn[best]) best = j;
+        s_heavy = best;
+    }
+    __syncthreads();
+    const int heavy = s_heavy;
+    for (int j = tid; j < k; j += 256) {
+        const int src = Cn[j] > 0 ? j : heavy;
+        const double w = (double)Cn[src];
+        const double alpha = 1.0 / w;
+        double ss = 0.0;
+        for (int t = 0; t < d; ++t) {
+            double v = S[(int64_t)src * d + t];
+            v = use_reciprocal ? v * alpha : v / w;
+            if (mean_sub) v -= mean_sub[(int64_t)b * d + t];
+            const double df = v - C[(int64_t)j * d + t];
+            ss = fma(df, df, ss);
+            C[(int64_t)j * d + t] = v;
+        }
+        const double s = sqrt(ss);
+        sh[j] = s * s;
+    }
+    __syncthreads();
+    if (tid == 0 && shift_tot) {
+        double tot = 0.0;
+        for (int j = 0; j < k; ++j) tot += sh[j];
+        shift_tot[b] = tot;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// empty-cluster relocation (_k_means_common.pyx:167-211): each empty cluster, in
+// index order, takes the farthest remaining point (squared distance to the OLD
+// centre of its label); labels are left untouched.  One CTA of 1024 threads per
+// problem; it returns at once when no cluster is empty, so the host launches it
+// unconditionally (no device->host round trip to decide).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) kmeans_relocate_kernel(const T* Xall, int64_t n, int d, int k, const double* mean_all,
+                                                                const int32_t* labels_all, const double* centres_all,
+                                                                double* sums_all, long long* counts_all,
+                                                                int raw_sums, const unsigned char* active) {
+    OFC_DYN_SMEM(long long, s_taken);                  // [k] indices already given away
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (active && !active[b]) return;
+    long long* counts = counts_all + (int64_t)b * k;
+    __shared__ int s_any;
+    if (tid == 0) {
+        int any = 0;
+        for (int j = 0; j < k; ++j) any |= counts[j] == 0;
+        s_any = any;
+    }
+    __syncthreads();
+    if (!s_any) return;
+    const T* X = Xall + (int64_t)b * n * d;
+    const int32_t* labels = labels_all + (int64_t)b * n;
+    const double* cen = centres_all + (int64_t)b * k * d;
+    const double* mean = mean_all ? mean_all + (int64_t)b * d : nullptr;
+    double* sums = sums_all + (int64_t)b * k * d;
+    __shared__ double s_val[32];
+    __shared__ long long s_idx[32];
+    __shared__ long long s_pick;
+    int n_taken = 0;
+    for (int e = 0; e < k; ++e) {
+        if (counts[e] != 0) continue;                  // uniform: written only behind a barrier
+        double bv = -1.0;
+        long long bi = -1;
+        for (int64_t i = tid; i < n; i += 1024) {
+            bool taken = false;
+            for (int q = 0; q < n_taken; ++q) taken |= s_taken[q] == i;
+            if (taken) continue;
+            const double* c = cen + (int64_t)labels[i] * d;
+            double v = 0.0;
+            for (int t = 0; t < d; ++t) {
+                const double df = ((double)X[i * d + t] - (mean ? mean[t] : 0.0)) - c[t];
+                v = fma(df, df, v);
+            }
+            if (v > bv) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double v = -1.0;
+            long long idx = -1;
+            for (int w = 0; w < 32; ++w)
+                if (s_idx[w] >= 0 && (idx < 0 || s_val[w] > v || (s_val[w] == v && s_idx[w] < idx))) { v = s_val[w]; idx = s_idx[w]; }
+            if (n_taken == 0 && !(v > 0.0)) idx = -1;               // np.max(distances) == 0: nothing to do
+            s_pick = idx;
+            if (idx >= 0) s_taken[n_taken] = idx;
+        }
+        __syncthreads();
+        const long long fi = s_pick;
+        if (fi < 0) return;
+        ++n_taken;
+        const int old = labels[fi];
+        for (int t = tid; t < d; t += 1024) {
+            const double x = (double)X[fi * d + t] - ((mean && !raw_sums) ? mean[t] : 0.0);
+            sums[(int64_t)old * d + t] -= x;
+            sums[(int64_t)e * d + t] = x;
+        }
+        if (tid == 0) {
+            counts[e] = 1;
+            counts[old] -= 1;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+int kmeans_assign_grid(int64_t n) {
+    int64_t tiles = (n + 255) / 256;
+    int64_t cap = 148 * 8;
+    return (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
+}
+
+int kmeans_sums_splits(int64_t n, int batch) {
+    int64_t want = (n + 4095) / 4096;                  // >= 4096 points per split
+    int64_t cap = (148 * 4 + batch - 1) / batch;
+    if (cap < 1) cap = 1;
+    if (want > cap) want = cap;
+    return (int)(want < 1 ? 1 : want);
+}
+
+template <typename T, typename W>
+static int assign_small_dispatch(const KmAssignParams& p, dim3 grid, size_t smem, void* stream) {
+#define OFC_KM_CASE(DPV)                                                                                     \
+    {                                                                                                        \
+        if (smem > 48 * 1024)                                                                                \
+            OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_small_kernel<T, W, DPV>,                             \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        OFC_LAUNCH((kmeans_assign_small_kernel<T, W, DPV>), grid, dim3(256), smem, stream, p);               \
+    }
+    if (p.d <= 4) OFC_KM_CASE(4)
+    else if (p.d <= 8) OFC_KM_CASE(8)
+    else if (p.d <= 16) OFC_KM_CASE(16)
+    else OFC_KM_CASE(32)
+#undef OFC_KM_CASE
+    return OFC_OK;
+}
+
+int launch_kmeans_assign(KmAssignParams p, int batch, double* c2_ws, void* stream) {
+    if (batch <= 0 || p.n <= 0) return OFC_OK;
+    if (batch > 65535) { set_error("batch=%d exceeds 65535", batch); return OFC_ERR_UNSUPPORTED; }
+    const size_t wsz = p.dtype == DT_F32 ? 4 : 8;
+    const size_t smem = ((size_t)p.k * p.d + p.k + p.d) * wsz;
+    ProfScope prof(PK_KMEANS, stream);
+    if (p.d <= 32 && smem <= 200 * 1024) {
+        dim3 grid(kmeans_assign_grid(p.n), batch);
+        int rc;
+        if (p.dtype == DT_U8) rc = assign_small_dispatch<unsigned char, double>(p, grid, smem, stream);
+        else if (p.dtype == DT_F32) rc = assign_small_dispatch<float, float>(p, grid, smem, stream);
+        else rc = assign_small_dispatch<double, double>(p, grid, smem, stream);
+        if (rc != OFC_OK) return rc;
+        OFC_CHECK_LAUNCH("kmeans_assign_small");
+        return OFC_OK;
+    }
+    if (!c2_ws) { set_error("k-means workspace missing"); return OFC_ERR_WORKSPACE; }
+    OFC_LAUNCH(kmeans_c2_kernel, dim3(cdiv(p.k, 128), batch), dim3(128), 0, stream, p.centres, c2_ws, p.d, p.k,
+               p.dtype == DT_F32 ? 1 : 0);
+    OFC_CHECK_LAUNCH("kmeans_c2");
+    p.c2 = c2_ws;
+    int64_t g = (p.n + 7) / 8;
+    if (g > 148 * 16) g = 148 * 16;
+    dim3 grid((int)g, batch);
+    // inertia partials are indexed by gridDim.x and sized with kmeans_assign_grid(n) by the caller:
+    // (n+7)/8 >= (n+255)/256 and the cap above is larger, so clamping gives exactly that count
+    const int parts = kmeans_assign_grid(p.n);
+    if ((int)grid.x > parts) grid.x = parts;
+    if (p.dtype == DT_U8) OFC_LAUNCH((kmeans_assign_generic_kernel<unsigned char, double>), grid, dim3(256), 0, stream, p);
+    else if (p.dtype == DT_F32) OFC_LAUNCH((kmeans_assign_generic_kernel<float, float>), grid, dim3(256), 0, stream, p);
+    else OFC_LAUNCH((kmeans_assign_generic_kernel<double, double>), grid, dim3(256), 0, stream, p);
+    OFC_CHECK_LAUNCH("kmeans_assign_generic");
+    return OFC_OK;
+}
+
+int launch_inertia_reduce(const double* partial, int parts, int batch, double* inertia, const unsigned char* active,
+                          void* stream) {
+    OFC_LAUNCH(inertia_reduce_kernel, dim3(batch), dim3(32), 0, stream, partial, parts, inertia, active);
+    OFC_CHECK_LAUNCH("inertia_reduce");
+    return OFC_OK;
+}
+
+int launch_kmeans_sums(const KmSumsParams& p, int batch, double* sums, long long* counts, void* stream) {
+    if (batch <= 0) return OFC_OK;
+    if (batch > 65535) { set_error("batch=%d exceeds 65535", batch); return OFC_ERR_UNSUPPORTED; }
+    const int G = 32 / p.dt;
+    const size_t smem = (size_t)8 * G * p.kt * p.dt * sizeof(double) + (size_t)8 * G * p.kt * sizeof(int);
+    dim3 grid(p.splits, cdiv(p.d, p.dt), batch);
+    ProfScope prof(PK_KMEANS, stream);
+#define OFC_KM_SUMS(TT)                                                                                      \
+    {                                                                                                        \
+        if (smem > 48 * 1024)                                                                                \
+            OFC_CUDA(cudaFuncSetAttribute(kmeans_sums_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        OFC_LAUNCH(kmeans_sums_kernel<TT>, grid, dim3(256), smem, stream, p);                                \
+    }
+    if (p.dtype == DT_U8) OFC_KM_SUMS(unsigned char)
+    else if (p.dtype == DT_F32) OFC_KM_SUMS(float)
+    else OFC_KM_SUMS(double)
+#undef OFC_KM_SUMS
+    OFC_CHECK_LAUNCH("kmeans_sums");
+    const int64_t kd = (int64_t)p.k * p.d;
+    OFC_LAUNCH(kmeans_fold_kernel, dim3((unsigned)((kd + 255) / 256), batch), dim3(256), 0, stream, p.partial,
+               p.cnt_partial, p.splits, p.k, p.d, sums, counts, p.active);
+    OFC_CHECK_LAUNCH("kmeans_fold");
+    return OFC_OK;
+}
+
+int launch_kmeans_centres(int batch, int d, int k, const double* sums, const long long* counts, const double* mean_sub,
+                          int use_reciprocal, double* centres, double* shift_tot, double* shift_ws,
+                          const unsigned char* active, void* stream) {
+    if (batch <= 0) return OFC_OK;
+    ProfScope prof(PK_KMEANS, stream);
+    OFC_LAUNCH(kmeans_centres_kernel, dim3(batch), dim3(256), 0, stream, d, k, sums, counts, mean_sub, use_reciprocal,
+               centres, shift_tot, shift_ws, active);
+    OFC_CHECK_LAUNCH("kmeans_centres");
+    return OFC_OK;
+}
+
+int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
+                           const int32_t* labels, const double* centres_old, double* sums, long long* counts,
+                           int raw_sums, const unsigned char* active, void* stream) {
+    if (batch <= 0) return OFC_OK;
+    ProfScope prof(PK_KMEANS, stream);
+    const size_t smem = (size_t)k * sizeof(long long);
+    if (smem > 40 * 1024) { set_error("k=%d too large for the relocation kernel", k); return OFC_ERR_UNSUPPORTED; }
+    if (dtype == DT_U8)
+        OFC_LAUNCH(kmeans_relocate_kernel<unsigned char>, dim3(batch), dim3(1024), smem, stream, (const unsigned char*)X, n, d, k,
+                   mean, labels, centres_old, sums, counts, raw_sums, active);
+    else if (dtype == DT_F32)
+        OFC_LAUNCH(kmeans_relocate_kernel<float>, dim3(batch), dim3(1024), smem, stream, (const float*)X, n, d, k, mean, labels,
+                   centres_old, sums, counts, raw_sums, active);
+    else
+        OFC_LAUNCH(kmeans_relocate_kernel<double>, dim3(batch), dim3(1024), smem, stream, (const double*)X, n, d, k, mean, labels,
+                   centres_old, sums, counts, raw_sums, active);
+    OFC_CHECK_LAUNCH("kmeans_relocate");
+    return OFC_OK;
+}
+
+}  // namespace ofc

@@ -11,6 +11,7 @@
 #include "ofc_common.cuh"
 #include "flow_kernels.cuh"
 #include "grid_kernels.cuh"
+#include "kmeans_kernels.cuh"
 #include "viz_kernels.cuh"
 
 namespace ofc {
@@ -399,6 +400,11 @@ int ofc_bgr2gray(const uint8_t* bgr, uint8_t* gray, int64_t n_pixels, void* stre
     return launch_bgr2gray(bgr, gray, n_pixels, stream);
 }
 
+int ofc_bgr2hsv(const uint8_t* bgr, uint8_t* hsv, int64_t n_pixels, void* stream) {
+    OFC_REQUIRE(n_pixels >= 0 && (n_pixels == 0 || (bgr && hsv)), "bad arguments");
+    return launch_bgr2hsv(bgr, hsv, n_pixels, stream);
+}
+
 int ofc_flow_minmax(const float* flow, int n_frames, int64_t n_pixels, uint32_t* minmax, void* stream) {
     OFC_REQUIRE(n_frames >= 0 && n_pixels >= 0, "bad sizes");
     if (n_frames == 0) return OFC_OK;
@@ -446,6 +452,141 @@ int ofc_draw_grid(uint8_t* bgr, int n_frames, int height, int width, int rows, i
     OFC_REQUIRE(bgr != nullptr, "null frame buffer");
     return launch_draw_grid(bgr, (int64_t)height * width * 3, width, height, rows, cols,
                             width / cols, height / rows, n_frames, stream);
+}
+
+// ---- k-means ---------------------------------------------------------------
+namespace {
+struct KmWorkspace {
+    size_t off_c2, off_inertia, off_partial, off_cnt, off_shift, total;
+    int parts, splits, dt, kt;
+};
+KmWorkspace km_layout(int batch, int64_t n, int d, int k) {
+    KmWorkspace w;
+    w.parts = kmeans_assign_grid(n);
+    w.splits = kmeans_sums_splits(n, batch);
+    w.dt = 1;
+    while (w.dt < 32 && w.dt < d) w.dt <<= 1;
+    w.kt = k < 32 ? k : 32;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    w.off_c2 = take((size_t)batch * k * 8);
+    w.off_inertia = take((size_t)batch * w.parts * 8);
+    w.off_partial = take((size_t)batch * w.splits * k * d * 8);
+    w.off_cnt = take((size_t)batch * w.splits * k * 8);
+    w.off_shift = take((size_t)batch * k * 8);
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+size_t ofc_kmeans_workspace_bytes(int batch, int64_t n, int d, int k) {
+    if (batch <= 0 || n <= 0 || d <= 0 || k <= 0) return 0;
+    return km_layout(batch, n, d, k).total;
+}
+
+static int km_check(const void* X, int dtype, int batch, int64_t n, int d, int k) {
+    OFC_REQUIRE(dtype == OFC_U8 || dtype == OFC_F32 || dtype == OFC_F64, "bad dtype %d", dtype);
+    OFC_REQUIRE(batch >= 0 && n >= 0 && d >= 1 && k >= 1, "bad k-means shape batch=%d n=%lld d=%d k=%d", batch, (long long)n, d, k);
+    OFC_REQUIRE(batch == 0 || n == 0 || X != nullptr, "null data");
+    return OFC_OK;
+}
+
+int ofc_kmeans_assign(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
+                      const double* centres, int32_t* labels, const int32_t* prev_labels, uint64_t* n_changed,
+                      double* inertia, double* min_dist, const uint8_t* active, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    int rc = km_check(X, dtype, batch, n, d, k);
+    if (rc != OFC_OK) return rc;
+    if (batch == 0 || n == 0) return OFC_OK;
+    OFC_REQUIRE(centres && labels, "null centres / labels");
+    KmWorkspace w = km_layout(batch, n, d, k);
+    if (!workspace || workspace_bytes < w.total) { set_error("k-means workspace too small: %zu < %zu", workspace_bytes, w.total); return OFC_ERR_WORKSPACE; }
+    char* ws = (char*)workspace;
+    KmAssignParams p;
+    p.X = X; p.dtype = dtype; p.n = n; p.d = d; p.k = k; p.mean = mean; p.centres = centres; p.c2 = nullptr;
+    p.labels = labels; p.prev_labels = prev_labels; p.n_changed = (unsigned long long*)n_changed;
+    p.inertia_partial = inertia ? (double*)(ws + w.off_inertia) : nullptr;
+    p.min_dist = min_dist; p.active = active;
+    if (n_changed) OFC_CUDA(cudaMemsetAsync(n_changed, 0, sizeof(uint64_t) * batch, (cudaStream_t)stream));
+    rc = launch_kmeans_assign(p, batch, (double*)(ws + w.off_c2), stream);
+    if (rc != OFC_OK) return rc;
+    if (inertia) return launch_inertia_reduce((const double*)(ws + w.off_inertia), w.parts, batch, inertia, active, stream);
+    return OFC_OK;
+}
+
+int ofc_kmeans_sums(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
+                    const int32_t* labels, int square, double* sums, int64_t* counts, const uint8_t* active,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = km_check(X, dtype, batch, n, d, k);
+    if (rc != OFC_OK) return rc;
+    if (batch == 0) return OFC_OK;
+    OFC_REQUIRE(sums != nullptr, "null sums");
+    OFC_REQUIRE(n > 0, "empty data");
+    KmWorkspace w = km_layout(batch, n, d, k);
+    if (!workspace || workspace_bytes < w.total) { set_error("k-means workspace too small: %zu < %zu", workspace_bytes, w.total); return OFC_ERR_WORKSPACE; }
+    char* ws = (char*)workspace;
+    KmSumsParams p;
+    p.X = X; p.dtype = dtype; p.n = n; p.d = d; p.k = k; p.mean = mean; p.labels = labels; p.square = square;
+    p.partial = (double*)(ws + w.off_partial); p.cnt_partial = (long long*)(ws + w.off_cnt);
+    p.splits = w.splits; p.dt = w.dt; p.kt = w.kt; p.active = active;
+    return launch_kmeans_sums(p, batch, sums, (long long*)counts, stream);
+}
+
+int ofc_kmeans_centres(int batch, int d, int k, const double* sums, const int64_t* counts, const double* mean_sub,
+                       int use_reciprocal, double* centres, double* shift_tot, const uint8_t* active, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    OFC_REQUIRE(batch >= 0 && d >= 1 && k >= 1, "bad shape");
+    if (batch == 0) return OFC_OK;
+    OFC_REQUIRE(sums && counts && centres, "null buffer");
+    OFC_REQUIRE(workspace && workspace_bytes >= align_up((size_t)batch * k * 8, 256), "k-means workspace too small");
+    // the shift scratch is the tail of the layout for any n; use the head of the workspace here
+    return launch_kmeans_centres(batch, d, k, sums, (const long long*)counts, mean_sub, use_reciprocal, centres, shift_tot,
+                                 (double*)workspace, active, stream);
+}
+
+int ofc_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
+                        const int32_t* labels, const double* centres_old, double* sums, int64_t* counts,
+                        int raw_sums, const uint8_t* active, void* stream) {
+    int rc = km_check(X, dtype, batch, n, d, k);
+    if (rc != OFC_OK) return rc;
+    if (batch == 0 || n == 0) return OFC_OK;
+    OFC_REQUIRE(labels && centres_old && sums && counts, "null buffer");
+    return launch_kmeans_relocate(X, dtype, batch, n, d, k, mean, labels, centres_old, sums, (long long*)counts, raw_sums, active, stream);
+}
+
+int ofc_grid_extract_cells(const uint8_t* bgr, int n_frames, int height, int width, int rows, int cols,
+                           int draw_lines, int threshold, int swap_rb, uint8_t* out, void* stream) {
+    OFC_REQUIRE(n_frames >= 0 && height > 0 && width > 0, "bad sizes");
+    OFC_REQUIRE(rows > 0 && cols > 0 && rows <= height && cols <= width, "grid %dx%d does not fit %dx%d", rows, cols, height, width);
+    OFC_REQUIRE(threshold >= 0 && threshold <= 255, "bad threshold");
+    if (n_frames == 0) return OFC_OK;
+    OFC_REQUIRE(bgr && out, "null buffer");
+    OFC_REQUIRE(((uintptr_t)out & 3) == 0, "out must be 4-byte aligned");
+    return launch_extract_cells(bgr, n_frames, height, width, rows, cols, draw_lines, threshold, swap_rb, out, stream);
+}
+
+// ---- cosine ----------------------------------------------------------------
+int ofc_sliding_cosine(const double* a, int n, const double* b, int64_t m, double* sims, double* best,
+                       int64_t* best_idx, void* stream) {
+    OFC_REQUIRE(n >= 1 && m >= n, "need 1 <= n <= m (n=%d, m=%lld)", n, (long long)m);
+    OFC_REQUIRE(a && b && sims && best && best_idx, "null buffer");
+    OFC_REQUIRE((size_t)n * 8 <= 200 * 1024, "short vector too long for shared memory (n=%d)", n);
+    return launch_sliding_cosine(a, n, b, m, sims, best, (long long*)best_idx, stream);
+}
+
+int ofc_row_cosine(const void* X, int dtype, int64_t n, int d, const double* q, double* out, void* stream) {
+    OFC_REQUIRE(dtype == OFC_U8 || dtype == OFC_F32 || dtype == OFC_F64, "bad dtype %d", dtype);
+    OFC_REQUIRE(n >= 0 && d >= 1, "bad shape");
+    if (n == 0) return OFC_OK;
+    OFC_REQUIRE(X && q && out, "null buffer");
+    OFC_REQUIRE((size_t)d * 8 <= 200 * 1024, "query too long for shared memory (d=%d)", d);
+    return launch_row_cosine(X, dtype, n, d, q, out, stream);
+}
+
+int ofc_vector_distance(const double* a, const double* b, int64_t n, double* cos_out, double* quirk_row, double* l1,
+                        void* stream) {
+    OFC_REQUIRE(n >= 1 && a && b, "bad arguments");
+    return launch_vector_distance(a, b, n, cos_out, quirk_row, l1, stream);
 }
 
 }  // extern "C"

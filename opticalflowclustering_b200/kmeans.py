@@ -1,0 +1,399 @@
+"""Host side of the k-means stage: the Lloyd loop around libofc's E-step / M-step kernels.
+
+Mirrors what the reference gets from scikit-learn at
+k-means-color-clustering/KmeanGrids.py:299-304 and color_kmeans.py:65-78::
+
+    clt = KMeans(n_clusters = k); clt.fit(X); labels = clt.predict(X); clt.cluster_centers_
+
+following sklearn 1.9.0's ``_kmeans_single_lloyd`` (sklearn/cluster/_kmeans.py:627-758,
+SURVEY.md Appendix A.5): data centred on its column mean, ``tol_ = mean(var(X)) * tol``,
+stop when the labels repeat (strict) or the squared centre shift is <= tol_, one more
+E-step when the stop was not strict.  uint8 rows are worked in float64 like sklearn does.
+
+Everything is batched: ``X`` may be ``[n, d]`` (one problem) or ``[B, n, d]`` (B independent
+problems of equal shape -- the reference runs one fit per grid cell).  Problems that have
+converged are frozen by an ``active`` mask while the others keep iterating.
+
+Multi-GPU: rows sharded over the ranks of ``group``; the only exchange is an all-reduce
+of ``[k*d sums | k counts | n_changed]`` per iteration (NCCL over NVLink on GPUs).  For
+uint8 data the sums are integers held exactly in float64, so the result does not depend
+on the number of ranks or the reduction order.
+
+torch is used for device memory, streams and torch.distributed only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from fractions import Fraction
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_vp = C.c_void_p
+_DT = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}
+
+
+class _Ctx:
+    """Library handle + device.  The product path is always libofc.so on a CUDA device;
+    tests pass the host-side debug emulation of the same kernels explicitly."""
+
+    def __init__(self, device, lib=None):
+        self.device = torch.device(device)
+        if lib is None:
+            if self.device.type != "cuda":
+                raise _lib.OfcError("a CUDA device is required: this package has no CPU fallback")
+            lib = _lib.lib()
+            self.check = _lib.check
+        else:
+            def _check(rc, _l=lib):
+                if rc != 0:
+                    raise RuntimeError(f"libofc rc={rc}: {_l.ofc_last_error().decode()}")
+            self.check = _check
+        self.lib = lib
+
+    def stream(self):
+        if self.device.type == "cuda":
+            return _vp(torch.cuda.current_stream(self.device).cuda_stream)
+        return _vp(0)
+
+
+def _ptr(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _target_device(X, lib_override):
+    """Where host inputs go: the current CUDA device (product) -- or the host when a test passes
+    the emulated library.  Fails loudly when neither the GPU nor the CUDA library is there."""
+    if lib_override is not None:
+        return None if (isinstance(X, torch.Tensor) and X.is_cuda) else "cpu"
+    if isinstance(X, torch.Tensor) and X.is_cuda:
+        return None
+    if not torch.cuda.is_available():
+        raise _lib.OfcError("a CUDA device is required: this package has no CPU fallback")
+    _lib.lib()
+    return "cuda"
+
+
+def _as_batch(X, device=None):
+    if isinstance(X, np.ndarray):
+        X = torch.from_numpy(np.ascontiguousarray(X))
+    if X.dtype not in _DT:
+        if X.dtype in (torch.int8, torch.int16, torch.int32, torch.int64, torch.bool, torch.float16, torch.bfloat16):
+            X = X.to(torch.float64)                      # sklearn: validate_data(dtype=[float64, float32])
+        else:
+            raise TypeError(f"unsupported dtype {X.dtype}")
+    if device is not None and X.device != torch.device(device):
+        X = X.to(device)
+    single = X.dim() == 2
+    if single:
+        X = X.unsqueeze(0)
+    if X.dim() != 3:
+        raise ValueError("X must be [n, d] or [batch, n, d]")
+    return X.contiguous(), single
+
+
+class LloydState:
+    """Buffers of one batched Lloyd run (all on the data's device)."""
+
+    def __init__(self, ctx: _Ctx, X: torch.Tensor, k: int):
+        self.ctx, self.X, self.k = ctx, X, int(k)
+        self.B, self.n, self.d = (int(s) for s in X.shape)
+        self.dtype = _DT[X.dtype]
+        dev = X.device
+        lib = ctx.lib
+        lib.ofc_kmeans_workspace_bytes.restype = C.c_size_t
+        lib.ofc_kmeans_workspace_bytes.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int]
+        self.ws_bytes = int(lib.ofc_kmeans_workspace_bytes(self.B, self.n, self.d, max(self.k, 1)))
+        self.ws = torch.empty(max(self.ws_bytes, 256), dtype=torch.uint8, device=dev)
+        self.labels = [torch.full((self.B, self.n), -1, dtype=torch.int32, device=dev) for _ in range(2)]
+        # one flat fp64 buffer so a single all-reduce moves sums, counts and n_changed together
+        kd = self.k * self.d
+        self.red = torch.zeros((self.B, kd + self.k + 1), dtype=torch.float64, device=dev)
+        self.sums = torch.empty((self.B, self.k, self.d), dtype=torch.float64, device=dev)
+        self.counts = torch.empty((self.B, self.k), dtype=torch.int64, device=dev)
+        self.n_changed = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.shift = torch.zeros(self.B, dtype=torch.float64, device=dev)
+        self.inertia = torch.zeros(self.B, dtype=torch.float64, device=dev)
+
+    # -- thin wrappers over the C-ABI -----------------------------------------------------
+    def assign(self, mean, centres, labels, prev=None, n_changed=None, inertia=None, min_dist=None, active=None):
+        c = self.ctx
+        c.check(c.lib.ofc_kmeans_assign(_ptr(self.X), self.dtype, self.B, C.c_int64(self.n), self.d, int(centres.shape[1]),
+                                        _ptr(mean), _ptr(centres), _ptr(labels), _ptr(prev), _ptr(n_changed),
+                                        _ptr(inertia), _ptr(min_dist), _ptr(active), _ptr(self.ws),
+                                        C.c_size_t(self.ws.numel()), c.stream()))
+
+    def sums_(self, mean, labels, sums, counts, k, square=0, active=None):
+        c = self.ctx
+        c.check(c.lib.ofc_kmeans_sums(_ptr(self.X), self.dtype, self.B, C.c_int64(self.n), self.d, int(k), _ptr(mean),
+                                      _ptr(labels), int(square), _ptr(sums), _ptr(counts), _ptr(active), _ptr(self.ws),
+                                      C.c_size_t(self.ws.numel()), c.stream()))
+
+    def centres_(self, sums, counts, mean_sub, use_reciprocal, centres, shift, active=None):
+        c = self.ctx
+        c.check(c.lib.ofc_kmeans_centres(self.B, self.d, int(centres.shape[1]), _ptr(sums), _ptr(counts), _ptr(mean_sub),
+                                         int(use_reciprocal), _ptr(centres), _ptr(shift), _ptr(active), _ptr(self.ws),
+                                         C.c_size_t(self.ws.numel()), c.stream()))
+
+    def relocate(self, mean, labels, centres_old, sums, counts, raw_sums, active=None):
+        c = self.ctx
+        c.check(c.lib.ofc_kmeans_relocate(_ptr(self.X), self.dtype, self.B, C.c_int64(self.n), self.d, self.k, _ptr(mean),
+                                          _ptr(labels), _ptr(centres_old), _ptr(sums), _ptr(counts), int(raw_sums),
+                                          _ptr(active), c.stream()))
+
+
+def _all_reduce(t, group):
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def column_mean_var(st: LloydState, group=None):
+    """Column mean and variance of every problem ([B, d] float64 each), as numpy computes
+    them for ``X.mean(axis=0)`` / ``np.var(X, axis=0)`` (_kmeans.py:285-293, 1487).
+    uint8 data: exact integer sums -> exact rational variance."""
+    B, d, dev = st.B, st.d, st.X.device
+    s1 = torch.empty((B, 1, d), dtype=torch.float64, device=dev)
+    cnt = torch.empty((B, 1), dtype=torch.int64, device=dev)
+    st.sums_(None, None, s1, cnt, 1)
+    red = torch.cat([s1.view(B, d), cnt.to(torch.float64)], dim=1)
+    if group is not None:
+        _all_reduce(red, group)
+    n_tot = red[:, d:d + 1]
+    mean = red[:, :d] / n_tot
+    s2 = torch.empty((B, 1, d), dtype=torch.float64, device=dev)
+    if st.dtype == 0:
+        # exact: var = (sum x^2 - (sum x)^2 / n) / n with integer sums
+        st.sums_(None, None, s2, None, 1, square=1)
+        sq = s2.view(B, d).clone()
+        if group is not None:
+            _all_reduce(sq, group)
+        sx = red[:, :d].cpu().numpy()
+        sxx = sq.cpu().numpy()
+        nn = n_tot.cpu().numpy().reshape(-1)
+        var = np.empty((B, d))
+        for b in range(B):
+            N = int(nn[b])
+            for t in range(d):
+                var[b, t] = float((Fraction(int(sxx[b, t])) - Fraction(int(sx[b, t])) ** 2 / N) / N)
+        var = torch.from_numpy(var).to(dev)
+    else:
+        st.sums_(mean.contiguous(), None, s2, None, 1, square=1)
+        sq = s2.view(B, d).clone()
+        if group is not None:
+            _all_reduce(sq, group)
+        var = sq / n_tot
+    return mean.contiguous(), var, n_tot.view(-1)
+
+
+def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_override=None):
+    """Batched ``KMeans(n_clusters=k, init=init, n_init=1, max_iter=max_iter, tol=tol).fit(X)``.
+
+    X ``[n,d]`` or ``[B,n,d]`` (uint8 / float32 / float64; torch on the compute device, or numpy);
+    init ``[k,d]`` or ``[B,k,d]``.  With ``group`` every rank passes its own rows (same B, d, k)
+    and receives the global centres / inertia and the labels of its rows.
+
+    Returns ``(labels int32, centres float64, inertia float64, n_iter int64)`` as torch
+    tensors on X's device, squeezed when X was ``[n,d]``.
+    """
+    Xb, single = _as_batch(X, _target_device(X, _lib_override))
+    ctx = _Ctx(Xb.device, _lib_override)
+    init = torch.as_tensor(np.asarray(init) if not isinstance(init, torch.Tensor) else init)
+    init = init.to(device=Xb.device, dtype=torch.float64)
+    if init.dim() == 2:
+        init = init.unsqueeze(0).expand(Xb.shape[0], -1, -1)
+    init = init.contiguous()
+    B, n, d = (int(s) for s in Xb.shape)
+    k = int(init.shape[1])
+    if init.shape[0] != B or init.shape[2] != d:
+        raise ValueError(f"init shape {tuple(init.shape)} does not match X {tuple(Xb.shape)}")
+    st = LloydState(ctx, Xb, k)
+    mean, var, n_tot = column_mean_var(st, group)
+    if int(n_tot.min().item()) < k:
+        raise ValueError(f"n_samples={int(n_tot.min().item())} should be >= n_clusters={k}.")   # _kmeans.py:876-879
+    tol_ = (var.mean(dim=1) * tol).cpu().numpy()
+    is_u8 = st.dtype == 0
+    if st.dtype == 1:
+        # sklearn keeps float32 data in float32: centre with the float32 mean
+        mean = mean.to(torch.float32).to(torch.float64).contiguous()
+    centres = (init - mean.unsqueeze(1)).contiguous()            # centred
+    if st.dtype == 1:
+        centres = centres.to(torch.float32).to(torch.float64).contiguous()
+    centres_old = torch.empty_like(centres)
+
+    active = torch.ones(B, dtype=torch.uint8, device=Xb.device)
+    active_h = np.ones(B, bool)
+    strict = np.zeros(B, bool)
+    n_iter = np.zeros(B, np.int64)
+    kd = k * d
+    cur = 0
+    for it in range(max_iter):
+        lab, lab_old = st.labels[cur], st.labels[cur ^ 1]
+        st.assign(mean, centres, lab, prev=lab_old, n_changed=st.n_changed, active=active)
+        # uint8: raw (exact integer) sums; floats: sums of the centred rows like sklearn
+        st.sums_(None if is_u8 else mean, lab, st.sums, st.counts, k, active=active)
+        if group is not None:
+            st.red[:, :kd] = st.sums.view(B, kd)
+            st.red[:, kd:kd + k] = st.counts.to(torch.float64)
+            st.red[:, kd + k] = st.n_changed.to(torch.float64)
+            _all_reduce(st.red, group)
+            st.sums.view(B, kd).copy_(st.red[:, :kd])
+            st.counts.copy_(st.red[:, kd:kd + k].to(torch.int64))
+            st.n_changed.copy_(st.red[:, kd + k].to(torch.int64))
+            if bool((st.counts == 0).any().item()):
+                raise NotImplementedError("empty-cluster relocation across ranks is not implemented")
+        else:
+            st.relocate(mean, lab, centres, st.sums, st.counts, is_u8, active=active)
+        centres_old.copy_(centres)
+        st.centres_(st.sums, st.counts, mean if is_u8 else None, 0 if is_u8 else 1, centres, st.shift, active=active)
+        if st.dtype == 1:
+            centres.copy_(centres.to(torch.float32).to(torch.float64))
+        host = torch.stack([st.n_changed.to(torch.float64), st.shift]).cpu().numpy()
+        changed, shift = host[0], host[1]
+        done_now = np.zeros(B, bool)
+        for b in range(B):
+            if not active_h[b]:
+                continue
+            n_iter[b] = it + 1
+            if changed[b] == 0:
+                strict[b] = True
+                done_now[b] = True
+            elif shift[b] <= tol_[b]:
+                done_now[b] = True
+        if done_now.any():
+            active_h &= ~done_now
+            active.copy_(torch.from_numpy(active_h.astype(np.uint8)))
+        # frozen problems must keep the labels they stopped with: both label buffers
+        # get them, so swapping buffers never resurrects stale labels
+        if done_now.any():
+            idx = torch.from_numpy(np.nonzero(done_now)[0]).to(Xb.device)
+            lab_old[idx] = lab[idx]
+        if not active_h.any():
+            break
+        cur ^= 1
+    final = st.labels[cur]
+    # strict stops already hold the labels of the final centres; the rest get one more E-step
+    # (_kmeans.py:745-755).  Re-running it for everyone is idempotent for the strict ones and
+    # yields the inertia of the final (centres, labels) in the same pass.
+    st.assign(mean, centres, final, inertia=st.inertia)
+    inertia = st.inertia.clone()
+    if group is not None:
+        _all_reduce(inertia, group)
+    out_centres = centres + mean.unsqueeze(1)
+    n_iter_t = torch.from_numpy(n_iter).to(Xb.device)
+    if single:
+        return final[0], out_centres[0], inertia[0], n_iter_t[0]
+    return final, out_centres, inertia, n_iter_t
+
+
+def predict(X, centres, _lib_override=None):
+    """``KMeans.predict``: E-step on the un-centred rows (_kmeans.py:1075-1107)."""
+    Xb, single = _as_batch(X, _target_device(X, _lib_override))
+    ctx = _Ctx(Xb.device, _lib_override)
+    c = torch.as_tensor(np.asarray(centres) if not isinstance(centres, torch.Tensor) else centres)
+    c = c.to(device=Xb.device, dtype=torch.float64)
+    if c.dim() == 2:
+        c = c.unsqueeze(0).expand(Xb.shape[0], -1, -1)
+    c = c.contiguous()
+    st = LloydState(ctx, Xb, int(c.shape[1]))
+    st.assign(None, c, st.labels[0])
+    return st.labels[0][0] if single else st.labels[0]
+
+
+def kmeans_plusplus(X, n_clusters: int, random_state=None, _lib_override=None):
+    """k-means++ seeding with sklearn's procedure and RNG call sequence
+    (sklearn/cluster/_kmeans.py:181-268): first centre by ``random_state.choice``, then
+    ``2 + int(log(k))`` candidates per step sampled in proportion to the squared distance to
+    the closest chosen centre, keeping the candidate that lowers the potential most.
+    Distances come from the E-step kernel (one candidate = a one-centre problem).
+    X ``[n, d]``; returns ``(centres float64 [k,d] tensor, indices)``.
+
+    The reference leaves ``random_state`` unset (KmeanGrids.py:300), so this seeding is not
+    pinned by any reference output."""
+    Xb, single = _as_batch(X, _target_device(X, _lib_override))
+    if not single:
+        raise ValueError("kmeans_plusplus takes one problem [n, d]")
+    ctx = _Ctx(Xb.device, _lib_override)
+    rs = random_state if isinstance(random_state, np.random.RandomState) else np.random.RandomState(random_state)
+    n, d = int(Xb.shape[1]), int(Xb.shape[2])
+    k = int(n_clusters)
+    st = LloydState(ctx, Xb, 1)
+    trials = 2 + int(math.log(k))
+    Xf = Xb[0]
+    centres = torch.empty((k, d), dtype=torch.float64, device=Xb.device)
+    indices = np.full(k, -1, dtype=np.int64)
+    cid = int(rs.choice(n, p=np.full(n, 1.0 / n)))
+    centres[0] = Xf[cid].to(torch.float64)
+    indices[0] = cid
+    closest = torch.empty((1, n), dtype=torch.float64, device=Xb.device)
+    cand = torch.empty((1, n), dtype=torch.float64, device=Xb.device)
+    st.assign(None, centres[0:1].unsqueeze(0).contiguous(), st.labels[0], min_dist=closest)
+    pot = float(closest.sum().item())
+    for c in range(1, k):
+        rand_vals = rs.uniform(size=trials) * pot
+        cum = torch.cumsum(closest[0], dim=0)
+        ids = torch.searchsorted(cum, torch.from_numpy(rand_vals).to(Xb.device)).clamp_(max=n - 1).cpu().numpy()
+        best = None
+        for cidx in ids:
+            st.assign(None, Xf[int(cidx)].to(torch.float64).view(1, 1, d).contiguous(), st.labels[0], min_dist=cand)
+            dmin = torch.minimum(closest, cand)
+            p = float(dmin.sum().item())
+            if best is None or p < best[0]:
+                best = (p, int(cidx), dmin)
+        pot, cid, closest = best[0], best[1], best[2].contiguous()
+        centres[c] = Xf[cid].to(torch.float64)
+        indices[c] = cid
+    return centres, indices
+
+
+class KMeans:
+    """The subset of ``sklearn.cluster.KMeans`` the reference uses (KmeanGrids.py:299-304,
+    color_kmeans.py:65-78): ``KMeans(n_clusters=k).fit(X)``, ``.predict(X)``,
+    ``.cluster_centers_``, ``.labels_``, ``.inertia_``, ``.n_iter_``.  ``init`` may be
+    ``'k-means++'`` (default, see :func:`kmeans_plusplus`) or an array ``[k, d]``."""
+
+    def __init__(self, n_clusters=8, *, init="k-means++", n_init="auto", max_iter=300, tol=1e-4, random_state=None,
+                 _lib_override=None):
+        self.n_clusters, self.init, self.n_init = int(n_clusters), init, n_init
+        self.max_iter, self.tol, self.random_state = int(max_iter), float(tol), random_state
+        self._lo = _lib_override
+
+    def fit(self, X, y=None):
+        Xa = X if isinstance(X, torch.Tensor) else np.asarray(X)
+        if Xa.ndim != 2:
+            raise ValueError("Expected 2D array")
+        if Xa.shape[0] < self.n_clusters:
+            raise ValueError(f"n_samples={Xa.shape[0]} should be >= n_clusters={self.n_clusters}.")
+        if isinstance(self.init, str):
+            if self.init != "k-means++":
+                raise NotImplementedError(f"init={self.init!r}")
+            if self.n_clusters == 1:
+                init = (Xa[:1].to(torch.float64) if isinstance(Xa, torch.Tensor) else Xa[:1].astype(np.float64))
+            else:
+                init, _ = kmeans_plusplus(Xa, self.n_clusters, self.random_state, _lib_override=self._lo)
+        else:
+            init = self.init
+        labels, centres, inertia, n_iter = lloyd(Xa, init, self.max_iter, self.tol, _lib_override=self._lo)
+        self._centres_t = centres
+        self.cluster_centers_ = centres.cpu().numpy()
+        if not isinstance(X, torch.Tensor) and np.asarray(X).dtype == np.float32:
+            self.cluster_centers_ = self.cluster_centers_.astype(np.float32)
+        self.labels_ = labels.cpu().numpy()
+        self.inertia_ = float(inertia.item())
+        self.n_iter_ = int(n_iter.item())
+        return self
+
+    def predict(self, X):
+        return predict(X, self._centres_t, _lib_override=self._lo).cpu().numpy()
+
+    def fit_predict(self, X, y=None):
+        return self.fit(X).labels_
+
+
+def kmeans_fit(X, init, max_iter: int = 300, tol: float = 1e-4):
+    """SURVEY.md §8(b) parity entry point: numpy in / numpy out
+    ``(labels int32[N], centers[k,D], inertia, n_iter)``."""
+    labels, centres, inertia, n_iter = lloyd(X, init, max_iter, tol)
+    return labels.cpu().numpy(), centres.cpu().numpy(), float(inertia.item()), int(n_iter.item())

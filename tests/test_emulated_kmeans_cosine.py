@@ -1,0 +1,185 @@
+"""k-means / cosine kernels + their Python host loop on CPU: the .cu sources under the fiber
+emulation (tests/emu), driven through the product's own host code (kmeans.py / cosine.py
+with the emulated library passed explicitly), compared with the oracle and with the
+sklearn / reference goldens.  The `-m gpu` twins are in tests/test_gpu_kmeans_cosine.py."""
+import csv
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grid_np as G
+from oracle import kmeans_np as K
+from tests.conftest import GOLDEN
+
+E = pytest.importorskip("tests.emu.emu_lib")
+from opticalflowclustering_b200 import cosine as cosm  # noqa: E402
+from opticalflowclustering_b200 import kmeans as km    # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def L():
+    E.build()
+    return E.lib()
+
+
+def _hue_col(path):
+    with open(path, encoding="utf-8-sig") as f:
+        return np.array([int(r[1]) for r in csv.reader(f) if r])
+
+
+@pytest.mark.parametrize("name", ["u8_d4_k3", "u8_d4_k8"])
+def test_lloyd_vs_sklearn_golden_u8(L, name):
+    z = np.load(os.path.join(GOLDEN, "kmeans_sklearn.npz"))
+    X = z[name + "_X"][:6000] if name == "u8_d4_k8" else z[name + "_X"]
+    init = z[name + "_init"]
+    labels, centres, inertia, n_iter = km.lloyd(X, init, _lib_override=L)
+    want = K.kmeans_fit(X, init)
+    assert (labels.numpy() == want[0]).all()
+    assert np.abs(centres.numpy() - want[1]).max() < 1e-9
+    assert abs(float(inertia) - want[2]) <= 1e-9 * want[2]
+    assert int(n_iter) == want[3]
+    if X.shape[0] == z[name + "_X"].shape[0]:
+        assert (labels.numpy() == z[name + "_labels"]).all()
+        assert int(n_iter) == int(z[name + "_niter"])
+        assert abs(float(inertia) - float(z[name + "_inertia"])) <= 1e-5 * float(z[name + "_inertia"])
+        assert (km.predict(X, centres, _lib_override=L).numpy() == z[name + "_predict"]).all()
+
+
+def test_lloyd_f32_golden(L):
+    z = np.load(os.path.join(GOLDEN, "kmeans_sklearn.npz"))
+    X, init = z["f32_d32_k16_X"][:1500], z["f32_d32_k16_init"]
+    labels, centres, inertia, n_iter = km.lloyd(X, init, _lib_override=L)
+    want = K.kmeans_fit(X, init)
+    assert (labels.numpy() == want[0]).mean() > 0.999
+    assert np.abs(centres.numpy() - want[1]).max() < 1e-3
+    assert abs(float(inertia) - want[2]) <= 1e-5 * want[2]
+
+
+def test_lloyd_batched_matches_single_and_freezes(L):
+    rng = np.random.default_rng(3)
+    B, n, d, k = 5, 700, 4, 3
+    cen = rng.uniform(10, 240, (B, k, d))
+    X = np.clip(np.rint(cen[np.arange(B)[:, None], rng.integers(k, size=(B, n))] + rng.normal(0, 9, (B, n, d))), 0, 255)
+    X = X.astype(np.uint8)
+    init = X[:, :k].astype(np.float64)
+    labels, centres, inertia, n_iter = km.lloyd(X, init, _lib_override=L)
+    assert len(set(n_iter.tolist())) > 1 or B == 1     # problems stop at different iterations
+    for b in range(B):
+        w = K.kmeans_fit(X[b], init[b])
+        assert (labels[b].numpy() == w[0]).all()
+        assert np.abs(centres[b].numpy() - w[1]).max() < 1e-9
+        assert int(n_iter[b]) == w[3]
+        assert abs(float(inertia[b]) - w[2]) <= 1e-9 * max(w[2], 1.0)
+
+
+def test_generic_path_large_d(L):
+    rng = np.random.default_rng(5)
+    n, d, k = 300, 70, 5
+    cen = rng.uniform(0, 255, (k, d))
+    X = np.clip(np.rint(cen[rng.integers(k, size=n)] + rng.normal(0, 20, (n, d))), 0, 255).astype(np.uint8)
+    init = X[:k].astype(np.float64)
+    labels, centres, inertia, n_iter = km.lloyd(X, init, _lib_override=L)
+    w = K.kmeans_fit(X, init)
+    assert (labels.numpy() == w[0]).all() and int(n_iter) == w[3]
+    assert np.abs(centres.numpy() - w[1]).max() < 1e-9
+
+
+def test_empty_cluster_relocation(L):
+    # a duplicated initial centre: its second copy starts empty (ties -> lowest index) and is relocated
+    rng = np.random.default_rng(11)
+    X = np.clip(np.rint(rng.normal(100, 20, (400, 4))), 0, 255).astype(np.uint8)
+    init = np.array([[100, 100, 100, 100], [100, 100, 100, 100], [70, 70, 70, 70]], np.float64)
+    labels, centres, inertia, n_iter = km.lloyd(X, init, _lib_override=L)
+    w = K.kmeans_fit(X, init)
+    assert int(n_iter) == w[3]
+    assert (labels.numpy() == w[0]).all()
+    assert abs(float(inertia) - w[2]) <= 1e-9 * w[2]
+
+
+def test_k1_is_the_mean_and_matches_g2_rint(L):
+    z = np.load(os.path.join(GOLDEN, "g23_cells.npz"))
+    cells = z["cells"][0, :40]                              # 40 cells of one frame, 51x51x3
+    X = np.stack([G.preprocess_image(c[..., ::-1].copy()).reshape(-1, 4) for c in cells])
+    labels, centres, inertia, n_iter = km.lloyd(X, X[:, :1].astype(np.float64), _lib_override=L)
+    assert (labels.numpy() == 0).all() and (n_iter.numpy() <= 2).all()
+    for b in range(len(cells)):
+        c, _ = G.cluster_colors_k1(X[b].reshape(51, 51, 4))
+        assert (np.rint(centres[b, 0].numpy()) == c).all()
+
+
+def test_kmeans_class_api(L):
+    rng = np.random.default_rng(2)
+    X = np.clip(np.rint(np.concatenate([rng.normal(60, 6, (300, 4)), rng.normal(190, 6, (200, 4))])), 0, 255).astype(np.uint8)
+    clt = km.KMeans(n_clusters=2, random_state=0, _lib_override=L).fit(X)
+    pred = clt.predict(X)
+    assert (pred == clt.labels_).all()
+    counts = np.bincount(pred)
+    assert sorted(counts.tolist()) == [200, 300]
+    assert clt.cluster_centers_.shape == (2, 4) and clt.inertia_ > 0 and clt.n_iter_ >= 1
+    with pytest.raises(ValueError):
+        km.KMeans(n_clusters=5, _lib_override=L).fit(X[:3])
+
+
+def test_sliding_cosine_goldens(L):
+    short = _hue_col(os.path.join(GOLDEN, "bounce.csv"))
+    for name, want_sim, want_frame in [("601_3_3_cropped.csv", 0.91448231723348, 24),
+                                       ("cropped_trimmed2.csv", 0.963475622684391, 7)]:
+        long_ = _hue_col(os.path.join(GOLDEN, name))
+        best, frame, sims = cosm.sliding_cosine(short, long_, return_sims=True, _lib_override=L)
+        ob, of = G.sliding_cosine(short, long_)
+        assert best == ob and frame == of                    # bit-exact vs the numpy restatement
+        assert frame == want_frame and abs(best - want_sim) < 1e-14
+        ref = np.array([G.cosine_similarity(short, long_[i:i + len(short)]) for i in range(len(sims))])
+        assert (sims == ref).all()
+
+
+def test_sliding_cosine_edge_cases(L):
+    assert cosm.sliding_cosine([1, 2, 3], [1, 2], _lib_override=L) == (-1, -1)
+    best, frame = cosm.sliding_cosine([0, 0], [0, 0, 5, 0], _lib_override=L)
+    assert best == 0 and frame == 2                            # zero norms -> 0; ties -> last index
+    best, frame = cosm.sliding_cosine([1, 1], [2, 2, 0, 3, 3], _lib_override=L)
+    assert frame == 3 and abs(best - 1.0) < 1e-15
+    assert cosm.calculate_cosine_similarity([0, 0], [1, 2], _lib_override=L) == 0
+
+
+def test_vector_distance_golden(L):
+    a = _hue_col(os.path.join(GOLDEN, "file1.csv"))
+    b = _hue_col(os.path.join(GOLDEN, "file2.csv"))
+    cos, row, dist = cosm.vector_distance(a, b, _lib_override=L)
+    ocos, orow, odist = G.vector_distance(a, b)
+    assert abs(cos[0, 0] - ocos[0, 0]) < 1e-15 and str(np.array([[round(cos[0, 0], 12)]])) == "[[1.]]"
+    assert np.array_equal(row, orow, equal_nan=True)
+    assert dist == odist == 0.0
+    assert np.allclose(row[:6], [1., 1.09756098, 0.91836735, 0.83333333, 0.8490566, 0.52023121])
+
+
+def test_row_cosine(L):
+    rng = np.random.default_rng(9)
+    for d, dt in [(3, np.uint8), (16, np.uint8), (350, np.uint8), (40, np.float32)]:
+        X = rng.integers(0, 180, (257, d)).astype(dt)
+        X[5] = 0
+        q = rng.integers(0, 180, d).astype(np.float64)
+        out = cosm.row_cosine(X, q, _lib_override=L).numpy()
+        ref = np.array([G.cosine_similarity(X[i].astype(np.float64), q) for i in range(len(X))], dtype=np.float64)
+        assert out[5] == 0
+        assert np.abs(out - ref).max() < 1e-14
+
+
+def test_extract_cells_matches_reference_rois(L):
+    import ctypes as C
+    rng = np.random.default_rng(4)
+    H, W, rows, cols = 60, 100, 3, 4
+    frame = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    ys, xs = H // rows, W // cols
+    out = np.zeros((2, rows * cols, ys * xs, 4), np.uint8)
+    rc = L.ofc_grid_extract_cells(C.c_void_p(frame.ctypes.data), 2, H, W, rows, cols, 1, 30, 0,
+                                  C.c_void_p(out.ctypes.data), C.c_void_p(0))
+    assert rc == 0
+    for f in range(2):
+        fr = frame[f].copy()
+        _, _, rois = G.grid_mean_hues(fr, rows, cols)        # draws the rectangles like the reference
+        for c, roi in enumerate(rois):
+            want = G.preprocess_image(roi.copy()).reshape(-1, 4)
+            assert (out[f, c] == want).all()

@@ -1,0 +1,213 @@
+"""GPU parity tests for the k-means / cosine stage and the reference-named drop-ins: the CUDA
+path through the C-ABI against the oracle, the sklearn goldens and the reference's G1/G2/G4/
+G5/G6 fixtures.  Bars (north_star): labels bit-exact given identical initial centres, inertia
+within 1e-5 relative; cosine index sets bit-exact; CSV text identical for k = 1."""
+import csv
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grid_np as G
+from oracle import kmeans_np as K
+from oracle import viz_np as V
+from tests.conftest import GOLDEN, unpack_images
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def km():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from opticalflowclustering_b200 import _lib, kmeans
+    _lib.lib()
+    return kmeans
+
+
+def _hue_col(path):
+    with open(path, encoding="utf-8-sig") as f:
+        return np.array([int(r[1]) for r in csv.reader(f) if r])
+
+
+@pytest.mark.parametrize("name", ["u8_d4_k3", "u8_d4_k8", "f32_d32_k16"])
+def test_kmeans_fit_vs_sklearn_golden(km, name):
+    z = np.load(os.path.join(GOLDEN, "kmeans_sklearn.npz"))
+    X, init = z[name + "_X"], z[name + "_init"]
+    labels, centres, inertia, n_iter = km.kmeans_fit(X, init)
+    if name.startswith("u8"):
+        assert (labels == z[name + "_labels"]).all()                     # bit-exact labels
+        assert n_iter == int(z[name + "_niter"])
+        assert np.abs(centres - z[name + "_centers"]).max() < 1e-9
+        assert (km.predict(X, centres).cpu().numpy() == z[name + "_predict"]).all()
+    else:
+        assert (labels == z[name + "_labels"]).mean() > 0.9995           # float32 data: fp32 rounding order
+        assert np.abs(centres - z[name + "_centers"]).max() < 1e-2
+    assert abs(inertia - float(z[name + "_inertia"])) <= 1e-5 * float(z[name + "_inertia"])
+
+
+def test_kmeans_large_n_properties(km):
+    """1M x 4 uint8 rows, k = 8: too slow for the numpy oracle in full, so check (a) labels equal
+    an independent fp64 torch restatement of the E-step on the final centres, (b) centres are the
+    exact member means, (c) inertia equals the direct sum, (d) two runs are bit-identical."""
+    g = torch.Generator().manual_seed(3)
+    cen = torch.randint(20, 230, (8, 4), generator=g).double()
+    X = (cen[torch.randint(0, 8, (1_000_000,), generator=g)] + 12 * torch.randn(1_000_000, 4, generator=g, dtype=torch.float64))
+    X = X.round().clamp(0, 255).to(torch.uint8).cuda()
+    init = X[:8].double()
+    l1, c1, i1, n1 = km.lloyd(X, init)
+    l2, c2, i2, n2 = km.lloyd(X, init)
+    assert torch.equal(l1, l2) and torch.equal(c1, c2) and float(i1) == float(i2) and int(n1) == int(n2)
+    Xd = X.double()
+    mean = Xd.mean(0)
+    d = ((c1 - mean) ** 2).sum(1)[None, :] - 2.0 * (Xd - mean) @ (c1 - mean).T
+    ref = d.argmin(1).to(torch.int32)
+    assert (ref != l1).sum().item() <= 2                                   # near-ties only
+    for j in range(8):
+        m = Xd[l1 == j].mean(0)
+        assert (m - c1[j]).abs().max().item() < 1e-9 or int(n1) == 300
+    direct = ((Xd - c1[l1.long()]) ** 2).sum().item()
+    assert abs(direct - float(i1)) <= 1e-9 * direct
+
+
+def test_kmeans_batched_cells_k3_vs_oracle(km):
+    z = np.load(os.path.join(GOLDEN, "g23_cells.npz"))
+    cells = z["cells"][0, 100:130]
+    X = np.stack([G.preprocess_image(c.copy()).reshape(-1, 4) for c in cells])
+    init = np.stack([np.unique(x, axis=0)[[0, len(np.unique(x, axis=0)) // 2, -1]] for x in X]).astype(np.float64)
+    labels, centres, inertia, n_iter = km.lloyd(X, init)
+    for b in range(len(X)):
+        w = K.kmeans_fit(X[b], init[b])
+        assert (labels[b].cpu().numpy() == w[0]).all()
+        assert int(n_iter[b]) == w[3]
+        assert np.abs(centres[b].cpu().numpy() - w[1]).max() < 1e-9
+        assert abs(float(inertia[b]) - w[2]) <= 1e-9 * max(w[2], 1.0)
+
+
+def test_kmeans_errors(km):
+    with pytest.raises(ValueError):
+        km.KMeans(n_clusters=4).fit(np.zeros((3, 4), np.uint8))
+    with pytest.raises(ValueError):
+        km.lloyd(np.zeros((10, 4), np.uint8), np.zeros((2, 5)))
+
+
+def test_color_kmeans_g1_csv_text(km, tmp_path, monkeypatch):
+    """G1: color_kmeans.py end to end, k = 1 -> cluster_centers.csv text identical (CRLF rows)."""
+    from opticalflowclustering_b200 import color_kmeans as ck
+    z = np.load(os.path.join(GOLDEN, "g1_images.npz"))
+    monkeypatch.chdir(tmp_path)
+    open("cluster_centers.csv", "w").close()
+    for im, name in zip(unpack_images(z), z["names"]):
+        rgb = np.ascontiguousarray(im[..., ::-1])            # read_image's BGR -> RGB
+        ck.cluster_colors(ck.preprocess_image(rgb), 1, "some/dir/" + str(name), "cluster_centers.csv")
+    got = open("cluster_centers.csv", newline="").read()
+    want = open(os.path.join(GOLDEN, "g1_cluster_centers.csv"), newline="").read()
+    assert got.replace("\r\n", "\n") == want.replace("\r\n", "\n")
+    assert "\r\n" in got                                       # csv.writer line ends, like the reference
+
+
+def test_preprocess_image_in_place(km):
+    from opticalflowclustering_b200 import color_kmeans as ck
+    rng = np.random.default_rng(0)
+    im = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    want_in = im.copy()
+    want = G.preprocess_image(want_in)
+    got = ck.preprocess_image(im)
+    assert (got == want).all() and (im == want_in).all()
+
+
+def test_g4_hues_through_dropin(km):
+    from opticalflowclustering_b200 import KmeanGrids as kg
+    z = np.load(os.path.join(GOLDEN, "g4_images.npz"))
+    for im, want in list(zip(unpack_images(z), z["hues"]))[:12]:
+        rgb = np.ascontiguousarray(im[..., ::-1])
+        c, hue = kg.cluster_colors(kg.preprocess_image(rgb), 1, "x", os.devnull)
+        assert hue == want
+
+
+def test_kmeangrids_frame_hues_and_outcsv(km, tmp_path):
+    """overlayGridAndComputeAvgColor + the main loop's per-cell k = 1 hues on a synthetic
+    visualisation frame vs the oracle's restatement of the reference loop; OutCSV row text."""
+    from opticalflowclustering_b200 import KmeanGrids as kg
+    rng = np.random.default_rng(5)
+    frame = rng.integers(0, 256, (714, 1275, 3), dtype=np.uint8)
+    ref = frame.copy()
+    _, _, rois = G.grid_mean_hues(ref, 14, 25)
+    want = [G.cluster_colors_k1(G.preprocess_image(r))[1] for r in rois]
+    kg.image_dict.clear()
+    kg.overlayGridAndComputeAvgColor(2, frame, kg.GRID_PARAMS, "unused.csv", "clip.mp4")
+    assert len(kg.image_dict) == 350 and kg.image_dict["2/1"].base is not None
+    assert (frame == ref).all()                                        # grid lines as the reference leaves them
+    hues = kg.frame_hues("2", [str(i) for i in range(1, 351)], 1)
+    assert hues == [int(h) for h in want]
+    # k = 1 through the generic path (image_dict ROI -> preprocess -> Lloyd kernels) agrees too
+    kg.frame_results.clear()
+    assert kg.frame_hues("2", ["1", "26", "350"], 1) == [int(want[0]), int(want[25]), int(want[349])]
+    p = tmp_path / "out.csv"
+    kg.write_outcsv_row(str(p), hues, True)
+    kg.write_outcsv_row(str(p), hues, False)
+    rows = list(csv.reader(open(p)))
+    assert rows[0][0] == "cell_0" and rows[0][-1] == "cell_349" and len(rows) == 3 and rows[1] == [str(h) for h in hues]
+
+
+def test_drawgrids_csv_row(km, tmp_path):
+    from opticalflowclustering_b200 import drawGridsAndOutputCSV as dg
+    rng = np.random.default_rng(6)
+    frame = rng.integers(0, 256, (200, 300, 3), dtype=np.uint8)
+    ref = frame.copy()
+    _, hues, _ = G.grid_mean_hues(ref, 10, 10)
+    p = tmp_path / "rgb_values.csv"
+    dg.overlayGridAndComputeAvgColor(2, frame, dg.GRID_PARAMS, str(p))
+    dg.overlayGridAndComputeAvgColor(3, frame.copy(), dg.GRID_PARAMS, str(p))
+    rows = list(csv.reader(open(p)))
+    assert len(rows) == 3 and rows[0][:2] == ["cell_0", "cell_1"]
+    assert rows[1] == [str(float(h)) for h in hues]
+    assert (frame == ref).all()                               # same white grid lines as the reference
+
+
+def test_cosine_goldens_g5_g6(km, capsys, tmp_path, monkeypatch):
+    from opticalflowclustering_b200 import computeVectorDistance as cvd
+    from opticalflowclustering_b200 import findCosineDifferentVectors as fc
+    best, frame = fc.main([os.path.join(GOLDEN, "bounce.csv"), os.path.join(GOLDEN, "601_3_3_cropped.csv")])
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "Vector sizes are:  16 75"
+    assert out[1] == "Maximum cosine similarity: 0.91448231723348"
+    assert out[2] == "Minimum sum of squared differences: 0" and out[3] == "Max frame: 24"
+    short = _hue_col(os.path.join(GOLDEN, "bounce.csv"))
+    long_ = _hue_col(os.path.join(GOLDEN, "cropped_trimmed2.csv"))
+    from opticalflowclustering_b200 import cosine
+    b2, f2, sims = cosine.sliding_cosine(short, long_, return_sims=True)
+    ob, of = G.sliding_cosine(short, long_)
+    assert (b2, f2) == (ob, of) and f2 == 7
+    ref = np.array([G.cosine_similarity(short, long_[i:i + 16]) for i in range(len(sims))])
+    assert (sims == ref).all()                                                    # bit-exact
+    sim, row, dist = cvd.main(os.path.join(GOLDEN, "file1.csv"), os.path.join(GOLDEN, "file2.csv"))
+    out = capsys.readouterr().out
+    assert out.startswith("[[1.]]\n") and "Euclidean distance: 0.0" in out
+    _, orow, _ = G.vector_distance(_hue_col(os.path.join(GOLDEN, "file1.csv")), _hue_col(os.path.join(GOLDEN, "file2.csv")))
+    assert np.array_equal(row, orow, equal_nan=True)
+
+
+def test_row_cosine_large(km):
+    from opticalflowclustering_b200 import cosine
+    g = torch.Generator().manual_seed(1)
+    X = torch.randint(0, 180, (1_000_000, 16), generator=g, dtype=torch.uint8).cuda()
+    q = torch.randint(0, 180, (16,), generator=g).double()
+    out = cosine.row_cosine(X, q)
+    Xd = X.double()
+    ref = (Xd @ q.cuda()) / (Xd.norm(dim=1) * q.norm())
+    assert (out - ref).abs().max().item() < 1e-14
+    sub = X[:64].cpu().numpy().astype(np.float64)
+    want = np.array([G.cosine_similarity(r, q.numpy()) for r in sub])
+    assert (out[:64].cpu().numpy() == want).all()                                 # integer data: exact
+
+
+def test_sliding_cosine_large_properties(km):
+    from opticalflowclustering_b200 import cosine
+    rng = np.random.default_rng(2)
+    long_ = rng.integers(0, 180, 1_000_000)
+    short = long_[777_000:777_016].copy()
+    long_[123_000:123_016] = short                                                # two exact matches: last wins
+    best, frame, sims = cosine.sliding_cosine(short, long_, return_sims=True)
+    assert frame == 777_000 and abs(best - 1.0) < 1e-15
+    assert sims[123_000] == sims[777_000] == sims.max()
