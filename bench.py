@@ -203,7 +203,8 @@ def main():
     ms_k = (C.c_float * 20)()
     n_k = (C.c_int * 20)()
     _lib.check(L.ofc_profile_end(ms_k, n_k, 20))
-    names = {0: "bgr2gray", 1: "prefilter", 2: "polyexp", 3: "minmax_init", 4: "flow_encode", 5: "grid_cells"}
+    names = {0: "bgr2gray", 1: "prefilter", 2: "polyexp", 3: "minmax_init", 4: "flow_encode", 5: "grid_cells",
+             10: "flow_upsample"}
     names.update({12 + l: f"flow_iter_L{l}" for l in range(8)})
     kernels = {names[k]: {"ms_per_step": ms_k[k] / prof_steps, "launches_per_step": n_k[k] // prof_steps}
                for k in names if n_k[k]}

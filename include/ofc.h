@@ -38,7 +38,7 @@ const char* ofc_last_error(void);
  * launch stream; end() synchronises on them and returns, per kernel kind, the
  * summed device time (ms) and the launch count.  Kinds: 0 bgr2gray, 1 prefilter,
  * 2 polyexp, 3 minmax_init, 4 flow_encode, 5 grid_cells, 6 flow_minmax,
- * 7 draw_grid, 8 kmeans, 9 cosine, 12+l flow_iter at pyramid level l (0 = full
+ * 7 draw_grid, 8 kmeans, 9 cosine, 10 flow_upsample, 12+l flow_iter at pyramid level l (0 = full
  * resolution).  n_kinds must be >= 20.  Not thread-safe. */
 int ofc_profile_begin(void);
 int ofc_profile_end(float* ms_by_kind, int* launches_by_kind, int n_kinds);

@@ -430,6 +430,257 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_kernel(IterParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// K4: x2 bilinear up-sample of the coarser level's flow (cv::resize INTER_LINEAR
+// of the float2 field, then * 1/pyr_scale) into this level's flow buffer.  Used
+// by the strip-walk iteration kernel, which reads a plain flow field.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flow_upsample_kernel(IterParams p, float2* dst, int64_t dst_stride) {
+    const int gx = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int gy = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (gx >= p.w || gy >= p.h) return;
+    const float2* fin = p.flow_in + (int64_t)blockIdx.z * p.flow_in_stride;
+    dst[(int64_t)blockIdx.z * dst_stride + (int64_t)gy * p.w + gx] = load_flow(p, fin, gx, gy);
+}
+
+// ---------------------------------------------------------------------------
+// K5+K6 fused, strip-walk form (the production iteration kernel, winsize 15).
+//
+// A CTA owns TW output columns and a strip of output rows and walks down the
+// strip.  Thread t < TW+2R owns halo column x0-R+t for the whole walk:
+//   A  per row it evaluates M (5 channels) for its column from R0, the warped R1
+//      and the current flow.  Everything that depends only on the column (clamped
+//      x, border factor) is hoisted out of the walk, and the walk is software-
+//      pipelined: flow / R0 of a row are loaded G rows ahead, the 8 bilinear taps
+//      of R1 one row ahead (double-buffered in registers), so a thread always has
+//      several rows of loads in flight;
+//   B  it keeps the vertical (2R+1)-row sums of its column as float64 running sums
+//      (OpenCV's vsum is double too), retiring the row that leaves the window from
+//      a ring buffer in shared memory that only this thread touches -- no barrier;
+//   C  every G rows the column sums of G output rows are handed over through shared
+//      memory and the CTA does the horizontal sliding sums (4 pixels per thread,
+//      128-bit shared loads), the 2x2 solve in float64 and the flow store.
+// Compared with the square-tile kernel above: the vertical halo is paid once per
+// strip instead of once per 30 rows (about 1.25x instead of 1.79x redundant M work
+// at 1080p) and shared memory does not grow with the strip (ring + hand-over).
+// ---------------------------------------------------------------------------
+struct Taps {
+    float4 q00, q01, q10, q11;
+    float s00, s01, s10, s11;
+    float fx, fy;
+    int inb;
+};
+
+__device__ __forceinline__ void issue_taps(Taps& g, const float4* __restrict__ RA1, const float* __restrict__ RB1,
+                                           int w, int h, float fgx, int gy, float dx, float dy) {
+    float fx = fgx + dx, fy = (float)gy + dy;
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    g.fx = fx - (float)x1;
+    g.fy = fy - (float)y1;
+    g.inb = ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) ? 1 : 0;
+    // loads are unconditional (clamped address) so that they can be issued back to back
+    const int xc = clampi(x1, 0, w - 2), yc = clampi(y1, 0, h - 2);
+    const int64_t o1 = (int64_t)yc * w + xc;
+    g.q00 = RA1[o1]; g.q01 = RA1[o1 + 1]; g.q10 = RA1[o1 + w]; g.q11 = RA1[o1 + w + 1];
+    g.s00 = RB1[o1]; g.s01 = RB1[o1 + 1]; g.s10 = RB1[o1 + w]; g.s11 = RB1[o1 + w + 1];
+}
+
+template <int R, int TW, int NT, int G, int MINB>
+__global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p, int strip_h) {
+    constexpr int K = 2 * R + 1;
+    constexpr int CW = TW + 2 * R;                       // halo'd columns
+    constexpr int CP = (CW + 3) / 4 * 4 + 4;             // hand-over pitch (room for the 128-bit over-read)
+    constexpr int SEG = TW / 4;                          // 4-pixel solver tasks per row
+    constexpr int RING = (K * 5 * CW + 3) / 4 * 4;       // keeps the hand-over buffer 16-byte aligned
+    static_assert(NT >= CW, "one thread per halo column");
+    static_assert(G % 2 == 0, "the tap double buffer alternates by row parity");
+    OFC_DYN_SMEM(float, sm);
+    float* ring = sm;                                    // [K][5][CW]
+    float* hand = sm + RING;                             // [G][5][CP]
+
+    const int t = threadIdx.x;
+    const int w = p.w, h = p.h;
+    const int x0 = blockIdx.x * TW;
+    const int ys = blockIdx.y * strip_h;
+    const int ye = min(ys + strip_h, h);
+    const int pair = blockIdx.z;
+    const float4* __restrict__ RA0 = p.RA + (int64_t)pair * p.r_stride;
+    const float* __restrict__ RB0 = p.RB + (int64_t)pair * p.r_stride;
+    const float4* __restrict__ RA1 = RA0 + p.r_next;
+    const float* __restrict__ RB1 = RB0 + p.r_next;
+    const float2* __restrict__ fin = p.flow_in ? p.flow_in + (int64_t)pair * p.flow_in_stride : nullptr;
+    float2* __restrict__ fout = p.flow_out + (int64_t)pair * p.flow_out_stride;
+
+    // ---- per-column constants ---------------------------------------------
+    const bool col_thread = t < CW;
+    const int gx = clampi(x0 - R + t, 0, w - 1);
+    const float bxs = (gx < 5 ? p.border[gx] : 1.f) * (gx >= w - 5 ? p.border[w - gx - 1] : 1.f);
+    const bool x_edge = (unsigned)(gx - 5) >= (unsigned)(w - 10);
+    const float fgx = (float)gx;
+    const int nrows = (ye - ys) + 2 * R;
+    const int row0 = ys - R;
+
+    double cs0 = 0.0, cs1 = 0.0, cs2 = 0.0, cs3 = 0.0, cs4 = 0.0;
+    float lmin = 3.402823466e38f, lmax = 0.f;
+    int slot = 0;
+
+    // ---- pipeline prologue: flow / R0 of the first G rows, taps of row 0 ----
+    float2 fl[G];
+    float4 na[G];
+    float nb[G];
+    Taps tp[2];
+    if (col_thread) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int64_t o = (int64_t)clampi(row0 + i, 0, h - 1) * w + gx;
+            fl[i] = fin ? fin[o] : make_float2(0.f, 0.f);
+            na[i] = RA0[o];
+            nb[i] = RB0[o];
+        }
+        issue_taps(tp[0], RA1, RB1, w, h, fgx, clampi(row0, 0, h - 1), fl[0].x, fl[0].y);
+    }
+
+    for (int g0 = 0; g0 < nrows; g0 += G) {
+        if (col_thread) {
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const int ri = g0 + i;
+                const int gy = clampi(row0 + ri, 0, h - 1);
+                // taps of the next row go out before this row's arithmetic
+                {
+                    const int in = (i + 1) % G;
+                    const int gyn = clampi(row0 + ri + 1, 0, h - 1);
+                    issue_taps(tp[(i + 1) & 1], RA1, RB1, w, h, fgx, gyn, fl[in].x, fl[in].y);
+                }
+                const Taps& g = tp[i & 1];
+                const float dx = fl[i].x, dy = fl[i].y;
+                const float4 a = na[i];
+                const float b = nb[i];
+                // flow / R0 of the row G steps ahead reuse this row's registers
+                {
+                    const int64_t o = (int64_t)clampi(row0 + ri + G, 0, h - 1) * w + gx;
+                    fl[i] = fin ? fin[o] : make_float2(0.f, 0.f);
+                    na[i] = RA0[o];
+                    nb[i] = RB0[o];
+                }
+                float r2, r3, r4, r5, r6;
+                {
+                    const float fx = g.fx, fy = g.fy;
+                    const float a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy, a00 = (1.f - fx) * (1.f - fy);
+                    r2 = a00 * g.q00.x + a01 * g.q01.x + a10 * g.q10.x + a11 * g.q11.x;
+                    r3 = a00 * g.q00.y + a01 * g.q01.y + a10 * g.q10.y + a11 * g.q11.y;
+                    r4 = a00 * g.q00.z + a01 * g.q01.z + a10 * g.q10.z + a11 * g.q11.z;
+                    r5 = a00 * g.q00.w + a01 * g.q01.w + a10 * g.q10.w + a11 * g.q11.w;
+                    r6 = a00 * g.s00 + a01 * g.s01 + a10 * g.s10 + a11 * g.s11;
+                    r4 = (a.z + r4) * 0.5f;
+                    r5 = (a.w + r5) * 0.5f;
+                    r6 = (b + r6) * 0.25f;
+                }
+                if (!g.inb) {
+                    r2 = r3 = 0.f;
+                    r4 = a.z; r5 = a.w; r6 = b * 0.5f;
+                }
+                r2 = (a.x - r2) * 0.5f;
+                r3 = (a.y - r3) * 0.5f;
+                r2 += r4 * dy + r6 * dx;
+                r3 += r6 * dy + r5 * dx;
+                if (x_edge || (unsigned)(gy - 5) >= (unsigned)(h - 10)) {
+                    const float sc = bxs * (gy < 5 ? p.border[gy] : 1.f) * (gy >= h - 5 ? p.border[h - gy - 1] : 1.f);
+                    r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+                }
+                const float m0 = r4 * r4 + r6 * r6, m1 = (r4 + r5) * r6, m2 = r5 * r5 + r6 * r6;
+                const float m3 = r4 * r2 + r6 * r3, m4 = r6 * r2 + r5 * r3;
+                if (ri < nrows) {
+                    // vertical running sums: retire the row that leaves the window
+                    float* rs = ring + slot * (5 * CW) + t;
+                    if (ri >= K) {
+                        cs0 -= (double)rs[0 * CW]; cs1 -= (double)rs[1 * CW]; cs2 -= (double)rs[2 * CW];
+                        cs3 -= (double)rs[3 * CW]; cs4 -= (double)rs[4 * CW];
+                    }
+                    rs[0 * CW] = m0; rs[1 * CW] = m1; rs[2 * CW] = m2; rs[3 * CW] = m3; rs[4 * CW] = m4;
+                    cs0 += (double)m0; cs1 += (double)m1; cs2 += (double)m2; cs3 += (double)m3; cs4 += (double)m4;
+                    slot = slot + 1 == K ? 0 : slot + 1;
+                    if (ri >= 2 * R) {
+                        float* hd = hand + i * (5 * CP) + t;
+                        hd[0 * CP] = (float)cs0; hd[1 * CP] = (float)cs1; hd[2 * CP] = (float)cs2;
+                        hd[3 * CP] = (float)cs3; hd[4 * CP] = (float)cs4;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- horizontal sums (4 px / task) + solve ------------------------
+        for (int task = t; task < G * SEG; task += NT) {
+            const int i = task / SEG, seg = task - i * SEG;
+            const int ri = g0 + i;
+            const int gx0 = x0 + seg * 4;
+            if (ri < 2 * R || ri >= nrows || gx0 >= w) continue;
+            const int gy = ys + ri - 2 * R;
+            constexpr int NV = (4 + 2 * R + 3) / 4 * 4;
+            float S[5][4];
+#pragma unroll
+            for (int ch = 0; ch < 5; ++ch) {
+                const float* src = hand + i * (5 * CP) + ch * CP + seg * 4;
+                float v[NV];
+#pragma unroll
+                for (int j = 0; j < NV / 4; ++j) {
+                    const float4 q = *reinterpret_cast<const float4*>(src + j * 4);
+                    v[j * 4 + 0] = q.x; v[j * 4 + 1] = q.y; v[j * 4 + 2] = q.z; v[j * 4 + 3] = q.w;
+                }
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < K; ++j) s += v[j];
+                S[ch][0] = s;
+#pragma unroll
+                for (int j = 1; j < 4; ++j) {
+                    s += v[j + 2 * R] - v[j - 1];
+                    S[ch][j] = s;
+                }
+            }
+            float2 res[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double g11 = (double)S[0][j] * p.blur_scale, g12 = (double)S[1][j] * p.blur_scale;
+                const double g22 = (double)S[2][j] * p.blur_scale;
+                const double h1 = (double)S[3][j] * p.blur_scale, h2 = (double)S[4][j] * p.blur_scale;
+                const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+                res[j].x = (float)((g11 * h2 - g12 * h1) * idet);
+                res[j].y = (float)((g22 * h1 - g12 * h2) * idet);
+            }
+            float2* out = fout + (int64_t)gy * w + gx0;
+            if (gx0 + 3 < w && (w & 1) == 0) {
+                float4* o4 = reinterpret_cast<float4*>(out);
+                o4[0] = make_float4(res[0].x, res[0].y, res[1].x, res[1].y);
+                o4[1] = make_float4(res[2].x, res[2].y, res[3].x, res[3].y);
+            } else {
+                for (int j = 0; j < 4 && gx0 + j < w; ++j) out[j] = res[j];
+            }
+            if (p.minmax) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (gx0 + j < w) {
+                        const float m = sqrtf(__fmaf_rn(res[j].x, res[j].x, __fmul_rn(res[j].y, res[j].y)));
+                        lmin = fminf(lmin, m);
+                        lmax = fmaxf(lmax, m);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (p.minmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        }
+        if ((t & 31) == 0) {
+            atomicMin(p.minmax + 2 * pair, __float_as_uint(lmin));
+            atomicMax(p.minmax + 2 * pair + 1, __float_as_uint(lmax));
+        }
+    }
+}
+
 __global__ void minmax_init_kernel(unsigned* mm, int n_pairs) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_pairs) {
@@ -495,7 +746,60 @@ static int launch_iter_r(const IterParams& p, int n_pairs, void* stream) {
     return OFC_OK;
 }
 
-int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, void* stream) {
+template <int R, int TW, int NT, int G, int MINB>
+static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
+    constexpr int K = 2 * R + 1, CW = TW + 2 * R, CP = (CW + 3) / 4 * 4 + 4;
+    constexpr size_t smem = (size_t)((K * 5 * CW + 3) / 4 * 4 + G * 5 * CP) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        OFC_CUDA(cudaFuncSetAttribute(flow_iter_strip_kernel<R, TW, NT, G, MINB>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    // strip height: tall strips amortise the 2R-row vertical halo, but the grid must still fill
+    // the 148 SMs a few CTAs deep: aim for >= 2 * 148 * MINB CTAs, never below 16 rows
+    const int cols = cdiv(p.w, TW);
+    const int want = 2 * 148 * MINB;
+    int strips = cdiv(want, cols * n_pairs);
+    if (strips < 1) strips = 1;
+    int strip_h = cdiv(p.h, strips);
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("OFC_STRIP_H"); forced = e ? atoi(e) : -1; }
+    if (forced > 0) strip_h = forced;
+    if (strip_h < 16) strip_h = 16;
+    if (strip_h > p.h) strip_h = p.h;
+    dim3 grid(cols, cdiv(p.h, strip_h), n_pairs);
+    ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
+    OFC_LAUNCH((flow_iter_strip_kernel<R, TW, NT, G, MINB>), grid, dim3(NT), smem, stream, p, strip_h);
+    OFC_CHECK_LAUNCH("flow_iter_strip");
+    return OFC_OK;
+}
+
+// The strip-walk kernel reads a plain flow field: when the input is the coarser level, up-sample
+// it first into `scratch` (this level's other ping-pong buffer, not otherwise live on iteration 0).
+static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, void* stream) {
+    IterParams p = p_in;
+    if (p.upsample) {
+        dim3 g(cdiv(p.w, 64), cdiv(p.h, 4), n_pairs);
+        {
+            ProfScope prof(PK_UPSAMPLE, stream);
+            OFC_LAUNCH(flow_upsample_kernel, g, dim3(256), 0, stream, p, scratch, (int64_t)p.w * p.h);
+            OFC_CHECK_LAUNCH("flow_upsample");
+        }
+        p.flow_in = scratch;
+        p.flow_in_stride = (int64_t)p.w * p.h;
+        p.upsample = 0;
+    }
+    if (p.w > 512) return launch_strip_r<7, 128, 160, 4, 3>(p, n_pairs, stream);
+    return launch_strip_r<7, 64, 96, 4, 5>(p, n_pairs, stream);
+}
+
+int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scratch, void* stream) {
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("OFC_ITER_VARIANT"); variant = e ? atoi(e) : 0; }
+    // winsize 15 (the reference's literal) runs the strip-walk kernel; other window sizes
+    // the square-tile kernel
+    if (variant == 0 && winsize == 15 && scratch != nullptr) return launch_strip(p, n_pairs, scratch, stream);
     switch (winsize / 2) {
         case 2: return launch_iter_r<2, 32, 256, 3>(p, n_pairs, stream);
         case 3: return launch_iter_r<3, 32, 256, 3>(p, n_pairs, stream);
@@ -504,10 +808,7 @@ int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, void* stream
         case 6: return launch_iter_r<6, 32, 256, 3>(p, n_pairs, stream);
         case 7: {
             // winsize 15 (the reference's value): 64x30 tile = 73.9 KB -> 3 CTAs/SM
-            static int variant = -1;
-            if (variant < 0) { const char* e = getenv("OFC_ITER_VARIANT"); variant = e ? atoi(e) : 0; }
-            if (variant == 1) return launch_iter_r<7, 48, 384, 2>(p, n_pairs, stream);
-            if (variant == 2) return launch_iter_r<7, 32, 256, 2>(p, n_pairs, stream);
+            if (variant == 2) return launch_iter_r<7, 48, 384, 2>(p, n_pairs, stream);
             return launch_iter_r<7, 30, 256, 3>(p, n_pairs, stream);
         }
         case 10: return launch_iter_r<10, 32, 256, 2>(p, n_pairs, stream);

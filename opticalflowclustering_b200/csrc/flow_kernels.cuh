@@ -50,7 +50,8 @@ struct IterParams {
 
 int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* stream);
 int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, void* stream);
-int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, void* stream);
+// scratch: a flow-sized buffer [n_pairs][h][w] the launch may overwrite (up-sampled input flow)
+int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scratch, void* stream);
 int launch_minmax_init(unsigned* mm, int n_pairs, void* stream);
 
 }  // namespace ofc

@@ -210,7 +210,7 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
             ip.flow_out_stride = npx;
             ip.minmax = last ? minmax : nullptr;
             g_prof_level = nl - 1 - l;
-            int rc = launch_flow_iter(ip, pl->winsize, n_pairs, stream);
+            int rc = launch_flow_iter(ip, pl->winsize, n_pairs, (float2*)(ws + L.off_flow[(it & 1) ^ 1]), stream);
             if (rc != OFC_OK) return rc;
         }
         prev_flow = (const float2*)(ws + L.off_flow[(pl->iterations - 1) & 1]);

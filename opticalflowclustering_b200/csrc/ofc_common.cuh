@@ -56,7 +56,7 @@ int check_cuda(cudaError_t e, const char* what);
 // stream.  Off by default; costs nothing then.
 enum ProfKind {
     PK_GRAY = 0, PK_PREFILTER, PK_POLYEXP, PK_MINMAX_INIT, PK_ENCODE, PK_GRID, PK_FLOW_MINMAX, PK_DRAW,
-    PK_KMEANS, PK_COSINE, PK_RESERVED0, PK_RESERVED1,
+    PK_KMEANS, PK_COSINE, PK_UPSAMPLE, PK_RESERVED1,
     PK_ITER_L0 = 12,             // flow_iter at full resolution; +1 per coarser level (up to 8)
     PK_COUNT = 20
 };
