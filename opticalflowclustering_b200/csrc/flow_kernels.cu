@@ -250,6 +250,280 @@ __global__ void __launch_bounds__(256) polyexp_kernel(PolyParams p) {
 }
 
 // ---------------------------------------------------------------------------
+// K2, direct form: one thread per output pixel of a down-sampled level.  The 8-bit
+// source frame is 2 MB at 1080p and lives in L1/L2, so nothing is staged: a thread
+// walks the ksz+1 source rows its two sample rows need, takes the horizontal taps
+// at its two sample columns (float32, tap order 0..ksz-1 like cv::sepFilter2D),
+// then the vertical taps and the bilinear lerp.  Replaces the tiled kernel above on
+// the hot path (it stays as the reference form for odd geometries).
+// ---------------------------------------------------------------------------
+template <int KSZ>
+__global__ void __launch_bounds__(256) prefilter_direct_kernel(PrefilterParams p) {
+    __shared__ float s_taps[64];
+    for (int i = threadIdx.x; i < p.ksz; i += blockDim.x) s_taps[i] = p.taps[i];
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= p.w || y >= p.h) return;
+    const int r = p.ksz >> 1, ksz = p.ksz;
+    int ci, ri;
+    float fx, fy;
+    src_coord(x, p.sx, p.W, ci, fx);
+    src_coord(y, p.sy, p.H, ri, fy);
+    const int cj = min(ci + 1, p.W - 1), rj = min(ri + 1, p.H - 1);
+    const unsigned char* src = p.gray + (int64_t)blockIdx.z * p.gray_stride;
+    const int d = cj - ci;                              // 1, or 0 at the right border
+    const bool words_ok = (p.W & 3) == 0 && (p.gray_stride & 3) == 0 && ((uintptr_t)p.gray & 3) == 0;
+    float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;  // vertical accumulators of the four sample points
+
+    if (KSZ > 0 && words_ok && ci - r >= 0 && ci + 1 + r < p.W && ri - r >= 0 && ri + 1 + r < p.H) {
+        // ---- interior, tap count known at compile time: everything unrolled ----------------------
+        constexpr int KS = KSZ > 0 ? KSZ : 1;
+        constexpr int RR = KS / 2;
+        constexpr int NW = (KS + 1 + 3) / 4;            // aligned words that hold the KS+1 window bytes
+        float tp[KS];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) tp[j] = s_taps[j];
+        const int off = (ci - RR) & 3;
+        const unsigned sh = (unsigned)off * 8u;
+        const unsigned char* base = src + (int64_t)(ri - RR) * p.W + (ci - RR - off);
+#pragma unroll
+        for (int q = 0; q <= KS; ++q) {                 // source rows ri-RR .. ri+1+RR
+            const unsigned* wp = reinterpret_cast<const unsigned*>(base + (int64_t)q * p.W);
+            unsigned wv[NW + 1];
+#pragma unroll
+            for (int i = 0; i <= NW; ++i) wv[i] = wp[i];
+            float ha = 0.f, hb = 0.f;
+#pragma unroll
+            for (int j = 0; j <= KS; ++j) {
+                // byte j of the window = byte (off + j) of the word sequence
+                const unsigned lo = wv[j >> 2], hi = wv[(j >> 2) + 1];
+                const unsigned al = __funnelshift_r(lo, hi, sh);         // word whose byte 0 is window byte 4*(j>>2)
+                const float b = (float)((al >> ((j & 3) * 8)) & 255u);
+                if (j < KS) ha = fmaf(tp[j], b, ha);
+                if (j >= 1) hb = fmaf(tp[j - 1], b, hb);
+            }
+            if (q < KS) { b00 = fmaf(tp[q < KS ? q : 0], ha, b00); b01 = fmaf(tp[q < KS ? q : 0], hb, b01); }
+            if (q >= 1) { b10 = fmaf(tp[q - 1], ha, b10); b11 = fmaf(tp[q - 1], hb, b11); }
+        }
+    } else {
+        // ---- borders / generic tap count: reflected indices, run-time loops ----------------------
+        const int rows = rj - ri + ksz;                 // source rows ri-r .. rj+r
+        for (int q = 0; q < rows; ++q) {
+            const unsigned char* row = src + (int64_t)reflect101(ri - r + q, p.H) * p.W;
+            float ha = 0.f, hb = 0.f;
+            for (int j = 0; j < ksz; ++j) {
+                const float t = s_taps[j];
+                ha = fmaf(t, (float)row[reflect101(ci - r + j, p.W)], ha);
+                hb = fmaf(t, (float)row[reflect101(cj - r + j, p.W)], hb);
+            }
+            // this source row is tap q of sample row ri and tap q-(rj-ri) of sample row rj
+            if (q < ksz) { b00 = fmaf(s_taps[q], ha, b00); b01 = fmaf(s_taps[q], hb, b01); }
+            const int q2 = q - (rj - ri);
+            if (q2 >= 0) { b10 = fmaf(s_taps[q2], ha, b10); b11 = fmaf(s_taps[q2], hb, b11); }
+        }
+    }
+    (void)d;
+    const float top = b00 * (1.f - fx) + b01 * fx;
+    const float bot = b10 * (1.f - fx) + b11 * fx;
+    p.out[(int64_t)blockIdx.z * p.out_stride + (int64_t)y * p.w + x] = top * (1.f - fy) + bot * fy;
+}
+
+// ---------------------------------------------------------------------------
+// K3, strip-walk form (production): thread t owns column x0-N+t and walks down a
+// strip of rows with the 2N+G-row vertical window of I in registers; every G rows
+// the vertical results (r0,r1,r2) of G rows go through shared memory and the CTA
+// does the horizontal pass, 4 pixels per thread, writing RA/RB with 128-bit
+// stores.  Only the horizontal halo is recomputed (1.08x at TW=128) and the
+// vertical halo once per strip, against 1.52x for the 64x32 tile kernel above.
+// FUSE3: the level is full resolution, so I is the fixed 3x3 blur [1 2 1]^2/16 of the
+// 8-bit frame (exact in integers): it is produced on the fly from `gray` and
+// written to p.I only as a by-product.
+// ---------------------------------------------------------------------------
+template <int N, int TW, int NT, bool FUSE3>
+__global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const unsigned char* __restrict__ gray_all,
+                                                           int64_t gray_stride, float* __restrict__ I_out, int n_cols,
+                                                           int64_t total_rows) {
+    constexpr int G = 4;
+    constexpr int CW = TW + 2 * N;
+    constexpr int CP = (CW + 3) / 4 * 4 + 4;
+    constexpr int SEG = TW / 4;
+    constexpr int NV = (4 + 2 * N + 3) / 4 * 4;
+    static_assert(NT >= CW && NT >= G * SEG, "thread count");
+    __shared__ __align__(16) float vbuf[G][3][CP];
+
+    const int t = threadIdx.x;
+    const int w = p.w, h = p.h;
+    // persistent CTAs over the flattened rows of all (frame, column strip) units (see flow_iter_strip_kernel)
+    const int64_t range_lo = total_rows * blockIdx.x / gridDim.x;
+    const int64_t range_hi = total_rows * (blockIdx.x + 1) / gridDim.x;
+    for (int64_t cur = range_lo; cur < range_hi;) {
+    const int unit = (int)(cur / h);
+    const int ys = (int)(cur - (int64_t)unit * h);
+    const int64_t left = range_hi - cur;
+    const int ye = left < (int64_t)(h - ys) ? ys + (int)left : h;
+    cur += ye - ys;
+    const int frame = unit / n_cols;
+    const int x0 = (unit - frame * n_cols) * TW;
+    const bool col_thread = t < CW;
+    const int gx = clampi(x0 - N + t, 0, w - 1);
+    const float* __restrict__ I = FUSE3 ? nullptr : p.I + (int64_t)frame * p.in_stride;
+    const unsigned char* __restrict__ gray = FUSE3 ? gray_all + (int64_t)frame * gray_stride : nullptr;
+    float4* __restrict__ RA = p.RA + (int64_t)frame * p.out_stride;
+    float* __restrict__ RB = p.RB + (int64_t)frame * p.out_stride;
+    float* __restrict__ Iw = (FUSE3 && I_out) ? I_out + (int64_t)frame * p.out_stride : nullptr;
+    const int xl = FUSE3 ? reflect101_near(gx - 1, w) : 0, xr = FUSE3 ? reflect101_near(gx + 1, w) : 0;
+
+    // I at (clamped row, this thread's column)
+    auto hsum = [&](int row) -> int {                   // [1 2 1] across columns of one (reflected) source row
+        const unsigned char* r = gray + (int64_t)reflect101_near(row, h) * w;
+        return (int)r[xl] + 2 * (int)r[gx] + (int)r[xr];
+    };
+    auto load_I = [&](int row) -> float {
+        const int rc = clampi(row, 0, h - 1);
+        if (!FUSE3) return I[(int64_t)rc * w + gx];
+        const int acc = hsum(rc - 1) + 2 * hsum(rc) + hsum(rc + 1);
+        return (float)acc * 0.0625f;                   // exact: acc <= 4080
+    };
+    // G consecutive un-clamped rows starting at `first`: each row needs only one new horizontal sum
+    auto load_I_run = [&](int first, float* dst) {
+        if (!FUSE3 || first < 0 || first + G > h) {
+#pragma unroll
+            for (int i = 0; i < G; ++i) dst[i] = load_I(first + i);
+            return;
+        }
+        int hs[G + 2];
+#pragma unroll
+        for (int i = 0; i < G + 2; ++i) hs[i] = hsum(first - 1 + i);
+#pragma unroll
+        for (int i = 0; i < G; ++i) dst[i] = (float)(hs[i] + 2 * hs[i + 1] + hs[i + 2]) * 0.0625f;
+    };
+
+    float v[2 * N + G];                                // I(rows r-N .. r+G-1+N) of the current group
+    float nxt[G];
+    if (col_thread) {
+#pragma unroll
+        for (int j = 0; j < 2 * N; ++j) v[G + j] = load_I(ys - N + j);      // becomes v[0..2N) after the first shift
+        load_I_run(ys + N, nxt);
+    }
+    for (int g0 = 0; g0 < ye - ys; g0 += G) {
+        if (col_thread) {
+#pragma unroll
+            for (int j = 0; j < 2 * N; ++j) v[j] = v[j + G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) v[2 * N + i] = nxt[i];
+            // rows of the next group: in flight while this group is processed
+            load_I_run(ys + g0 + G + N, nxt);
+            if (FUSE3 && Iw && t >= N && t < N + TW && x0 + t - N < w) {
+#pragma unroll
+                for (int i = 0; i < G; ++i)
+                    if (ys + g0 + i < ye) Iw[(int64_t)(ys + g0 + i) * w + gx] = v[N + i];
+            }
+#pragma unroll
+            for (int o = 0; o < G; ++o) {
+                const float c = v[o + N];
+                float r0 = c * p.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+                for (int k = 1; k <= N; ++k) {
+                    const float up = v[o + N - k], dn = v[o + N + k];
+                    const float sm = dn + up;
+                    r0 = fmaf(p.g[k], sm, r0);
+                    r1 = fmaf(p.xg[k], dn - up, r1);
+                    r2 = fmaf(p.xxg[k], sm, r2);
+                }
+                vbuf[o][0][t] = r0;
+                vbuf[o][1][t] = r1;
+                vbuf[o][2][t] = r2;
+            }
+        }
+        __syncthreads();
+        if (t < G * SEG) {
+            const int o = t / SEG, seg = t - o * SEG;
+            const int gy = ys + g0 + o, gx0 = x0 + seg * 4;
+            if (gy < ye && gx0 < w) {
+                float a[NV];
+                float b1[4], b2[4], b3[4], b4[4], b5[4], b6[4];
+                // channel r0 -> b1, b4, b2
+#pragma unroll
+                for (int j = 0; j < NV / 4; ++j) {
+                    const float4 q = *reinterpret_cast<const float4*>(&vbuf[o][0][seg * 4 + j * 4]);
+                    a[j * 4 + 0] = q.x; a[j * 4 + 1] = q.y; a[j * 4 + 2] = q.z; a[j * 4 + 3] = q.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = e + N;
+                    float x1 = a[c] * p.g[0], x4 = 0.f, x2 = 0.f;
+#pragma unroll
+                    for (int k = 1; k <= N; ++k) {
+                        const float tg = a[c + k] + a[c - k];
+                        x1 = fmaf(tg, p.g[k], x1);
+                        x4 = fmaf(tg, p.xxg[k], x4);
+                        x2 = fmaf(a[c + k] - a[c - k], p.xg[k], x2);
+                    }
+                    b1[e] = x1; b4[e] = x4; b2[e] = x2;
+                }
+                // channel r1 -> b3, b6
+#pragma unroll
+                for (int j = 0; j < NV / 4; ++j) {
+                    const float4 q = *reinterpret_cast<const float4*>(&vbuf[o][1][seg * 4 + j * 4]);
+                    a[j * 4 + 0] = q.x; a[j * 4 + 1] = q.y; a[j * 4 + 2] = q.z; a[j * 4 + 3] = q.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = e + N;
+                    float x3 = a[c] * p.g[0], x6 = 0.f;
+#pragma unroll
+                    for (int k = 1; k <= N; ++k) {
+                        x3 = fmaf(a[c + k] + a[c - k], p.g[k], x3);
+                        x6 = fmaf(a[c + k] - a[c - k], p.xg[k], x6);
+                    }
+                    b3[e] = x3; b6[e] = x6;
+                }
+                // channel r2 -> b5
+#pragma unroll
+                for (int j = 0; j < NV / 4; ++j) {
+                    const float4 q = *reinterpret_cast<const float4*>(&vbuf[o][2][seg * 4 + j * 4]);
+                    a[j * 4 + 0] = q.x; a[j * 4 + 1] = q.y; a[j * 4 + 2] = q.z; a[j * 4 + 3] = q.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = e + N;
+                    float x5 = a[c] * p.g[0];
+#pragma unroll
+                    for (int k = 1; k <= N; ++k) x5 = fmaf(a[c + k] + a[c - k], p.g[k], x5);
+                    b5[e] = x5;
+                }
+                float4 ra[4];
+                float rb[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ra[e].x = b3[e] * p.ig11;
+                    ra[e].y = b2[e] * p.ig11;
+                    ra[e].z = fmaf(b1[e], p.ig03, b5[e] * p.ig33);
+                    ra[e].w = fmaf(b1[e], p.ig03, b4[e] * p.ig33);
+                    rb[e] = b6[e] * p.ig55;
+                }
+                const int64_t base = (int64_t)gy * w + gx0;
+                if (gx0 + 3 < w) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) RA[base + e] = ra[e];
+                    if ((w & 3) == 0) {
+                        *reinterpret_cast<float4*>(RB + base) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) RB[base + e] = rb[e];
+                    }
+                } else {
+                    for (int e = 0; e < 4 && gx0 + e < w; ++e) { RA[base + e] = ra[e]; RB[base + e] = rb[e]; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    }   // segments of this CTA's row range
+}
+
+// ---------------------------------------------------------------------------
 // K4+K5+K6 fused: one Farneback iteration.
 //   phase 1  M(y,x) for the tile + box-filter halo, straight from R0, warped R1
 //            and the current flow (optionally the x2 up-sampled coarse flow):
@@ -478,15 +752,17 @@ __device__ __forceinline__ void issue_taps(Taps& g, const float4* __restrict__ R
     g.fx = fx - (float)x1;
     g.fy = fy - (float)y1;
     g.inb = ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) ? 1 : 0;
-    // loads are unconditional (clamped address) so that they can be issued back to back
-    const int xc = clampi(x1, 0, w - 2), yc = clampi(y1, 0, h - 2);
-    const int64_t o1 = (int64_t)yc * w + xc;
-    g.q00 = RA1[o1]; g.q01 = RA1[o1 + 1]; g.q10 = RA1[o1 + w]; g.q11 = RA1[o1 + w + 1];
-    g.s00 = RB1[o1]; g.s01 = RB1[o1 + 1]; g.s10 = RB1[o1 + w]; g.s11 = RB1[o1 + w + 1];
+    // loads are unconditional (clamped address) so that they can be issued back to back;
+    // a level has < 2^31 pixels, so the pixel offset is a 32-bit integer
+    const int o1 = clampi(y1, 0, h - 2) * w + clampi(x1, 0, w - 2);
+    const float4* pa = RA1 + o1;
+    const float* pb = RB1 + o1;
+    g.q00 = pa[0]; g.q01 = pa[1]; g.q10 = pa[w]; g.q11 = pa[w + 1];
+    g.s00 = pb[0]; g.s01 = pb[1]; g.s10 = pb[w]; g.s11 = pb[w + 1];
 }
 
 template <int R, int TW, int NT, int G, int MINB>
-__global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p, int strip_h) {
+__global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p, int n_cols, int64_t total_rows) {
     constexpr int K = 2 * R + 1;
     constexpr int CW = TW + 2 * R;                       // halo'd columns
     constexpr int CP = (CW + 3) / 4 * 4 + 4;             // hand-over pitch (room for the 128-bit over-read)
@@ -500,10 +776,19 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
 
     const int t = threadIdx.x;
     const int w = p.w, h = p.h;
-    const int x0 = blockIdx.x * TW;
-    const int ys = blockIdx.y * strip_h;
-    const int ye = min(ys + strip_h, h);
-    const int pair = blockIdx.z;
+    // Persistent CTAs: the output rows of all (pair, column strip) units are laid end to end
+    // (total_rows = n_pairs * n_cols * h) and cut into gridDim.x equal ranges; a CTA walks its
+    // range, restarting the pipeline where it crosses into the next unit.
+    const int64_t range_lo = total_rows * blockIdx.x / gridDim.x;
+    const int64_t range_hi = total_rows * (blockIdx.x + 1) / gridDim.x;
+    for (int64_t cur = range_lo; cur < range_hi;) {
+    const int unit = (int)(cur / h);
+    const int ys = (int)(cur - (int64_t)unit * h);
+    const int64_t left = range_hi - cur;
+    const int ye = left < (int64_t)(h - ys) ? ys + (int)left : h;
+    cur += ye - ys;
+    const int pair = unit / n_cols;
+    const int x0 = (unit - pair * n_cols) * TW;
     const float4* __restrict__ RA0 = p.RA + (int64_t)pair * p.r_stride;
     const float* __restrict__ RB0 = p.RB + (int64_t)pair * p.r_stride;
     const float4* __restrict__ RA1 = RA0 + p.r_next;
@@ -523,45 +808,51 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
     double cs0 = 0.0, cs1 = 0.0, cs2 = 0.0, cs3 = 0.0, cs4 = 0.0;
     float lmin = 3.402823466e38f, lmax = 0.f;
     int slot = 0;
+    // an all-zero ring lets every row retire "the row K steps back" unconditionally
+    for (int i = t; i < K * 5 * CW; i += NT) ring[i] = 0.f;
+    __syncthreads();
 
     // ---- pipeline prologue: flow / R0 of the first G rows, taps of row 0 ----
-    float2 fl[G];
-    float4 na[G];
-    float nb[G];
+    constexpr int PD = 2;                                // rows of flow / R0 in flight ahead of the arithmetic
+    static_assert(G % PD == 0, "prefetch slots are indexed by the unrolled row number");
+    float2 fl[PD];
+    float4 na[PD];
+    float nb[PD];
     Taps tp[2];
     if (col_thread) {
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
-            const int64_t o = (int64_t)clampi(row0 + i, 0, h - 1) * w + gx;
+        for (int i = 0; i < PD; ++i) {
+            const int o = clampi(row0 + i, 0, h - 1) * w + gx;
             fl[i] = fin ? fin[o] : make_float2(0.f, 0.f);
             na[i] = RA0[o];
             nb[i] = RB0[o];
         }
         issue_taps(tp[0], RA1, RB1, w, h, fgx, clampi(row0, 0, h - 1), fl[0].x, fl[0].y);
     }
+    int gy_next = clampi(row0, 0, h - 1);
 
     for (int g0 = 0; g0 < nrows; g0 += G) {
         if (col_thread) {
 #pragma unroll
             for (int i = 0; i < G; ++i) {
                 const int ri = g0 + i;
-                const int gy = clampi(row0 + ri, 0, h - 1);
+                const int gy = gy_next;
                 // taps of the next row go out before this row's arithmetic
                 {
-                    const int in = (i + 1) % G;
-                    const int gyn = clampi(row0 + ri + 1, 0, h - 1);
-                    issue_taps(tp[(i + 1) & 1], RA1, RB1, w, h, fgx, gyn, fl[in].x, fl[in].y);
+                    const int in = (i + 1) % PD;
+                    gy_next = clampi(row0 + ri + 1, 0, h - 1);
+                    issue_taps(tp[(i + 1) & 1], RA1, RB1, w, h, fgx, gy_next, fl[in].x, fl[in].y);
                 }
                 const Taps& g = tp[i & 1];
-                const float dx = fl[i].x, dy = fl[i].y;
-                const float4 a = na[i];
-                const float b = nb[i];
-                // flow / R0 of the row G steps ahead reuse this row's registers
+                const float dx = fl[i % PD].x, dy = fl[i % PD].y;
+                const float4 a = na[i % PD];
+                const float b = nb[i % PD];
+                // flow / R0 of the row PD steps ahead reuse this row's registers
                 {
-                    const int64_t o = (int64_t)clampi(row0 + ri + G, 0, h - 1) * w + gx;
-                    fl[i] = fin ? fin[o] : make_float2(0.f, 0.f);
-                    na[i] = RA0[o];
-                    nb[i] = RB0[o];
+                    const int o = clampi(row0 + ri + PD, 0, h - 1) * w + gx;
+                    fl[i % PD] = fin ? fin[o] : make_float2(0.f, 0.f);
+                    na[i % PD] = RA0[o];
+                    nb[i % PD] = RB0[o];
                 }
                 float r2, r3, r4, r5, r6;
                 {
@@ -592,11 +883,12 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
                 const float m3 = r4 * r2 + r6 * r3, m4 = r6 * r2 + r5 * r3;
                 if (ri < nrows) {
                     // vertical running sums: retire the row that leaves the window
+                    // float64 sums of <= 2R+1 float32 terms are exact (no rounding until the spread of the
+                    // terms exceeds 2^29), so the result does not depend on where the walk started:
+                    // any partition of the rows into strips gives the same bits
                     float* rs = ring + slot * (5 * CW) + t;
-                    if (ri >= K) {
-                        cs0 -= (double)rs[0 * CW]; cs1 -= (double)rs[1 * CW]; cs2 -= (double)rs[2 * CW];
-                        cs3 -= (double)rs[3 * CW]; cs4 -= (double)rs[4 * CW];
-                    }
+                    cs0 -= (double)rs[0 * CW]; cs1 -= (double)rs[1 * CW]; cs2 -= (double)rs[2 * CW];
+                    cs3 -= (double)rs[3 * CW]; cs4 -= (double)rs[4 * CW];
                     rs[0 * CW] = m0; rs[1 * CW] = m1; rs[2 * CW] = m2; rs[3 * CW] = m3; rs[4 * CW] = m4;
                     cs0 += (double)m0; cs1 += (double)m1; cs2 += (double)m2; cs3 += (double)m3; cs4 += (double)m4;
                     slot = slot + 1 == K ? 0 : slot + 1;
@@ -679,6 +971,7 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
             atomicMax(p.minmax + 2 * pair + 1, __float_as_uint(lmax));
         }
     }
+    }   // segments of this CTA's row range
 }
 
 __global__ void minmax_init_kernel(unsigned* mm, int n_pairs) {
@@ -692,12 +985,40 @@ __global__ void minmax_init_kernel(unsigned* mm, int n_pairs) {
 // ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        n = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    }
+    return n;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* stream) {
+    static const int legacy = env_int("OFC_PREFILTER_LEGACY", 0);
     if (p.w == p.W && p.h == p.H && p.ksz == 3 && p.identity3) {
         dim3 g(cdiv(p.W, 256), cdiv(p.H, 4), n_frames);
         ProfScope prof(PK_PREFILTER, stream);
         OFC_LAUNCH(prefilter_identity3_kernel, g, dim3(256), 0, stream, p);
         OFC_CHECK_LAUNCH("prefilter_identity3");
+        return OFC_OK;
+    }
+    if (!legacy && p.ksz <= 64) {
+        dim3 g(cdiv(p.w, 32), cdiv(p.h, 8), n_frames);
+        ProfScope prof(PK_PREFILTER, stream);
+        // tap counts of the reference's pyramid (pyr_scale 0.5: 3, 9, 19, 39, 79) get unrolled fast paths
+        if (p.ksz == 3) OFC_LAUNCH(prefilter_direct_kernel<3>, g, dim3(256), 0, stream, p);
+        else if (p.ksz == 9) OFC_LAUNCH(prefilter_direct_kernel<9>, g, dim3(256), 0, stream, p);
+        else if (p.ksz == 19) OFC_LAUNCH(prefilter_direct_kernel<19>, g, dim3(256), 0, stream, p);
+        else OFC_LAUNCH(prefilter_direct_kernel<0>, g, dim3(256), 0, stream, p);
+        OFC_CHECK_LAUNCH("prefilter_direct");
         return OFC_OK;
     }
     dim3 grid(cdiv(p.w, p.tx), cdiv(p.h, p.ty), n_frames);
@@ -712,7 +1033,46 @@ int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* 
     return OFC_OK;
 }
 
-int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, void* stream) {
+template <int N, int TW, int NT, bool FUSE3>
+static int launch_polyexp_strip(const PolyParams& p, const unsigned char* gray, int64_t gray_stride, float* I_out,
+                                int n_frames, void* stream) {
+    static int resident = 0;
+    if (!resident) {
+        OFC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, polyexp_strip_kernel<N, TW, NT, FUSE3>, NT, 0));
+        if (resident < 1) resident = 1;
+    }
+    const int cols = cdiv(p.w, TW);
+    const int64_t total_rows = (int64_t)n_frames * cols * p.h;
+    int64_t ctas = (int64_t)num_sms() * resident;
+    const int64_t max_ctas = (total_rows + 23) / 24;     // keep ranges >= 24 rows (vertical halo 2N per segment)
+    if (ctas > max_ctas) ctas = max_ctas;
+    ProfScope prof(PK_POLYEXP, stream);
+    OFC_LAUNCH((polyexp_strip_kernel<N, TW, NT, FUSE3>), dim3((unsigned)ctas), dim3(NT), 0, stream, p, gray, gray_stride, I_out,
+               cols, total_rows);
+    OFC_CHECK_LAUNCH("polyexp_strip");
+    return OFC_OK;
+}
+
+// gray != null: the level is full resolution with the fixed 3-tap pre-filter -> fused
+int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, const unsigned char* gray, int64_t gray_stride,
+                   float* I_out, void* stream) {
+    static const int legacy = env_int("OFC_POLYEXP_LEGACY", 0);
+    if (!legacy && poly_n == 5) {
+        if (gray) {
+            if (p.w > 512) return launch_polyexp_strip<5, 128, 160, true>(p, gray, gray_stride, I_out, n_frames, stream);
+            return launch_polyexp_strip<5, 64, 96, true>(p, gray, gray_stride, I_out, n_frames, stream);
+        }
+        if (p.w > 512) return launch_polyexp_strip<5, 128, 160, false>(p, nullptr, 0, nullptr, n_frames, stream);
+        return launch_polyexp_strip<5, 64, 96, false>(p, nullptr, 0, nullptr, n_frames, stream);
+    }
+    if (gray) {     // un-fused fallback: materialise I first
+        PrefilterParams pf;
+        pf.gray = gray; pf.gray_stride = gray_stride; pf.out = I_out; pf.out_stride = p.out_stride;
+        pf.W = p.w; pf.H = p.h; pf.w = p.w; pf.h = p.h; pf.ksz = 3; pf.sx = pf.sy = 1.0; pf.taps = nullptr;
+        pf.tx = pf.ty = pf.in_rows = pf.in_pitch = pf.taps_pad = 0; pf.identity3 = 1;
+        int rc = launch_prefilter(pf, n_frames, 0, stream);
+        if (rc != OFC_OK) return rc;
+    }
     dim3 grid(cdiv(p.w, 64), cdiv(p.h, 32), n_frames);
     ProfScope prof(PK_POLYEXP, stream);
     if (poly_n == 5) {
@@ -756,21 +1116,19 @@ static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    // strip height: tall strips amortise the 2R-row vertical halo, but the grid must still fill
-    // the 148 SMs a few CTAs deep: aim for >= 2 * 148 * MINB CTAs, never below 16 rows
+    // persistent grid: every SM holds as many CTAs as fit, each gets an equal share of the rows
+    static int resident = 0;
+    if (!resident) {
+        OFC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, flow_iter_strip_kernel<R, TW, NT, G, MINB>, NT, smem));
+        if (resident < 1) resident = 1;
+    }
     const int cols = cdiv(p.w, TW);
-    const int want = 2 * 148 * MINB;
-    int strips = cdiv(want, cols * n_pairs);
-    if (strips < 1) strips = 1;
-    int strip_h = cdiv(p.h, strips);
-    static int forced = -2;
-    if (forced == -2) { const char* e = getenv("OFC_STRIP_H"); forced = e ? atoi(e) : -1; }
-    if (forced > 0) strip_h = forced;
-    if (strip_h < 16) strip_h = 16;
-    if (strip_h > p.h) strip_h = p.h;
-    dim3 grid(cols, cdiv(p.h, strip_h), n_pairs);
+    const int64_t total_rows = (int64_t)n_pairs * cols * p.h;
+    int64_t ctas = (int64_t)num_sms() * resident;
+    const int64_t max_ctas = (total_rows + 15) / 16;     // keep ranges >= 16 rows
+    if (ctas > max_ctas) ctas = max_ctas;
     ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
-    OFC_LAUNCH((flow_iter_strip_kernel<R, TW, NT, G, MINB>), grid, dim3(NT), smem, stream, p, strip_h);
+    OFC_LAUNCH((flow_iter_strip_kernel<R, TW, NT, G, MINB>), dim3((unsigned)ctas), dim3(NT), smem, stream, p, cols, total_rows);
     OFC_CHECK_LAUNCH("flow_iter_strip");
     return OFC_OK;
 }
@@ -790,6 +1148,8 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
         p.flow_in_stride = (int64_t)p.w * p.h;
         p.upsample = 0;
     }
+    static const int minb4 = env_int("OFC_STRIP_MINB4", 1);
+    if (p.w > 512 && minb4) return launch_strip_r<7, 128, 160, 4, 4>(p, n_pairs, stream);
     if (p.w > 512) return launch_strip_r<7, 128, 160, 4, 3>(p, n_pairs, stream);
     return launch_strip_r<7, 64, 96, 4, 5>(p, n_pairs, stream);
 }

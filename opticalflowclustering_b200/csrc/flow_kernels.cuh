@@ -49,7 +49,10 @@ struct IterParams {
 };
 
 int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* stream);
-int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, void* stream);
+// gray != null: full-resolution level with the fixed 3-tap pre-filter; I is produced from the 8-bit
+// frame inside the expansion kernel (and written to I_out as a by-product)
+int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, const unsigned char* gray, int64_t gray_stride,
+                   float* I_out, void* stream);
 // scratch: a flow-sized buffer [n_pairs][h][w] the launch may overwrite (up-sampled input flow)
 int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scratch, void* stream);
 int launch_minmax_init(unsigned* mm, int n_pairs, void* stream);

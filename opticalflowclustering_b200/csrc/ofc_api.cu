@@ -164,13 +164,16 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         pf.taps = pl->d_taps + L.taps_off;
         pf.identity3 = (L.sigma <= 0 && L.ksz == 3 && L.w == pl->W && L.h == pl->H) ? 1 : 0;
         pf.tx = L.tx; pf.ty = L.ty; pf.in_rows = L.in_rows; pf.in_pitch = L.in_pitch; pf.taps_pad = L.taps_pad;
-        int rc = launch_prefilter(pf, n_frames, L.prefilter_smem, stream);
-        if (rc != OFC_OK) return rc;
+        int rc = OFC_OK;
+        if (!pf.identity3) {
+            rc = launch_prefilter(pf, n_frames, L.prefilter_smem, stream);
+            if (rc != OFC_OK) return rc;
+        }
         PolyParams pp = pl->poly;
         pp.I = pf.out; pp.in_stride = pf.out_stride;
         pp.RA = (float4*)(ws + L.off_RA); pp.RB = (float*)(ws + L.off_RB);
         pp.out_stride = (int64_t)L.w * L.h; pp.w = L.w; pp.h = L.h;
-        rc = launch_polyexp(pp, pl->poly_n, n_frames, stream);
+        rc = launch_polyexp(pp, pl->poly_n, n_frames, pf.identity3 ? gray : nullptr, gray_stride, pf.out, stream);
         if (rc != OFC_OK) return rc;
     }
     if (minmax) {

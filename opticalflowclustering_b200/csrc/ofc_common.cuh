@@ -84,4 +84,9 @@ __host__ __device__ __forceinline__ int reflect101(int i, int n) {
     return i >= n ? p - i : i;
 }
 
+// same map for -n < i < 2n-1 without the modulo (n >= 2)
+__host__ __device__ __forceinline__ int reflect101_near(int i, int n) {
+    return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i);
+}
+
 }  // namespace ofc

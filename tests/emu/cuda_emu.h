@@ -79,6 +79,9 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cu
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+struct cudaDeviceProp { int multiProcessorCount; };
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 3; return cudaSuccess; }
+template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return cudaSuccess; }
 
 namespace ofc_emu {
 
@@ -290,6 +293,11 @@ static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f
 static inline long long __double_as_longlong(double d) { long long u; memcpy(&u, &d, 8); return u; }
 static inline double __longlong_as_double(long long u) { double d; memcpy(&d, &u, 8); return d; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+// funnel shift right: low 32 bits of ((hi:lo) >> (shift & 31))
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+    shift &= 31u;
+    return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> shift);
+}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
