@@ -710,11 +710,34 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_kernel(IterParams p) {
 // by the strip-walk iteration kernel, which reads a plain flow field.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) flow_upsample_kernel(IterParams p, float2* dst, int64_t dst_stride) {
-    const int gx = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int gy = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (gx >= p.w || gy >= p.h) return;
+    // 64 x 16 output tile per CTA; the resize taps of its 64 columns and 16 rows are worked out once
+    // (float64 coordinate like cv::resize) and shared
+    __shared__ int s_xi[64], s_yi[16];
+    __shared__ float s_fx[64], s_fy[16];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 16;
+    if (threadIdx.x < 64) src_coord(min(x0 + tx, p.w - 1), p.usx, p.wc, s_xi[tx], s_fx[tx]);
+    else if (threadIdx.x < 80) src_coord(min(y0 + (int)threadIdx.x - 64, p.h - 1), p.usy, p.hc, s_yi[threadIdx.x - 64], s_fy[threadIdx.x - 64]);
+    __syncthreads();
+    const int gx = x0 + tx;
+    if (gx >= p.w) return;
     const float2* fin = p.flow_in + (int64_t)blockIdx.z * p.flow_in_stride;
-    dst[(int64_t)blockIdx.z * dst_stride + (int64_t)gy * p.w + gx] = load_flow(p, fin, gx, gy);
+    float2* out = dst + (int64_t)blockIdx.z * dst_stride;
+    const int xi = s_xi[tx], xj = min(xi + 1, p.wc - 1);
+    const float fx = s_fx[tx], ax = 1.f - fx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ly = ty + r * 4, gy = y0 + ly;
+        if (gy >= p.h) break;
+        const int yi = s_yi[ly], yj = min(yi + 1, p.hc - 1);
+        const float fy = s_fy[ly], ay = 1.f - fy;
+        const float2 q00 = fin[yi * p.wc + xi], q01 = fin[yi * p.wc + xj];
+        const float2 q10 = fin[yj * p.wc + xi], q11 = fin[yj * p.wc + xj];
+        const float tx0 = q00.x * ax + q01.x * fx, tx1 = q10.x * ax + q11.x * fx;
+        const float ty0 = q00.y * ax + q01.y * fx, ty1 = q10.y * ax + q11.y * fx;
+        const float u = tx0 * ay + tx1 * fy, v = ty0 * ay + ty1 * fy;
+        out[(int64_t)gy * p.w + gx] = make_float2((float)((double)u * p.flow_mul), (float)((double)v * p.flow_mul));
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1010,14 +1033,14 @@ int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* 
         OFC_CHECK_LAUNCH("prefilter_identity3");
         return OFC_OK;
     }
-    if (!legacy && p.ksz <= 64) {
+    // Short kernels (the two finest down-sampled levels of the reference's pyramid: 3 and 9 taps) go
+    // through the direct form; for the long kernels of the small coarse levels (19+ taps, 1/64 of the
+    // pixels and less) sharing the horizontal pass through shared memory (tiled form) wins.
+    if (!legacy && (p.ksz == 3 || p.ksz == 9)) {
         dim3 g(cdiv(p.w, 32), cdiv(p.h, 8), n_frames);
         ProfScope prof(PK_PREFILTER, stream);
-        // tap counts of the reference's pyramid (pyr_scale 0.5: 3, 9, 19, 39, 79) get unrolled fast paths
         if (p.ksz == 3) OFC_LAUNCH(prefilter_direct_kernel<3>, g, dim3(256), 0, stream, p);
-        else if (p.ksz == 9) OFC_LAUNCH(prefilter_direct_kernel<9>, g, dim3(256), 0, stream, p);
-        else if (p.ksz == 19) OFC_LAUNCH(prefilter_direct_kernel<19>, g, dim3(256), 0, stream, p);
-        else OFC_LAUNCH(prefilter_direct_kernel<0>, g, dim3(256), 0, stream, p);
+        else OFC_LAUNCH(prefilter_direct_kernel<9>, g, dim3(256), 0, stream, p);
         OFC_CHECK_LAUNCH("prefilter_direct");
         return OFC_OK;
     }
@@ -1138,7 +1161,7 @@ static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
 static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, void* stream) {
     IterParams p = p_in;
     if (p.upsample) {
-        dim3 g(cdiv(p.w, 64), cdiv(p.h, 4), n_pairs);
+        dim3 g(cdiv(p.w, 64), cdiv(p.h, 16), n_pairs);
         {
             ProfScope prof(PK_UPSAMPLE, stream);
             OFC_LAUNCH(flow_upsample_kernel, g, dim3(256), 0, stream, p, scratch, (int64_t)p.w * p.h);
@@ -1157,9 +1180,12 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
 int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scratch, void* stream) {
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("OFC_ITER_VARIANT"); variant = e ? atoi(e) : 0; }
-    // winsize 15 (the reference's literal) runs the strip-walk kernel; other window sizes
-    // the square-tile kernel
-    if (variant == 0 && winsize == 15 && scratch != nullptr) return launch_strip(p, n_pairs, scratch, stream);
+    // winsize 15 (the reference's literal) on the wide levels runs the strip-walk kernel; the small
+    // pyramid levels (too few rows per SM for a column walk to hide latency) and other window sizes
+    // run the square-tile kernel
+    static const int strip_min_w = env_int("OFC_STRIP_MIN_W", 513);
+    if (variant == 0 && winsize == 15 && scratch != nullptr && p.w >= strip_min_w)
+        return launch_strip(p, n_pairs, scratch, stream);
     switch (winsize / 2) {
         case 2: return launch_iter_r<2, 32, 256, 3>(p, n_pairs, stream);
         case 3: return launch_iter_r<3, 32, 256, 3>(p, n_pairs, stream);

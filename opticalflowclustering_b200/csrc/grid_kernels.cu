@@ -43,13 +43,10 @@ __global__ void __launch_bounds__(256) grid_cells_kernel(GridParams p) {
     unsigned sa[3] = {0, 0, 0};          // sums for the mean stage
     unsigned sb[4] = {0, 0, 0, 0};       // sums for the k=1 stage (thresholded, + alpha count)
     const int n = cw * chh;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int ly = i / cw, lx = i - ly * cw;
-        const unsigned char* px = img + ((int64_t)(y1 + ly) * p.W + (x1 + lx)) * 3;
-        unsigned c0 = px[0], c1 = px[1], c2 = px[2];
-        bool wa = (ly == 0 && mean_row) || (lx == 0 && mean_col);
+    auto add_pixel = [&](unsigned c0, unsigned c1, unsigned c2, int ly, int lx) {
+        const bool wa = (ly == 0 && mean_row) || (lx == 0 && mean_col);
         sa[0] += wa ? 255u : c0; sa[1] += wa ? 255u : c1; sa[2] += wa ? 255u : c2;
-        bool wb = p.draw_lines && (ly == 0 || lx == 0);
+        const bool wb = p.draw_lines && (ly == 0 || lx == 0);
         unsigned k0 = wb ? 255u : c0, k1 = wb ? 255u : c1, k2 = wb ? 255u : c2;
         if (p.threshold) {
             k0 = k0 < (unsigned)p.threshold ? 0u : k0;
@@ -57,8 +54,29 @@ __global__ void __launch_bounds__(256) grid_cells_kernel(GridParams p) {
             k2 = k2 < (unsigned)p.threshold ? 0u : k2;
         }
         // alpha = 255 * (BGR2GRAY(thresholded) > 0)
-        unsigned gray = (3735u * k0 + 19235u * k1 + 9798u * k2 + 16384u) >> 15;
+        const unsigned gray = (3735u * k0 + 19235u * k1 + 9798u * k2 + 16384u) >> 15;
         sb[0] += k0; sb[1] += k1; sb[2] += k2; sb[3] += gray > 0 ? 1u : 0u;
+    };
+    const bool quads = (cw & 3) == 0 && ((x1 * 3) & 3) == 0 && ((p.W * 3) & 3) == 0 && (p.frame_stride & 3) == 0 &&
+                       ((uintptr_t)p.bgr & 3) == 0;
+    if (quads) {
+        // 4 pixels = 12 bytes = three aligned words per thread step
+        const int qpr = cw >> 2, nq = qpr * chh;
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+            const int ly = i / qpr, lq = i - ly * qpr;
+            const unsigned* wp = reinterpret_cast<const unsigned*>(img + ((int64_t)(y1 + ly) * p.W + x1 + lq * 4) * 3);
+            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+            add_pixel(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, ly, lq * 4);
+            add_pixel(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u, ly, lq * 4 + 1);
+            add_pixel((w1 >> 16) & 255u, w1 >> 24, w2 & 255u, ly, lq * 4 + 2);
+            add_pixel((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24, ly, lq * 4 + 3);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int ly = i / cw, lx = i - ly * cw;
+            const unsigned char* px = img + ((int64_t)(y1 + ly) * p.W + (x1 + lx)) * 3;
+            add_pixel(px[0], px[1], px[2], ly, lx);
+        }
     }
     __shared__ unsigned s_red[8][7];
     unsigned vals[7] = {sa[0], sa[1], sa[2], sb[0], sb[1], sb[2], sb[3]};

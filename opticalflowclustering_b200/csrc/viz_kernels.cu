@@ -63,7 +63,7 @@ __device__ __forceinline__ void encode_pixel(float fxv, float fyv, float fscale,
     mag = magnitude(fxv, fyv);
     float rad = __fmul_rn(angle_deg(fxv, fyv), 0.017453292f);          // f32(pi/180)
     // mask[...,0] = angle*180/np.pi/2 evaluated in float32, truncated to uint8
-    float hv = __fdiv_rn(__fdiv_rn(__fmul_rn(rad, 180.f), 3.1415927f), 2.f);
+    float hv = __fmul_rn(__fdiv_rn(__fmul_rn(rad, 180.f), 3.1415927f), 0.5f);      // /2 is exact either way
     int H = (int)hv;
     // cv.normalize(NORM_MINMAX): fmaf(m, f32(scale), f32(shift)), truncated to uint8
     float vv = __fmaf_rn(mag, fscale, fshift);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) flow_encode_kernel(VizParams p) {
             float4 a = f4[0], b = f4[1];
             unsigned char c[12];
             float m0, m1, m2, m3;
-            const int x = (int)(px % p.width);
+            const int x = (int)((unsigned)px % (unsigned)p.width);          // a frame has < 2^32 pixels
             encode_pixel(a.x, a.y, fscale, fshift, is_tail(x, p.width, tail_from), c[0], c[1], c[2], m0);
             encode_pixel(a.z, a.w, fscale, fshift, is_tail(x + 1, p.width, tail_from), c[3], c[4], c[5], m1);
             encode_pixel(b.x, b.y, fscale, fshift, is_tail(x + 2, p.width, tail_from), c[6], c[7], c[8], m2);
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) flow_encode_kernel(VizParams p) {
             for (int64_t i = px; i < px + 4 && i < p.n_px; ++i) {
                 float2 f = flow[i];
                 float m;
-                encode_pixel(f.x, f.y, fscale, fshift, (int)(i % p.width) >= tail_from, out[i * 3], out[i * 3 + 1],
+                encode_pixel(f.x, f.y, fscale, fshift, (int)((unsigned)i % (unsigned)p.width) >= tail_from, out[i * 3], out[i * 3 + 1],
                              out[i * 3 + 2], m);
                 local += (double)m;
             }

@@ -65,6 +65,21 @@ def test_emu_viz_and_grid_exact():
         assert (E.draw_grid(z["viz"][i:i + 1], 14, 25)[0] == lined).all()
 
 
+def test_emu_grid_quad_path_and_ragged_grid():
+    """cells whose width is a multiple of 4 take the word-load path; ragged right/bottom remainders are ignored"""
+    rng = np.random.default_rng(12)
+    for (H, W, rows, cols) in [(70, 100, 4, 4), (1080 // 8, 1920 // 8, 7, 5), (50, 64, 3, 8)]:
+        fr = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+        out = E.grid_cells(fr, rows, cols)
+        for i in range(2):
+            work = fr[i].copy()
+            avg, hue, rois = G.grid_mean_hues(work, rows, cols)
+            assert (avg == out["avg_bgr"][i]).all() and (hue == out["avg_hue"][i]).all()
+            kc = np.array([G.cluster_colors_k1(G.preprocess_image(r))[0] for r in rois])
+            kh = np.array([G.cluster_colors_k1(G.preprocess_image(r))[1] for r in rois])
+            assert (kc == out["km_centre"][i]).all() and (kh == out["km_hue"][i]).all()
+
+
 def test_emu_unsupported_flags():
     with pytest.raises(RuntimeError, match="flags"):
         E.Plan(64, 64, flags=256)
