@@ -223,7 +223,8 @@ def main():
         except Exception:
             pass
         total_ms = sum(v["ms_per_step"] for v in kernels.values())
-        roofline = {"bound": "hbm", "kernel": "flow_iter_kernel<R=7> @1920x1080 (update-matrices + 15x15 box + solve, fused)",
+        roofline = {"bound": "hbm", "kernel": "flow_iter_strip_kernel<R=7,TW=128> @1920x1080 (update-matrices + 15x15 box + 2x2 solve fused, "
+                              "persistent strip walk; 3 launches per step)",
                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "algorithmic_bytes_per_launch": algo, "ms_per_launch": per_launch_ms,
                     "share_of_step": it0["ms_per_step"] / total_ms,

@@ -764,27 +764,38 @@ __global__ void __launch_bounds__(256) flow_upsample_kernel(IterParams p, float2
 struct Taps {
     float4 q00, q01, q10, q11;
     float s00, s01, s10, s11;
-    float fx, fy;
-    int inb;
 };
 
-__device__ __forceinline__ void issue_taps(Taps& g, const float4* __restrict__ RA1, const float* __restrict__ RB1,
+// Where the warped sample of (gx, gy) falls: integer corner, fractions, in-bounds flag.  Cheap enough
+// to evaluate twice (when the taps are issued and when they are consumed) instead of carrying it.
+__device__ __forceinline__ void warp_point(float fgx, int gy, float dx, float dy, int w, int h,
+                                           int& x1, int& y1, float& fx, float& fy, bool& inb) {
+    fx = fgx + dx;
+    fy = (float)gy + dy;
+    x1 = (int)floorf(fx);
+    y1 = (int)floorf(fy);
+    fx -= (float)x1;
+    fy -= (float)y1;
+    inb = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+}
+
+// `RA` / `RB` point at the pair's "prev" frame; the "next" frame is r_next pixels further
+__device__ __forceinline__ void issue_taps(Taps& g, const float4* __restrict__ RA, const float* __restrict__ RB, int r_next,
                                            int w, int h, float fgx, int gy, float dx, float dy) {
-    float fx = fgx + dx, fy = (float)gy + dy;
-    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-    g.fx = fx - (float)x1;
-    g.fy = fy - (float)y1;
-    g.inb = ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) ? 1 : 0;
+    int x1, y1;
+    float fx, fy;
+    bool inb;
+    warp_point(fgx, gy, dx, dy, w, h, x1, y1, fx, fy, inb);
     // loads are unconditional (clamped address) so that they can be issued back to back;
-    // a level has < 2^31 pixels, so the pixel offset is a 32-bit integer
-    const int o1 = clampi(y1, 0, h - 2) * w + clampi(x1, 0, w - 2);
-    const float4* pa = RA1 + o1;
-    const float* pb = RB1 + o1;
+    // a level has < 2^30 pixels, so pixel offsets are 32-bit integers
+    const int o1 = clampi(y1, 0, h - 2) * w + clampi(x1, 0, w - 2) + r_next;
+    const float4* pa = RA + o1;
+    const float* pb = RB + o1;
     g.q00 = pa[0]; g.q01 = pa[1]; g.q10 = pa[w]; g.q11 = pa[w + 1];
     g.s00 = pb[0]; g.s01 = pb[1]; g.s10 = pb[w]; g.s11 = pb[w + 1];
 }
 
-template <int R, int TW, int NT, int G, int MINB>
+template <int R, int TW, int NT, int G, int MINB, bool MINMAX>
 __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p, int n_cols, int64_t total_rows) {
     constexpr int K = 2 * R + 1;
     constexpr int CW = TW + 2 * R;                       // halo'd columns
@@ -814,8 +825,7 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
     const int x0 = (unit - pair * n_cols) * TW;
     const float4* __restrict__ RA0 = p.RA + (int64_t)pair * p.r_stride;
     const float* __restrict__ RB0 = p.RB + (int64_t)pair * p.r_stride;
-    const float4* __restrict__ RA1 = RA0 + p.r_next;
-    const float* __restrict__ RB1 = RB0 + p.r_next;
+    const int r_next = (int)p.r_next;
     const float2* __restrict__ fin = p.flow_in ? p.flow_in + (int64_t)pair * p.flow_in_stride : nullptr;
     float2* __restrict__ fout = p.flow_out + (int64_t)pair * p.flow_out_stride;
 
@@ -839,18 +849,17 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
     constexpr int PD = 2;                                // rows of flow / R0 in flight ahead of the arithmetic
     static_assert(G % PD == 0, "prefetch slots are indexed by the unrolled row number");
     float2 fl[PD];
-    float4 na[PD];
-    float nb[PD];
+    float4 na;                                           // R0 of the next row (distance 1, like the taps)
+    float nb;
     Taps tp[2];
     if (col_thread) {
 #pragma unroll
         for (int i = 0; i < PD; ++i) {
             const int o = clampi(row0 + i, 0, h - 1) * w + gx;
             fl[i] = fin ? fin[o] : make_float2(0.f, 0.f);
-            na[i] = RA0[o];
-            nb[i] = RB0[o];
+            if (i == 0) { na = RA0[o]; nb = RB0[o]; }
         }
-        issue_taps(tp[0], RA1, RB1, w, h, fgx, clampi(row0, 0, h - 1), fl[0].x, fl[0].y);
+        issue_taps(tp[0], RA0, RB0, r_next, w, h, fgx, clampi(row0, 0, h - 1), fl[0].x, fl[0].y);
     }
     int gy_next = clampi(row0, 0, h - 1);
 
@@ -864,22 +873,25 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
                 {
                     const int in = (i + 1) % PD;
                     gy_next = clampi(row0 + ri + 1, 0, h - 1);
-                    issue_taps(tp[(i + 1) & 1], RA1, RB1, w, h, fgx, gy_next, fl[in].x, fl[in].y);
+                    issue_taps(tp[(i + 1) & 1], RA0, RB0, r_next, w, h, fgx, gy_next, fl[in].x, fl[in].y);
                 }
                 const Taps& g = tp[i & 1];
                 const float dx = fl[i % PD].x, dy = fl[i % PD].y;
-                const float4 a = na[i % PD];
-                const float b = nb[i % PD];
-                // flow / R0 of the row PD steps ahead reuse this row's registers
+                const float4 a = na;
+                const float b = nb;
                 {
-                    const int o = clampi(row0 + ri + PD, 0, h - 1) * w + gx;
-                    fl[i % PD] = fin ? fin[o] : make_float2(0.f, 0.f);
-                    na[i % PD] = RA0[o];
-                    nb[i % PD] = RB0[o];
+                    const int o = gy_next * w + gx;      // R0 of the next row
+                    na = RA0[o];
+                    nb = RB0[o];
                 }
+                // flow of the row PD steps ahead reuses this row's registers
+                if (fin) fl[i % PD] = fin[clampi(row0 + ri + PD, 0, h - 1) * w + gx];
                 float r2, r3, r4, r5, r6;
+                int wx1, wy1;
+                float fx, fy;
+                bool inb;
+                warp_point(fgx, gy, dx, dy, w, h, wx1, wy1, fx, fy, inb);
                 {
-                    const float fx = g.fx, fy = g.fy;
                     const float a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy, a00 = (1.f - fx) * (1.f - fy);
                     r2 = a00 * g.q00.x + a01 * g.q01.x + a10 * g.q10.x + a11 * g.q11.x;
                     r3 = a00 * g.q00.y + a01 * g.q01.y + a10 * g.q10.y + a11 * g.q11.y;
@@ -890,7 +902,7 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
                     r5 = (a.w + r5) * 0.5f;
                     r6 = (b + r6) * 0.25f;
                 }
-                if (!g.inb) {
+                if (!inb) {
                     r2 = r3 = 0.f;
                     r4 = a.z; r5 = a.w; r6 = b * 0.5f;
                 }
@@ -970,7 +982,7 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
             } else {
                 for (int j = 0; j < 4 && gx0 + j < w; ++j) out[j] = res[j];
             }
-            if (p.minmax) {
+            if (MINMAX) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (gx0 + j < w) {
@@ -983,7 +995,7 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
         }
         __syncthreads();
     }
-    if (p.minmax) {
+    if (MINMAX) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
@@ -1129,20 +1141,20 @@ static int launch_iter_r(const IterParams& p, int n_pairs, void* stream) {
     return OFC_OK;
 }
 
-template <int R, int TW, int NT, int G, int MINB>
-static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
+template <int R, int TW, int NT, int G, int MINB, bool MINMAX>
+static int launch_strip_rm(const IterParams& p, int n_pairs, void* stream) {
     constexpr int K = 2 * R + 1, CW = TW + 2 * R, CP = (CW + 3) / 4 * 4 + 4;
     constexpr size_t smem = (size_t)((K * 5 * CW + 3) / 4 * 4 + G * 5 * CP) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        OFC_CUDA(cudaFuncSetAttribute(flow_iter_strip_kernel<R, TW, NT, G, MINB>,
+        OFC_CUDA(cudaFuncSetAttribute(flow_iter_strip_kernel<R, TW, NT, G, MINB, MINMAX>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     // persistent grid: every SM holds as many CTAs as fit, each gets an equal share of the rows
     static int resident = 0;
     if (!resident) {
-        OFC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, flow_iter_strip_kernel<R, TW, NT, G, MINB>, NT, smem));
+        OFC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, flow_iter_strip_kernel<R, TW, NT, G, MINB, MINMAX>, NT, smem));
         if (resident < 1) resident = 1;
     }
     const int cols = cdiv(p.w, TW);
@@ -1151,9 +1163,15 @@ static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
     const int64_t max_ctas = (total_rows + 15) / 16;     // keep ranges >= 16 rows
     if (ctas > max_ctas) ctas = max_ctas;
     ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
-    OFC_LAUNCH((flow_iter_strip_kernel<R, TW, NT, G, MINB>), dim3((unsigned)ctas), dim3(NT), smem, stream, p, cols, total_rows);
+    OFC_LAUNCH((flow_iter_strip_kernel<R, TW, NT, G, MINB, MINMAX>), dim3((unsigned)ctas), dim3(NT), smem, stream, p, cols, total_rows);
     OFC_CHECK_LAUNCH("flow_iter_strip");
     return OFC_OK;
+}
+
+template <int R, int TW, int NT, int G, int MINB>
+static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
+    return p.minmax ? launch_strip_rm<R, TW, NT, G, MINB, true>(p, n_pairs, stream)
+                    : launch_strip_rm<R, TW, NT, G, MINB, false>(p, n_pairs, stream);
 }
 
 // The strip-walk kernel reads a plain flow field: when the input is the coarser level, up-sample

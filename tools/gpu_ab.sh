@@ -2,10 +2,8 @@
 python -c "from opticalflowclustering_b200 import _build; _build.build()"
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; echo "pytest rc=${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
-tail -6 gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
 summ() { python -c "
 import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1 value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'frac',round(d['roofline']['frac'],3),{k:round(v['ms_per_step'],3) for k,v in d['kernels'].items()})"; }
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | summ "default"
-OFC_STRIP_MINB4=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | summ "minb4"
-
+for v in $VARIANTS; do env $v python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | summ "$v"; done
