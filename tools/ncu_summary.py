@@ -110,7 +110,7 @@ def main():
                    f"L2 hit {d.get('lts__t_sector_hit_rate.pct', 0):.1f} %"]
         md.append("")
         if name.startswith("flow_iter") and rows:
-            d = rows[0]
+            d = max(rows, key=lambda r: r.get("gpu__time_duration.sum", 0.0))     # the full-resolution launch
             with open(os.path.join(PROF, "flow_iter_traffic.json"), "w") as f:
                 json.dump({"source": f"profiles/{tag}_{name}.json", "kernel": d["kernel"], "grid": d["grid"],
                            "dram_bytes_per_launch": d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0),
