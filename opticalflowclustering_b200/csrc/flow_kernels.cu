@@ -761,6 +761,76 @@ __global__ void __launch_bounds__(256) flow_upsample_kernel(IterParams p, float2
 // strip instead of once per 30 rows (about 1.25x instead of 1.79x redundant M work
 // at 1080p) and shared memory does not grow with the strip (ring + hand-over).
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// Phase C of the strip-walk kernels: the column sums of G output rows sit in `hand`
+// ([G][5][CP] floats, halo columns included); every task is 4 neighbouring pixels of one
+// row: horizontal sliding sums (128-bit shared loads), 2x2 solve in float64, flow store.
+// ---------------------------------------------------------------------------
+template <int R, int TW, int NT, int G, bool MINMAX>
+__device__ __forceinline__ void solve_rows(const IterParams& p, const float* hand, float2* __restrict__ fout, int t, int g0,
+                                           int nrows, int x0, int ys, int w, float& lmin, float& lmax) {
+    constexpr int K = 2 * R + 1;
+    constexpr int CW = TW + 2 * R;
+    constexpr int CP = (CW + 3) / 4 * 4 + 4;
+    constexpr int SEG = TW / 4;
+    for (int task = t; task < G * SEG; task += NT) {
+        const int i = task / SEG, seg = task - i * SEG;
+        const int ri = g0 + i;
+        const int gx0 = x0 + seg * 4;
+        if (ri < 2 * R || ri >= nrows || gx0 >= w) continue;
+        const int gy = ys + ri - 2 * R;
+        constexpr int NV = (4 + 2 * R + 3) / 4 * 4;
+        float S[5][4];
+#pragma unroll
+        for (int ch = 0; ch < 5; ++ch) {
+            const float* src = hand + i * (5 * CP) + ch * CP + seg * 4;
+            float v[NV];
+#pragma unroll
+            for (int j = 0; j < NV / 4; ++j) {
+                const float4 q = *reinterpret_cast<const float4*>(src + j * 4);
+                v[j * 4 + 0] = q.x; v[j * 4 + 1] = q.y; v[j * 4 + 2] = q.z; v[j * 4 + 3] = q.w;
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) sum += v[j];
+            S[ch][0] = sum;
+#pragma unroll
+            for (int j = 1; j < 4; ++j) {
+                sum += v[j + 2 * R] - v[j - 1];
+                S[ch][j] = sum;
+            }
+        }
+        float2 res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double g11 = (double)S[0][j] * p.blur_scale, g12 = (double)S[1][j] * p.blur_scale;
+            const double g22 = (double)S[2][j] * p.blur_scale;
+            const double h1 = (double)S[3][j] * p.blur_scale, h2 = (double)S[4][j] * p.blur_scale;
+            const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+            res[j].x = (float)((g11 * h2 - g12 * h1) * idet);
+            res[j].y = (float)((g22 * h1 - g12 * h2) * idet);
+        }
+        float2* out = fout + (int64_t)gy * w + gx0;
+        if (gx0 + 3 < w && (w & 1) == 0) {
+            float4* o4 = reinterpret_cast<float4*>(out);
+            o4[0] = make_float4(res[0].x, res[0].y, res[1].x, res[1].y);
+            o4[1] = make_float4(res[2].x, res[2].y, res[3].x, res[3].y);
+        } else {
+            for (int j = 0; j < 4 && gx0 + j < w; ++j) out[j] = res[j];
+        }
+        if (MINMAX) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (gx0 + j < w) {
+                    const float m = sqrtf(__fmaf_rn(res[j].x, res[j].x, __fmul_rn(res[j].y, res[j].y)));
+                    lmin = fminf(lmin, m);
+                    lmax = fmaxf(lmax, m);
+                }
+            }
+        }
+    }
+}
+
 struct Taps {
     float4 q00, q01, q10, q11;
     float s00, s01, s10, s11;
@@ -936,63 +1006,7 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
             }
         }
         __syncthreads();
-        // ---- horizontal sums (4 px / task) + solve ------------------------
-        for (int task = t; task < G * SEG; task += NT) {
-            const int i = task / SEG, seg = task - i * SEG;
-            const int ri = g0 + i;
-            const int gx0 = x0 + seg * 4;
-            if (ri < 2 * R || ri >= nrows || gx0 >= w) continue;
-            const int gy = ys + ri - 2 * R;
-            constexpr int NV = (4 + 2 * R + 3) / 4 * 4;
-            float S[5][4];
-#pragma unroll
-            for (int ch = 0; ch < 5; ++ch) {
-                const float* src = hand + i * (5 * CP) + ch * CP + seg * 4;
-                float v[NV];
-#pragma unroll
-                for (int j = 0; j < NV / 4; ++j) {
-                    const float4 q = *reinterpret_cast<const float4*>(src + j * 4);
-                    v[j * 4 + 0] = q.x; v[j * 4 + 1] = q.y; v[j * 4 + 2] = q.z; v[j * 4 + 3] = q.w;
-                }
-                float s = 0.f;
-#pragma unroll
-                for (int j = 0; j < K; ++j) s += v[j];
-                S[ch][0] = s;
-#pragma unroll
-                for (int j = 1; j < 4; ++j) {
-                    s += v[j + 2 * R] - v[j - 1];
-                    S[ch][j] = s;
-                }
-            }
-            float2 res[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double g11 = (double)S[0][j] * p.blur_scale, g12 = (double)S[1][j] * p.blur_scale;
-                const double g22 = (double)S[2][j] * p.blur_scale;
-                const double h1 = (double)S[3][j] * p.blur_scale, h2 = (double)S[4][j] * p.blur_scale;
-                const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-                res[j].x = (float)((g11 * h2 - g12 * h1) * idet);
-                res[j].y = (float)((g22 * h1 - g12 * h2) * idet);
-            }
-            float2* out = fout + (int64_t)gy * w + gx0;
-            if (gx0 + 3 < w && (w & 1) == 0) {
-                float4* o4 = reinterpret_cast<float4*>(out);
-                o4[0] = make_float4(res[0].x, res[0].y, res[1].x, res[1].y);
-                o4[1] = make_float4(res[2].x, res[2].y, res[3].x, res[3].y);
-            } else {
-                for (int j = 0; j < 4 && gx0 + j < w; ++j) out[j] = res[j];
-            }
-            if (MINMAX) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (gx0 + j < w) {
-                        const float m = sqrtf(__fmaf_rn(res[j].x, res[j].x, __fmul_rn(res[j].y, res[j].y)));
-                        lmin = fminf(lmin, m);
-                        lmax = fmaxf(lmax, m);
-                    }
-                }
-            }
-        }
+        solve_rows<R, TW, NT, G, MINMAX>(p, hand, fout, t, g0, nrows, x0, ys, w, lmin, lmax);
         __syncthreads();
     }
     if (MINMAX) {
@@ -1007,6 +1021,252 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
         }
     }
     }   // segments of this CTA's row range
+}
+
+// ---------------------------------------------------------------------------
+// K5+K6 fused, strip walk with the ring in TENSOR MEMORY and asynchronous tap landing.
+//
+// Same algorithm and results as flow_iter_strip_kernel; what changes is where state lives:
+//   * the (2R+1)-row ring of M that a column thread keeps is thread-private and only ever
+//     read back by its writer -- exactly the access pattern of tcgen05.ld/st.32x32b (lane =
+//     thread, columns = words).  It moves from shared memory (42 KB per 128 columns) to TMEM
+//     (256 KB per SM, otherwise idle on this path): 8 columns per ring slot, 120 per thread;
+//   * the shared memory that frees up becomes a landing zone for cp.async (LDGSTS): the 8
+//     bilinear taps of R1 and R0 of a row are requested two rows ahead without occupying
+//     registers, so every thread keeps two rows of gathers in flight where the register
+//     version keeps one.  Flow rows are pre-loaded four rows ahead in registers (8 B).
+// Geometry: 256 threads = 254 halo columns of a 240-column strip (1920 = 8 x 240, halo
+// 1.06x); 2 CTAs per SM x 256 TMEM columns = all 512 columns.
+// ---------------------------------------------------------------------------
+#ifndef OFC_EMULATE
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
+    unsigned r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#else
+// host-side debug emulation: copies are immediate, the "tensor memory" is a per-thread array
+static float ofc_emu_tmem[1024][128];
+static inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+static inline void cp_async4(void* dst, const void* src) { memcpy(dst, src, 4); }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+static inline void tmem_ld8(unsigned taddr, float (&v)[8]) { memcpy(v, &ofc_emu_tmem[threadIdx.x][taddr & 127u], 32); }
+static inline void tmem_st8(unsigned taddr, const float (&v)[8]) { memcpy(&ofc_emu_tmem[threadIdx.x][taddr & 127u], v, 32); }
+static inline void tmem_wait_st() {}
+#endif
+
+template <int R, int TW, int NT, int G, bool MINMAX>
+__global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int n_cols, int64_t total_rows) {
+    constexpr int K = 2 * R + 1;
+    constexpr int CW = TW + 2 * R;
+    constexpr int CP = (CW + 3) / 4 * 4 + 4;
+    constexpr int S = 3;                                 // landing slots: rows r, r+1, r+2
+    constexpr int TCOLS = 256;                           // TMEM columns per CTA (two warps share a lane quarter)
+    static_assert(NT == 256 && CW <= NT, "8 warps, one thread per halo column");
+    static_assert(K * 8 <= 128, "ring slots of 8 columns must fit the thread's 128 columns");
+    static_assert(G == 4, "the flow pre-load ring is indexed by the unrolled row number");
+    OFC_DYN_SMEM(float, sm);
+    float* hand = sm;                                                    // [G][5][CP]
+    float4* land_q = reinterpret_cast<float4*>(sm + G * 5 * CP);         // [S][4][NT] taps of R1 (RA part)
+    float4* land_a = land_q + S * 4 * NT;                                // [S][NT]    R0 (RA part)
+    float* land_s = reinterpret_cast<float*>(land_a + S * NT);           // [S][4][NT] taps of R1 (RB part)
+    float* land_b = land_s + S * 4 * NT;                                 // [S][NT]    R0 (RB part)
+    __shared__ unsigned s_tmem_base;
+
+    const int t = threadIdx.x;
+    const int w = p.w, h = p.h;
+#ifndef OFC_EMULATE
+    if (t < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // this thread's ring: lane quarter of its warp, upper or lower half of the CTA's columns
+    const unsigned ring_base = s_tmem_base + ((unsigned)(((t >> 5) & 3) * 32) << 16) + (unsigned)((t >> 7) * 128);
+#else
+    const unsigned ring_base = 0;
+    if (t == 0) s_tmem_base = 0;
+#endif
+
+    const int64_t range_lo = total_rows * blockIdx.x / gridDim.x;
+    const int64_t range_hi = total_rows * (blockIdx.x + 1) / gridDim.x;
+    for (int64_t cur = range_lo; cur < range_hi;) {
+    const int unit = (int)(cur / h);
+    const int ys = (int)(cur - (int64_t)unit * h);
+    const int64_t left = range_hi - cur;
+    const int ye = left < (int64_t)(h - ys) ? ys + (int)left : h;
+    cur += ye - ys;
+    const int pair = unit / n_cols;
+    const int x0 = (unit - pair * n_cols) * TW;
+    const float4* __restrict__ RA0 = p.RA + (int64_t)pair * p.r_stride;
+    const float* __restrict__ RB0 = p.RB + (int64_t)pair * p.r_stride;
+    const int r_next = (int)p.r_next;
+    const float2* __restrict__ fin = p.flow_in ? p.flow_in + (int64_t)pair * p.flow_in_stride : nullptr;
+    float2* __restrict__ fout = p.flow_out + (int64_t)pair * p.flow_out_stride;
+
+    const int gx = clampi(x0 - R + t, 0, w - 1);
+    const float bxs = (gx < 5 ? p.border[gx] : 1.f) * (gx >= w - 5 ? p.border[w - gx - 1] : 1.f);
+    const bool x_edge = (unsigned)(gx - 5) >= (unsigned)(w - 10);
+    const float fgx = (float)gx;
+    const int nrows = (ye - ys) + 2 * R;
+    const int row0 = ys - R;
+
+    double cs0 = 0.0, cs1 = 0.0, cs2 = 0.0, cs3 = 0.0, cs4 = 0.0;
+    float lmin = 3.402823466e38f, lmax = 0.f;
+    {   // all-zero ring: every row retires "the row K steps back" unconditionally
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < K; ++q) tmem_st8(ring_base + q * 8, z);
+        tmem_wait_st();
+    }
+    int slot = 0;                                        // ring slot of the current row
+    int ls = 0;                                          // landing slot of the current row (row index mod S)
+
+    // request the taps of R1 and R0 for `row` (already clamped) into landing slot `dst_slot`
+    auto request_row = [&](int row, float dx, float dy, int dst_slot) {
+        int x1, y1;
+        float fx, fy;
+        bool inb;
+        warp_point(fgx, row, dx, dy, w, h, x1, y1, fx, fy, inb);
+        const int o1 = clampi(y1, 0, h - 2) * w + clampi(x1, 0, w - 2) + r_next;
+        const float4* pa = RA0 + o1;
+        const float* pb = RB0 + o1;
+        float4* lq = land_q + (dst_slot * 4) * NT + t;
+        float* lsb = land_s + (dst_slot * 4) * NT + t;
+        cp_async16(lq, pa); cp_async16(lq + NT, pa + 1); cp_async16(lq + 2 * NT, pa + w); cp_async16(lq + 3 * NT, pa + w + 1);
+        cp_async4(lsb, pb); cp_async4(lsb + NT, pb + 1); cp_async4(lsb + 2 * NT, pb + w); cp_async4(lsb + 3 * NT, pb + w + 1);
+        const int o0 = row * w + gx;
+        cp_async16(land_a + dst_slot * NT + t, RA0 + o0);
+        cp_async4(land_b + dst_slot * NT + t, RB0 + o0);
+        cp_async_commit();
+    };
+
+    // ---- prologue: flow of rows 0..3 in registers, requests for rows 0 and 1 ------------
+    float2 fl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int o = clampi(row0 + i, 0, h - 1) * w + gx;
+        fl[i] = fin ? fin[o] : make_float2(0.f, 0.f);
+    }
+    request_row(clampi(row0, 0, h - 1), fl[0].x, fl[0].y, 0);
+    request_row(clampi(row0 + 1, 0, h - 1), fl[1].x, fl[1].y, 1);
+
+    for (int g0 = 0; g0 < nrows; g0 += G) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int ri = g0 + i;
+            const int gy = clampi(row0 + ri, 0, h - 1);
+            // row ri+2 goes out first; its flow was loaded four steps ago
+            {
+                const int l2 = ls + 2 >= S ? ls + 2 - S : ls + 2;
+                request_row(clampi(row0 + ri + 2, 0, h - 1), fl[(i + 2) & 3].x, fl[(i + 2) & 3].y, l2);
+            }
+            const float dx = fl[i].x, dy = fl[i].y;
+            if (fin) fl[i] = fin[clampi(row0 + ri + 4, 0, h - 1) * w + gx];
+            // old ring row (leaves the window) -- TMEM read overlaps the wait for the landing zone
+            float old[8];
+            tmem_ld8(ring_base + slot * 8, old);
+            cp_async_wait<2>();                          // everything but the two newest requests has landed
+            const float4 q00 = land_q[(ls * 4 + 0) * NT + t], q01 = land_q[(ls * 4 + 1) * NT + t];
+            const float4 q10 = land_q[(ls * 4 + 2) * NT + t], q11 = land_q[(ls * 4 + 3) * NT + t];
+            const float s00 = land_s[(ls * 4 + 0) * NT + t], s01 = land_s[(ls * 4 + 1) * NT + t];
+            const float s10 = land_s[(ls * 4 + 2) * NT + t], s11 = land_s[(ls * 4 + 3) * NT + t];
+            const float4 a = land_a[ls * NT + t];
+            const float b = land_b[ls * NT + t];
+            float r2, r3, r4, r5, r6;
+            int wx1, wy1;
+            float fx, fy;
+            bool inb;
+            warp_point(fgx, gy, dx, dy, w, h, wx1, wy1, fx, fy, inb);
+            {
+                const float a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy, a00 = (1.f - fx) * (1.f - fy);
+                r2 = a00 * q00.x + a01 * q01.x + a10 * q10.x + a11 * q11.x;
+                r3 = a00 * q00.y + a01 * q01.y + a10 * q10.y + a11 * q11.y;
+                r4 = a00 * q00.z + a01 * q01.z + a10 * q10.z + a11 * q11.z;
+                r5 = a00 * q00.w + a01 * q01.w + a10 * q10.w + a11 * q11.w;
+                r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
+                r4 = (a.z + r4) * 0.5f;
+                r5 = (a.w + r5) * 0.5f;
+                r6 = (b + r6) * 0.25f;
+            }
+            if (!inb) {
+                r2 = r3 = 0.f;
+                r4 = a.z; r5 = a.w; r6 = b * 0.5f;
+            }
+            r2 = (a.x - r2) * 0.5f;
+            r3 = (a.y - r3) * 0.5f;
+            r2 += r4 * dy + r6 * dx;
+            r3 += r6 * dy + r5 * dx;
+            if (x_edge || (unsigned)(gy - 5) >= (unsigned)(h - 10)) {
+                const float sc = bxs * (gy < 5 ? p.border[gy] : 1.f) * (gy >= h - 5 ? p.border[h - gy - 1] : 1.f);
+                r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+            }
+            float m[8];
+            m[0] = r4 * r4 + r6 * r6; m[1] = (r4 + r5) * r6; m[2] = r5 * r5 + r6 * r6;
+            m[3] = r4 * r2 + r6 * r3; m[4] = r6 * r2 + r5 * r3;
+            m[5] = m[6] = m[7] = 0.f;
+            if (ri < nrows) {
+                // float64 sums of <= 2R+1 float32 terms are exact: the result does not depend on
+                // where the walk started (see flow_iter_strip_kernel)
+                cs0 -= (double)old[0]; cs1 -= (double)old[1]; cs2 -= (double)old[2]; cs3 -= (double)old[3]; cs4 -= (double)old[4];
+                cs0 += (double)m[0]; cs1 += (double)m[1]; cs2 += (double)m[2]; cs3 += (double)m[3]; cs4 += (double)m[4];
+                if (ri >= 2 * R) {
+                    float* hd = hand + i * (5 * CP) + t;
+                    hd[0 * CP] = (float)cs0; hd[1 * CP] = (float)cs1; hd[2 * CP] = (float)cs2;
+                    hd[3 * CP] = (float)cs3; hd[4 * CP] = (float)cs4;
+                }
+            }
+            // the store is warp-collective: issued on every path (rows past the end rewrite the slot
+            // with values nobody reads)
+            tmem_st8(ring_base + slot * 8, m);
+            tmem_wait_st();
+            slot = slot + 1 == K ? 0 : slot + 1;
+            ls = ls + 1 == S ? 0 : ls + 1;
+        }
+        __syncthreads();
+        solve_rows<R, TW, NT, G, MINMAX>(p, hand, fout, t, g0, nrows, x0, ys, w, lmin, lmax);
+        __syncthreads();
+    }
+    cp_async_wait<0>();                                  // drain requests that ran past the segment
+    if (MINMAX) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        }
+        if ((t & 31) == 0) {
+            atomicMin(p.minmax + 2 * pair, __float_as_uint(lmin));
+            atomicMax(p.minmax + 2 * pair + 1, __float_as_uint(lmax));
+        }
+    }
+    }   // segments of this CTA's row range
+#ifndef OFC_EMULATE
+    __syncthreads();
+    if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "n"(TCOLS));
+#endif
 }
 
 __global__ void minmax_init_kernel(unsigned* mm, int n_pairs) {
@@ -1174,6 +1434,28 @@ static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
                     : launch_strip_rm<R, TW, NT, G, MINB, false>(p, n_pairs, stream);
 }
 
+template <bool MINMAX>
+static int launch_tmem(const IterParams& p, int n_pairs, void* stream) {
+    constexpr int R = 7, TW = 240, NT = 256, G = 4;
+    constexpr int CW = TW + 2 * R, CP = (CW + 3) / 4 * 4 + 4, S = 3;
+    constexpr size_t smem = (size_t)(G * 5 * CP) * 4 + (size_t)S * 4 * NT * 16 + (size_t)S * NT * 16 + (size_t)S * 4 * NT * 4 +
+                            (size_t)S * NT * 4;
+    static bool configured = false;
+    if (!configured) {
+        OFC_CUDA(cudaFuncSetAttribute(flow_iter_tmem_kernel<R, TW, NT, G, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int cols = cdiv(p.w, TW);
+    const int64_t total_rows = (int64_t)n_pairs * cols * p.h;
+    int64_t ctas = (int64_t)num_sms() * 2;              // 2 CTAs per SM: 2 x 256 TMEM columns
+    const int64_t max_ctas = (total_rows + 15) / 16;
+    if (ctas > max_ctas) ctas = max_ctas;
+    ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
+    OFC_LAUNCH((flow_iter_tmem_kernel<R, TW, NT, G, MINMAX>), dim3((unsigned)ctas), dim3(NT), smem, stream, p, cols, total_rows);
+    OFC_CHECK_LAUNCH("flow_iter_tmem");
+    return OFC_OK;
+}
+
 // The strip-walk kernel reads a plain flow field: when the input is the coarser level, up-sample
 // it first into `scratch` (this level's other ping-pong buffer, not otherwise live on iteration 0).
 static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, void* stream) {
@@ -1189,6 +1471,8 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
         p.flow_in_stride = (int64_t)p.w * p.h;
         p.upsample = 0;
     }
+    static const int use_tmem = env_int("OFC_ITER_TMEM", 0);
+    if (use_tmem && p.w >= use_tmem) return p.minmax ? launch_tmem<true>(p, n_pairs, stream) : launch_tmem<false>(p, n_pairs, stream);
     static const int minb4 = env_int("OFC_STRIP_MINB4", 1);
     if (p.w > 512 && minb4) return launch_strip_r<7, 128, 160, 4, 4>(p, n_pairs, stream);
     if (p.w > 512) return launch_strip_r<7, 128, 160, 4, 3>(p, n_pairs, stream);
