@@ -1188,6 +1188,7 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
             if (fin) fl[i] = fin[clampi(row0 + ri + 4, 0, h - 1) * w + gx];
             // old ring row (leaves the window) -- TMEM read overlaps the wait for the landing zone
             float old[8];
+            tmem_wait_st();                              // last row's ring store
             tmem_ld8(ring_base + slot * 8, old);
             cp_async_wait<2>();                          // everything but the two newest requests has landed
             const float4 q00 = land_q[(ls * 4 + 0) * NT + t], q01 = land_q[(ls * 4 + 1) * NT + t];
@@ -1242,7 +1243,6 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
             // the store is warp-collective: issued on every path (rows past the end rewrite the slot
             // with values nobody reads)
             tmem_st8(ring_base + slot * 8, m);
-            tmem_wait_st();
             slot = slot + 1 == K ? 0 : slot + 1;
             ls = ls + 1 == S ? 0 : ls + 1;
         }
@@ -1251,6 +1251,7 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
         __syncthreads();
     }
     cp_async_wait<0>();                                  // drain requests that ran past the segment
+    tmem_wait_st();
     if (MINMAX) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -1471,7 +1472,7 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
         p.flow_in_stride = (int64_t)p.w * p.h;
         p.upsample = 0;
     }
-    static const int use_tmem = env_int("OFC_ITER_TMEM", 0);
+    static const int use_tmem = env_int("OFC_ITER_TMEM", 513);      // minimum level width; 0 = off
     if (use_tmem && p.w >= use_tmem) return p.minmax ? launch_tmem<true>(p, n_pairs, stream) : launch_tmem<false>(p, n_pairs, stream);
     static const int minb4 = env_int("OFC_STRIP_MINB4", 1);
     if (p.w > 512 && minb4) return launch_strip_r<7, 128, 160, 4, 4>(p, n_pairs, stream);
