@@ -1046,6 +1046,13 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// dst / src byte offsets as immediates: one address register serves several copies
+template <int DOFF, int SOFF> __device__ __forceinline__ void cp_async16_o(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
+}
+template <int DOFF, int SOFF> __device__ __forceinline__ void cp_async4_o(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 4;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
@@ -1069,6 +1076,13 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 static float ofc_emu_tmem[1024][128];
 static inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
 static inline void cp_async4(void* dst, const void* src) { memcpy(dst, src, 4); }
+static inline unsigned long long smem_u32(const void* p) { return (unsigned long long)p; }
+template <int DOFF, int SOFF> static inline void cp_async16_o(unsigned long long dst, const void* src) {
+    memcpy((char*)dst + DOFF, (const char*)src + SOFF, 16);
+}
+template <int DOFF, int SOFF> static inline void cp_async4_o(unsigned long long dst, const void* src) {
+    memcpy((char*)dst + DOFF, (const char*)src + SOFF, 4);
+}
 static inline void cp_async_commit() {}
 template <int N> static inline void cp_async_wait() {}
 static inline void tmem_ld8(unsigned taddr, float (&v)[8]) { memcpy(v, &ofc_emu_tmem[threadIdx.x][taddr & 127u], 32); }
@@ -1154,10 +1168,12 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
         const int o1 = clampi(y1, 0, h - 2) * w + clampi(x1, 0, w - 2) + r_next;
         const float4* pa = RA0 + o1;
         const float* pb = RB0 + o1;
-        float4* lq = land_q + (dst_slot * 4) * NT + t;
-        float* lsb = land_s + (dst_slot * 4) * NT + t;
-        cp_async16(lq, pa); cp_async16(lq + NT, pa + 1); cp_async16(lq + 2 * NT, pa + w); cp_async16(lq + 3 * NT, pa + w + 1);
-        cp_async4(lsb, pb); cp_async4(lsb + NT, pb + 1); cp_async4(lsb + 2 * NT, pb + w); cp_async4(lsb + 3 * NT, pb + w + 1);
+        const auto lq = smem_u32(land_q + (dst_slot * 4) * NT + t);
+        const auto lsb = smem_u32(land_s + (dst_slot * 4) * NT + t);
+        cp_async16_o<0, 0>(lq, pa); cp_async16_o<NT * 16, 16>(lq, pa);
+        cp_async16_o<2 * NT * 16, 0>(lq, pa + w); cp_async16_o<3 * NT * 16, 16>(lq, pa + w);
+        cp_async4_o<0, 0>(lsb, pb); cp_async4_o<NT * 4, 4>(lsb, pb);
+        cp_async4_o<2 * NT * 4, 0>(lsb, pb + w); cp_async4_o<3 * NT * 4, 4>(lsb, pb + w);
         const int o0 = row * w + gx;
         cp_async16(land_a + dst_slot * NT + t, RA0 + o0);
         cp_async4(land_b + dst_slot * NT + t, RB0 + o0);
