@@ -330,6 +330,97 @@ __global__ void __launch_bounds__(256) prefilter_direct_kernel(PrefilterParams p
 }
 
 // ---------------------------------------------------------------------------
+// K2, lean tiled form for the down-sampled levels (tap count known at compile time).
+// A 256-thread CTA produces a 32x8 output tile:
+//   1  source window (8-bit) of the tile -> shared memory, aligned 32-bit loads in the
+//      interior, reflected byte loads at the frame border;
+//   2  horizontal taps for every window row at the two sample columns of each output
+//      column (they are neighbours, so one pass over KSZ+1 bytes feeds both), float32,
+//      tap order 0..KSZ-1 like cv::sepFilter2D;
+//   3  vertical taps at the two sample rows of each output row + the bilinear lerp.
+// Taps live in registers and every tap loop is unrolled.
+// ---------------------------------------------------------------------------
+template <int KSZ>
+__global__ void __launch_bounds__(256) prefilter_tile_kernel(PrefilterParams p, int in_rows, int in_pitch) {
+    constexpr int RR = KSZ / 2;
+    constexpr int TX = 32, TY = 8;
+    OFC_DYN_SMEM(unsigned char, smem);
+    float2* hbuf = reinterpret_cast<float2*>(smem);                        // [in_rows][TX] (ha, hb)
+    unsigned char* tile = smem + (size_t)in_rows * TX * sizeof(float2);     // [in_rows][in_pitch]
+    __shared__ int s_ci[TX], s_ri[TY];
+    __shared__ float s_fx[TX], s_fy[TY];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int nx = min(TX, p.w - x0), ny = min(TY, p.h - y0);
+    const unsigned char* src = p.gray + (int64_t)blockIdx.z * p.gray_stride;
+    if (tid < TX) src_coord(min(x0 + tid, p.w - 1), p.sx, p.W, s_ci[tid], s_fx[tid]);
+    else if (tid < TX + TY) src_coord(min(y0 + tid - TX, p.h - 1), p.sy, p.H, s_ri[tid - TX], s_fy[tid - TX]);
+    float tp[KSZ];
+#pragma unroll
+    for (int j = 0; j < KSZ; ++j) tp[j] = p.taps[j];
+    __syncthreads();
+    // window: columns [c_lo, c_lo + ncols), rows [r_lo, r_lo + nrows); c_lo rounded down to a word
+    const int c_first = s_ci[0] - RR, r_lo = s_ri[0] - RR;
+    const int c_lo = c_first & ~3;
+    const int ncols = min(s_ci[nx - 1] + 1, p.W - 1) + RR - c_lo + 1;
+    const int nrows = min(s_ri[ny - 1] + 1, p.H - 1) + RR - r_lo + 1;
+    const bool interior = c_lo >= 0 && c_lo + ((ncols + 3) & ~3) <= p.W && r_lo >= 0 && r_lo + nrows <= p.H &&
+                          (p.W & 3) == 0 && (p.gray_stride & 3) == 0 && ((uintptr_t)p.gray & 3) == 0;
+    if (interior) {
+        const int nwords = (ncols + 3) >> 2;
+        for (int i = tid; i < nrows * nwords; i += 256) {
+            const int rr = i / nwords, wc = i - rr * nwords;
+            *reinterpret_cast<unsigned*>(tile + rr * in_pitch + wc * 4) =
+                *reinterpret_cast<const unsigned*>(src + (int64_t)(r_lo + rr) * p.W + c_lo + wc * 4);
+        }
+    } else {
+        for (int rr = warp; rr < nrows; rr += 8) {
+            const unsigned char* row = src + (int64_t)reflect101(r_lo + rr, p.H) * p.W;
+            for (int cc = lane; cc < ncols; cc += 32) tile[rr * in_pitch + cc] = row[reflect101(c_lo + cc, p.W)];
+        }
+    }
+    __syncthreads();
+    // horizontal taps: lane = output column, warps stride over the window rows
+    {
+        const int xx = lane < nx ? lane : nx - 1;
+        const int ci = s_ci[xx];
+        const int d = min(ci + 1, p.W - 1) - ci;         // 1, or 0 at the right frame border
+        const unsigned char* base = tile + (ci - RR - c_lo);
+        for (int rr = warp; rr < nrows; rr += 8) {
+            const unsigned char* t = base + rr * in_pitch;
+            float ha = 0.f, hb = 0.f;
+            float prev = (float)t[0];
+#pragma unroll
+            for (int j = 0; j < KSZ; ++j) {
+                const float nxt = (float)t[j + 1];       // one byte past the window is inside the padded pitch
+                ha = fmaf(tp[j], prev, ha);
+                hb = fmaf(tp[j], d ? nxt : prev, hb);
+                prev = nxt;
+            }
+            hbuf[rr * TX + lane] = make_float2(ha, hb);
+        }
+    }
+    __syncthreads();
+    // vertical taps + lerp: one output per thread
+    if (lane < nx && warp < ny) {
+        const int ri = s_ri[warp];
+        const int ra = ri - RR - r_lo, rb = min(ri + 1, p.H - 1) - RR - r_lo;
+        float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+#pragma unroll
+        for (int j = 0; j < KSZ; ++j) {
+            const float2 ha = hbuf[(ra + j) * TX + lane], hb = hbuf[(rb + j) * TX + lane];
+            b00 = fmaf(tp[j], ha.x, b00); b01 = fmaf(tp[j], ha.y, b01);
+            b10 = fmaf(tp[j], hb.x, b10); b11 = fmaf(tp[j], hb.y, b11);
+        }
+        const float fx = s_fx[lane], fy = s_fy[warp];
+        const float top = b00 * (1.f - fx) + b01 * fx;
+        const float bot = b10 * (1.f - fx) + b11 * fx;
+        p.out[(int64_t)blockIdx.z * p.out_stride + (int64_t)(y0 + warp) * p.w + x0 + lane] = top * (1.f - fy) + bot * fy;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K3, strip-walk form (production): thread t owns column x0-N+t and walks down a
 // strip of rows with the 2N+G-row vertical window of I in registers; every G rows
 // the vertical results (r0,r1,r2) of G rows go through shared memory and the CTA
@@ -1322,16 +1413,31 @@ int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* 
         OFC_CHECK_LAUNCH("prefilter_identity3");
         return OFC_OK;
     }
-    // Short kernels (the two finest down-sampled levels of the reference's pyramid: 3 and 9 taps) go
-    // through the direct form; for the long kernels of the small coarse levels (19+ taps, 1/64 of the
-    // pixels and less) sharing the horizontal pass through shared memory (tiled form) wins.
-    if (!legacy && (p.ksz == 3 || p.ksz == 9)) {
-        dim3 g(cdiv(p.w, 32), cdiv(p.h, 8), n_frames);
-        ProfScope prof(PK_PREFILTER, stream);
-        if (p.ksz == 3) OFC_LAUNCH(prefilter_direct_kernel<3>, g, dim3(256), 0, stream, p);
-        else OFC_LAUNCH(prefilter_direct_kernel<9>, g, dim3(256), 0, stream, p);
-        OFC_CHECK_LAUNCH("prefilter_direct");
-        return OFC_OK;
+    // tap counts of the reference's pyramid (pyr_scale 0.5 -> 3, 9, 19 taps) have unrolled lean kernels
+    if (!legacy && (p.ksz == 3 || p.ksz == 9 || p.ksz == 19)) {
+        // window of a 32x8 tile (+4 columns: word alignment and the one-byte over-read of the tap loop)
+        const int in_rows = (int)ceil(7 * p.sy) + p.ksz + 3;
+        const int in_pitch = (((int)ceil(31 * p.sx) + p.ksz + 3 + 8) + 3) / 4 * 4;
+        const size_t sm = (size_t)in_rows * 32 * 8 + (size_t)in_rows * in_pitch + 16;
+        if (sm <= 200 * 1024) {
+            dim3 g(cdiv(p.w, 32), cdiv(p.h, 8), n_frames);
+            ProfScope prof(PK_PREFILTER, stream);
+#define OFC_PF_TILE(KS)                                                                                                \
+    {                                                                                                                  \
+        static size_t conf = 0;                                                                                        \
+        if (sm > 48 * 1024 && sm > conf) {                                                                             \
+            OFC_CUDA(cudaFuncSetAttribute(prefilter_tile_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            conf = sm;                                                                                                 \
+        }                                                                                                              \
+        OFC_LAUNCH(prefilter_tile_kernel<KS>, g, dim3(256), sm, stream, p, in_rows, in_pitch);                          \
+    }
+            if (p.ksz == 3) OFC_PF_TILE(3)
+            else if (p.ksz == 9) OFC_PF_TILE(9)
+            else OFC_PF_TILE(19)
+#undef OFC_PF_TILE
+            OFC_CHECK_LAUNCH("prefilter_tile");
+            return OFC_OK;
+        }
     }
     dim3 grid(cdiv(p.w, p.tx), cdiv(p.h, p.ty), n_frames);
     static size_t configured = 0;
