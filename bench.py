@@ -142,6 +142,47 @@ def run_reference(args):
     }))
 
 
+def kmeans_cosine_extras(dev, peak):
+    """Secondary numbers for BASELINE.json configs[4] (k-means / cosine over 1M grid vectors): one Lloyd
+    iteration (E-step + M-step kernels) and the row-cosine kernel, CUDA-event timed, against their
+    algorithmic bytes (N*D*sizeof(x) + 4N per iteration; N*D*sizeof(x) for cosine)."""
+    import torch
+    from opticalflowclustering_b200 import cosine as cosm
+    from opticalflowclustering_b200 import kmeans as km
+    out = {}
+    g = torch.Generator().manual_seed(0)
+    for name, (N, D, K, dt) in {"u8_d4_k8": (1_000_000, 4, 8, torch.uint8), "u8_d350_k8": (200_000, 350, 8, torch.uint8),
+                                "f32_d32_k16": (1_000_000, 32, 16, torch.float32)}.items():
+        X = torch.randint(0, 180, (N, D), generator=g).to(dt).to(dev)
+        ctx = km._Ctx(dev)
+        st = km.LloydState(ctx, X.unsqueeze(0).contiguous(), K)
+        centres = X[:K].double().unsqueeze(0).contiguous()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(6):
+            if it == 1:
+                e0.record()
+            st.assign(None, centres, st.labels[0])
+            st.sums_(None, st.labels[0], st.sums, st.counts, K)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        nbytes = 2 * (N * D * X.element_size()) + 2 * 4 * N          # both kernels read X once and touch the labels
+        out["kmeans_iter_" + name] = {"ms": ms, "rows_per_s": N / (ms / 1e3), "gb_s": nbytes / (ms / 1e3) / 1e9,
+                                      "frac_of_hbm_peak": nbytes / (ms / 1e3) / 1e9 / peak}
+    X = torch.randint(0, 180, (1_000_000, 16), generator=g).to(torch.uint8).to(dev)
+    q = torch.randint(0, 180, (16,), generator=g).double()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(6):
+        if it == 1:
+            e0.record()
+        cosm.row_cosine(X, q)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out["row_cosine_u8_1Mx16"] = {"ms": ms, "rows_per_s": 1e6 / (ms / 1e3), "gb_s": (16e6 + 8e6) / (ms / 1e3) / 1e9}
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -281,6 +322,8 @@ def main():
            "d2h_bytes_per_step": P * (2 * ROWS * COLS + 8),
            "api": "ClipPipeline.run_chunk on pinned host frames, double-buffered upload"}
 
+    extras = kmeans_cosine_extras(dev, peak) if rank == 0 else None
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -301,7 +344,7 @@ def main():
                        "l2": f"steps walk a {T}-frame clip ({T * H * W * 3 / 1e6:.0f} MB > L2); intermediates "
                              f"({pipe.plan.workspace_bytes / 1e6:.0f} MB workspace) are rewritten every step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels, "extras": extras,
         }))
     if world > 1:
         dist.destroy_process_group()

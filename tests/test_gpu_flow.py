@@ -245,3 +245,30 @@ def test_full_size_properties(ofc, size):
         ref = cv2.calcOpticalFlowFarneback(g[0], g[1], None, 0.5, 3, 15, 3, 5, 1.2, 0)
         e = _epe(f1[0].cpu().numpy(), ref)
         assert e.mean() <= MEAN_EPE and e.max() <= MAX_EPE, (e.mean(), e.max())
+
+
+def test_4k_five_level_pyramid_properties(ofc):
+    """BASELINE configs[3] geometry: 3840x2160, levels=5 (6 scales down to 120x68, 79-tap pre-filter).
+    Too large for the numpy oracle, so: determinism, pair-vs-sequence invariance, translation recovery,
+    and agreement with live cv2 on the same frames when the wheel is importable."""
+    from opticalflowclustering_b200.flow import FarnebackPlan, bgr2gray
+    from opticalflowclustering_b200.synthetic import synthetic_clip, true_flow
+    H, W = 2160, 3840
+    clip = synthetic_clip(3, H, W, seed=8, device="cuda")
+    gray = bgr2gray(clip)
+    plan = FarnebackPlan(W, H, max_frames=3, levels=5)
+    assert plan.num_levels == 6 and plan.level_size(0) == (120, 68)
+    f1 = plan.sequence(gray).clone()
+    f2 = plan.sequence(gray).clone()
+    assert torch.equal(f1, f2)
+    solo = FarnebackPlan(W, H, max_frames=2, levels=5).pair(gray[0], gray[1])
+    assert torch.equal(solo, f1[0])
+    truth = true_flow(H, W, device="cuda")
+    inner = (slice(60, H - 60), slice(60, W - 60))
+    assert (f1[0][inner] - truth[inner]).norm(dim=-1).mean().item() < 0.1
+    if have_cv2():
+        import cv2
+        g = gray.cpu().numpy()
+        ref = cv2.calcOpticalFlowFarneback(g[0], g[1], None, 0.5, 5, 15, 3, 5, 1.2, 0)
+        e = _epe(f1[0].cpu().numpy(), ref)
+        assert e.mean() <= MEAN_EPE and e.max() <= 5 * MAX_EPE, (e.mean(), e.max())
