@@ -273,33 +273,43 @@ def main():
                     "step_frac": ALGO_BYTES_PER_PAIR * P / (ms_total / args.steps / 1e3) / 1e9 / peak}
 
     # ---- e2e: host frames in, hue rows out ----------------------------------
-    host = clip.cpu().pin_memory()
+    # The public call a user makes: ClipPipeline.run_chunk(new frames, carry=True) -- every step uploads
+    # the P new frames of its chunk from pinned host memory (the frame shared with the previous chunk
+    # stays on the device as prev_gray, like the reference's ComputeOpticalFLow state) and reads back
+    # the hue rows and magnitudes.
+    # walk the clip forwards then backwards so that consecutive chunks are always consecutive frames
+    host_clip = clip.cpu()
+    host = torch.cat([host_clip[1:], host_clip[:-1].flip(0)]).pin_memory()
     res_avg = torch.empty((P, ROWS * COLS), dtype=torch.uint8).pin_memory()
     res_km = torch.empty((P, ROWS * COLS), dtype=torch.uint8).pin_memory()
     res_mag = torch.empty(P, dtype=torch.float64).pin_memory()
-    stage = [torch.empty((F, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+    stage = [torch.empty((P, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
+    n_chunks = host.shape[0] // P               # consecutive P-frame chunks of the there-and-back walk
 
     def e2e_loop(lo, hi):
         main = torch.cuda.current_stream()
         for b in range(2):
             freed[b].record(main)
-        # prefetch first
+
         def upload(i):
             b = i & 1
+            c = i % n_chunks
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[b])
-                stage[b].copy_(host[starts[i]:starts[i] + F], non_blocking=True)
+                stage[b].copy_(host[c * P:(c + 1) * P], non_blocking=True)
                 ready[b].record(copy_stream)
+        # frame 0 of the clip seeds prev_gray (outside the steady state, like the reference's first cap.read())
+        pipe.run_chunk(clip[0:2])
         upload(lo)
         for i in range(lo, hi):
             b = i & 1
             if i + 1 < hi:
                 upload(i + 1)
             main.wait_event(ready[b])
-            pipe.run_chunk(stage[b])
+            pipe.run_chunk(stage[b], carry=True)
             freed[b].record(main)
             res_avg.copy_(pipe.avg_hue[:P], non_blocking=True)
             res_km.copy_(pipe.km_hue[:P], non_blocking=True)
@@ -318,9 +328,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps * P / (float(t.item()) / 1e3)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * H * W * 3,
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": P * H * W * 3,
            "d2h_bytes_per_step": P * (2 * ROWS * COLS + 8),
-           "api": "ClipPipeline.run_chunk on pinned host frames, double-buffered upload"}
+           "api": "ClipPipeline.run_chunk(new frames, carry=True) on pinned host frames, double-buffered upload"}
 
     extras = kmeans_cosine_extras(dev, peak) if rank == 0 else None
 
@@ -328,7 +338,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         workers = max(1, min(cores, 64))
-        frames_np = host[:min(T, 33)].numpy()
+        frames_np = host_clip[:min(T, 33)].numpy()
         v, wall = cpu_reference_throughput(frames_np, workers, 2)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
                         "sample": f"{workers} processes x 2 consecutive 1080p pairs of the same clip "

@@ -45,16 +45,25 @@ class ClipPipeline:
         self.km_centre = torch.empty((P, self.cells, 4), dtype=torch.uint8, device=dev)
         self.km_hue = torch.empty((P, self.cells), dtype=torch.uint8, device=dev)
         self.keep_viz = keep_viz
+        self._last_gray_index = None     # where the last processed frame's gray image sits in self.gray
         #: kernels launched by one full-chunk call of :meth:`run_chunk`
         self.launches_per_chunk = 1 + 2 * self.plan.num_levels + 1 + self.plan.num_levels * iterations + 1 + 1
 
-    def run_chunk(self, frames: torch.Tensor, n_frames: int | None = None):
+    def run_chunk(self, frames: torch.Tensor, n_frames: int | None = None, carry: bool = False):
         """frames: CUDA uint8 [n,H,W,3] (n <= chunk_frames).  Results stay in the
         pipeline's buffers (``avg_hue``, ``km_hue``, ``km_centre``, ``mag_sum``, ``viz``,
-        ``flow``) for pairs 0..n-2; returns n-1."""
-        n = int(frames.shape[0]) if n_frames is None else int(n_frames)
+        ``flow``) for pairs 0..n-2; returns n-1.
+
+        ``carry=True``: ``frames`` are the m NEW frames that follow the previous call's last
+        frame (m <= chunk_frames - 1); the pipeline keeps that frame's gray image on the device
+        (the reference's ``prev_gray``, computeOpticalFlowModule.py:34), so the one-frame halo
+        between chunks is neither uploaded nor converted again.  Returns m pairs."""
+        m = int(frames.shape[0]) if n_frames is None else int(n_frames)
+        n = m + 1 if carry else m
         if n < 2 or n > self.F:
             raise ValueError(f"n_frames={n} outside [2, {self.F}]")
+        if carry and self._last_gray_index is None:
+            raise ValueError("carry=True needs a previous run_chunk call on this pipeline")
         if tuple(frames.shape[1:]) != (self.H, self.W, 3) or frames.dtype != torch.uint8 or not frames.is_cuda:
             raise ValueError("frames must be CUDA uint8 [n,H,W,3] of the pipeline's size")
         if not frames.is_contiguous():
@@ -63,7 +72,13 @@ class ClipPipeline:
         s = _stream_ptr()
         P = n - 1
         with torch.cuda.device(self.device):
-            _lib.check(L.ofc_bgr2gray(_ptr(frames), _ptr(self.gray), n * self.H * self.W, s))
+            if carry:
+                if self._last_gray_index != 0:
+                    self.gray[0].copy_(self.gray[self._last_gray_index])
+                _lib.check(L.ofc_bgr2gray(_ptr(frames), _ptr(self.gray[1:]), m * self.H * self.W, s))
+            else:
+                _lib.check(L.ofc_bgr2gray(_ptr(frames), _ptr(self.gray), n * self.H * self.W, s))
+            self._last_gray_index = n - 1
             _lib.check(L.ofc_farneback_sequence(self.plan._ptr, _ptr(self.gray), n, _ptr(self.flow), _ptr(self.minmax),
                                                 _ptr(self.plan.workspace), self.plan.workspace_bytes, s))
             _lib.check(L.ofc_flow_to_bgr(_ptr(self.flow), P, self.H, self.W, _ptr(self.minmax), _ptr(self.viz),
@@ -86,11 +101,13 @@ class ClipPipeline:
         mag = torch.empty(T - 1, dtype=torch.float64)
         t = 0
         while t < T - 1:
-            n = min(self.F, T - t)
-            chunk = frames[t:t + n]
+            # the first chunk carries its own first frame; later chunks only the new frames
+            first = t == 0
+            n = min(self.F, T - t) if first else min(self.F - 1, T - 1 - t)
+            chunk = frames[t:t + n] if first else frames[t + 1:t + 1 + n]
             if not chunk.is_cuda:
                 chunk = chunk.to(self.device, non_blocking=True)
-            P = self.run_chunk(chunk)
+            P = self.run_chunk(chunk, carry=not first)
             avg[t:t + P] = self.avg_hue[:P].cpu()
             km[t:t + P] = self.km_hue[:P].cpu()
             mag[t:t + P] = (self.mag_sum[:P] / float(self.H * self.W)).cpu()

@@ -202,6 +202,18 @@ def test_pipeline_chunking_invariance_and_oracle(ofc):
     b = ClipPipeline(W, H, chunk_frames=3, rows=6, cols=8).process_clip(clip)
     for k in a:
         assert torch.equal(a[k], b[k]), k
+    # carry=True: new frames only, the shared frame stays on the device as prev_gray
+    c = ClipPipeline(W, H, chunk_frames=4, rows=6, cols=8)
+    dev_clip = clip.cuda()
+    assert c.run_chunk(dev_clip[0:3]) == 2
+    got = [c.avg_hue[:2].cpu()]
+    assert c.run_chunk(dev_clip[3:6], carry=True) == 3
+    got.append(c.avg_hue[:3].cpu())
+    assert c.run_chunk(dev_clip[6:7], carry=True) == 1
+    got.append(c.avg_hue[:1].cpu())
+    assert torch.equal(torch.cat(got), a["avg_hue"])
+    with pytest.raises(ValueError):
+        ClipPipeline(W, H, chunk_frames=4, rows=6, cols=8).run_chunk(dev_clip[0:2], carry=True)
     pipe = ClipPipeline(W, H, chunk_frames=T, rows=6, cols=8)
     pipe.run_chunk(clip.cuda())
     flow = pipe.flow.cpu().numpy()
