@@ -57,6 +57,9 @@ int ofc_flow_plan_create(ofc_flow_plan** plan, int width, int height, int max_fr
                          int poly_n, double poly_sigma, int flags);
 void ofc_flow_plan_destroy(ofc_flow_plan* plan);
 size_t ofc_flow_plan_workspace_bytes(const ofc_flow_plan* plan);
+/* keep != 0: also write the pre-filtered image I of the full-resolution level to the workspace
+ * (buffer kind 0 below); by default it is fused into the polynomial expansion and never stored. */
+int ofc_flow_plan_keep_intermediates(ofc_flow_plan* plan, int keep);
 int ofc_flow_plan_num_levels(const ofc_flow_plan* plan);
 /* level 0 = coarsest ... num_levels-1 = full resolution */
 int ofc_flow_plan_level_size(const ofc_flow_plan* plan, int level, int* w, int* h);

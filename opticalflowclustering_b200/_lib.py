@@ -24,6 +24,7 @@ SIGNATURES = {
     "ofc_flow_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _d, _i, _i, _i, _i, _d, _i]),
     "ofc_flow_plan_destroy": (None, [_vp]),
     "ofc_flow_plan_workspace_bytes": (_sz, [_vp]),
+    "ofc_flow_plan_keep_intermediates": (_i, [_vp, _i]),
     "ofc_flow_plan_num_levels": (_i, [_vp]),
     "ofc_flow_plan_level_size": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "ofc_flow_plan_buffer": (_i, [_vp, _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),

@@ -71,6 +71,7 @@ struct ofc_flow_plan {
     double pyr_scale;
     int levels, winsize, iterations, poly_n;
     double poly_sigma;
+    int keep_level0_I;               // also materialise I of the full-resolution level (fused away by default)
     std::vector<ofc::Level> lv;      // coarsest first
     size_t workspace_bytes;
     float* d_taps;
@@ -173,7 +174,8 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         pp.I = pf.out; pp.in_stride = pf.out_stride;
         pp.RA = (float4*)(ws + L.off_RA); pp.RB = (float*)(ws + L.off_RB);
         pp.out_stride = (int64_t)L.w * L.h; pp.w = L.w; pp.h = L.h;
-        rc = launch_polyexp(pp, pl->poly_n, n_frames, pf.identity3 ? gray : nullptr, gray_stride, pf.out, stream);
+        rc = launch_polyexp(pp, pl->poly_n, n_frames, pf.identity3 ? gray : nullptr, gray_stride,
+                            (pl->keep_level0_I || pl->poly_n != 5) ? pf.out : nullptr, stream);
         if (rc != OFC_OK) return rc;
     }
     if (minmax) {
@@ -275,6 +277,7 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
     pl->pyr_scale = pyr_scale; pl->levels = levels; pl->winsize = winsize;
     pl->iterations = iterations; pl->poly_n = poly_n; pl->poly_sigma = poly_sigma;
     pl->d_taps = nullptr;
+    pl->keep_level0_I = 0;
     memset(&pl->poly, 0, sizeof(pl->poly));
     int rc = prepare_poly(poly_n, poly_sigma, pl->poly);
     if (rc != OFC_OK) { delete pl; return rc; }
@@ -357,6 +360,12 @@ void ofc_flow_plan_destroy(ofc_flow_plan* pl) {
 }
 
 size_t ofc_flow_plan_workspace_bytes(const ofc_flow_plan* pl) { return pl ? pl->workspace_bytes : 0; }
+
+int ofc_flow_plan_keep_intermediates(ofc_flow_plan* pl, int keep) {
+    OFC_REQUIRE(pl != nullptr, "null plan");
+    pl->keep_level0_I = keep ? 1 : 0;
+    return OFC_OK;
+}
 
 int ofc_flow_plan_num_levels(const ofc_flow_plan* pl) { return pl ? (int)pl->lv.size() : 0; }
 

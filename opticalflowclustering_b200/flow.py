@@ -70,6 +70,11 @@ class FarnebackPlan:
         self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
         self.num_levels = int(L.ofc_flow_plan_num_levels(self._ptr))
 
+    def keep_intermediates(self, keep: bool = True):
+        """Also store the full-resolution pre-filtered image (``buffer(level, 0)``); fused away by default."""
+        _lib.check(_lib.lib().ofc_flow_plan_keep_intermediates(self._ptr, int(bool(keep))))
+        return self
+
     def level_size(self, level: int):
         w, h = C.c_int(), C.c_int()
         _lib.check(_lib.lib().ofc_flow_plan_level_size(self._ptr, level, C.byref(w), C.byref(h)))

@@ -67,6 +67,7 @@ class Plan:
         off = (-raw.ctypes.data) % 256
         self.ws = raw[off:off + self.ws_bytes]
         self.n_levels = L.ofc_flow_plan_num_levels(self.ptr)
+        _check(L.ofc_flow_plan_keep_intermediates(self.ptr, 1))
 
     def level_size(self, l):
         w, h = C.c_int(), C.c_int()

@@ -57,7 +57,7 @@ def test_flow_intermediates_vs_oracle(ofc):
     from opticalflowclustering_b200.flow import FarnebackPlan
     z = np.load(os.path.join(GOLDEN, "flow_135x240.npz"))
     gray = torch.from_numpy(z["gray"]).cuda()
-    plan = FarnebackPlan(240, 135, max_frames=3)
+    plan = FarnebackPlan(240, 135, max_frames=3).keep_intermediates()
     plan.sequence(gray)
     torch.cuda.synchronize()
     _, inter = FB.calc_optical_flow_farneback(z["gray"][0], z["gray"][1], return_intermediates=True)
