@@ -1461,7 +1461,11 @@ static int launch_polyexp_strip(const PolyParams& p, const unsigned char* gray, 
     }
     const int cols = cdiv(p.w, TW);
     const int64_t total_rows = (int64_t)n_frames * cols * p.h;
-    int64_t ctas = (int64_t)num_sms() * resident;
+    // leave part of every SM to the coarse-level iterations that run beside this kernel on the caller's
+    // stream (ofc_api.cu forks the per-frame work onto a side stream)
+    static const int cap = env_int("OFC_POLY_RESIDENT", 0);
+    const int use = (cap > 0 && cap < resident) ? cap : resident;
+    int64_t ctas = (int64_t)num_sms() * use;
     const int64_t max_ctas = (total_rows + 23) / 24;     // keep ranges >= 24 rows (vertical halo 2N per segment)
     if (ctas > max_ctas) ctas = max_ctas;
     ProfScope prof(PK_POLYEXP, stream);

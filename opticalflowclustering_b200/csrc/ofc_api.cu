@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -72,6 +73,11 @@ struct ofc_flow_plan {
     int levels, winsize, iterations, poly_n;
     double poly_sigma;
     int keep_level0_I;               // also materialise I of the full-resolution level (fused away by default)
+    // Side stream for the per-frame work (pre-filter + polynomial expansion), so that the large
+    // full-resolution expansion overlaps the small, latency-bound iterations of the coarse levels.
+    cudaStream_t side;
+    cudaEvent_t ev_fork;
+    std::vector<cudaEvent_t> ev_level;
     std::vector<ofc::Level> lv;      // coarsest first
     size_t workspace_bytes;
     float* d_taps;
@@ -154,7 +160,16 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
     const int F = pl->max_frames;
     const int nl = (int)pl->lv.size();
 
-    // stage 1: pre-filter + polynomial expansion of every frame at every level
+    // stage 1: pre-filter + polynomial expansion of every frame at every level, coarsest first, on the
+    // plan's side stream when it has one: level l's iterations (stage 2, caller's stream) wait only for
+    // level l's event, so the big fine-level expansions run under the small coarse-level iterations.
+    // (ofc_profile_begin turns the fork off: per-kernel event timing wants one stream.)
+    const bool fork = pl->side != nullptr && !g_prof_on;
+    void* const stream1 = fork ? (void*)pl->side : stream;
+    if (fork) {
+        OFC_CUDA(cudaEventRecord(pl->ev_fork, (cudaStream_t)stream));
+        OFC_CUDA(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
+    }
     for (int l = 0; l < nl; ++l) {
         const Level& L = pl->lv[l];
         PrefilterParams pf;
@@ -167,7 +182,7 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         pf.tx = L.tx; pf.ty = L.ty; pf.in_rows = L.in_rows; pf.in_pitch = L.in_pitch; pf.taps_pad = L.taps_pad;
         int rc = OFC_OK;
         if (!pf.identity3) {
-            rc = launch_prefilter(pf, n_frames, L.prefilter_smem, stream);
+            rc = launch_prefilter(pf, n_frames, L.prefilter_smem, stream1);
             if (rc != OFC_OK) return rc;
         }
         PolyParams pp = pl->poly;
@@ -175,8 +190,9 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         pp.RA = (float4*)(ws + L.off_RA); pp.RB = (float*)(ws + L.off_RB);
         pp.out_stride = (int64_t)L.w * L.h; pp.w = L.w; pp.h = L.h;
         rc = launch_polyexp(pp, pl->poly_n, n_frames, pf.identity3 ? gray : nullptr, gray_stride,
-                            (pl->keep_level0_I || pl->poly_n != 5) ? pf.out : nullptr, stream);
+                            (pl->keep_level0_I || pl->poly_n != 5) ? pf.out : nullptr, stream1);
         if (rc != OFC_OK) return rc;
+        if (fork) OFC_CUDA(cudaEventRecord(pl->ev_level[l], pl->side));
     }
     if (minmax) {
         int rc = launch_minmax_init(minmax, n_pairs, stream);
@@ -189,6 +205,7 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
     for (int l = 0; l < nl; ++l) {
         const Level& L = pl->lv[l];
         const int64_t npx = (int64_t)L.w * L.h;
+        if (fork) OFC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, pl->ev_level[l], 0));
         for (int it = 0; it < pl->iterations; ++it) {
             IterParams ip;
             ip.RA = (const float4*)(ws + L.off_RA); ip.RB = (const float*)(ws + L.off_RB);
@@ -278,6 +295,8 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
     pl->iterations = iterations; pl->poly_n = poly_n; pl->poly_sigma = poly_sigma;
     pl->d_taps = nullptr;
     pl->keep_level0_I = 0;
+    pl->side = nullptr;
+    pl->ev_fork = cudaEvent_t();
     memset(&pl->poly, 0, sizeof(pl->poly));
     int rc = prepare_poly(poly_n, poly_sigma, pl->poly);
     if (rc != OFC_OK) { delete pl; return rc; }
@@ -349,6 +368,19 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
     pl->d_taps = (float*)d;
     rc = check_cuda(cudaMemcpy(pl->d_taps, all_taps.data(), all_taps.size() * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy(taps)");
     if (rc != OFC_OK) { cudaFree(d); delete pl; return rc; }
+    {
+        const char* e = getenv("OFC_OVERLAP");
+        if (!(e && atoi(e) == 0)) {
+            if (cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess) pl->side = nullptr;
+            if (pl->side) {
+                bool ok = cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+                pl->ev_level.resize(pl->lv.size());
+                for (size_t i = 0; ok && i < pl->lv.size(); ++i)
+                    ok = cudaEventCreateWithFlags(&pl->ev_level[i], cudaEventDisableTiming) == cudaSuccess;
+                if (!ok) { cudaStreamDestroy(pl->side); pl->side = nullptr; }
+            }
+        }
+    }
     *out = pl;
     return OFC_OK;
 }
@@ -356,6 +388,12 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
 void ofc_flow_plan_destroy(ofc_flow_plan* pl) {
     if (!pl) return;
     if (pl->d_taps) cudaFree(pl->d_taps);
+    if (pl->side) {
+        cudaStreamSynchronize(pl->side);
+        cudaEventDestroy(pl->ev_fork);
+        for (auto& e : pl->ev_level) cudaEventDestroy(e);
+        cudaStreamDestroy(pl->side);
+    }
     delete pl;
 }
 
