@@ -169,6 +169,17 @@ def kmeans_cosine_extras(dev, peak):
         nbytes = 2 * (N * D * X.element_size()) + 2 * 4 * N          # both kernels read X once and touch the labels
         out["kmeans_iter_" + name] = {"ms": ms, "rows_per_s": N / (ms / 1e3), "gb_s": nbytes / (ms / 1e3) / 1e9,
                                       "frac_of_hbm_peak": nbytes / (ms / 1e3) / 1e9 / peak}
+    # host link: what a pinned 50 MB upload (one step's frames) achieves on this box
+    hbuf = torch.empty(50 * 1024 * 1024, dtype=torch.uint8).pin_memory()
+    dbuf = torch.empty_like(hbuf, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dbuf.copy_(hbuf, non_blocking=True)
+    e0.record()
+    for _ in range(4):
+        dbuf.copy_(hbuf, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    out["h2d_pinned_gb_s"] = 4 * hbuf.numel() / (e0.elapsed_time(e1) / 1e3) / 1e9
     X = torch.randint(0, 180, (1_000_000, 16), generator=g).to(torch.uint8).to(dev)
     q = torch.randint(0, 180, (16,), generator=g).double()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -283,19 +294,20 @@ def main():
     res_avg = torch.empty((P, ROWS * COLS), dtype=torch.uint8).pin_memory()
     res_km = torch.empty((P, ROWS * COLS), dtype=torch.uint8).pin_memory()
     res_mag = torch.empty(P, dtype=torch.float64).pin_memory()
-    stage = [torch.empty((P, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+    NBUF = 3        # the upload of step i+1 must not wait for step i-1's kernels to drain: three staging buffers
+    stage = [torch.empty((P, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(NBUF)]
     copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(NBUF)]
+    freed = [torch.cuda.Event() for _ in range(NBUF)]
     n_chunks = host.shape[0] // P               # consecutive P-frame chunks of the there-and-back walk
 
     def e2e_loop(lo, hi):
         main = torch.cuda.current_stream()
-        for b in range(2):
+        for b in range(NBUF):
             freed[b].record(main)
 
         def upload(i):
-            b = i & 1
+            b = i % NBUF
             c = i % n_chunks
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[b])
@@ -305,7 +317,7 @@ def main():
         pipe.run_chunk(clip[0:2])
         upload(lo)
         for i in range(lo, hi):
-            b = i & 1
+            b = i % NBUF
             if i + 1 < hi:
                 upload(i + 1)
             main.wait_event(ready[b])
@@ -330,7 +342,7 @@ def main():
     e2e_value = world * args.steps * P / (float(t.item()) / 1e3)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": P * H * W * 3,
            "d2h_bytes_per_step": P * (2 * ROWS * COLS + 8),
-           "api": "ClipPipeline.run_chunk(new frames, carry=True) on pinned host frames, double-buffered upload"}
+           "api": "ClipPipeline.run_chunk(new frames, carry=True) on pinned host frames, triple-buffered upload"}
 
     extras = kmeans_cosine_extras(dev, peak) if rank == 0 else None
 
