@@ -29,6 +29,10 @@ sys.path.insert(0, ROOT)
 METRIC = "1080p frame-pairs/sec (flow+grid+k-means)"
 UNIT = "frame-pairs/s"
 H, W = 1080, 1920
+LEVELS = 3
+SIZE_NAME = "1080p"
+# other BASELINE.json configs (parity-test / documentation runs, not the headline): --size 720p | 4k
+SIZES = {"720p": (720, 1280, 3, 422.8e6), "1080p": (1080, 1920, 3, 951.4e6), "4k": (2160, 3840, 5, 3836.6e6)}
 ROWS, COLS = 14, 25
 # algorithmic bytes per 1080p pair (levels=3) for flow+viz+grid, and
 # per flow_iter launch per pixel (update-matrices 68 B + blur/solve 28 B)
@@ -45,7 +49,16 @@ def parse():
     ap.add_argument("--chunk", type=int, default=9, help="frames per step (pairs = chunk-1)")
     ap.add_argument("--clip-frames", type=int, default=65)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--size", default="1080p", choices=sorted(SIZES), help="frame size (the metric is quoted on 1080p)")
+    args = ap.parse_args()
+    global H, W, LEVELS, ALGO_BYTES_PER_PAIR, SIZE_NAME, METRIC
+    H, W, LEVELS, ALGO_BYTES_PER_PAIR = SIZES[args.size]
+    SIZE_NAME = args.size
+    if args.size != "1080p":
+        METRIC = f"{args.size} frame-pairs/sec (flow+grid+k-means)"
+        if args.size == "4k" and args.clip_frames == 65:
+            args.clip_frames = 33
+    return args
 
 
 def measured_peak():
@@ -134,7 +147,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic 1080p clip, Farneback levels=3 winsize=15 iters=3, 14x25 grid, k=1",
+        "config": {"workload": f"synthetic {SIZE_NAME} clip, Farneback levels={LEVELS} winsize=15 iters=3, 14x25 grid, k=1",
                    "impl": "oracle/reference_chain.py: cv2 4.13 calcOpticalFlowFarneback + sklearn KMeans, as the reference calls them"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -223,7 +236,7 @@ def main():
     P = F - 1
     T = max(args.clip_frames, F)
     clip = synthetic_clip(T, H, W, seed=rank, device=dev)              # resident in HBM, > L2
-    pipe = ClipPipeline(W, H, chunk_frames=F, rows=ROWS, cols=COLS, device=dev)
+    pipe = ClipPipeline(W, H, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=LEVELS)
     starts = [(i * P) % (T - F + 1) for i in range(args.warmup + args.steps)]
 
     # ---- value: inputs resident in HBM --------------------------------------
@@ -270,13 +283,15 @@ def main():
         achieved = algo / (per_launch_ms / 1e3) / 1e9
         traffic = None
         try:
+            if SIZE_NAME != "1080p":
+                raise KeyError("the ncu capture is of the 1080p launch")
             with open(os.path.join(ROOT, "profiles", "flow_iter_traffic.json")) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
         total_ms = sum(v["ms_per_step"] for v in kernels.values())
-        roofline = {"bound": "hbm", "kernel": "flow_iter_strip_kernel<R=7,TW=128> @1920x1080 (update-matrices + 15x15 box + 2x2 solve fused, "
-                              "persistent strip walk; 3 launches per step)",
+        roofline = {"bound": "hbm", "kernel": f"flow_iter_tmem_kernel<R=7,TW=240> @{W}x{H} (update-matrices + 15x15 box + 2x2 solve fused, "
+                              "persistent strip walk, ring in TMEM, cp.async tap landing; 3 launches per step)",
                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "algorithmic_bytes_per_launch": algo, "ms_per_launch": per_launch_ms,
                     "share_of_step": it0["ms_per_step"] / total_ms,
@@ -347,7 +362,7 @@ def main():
     extras = kmeans_cosine_extras(dev, peak) if rank == 0 else None
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and LEVELS == 3:
         cores = os.cpu_count() or 1
         workers = max(1, min(cores, 64))
         frames_np = host_clip[:min(T, 33)].numpy()
@@ -361,7 +376,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic 1080p clip, Farneback levels=3 winsize=15 iters=3, 14x25 grid, k=1",
+            "config": {"workload": f"synthetic {SIZE_NAME} clip, Farneback levels={LEVELS} winsize=15 iters=3, 14x25 grid, k=1",
                        "frames_per_step": F, "pairs_per_step": P, "clip_frames": T,
                        "l2": f"steps walk a {T}-frame clip ({T * H * W * 3 / 1e6:.0f} MB > L2); intermediates "
                              f"({pipe.plan.workspace_bytes / 1e6:.0f} MB workspace) are rewritten every step"},

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) polyexp_kernel(PolyParams p) {
 // ---------------------------------------------------------------------------
 template <int KSZ>
 __global__ void __launch_bounds__(256) prefilter_direct_kernel(PrefilterParams p) {
-    __shared__ float s_taps[64];
+    __shared__ float s_taps[128];
     for (int i = threadIdx.x; i < p.ksz; i += blockDim.x) s_taps[i] = p.taps[i];
     __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -307,15 +307,25 @@ __global__ void __launch_bounds__(256) prefilter_direct_kernel(PrefilterParams p
             if (q >= 1) { b10 = fmaf(tp[q - 1], ha, b10); b11 = fmaf(tp[q - 1], hb, b11); }
         }
     } else {
-        // ---- borders / generic tap count: reflected indices, run-time loops ----------------------
+        // ---- borders / generic tap count: run-time loops; reflected indices only where needed ------
         const int rows = rj - ri + ksz;                 // source rows ri-r .. rj+r
+        const bool cols_in = ci - r >= 0 && cj + r < p.W;
         for (int q = 0; q < rows; ++q) {
             const unsigned char* row = src + (int64_t)reflect101(ri - r + q, p.H) * p.W;
             float ha = 0.f, hb = 0.f;
-            for (int j = 0; j < ksz; ++j) {
-                const float t = s_taps[j];
-                ha = fmaf(t, (float)row[reflect101(ci - r + j, p.W)], ha);
-                hb = fmaf(t, (float)row[reflect101(cj - r + j, p.W)], hb);
+            if (cols_in) {
+                const unsigned char* pa = row + ci - r;
+                for (int j = 0; j < ksz; ++j) {
+                    const float t = s_taps[j];
+                    ha = fmaf(t, (float)pa[j], ha);
+                    hb = fmaf(t, (float)pa[j + d], hb);       // d = 0 only on the last column, where hb = ha
+                }
+            } else {
+                for (int j = 0; j < ksz; ++j) {
+                    const float t = s_taps[j];
+                    ha = fmaf(t, (float)row[reflect101(ci - r + j, p.W)], ha);
+                    hb = fmaf(t, (float)row[reflect101(cj - r + j, p.W)], hb);
+                }
             }
             // this source row is tap q of sample row ri and tap q-(rj-ri) of sample row rj
             if (q < ksz) { b00 = fmaf(s_taps[q], ha, b00); b01 = fmaf(s_taps[q], hb, b01); }
@@ -1414,7 +1424,7 @@ int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* 
         return OFC_OK;
     }
     // tap counts of the reference's pyramid (pyr_scale 0.5 -> 3, 9, 19 taps) have unrolled lean kernels
-    if (!legacy && (p.ksz == 3 || p.ksz == 9 || p.ksz == 19)) {
+    if (!legacy && (p.ksz == 3 || p.ksz == 9 || p.ksz == 19 || p.ksz == 39)) {
         // window of a 32x8 tile (+4 columns: word alignment and the one-byte over-read of the tap loop)
         const int in_rows = (int)ceil(7 * p.sy) + p.ksz + 3;
         const int in_pitch = (((int)ceil(31 * p.sx) + p.ksz + 3 + 8) + 3) / 4 * 4;
@@ -1433,11 +1443,21 @@ int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* 
     }
             if (p.ksz == 3) OFC_PF_TILE(3)
             else if (p.ksz == 9) OFC_PF_TILE(9)
-            else OFC_PF_TILE(19)
+            else if (p.ksz == 19) OFC_PF_TILE(19)
+            else OFC_PF_TILE(39)
 #undef OFC_PF_TILE
             OFC_CHECK_LAUNCH("prefilter_tile");
             return OFC_OK;
         }
+    }
+    if (!legacy && p.ksz > 39 && p.ksz <= 128) {
+        // very long kernels only occur on the tiny coarsest levels of deep pyramids (4K, levels = 5: 79 taps on
+        // 120x68): one thread per output, no staging
+        dim3 g(cdiv(p.w, 32), cdiv(p.h, 8), n_frames);
+        ProfScope prof(PK_PREFILTER, stream);
+        OFC_LAUNCH(prefilter_direct_kernel<0>, g, dim3(256), 0, stream, p);
+        OFC_CHECK_LAUNCH("prefilter_direct");
+        return OFC_OK;
     }
     dim3 grid(cdiv(p.w, p.tx), cdiv(p.h, p.ty), n_frames);
     static size_t configured = 0;
@@ -1599,7 +1619,9 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
         p.upsample = 0;
     }
     static const int use_tmem = env_int("OFC_ITER_TMEM", 513);      // minimum level width; 0 = off
-    if (use_tmem && p.w >= use_tmem) return p.minmax ? launch_tmem<true>(p, n_pairs, stream) : launch_tmem<false>(p, n_pairs, stream);
+    // (strips of 240 columns: on widths that are not a multiple of 240 -- 1280, 640 -- the measured time
+    // of this kernel doubles, cause not yet understood, so those widths take the 128-column strip kernel)
+    if (use_tmem && p.w >= use_tmem && p.w % 240 == 0) return p.minmax ? launch_tmem<true>(p, n_pairs, stream) : launch_tmem<false>(p, n_pairs, stream);
     static const int minb4 = env_int("OFC_STRIP_MINB4", 1);
     if (p.w > 512 && minb4) return launch_strip_r<7, 128, 160, 4, 4>(p, n_pairs, stream);
     if (p.w > 512) return launch_strip_r<7, 128, 160, 4, 3>(p, n_pairs, stream);
