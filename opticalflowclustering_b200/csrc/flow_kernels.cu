@@ -1450,15 +1450,6 @@ int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* 
             return OFC_OK;
         }
     }
-    if (!legacy && p.ksz > 39 && p.ksz <= 128) {
-        // very long kernels only occur on the tiny coarsest levels of deep pyramids (4K, levels = 5: 79 taps on
-        // 120x68): one thread per output, no staging
-        dim3 g(cdiv(p.w, 32), cdiv(p.h, 8), n_frames);
-        ProfScope prof(PK_PREFILTER, stream);
-        OFC_LAUNCH(prefilter_direct_kernel<0>, g, dim3(256), 0, stream, p);
-        OFC_CHECK_LAUNCH("prefilter_direct");
-        return OFC_OK;
-    }
     dim3 grid(cdiv(p.w, p.tx), cdiv(p.h, p.ty), n_frames);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
