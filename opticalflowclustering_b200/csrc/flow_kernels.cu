@@ -1243,6 +1243,9 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
     float2* __restrict__ fout = p.flow_out + (int64_t)pair * p.flow_out_stride;
 
     const int gx = clampi(x0 - R + t, 0, w - 1);
+    // columns past the frame's replicated border (only in a strip that sticks out of the frame) carry no
+    // data: they skip all loads -- hundreds of lanes copying one address serialise in the LDGSTS path
+    const bool live = x0 - R + t <= w - 1 + R;
     const float bxs = (gx < 5 ? p.border[gx] : 1.f) * (gx >= w - 5 ? p.border[w - gx - 1] : 1.f);
     const bool x_edge = (unsigned)(gx - 5) >= (unsigned)(w - 10);
     const float fgx = (float)gx;
@@ -1262,6 +1265,7 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
 
     // request the taps of R1 and R0 for `row` (already clamped) into landing slot `dst_slot`
     auto request_row = [&](int row, float dx, float dy, int dst_slot) {
+        if (!live) { cp_async_commit(); return; }
         int x1, y1;
         float fx, fy;
         bool inb;
@@ -1286,7 +1290,7 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int o = clampi(row0 + i, 0, h - 1) * w + gx;
-        fl[i] = fin ? fin[o] : make_float2(0.f, 0.f);
+        fl[i] = (fin && live) ? fin[o] : make_float2(0.f, 0.f);
     }
     request_row(clampi(row0, 0, h - 1), fl[0].x, fl[0].y, 0);
     request_row(clampi(row0 + 1, 0, h - 1), fl[1].x, fl[1].y, 1);
@@ -1302,7 +1306,7 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
                 request_row(clampi(row0 + ri + 2, 0, h - 1), fl[(i + 2) & 3].x, fl[(i + 2) & 3].y, l2);
             }
             const float dx = fl[i].x, dy = fl[i].y;
-            if (fin) fl[i] = fin[clampi(row0 + ri + 4, 0, h - 1) * w + gx];
+            if (fin && live) fl[i] = fin[clampi(row0 + ri + 4, 0, h - 1) * w + gx];
             // old ring row (leaves the window) -- TMEM read overlaps the wait for the landing zone
             float old[8];
             tmem_wait_st();                              // last row's ring store
@@ -1610,9 +1614,9 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
         p.upsample = 0;
     }
     static const int use_tmem = env_int("OFC_ITER_TMEM", 513);      // minimum level width; 0 = off
-    // (strips of 240 columns: on widths that are not a multiple of 240 -- 1280, 640 -- the measured time
-    // of this kernel doubles, cause not yet understood, so those widths take the 128-column strip kernel)
-    if (use_tmem && p.w >= use_tmem && p.w % 240 == 0) return p.minmax ? launch_tmem<true>(p, n_pairs, stream) : launch_tmem<false>(p, n_pairs, stream);
+    // (OFC_TMEM_ANYW=0 restricts it to widths that are a multiple of its 240-column strips)
+    static const int any_w = env_int("OFC_TMEM_ANYW", 1);
+    if (use_tmem && p.w >= use_tmem && (any_w || p.w % 240 == 0)) return p.minmax ? launch_tmem<true>(p, n_pairs, stream) : launch_tmem<false>(p, n_pairs, stream);
     static const int minb4 = env_int("OFC_STRIP_MINB4", 1);
     if (p.w > 512 && minb4) return launch_strip_r<7, 128, 160, 4, 4>(p, n_pairs, stream);
     if (p.w > 512) return launch_strip_r<7, 128, 160, 4, 3>(p, n_pairs, stream);

@@ -7,7 +7,8 @@ import torch
 from opticalflowclustering_b200.pipeline import ClipPipeline
 from opticalflowclustering_b200.synthetic import synthetic_clip
 
-H, W, F = 1080, 1920, int(os.environ.get("OFC_CHUNK", "9"))
+H, W = {"720p": (720, 1280), "1080p": (1080, 1920), "4k": (2160, 3840)}[os.environ.get("OFC_SIZE", "1080p")]
+F = int(os.environ.get("OFC_CHUNK", "9"))
 clip = synthetic_clip(F, H, W, seed=0, device="cuda")
 pipe = ClipPipeline(W, H, chunk_frames=F)
 for _ in range(3):
