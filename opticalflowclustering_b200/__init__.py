@@ -6,4 +6,4 @@ The operators need the in-tree CUDA library ``libofc.so`` (built by
 ``__graft_entry__.build()``); there is no CPU fallback.
 """
 __all__ = ["flow", "grid", "pipeline", "synthetic", "kmeans", "cosine", "computeOpticalFlowModule", "computeOpticalFlow",
-           "KmeanGrids", "drawGridsAndOutputCSV", "color_kmeans", "findCosineDifferentVectors", "computeVectorDistance"]
+           "KmeanGrids", "drawGridsAndOutputCSV", "drawGridsAndOutputCSVChange", "color_kmeans", "color_kmeansChange", "findCosineDifferentVectors", "computeVectorDistance"]

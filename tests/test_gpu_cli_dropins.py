@@ -78,3 +78,36 @@ def test_compute_optical_flow_cli(tmp_path, monkeypatch):
         assert abs(float(rows[1 + t][2]) - float(np.mean(mag))) <= 1e-4 * max(float(np.mean(mag)), 1e-3)
     cap = cv2.VideoCapture("clipB.mp4onlyOpticalflow.mp4")
     assert cap.isOpened() and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == len(frames) - 1
+
+
+def test_drawgrids_change_then_color_kmeans_change(tmp_path, monkeypatch):
+    """The two-step workflow that produced the reference's fixtures: drawGridsAndOutputCSVChange.py writes the
+    cell PNGs + <video>_rgb_values.csv, color_kmeansChange.py -d OutImgs/<video>/ -c 1 clusters them."""
+    from opticalflowclustering_b200 import color_kmeansChange as ckc
+    from opticalflowclustering_b200 import drawGridsAndOutputCSVChange as dgc
+    from oracle import grid_np as G
+    from oracle import reference_chain as RC
+    monkeypatch.chdir(tmp_path)
+    frames = _write_clip("clipC.mp4", n=3)
+    dgc.main(["--noyolo", "--nocontour", "--path", "clipC.mp4"])
+    assert sorted(os.listdir("OutImgs/clipC"), key=int) == ["2", "3"] and len(os.listdir("OutImgs/clipC/2")) == 350
+    rows = list(csv.reader(open("clipC.mp4_rgb_values.csv")))
+    assert len(rows) == 3 and rows[0][0] == "cell_0"
+    # reference chain on the same frames: grid hues of the flow visualisation
+    st = RC.FlowState(frames[0])
+    viz = st.compute(frames[1])
+    hues, rois = RC.grid_pass(viz.copy())
+    got = np.array([float(v) for v in rows[1]])
+    assert (got != hues).mean() <= 0.01
+    # a saved cell = ROI of the lined frame: white first row / column
+    cell = cv2.imread("OutImgs/clipC/2/27.png")
+    assert (cell[0] == 255).all() and (cell[:, 0] == 255).all()
+    open("cluster_centers.csv", "w").close()
+    ckc.main(["-d", "OutImgs/clipC/", "-c", "1", "-f", "cluster_centers.csv"])
+    out = list(csv.reader(open("cluster_centers.csv", newline="")))
+    assert out[0] == ["File name", "Cluster 1", "HSV Cluster 1", "Hue 0"] and len(out) == 1 + 700
+    assert out[1][0] == "2/1.png" and out[350][0] == "2/350.png" and out[351][0] == "3/1.png"
+    for k in (1, 27, 350):
+        im = cv2.cvtColor(cv2.imread(f"OutImgs/clipC/2/{k}.png"), cv2.COLOR_BGR2RGB)
+        c, h = G.cluster_colors_k1(G.preprocess_image(im))
+        assert out[k][1] == str(c) and out[k][3] == str(h)
