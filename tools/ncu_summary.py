@@ -113,6 +113,7 @@ def main():
             d = max(rows, key=lambda r: r.get("gpu__time_duration.sum", 0.0))     # the full-resolution launch
             with open(os.path.join(PROF, "flow_iter_traffic.json"), "w") as f:
                 json.dump({"source": f"profiles/{tag}_{name}.json", "kernel": d["kernel"], "grid": d["grid"],
+                           "pairs_per_launch": int(os.environ.get("OFC_CHUNK", "9")) - 1,
                            "dram_bytes_per_launch": d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0),
                            "duration_us_under_ncu": d.get("gpu__time_duration.sum", 0.0) * 1e6}, f, indent=1)
     with open(os.path.join(PROF, f"{tag}_summary.md"), "w") as f:
