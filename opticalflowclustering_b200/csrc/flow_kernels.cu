@@ -1616,7 +1616,7 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
     static const int use_tmem = env_int("OFC_ITER_TMEM", 513);      // minimum level width; 0 = off
     // (OFC_TMEM_ANYW=0 restricts it to widths that are a multiple of its 240-column strips)
     static const int any_w = env_int("OFC_TMEM_ANYW", 1);
-    if (use_tmem && p.w >= use_tmem && (any_w || p.w % 240 == 0)) return p.minmax ? launch_tmem<true>(p, n_pairs, stream) : launch_tmem<false>(p, n_pairs, stream);
+    if (use_tmem && (p.w >= use_tmem || p.w % 240 == 0) && (any_w || p.w % 240 == 0)) return p.minmax ? launch_tmem<true>(p, n_pairs, stream) : launch_tmem<false>(p, n_pairs, stream);
     static const int minb4 = env_int("OFC_STRIP_MINB4", 1);
     if (p.w > 512 && minb4) return launch_strip_r<7, 128, 160, 4, 4>(p, n_pairs, stream);
     if (p.w > 512) return launch_strip_r<7, 128, 160, 4, 3>(p, n_pairs, stream);
@@ -1630,7 +1630,14 @@ int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scra
     // pyramid levels (too few rows per SM for a column walk to hide latency) and other window sizes
     // run the square-tile kernel
     static const int strip_min_w = env_int("OFC_STRIP_MIN_W", 513);
-    if (variant == 0 && winsize == 15 && scratch != nullptr && p.w >= strip_min_w)
+    // (opt-in, OFC_STRIP_SMALL_ROWS=48: measured neutral) a narrower level also walks strips when the batch
+    // gives every persistent CTA a long enough range
+    // (>= 48 rows per CTA of 2 x 148) and its width is a whole number of 240-column strips
+    static const int small_rows = env_int("OFC_STRIP_SMALL_ROWS", 0);
+    const bool wide = p.w >= strip_min_w;
+    const bool batched = small_rows > 0 && p.w % 240 == 0 &&
+                         (int64_t)n_pairs * (p.w / 240) * p.h >= (int64_t)2 * num_sms() * small_rows;
+    if (variant == 0 && winsize == 15 && scratch != nullptr && (wide || batched))
         return launch_strip(p, n_pairs, scratch, stream);
     switch (winsize / 2) {
         case 2: return launch_iter_r<2, 32, 256, 3>(p, n_pairs, stream);
