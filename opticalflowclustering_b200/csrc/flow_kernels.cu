@@ -250,96 +250,6 @@ __global__ void __launch_bounds__(256) polyexp_kernel(PolyParams p) {
 }
 
 // ---------------------------------------------------------------------------
-// K2, direct form: one thread per output pixel of a down-sampled level.  The 8-bit
-// source frame is 2 MB at 1080p and lives in L1/L2, so nothing is staged: a thread
-// walks the ksz+1 source rows its two sample rows need, takes the horizontal taps
-// at its two sample columns (float32, tap order 0..ksz-1 like cv::sepFilter2D),
-// then the vertical taps and the bilinear lerp.  Replaces the tiled kernel above on
-// the hot path (it stays as the reference form for odd geometries).
-// ---------------------------------------------------------------------------
-template <int KSZ>
-__global__ void __launch_bounds__(256) prefilter_direct_kernel(PrefilterParams p) {
-    __shared__ float s_taps[128];
-    for (int i = threadIdx.x; i < p.ksz; i += blockDim.x) s_taps[i] = p.taps[i];
-    __syncthreads();
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= p.w || y >= p.h) return;
-    const int r = p.ksz >> 1, ksz = p.ksz;
-    int ci, ri;
-    float fx, fy;
-    src_coord(x, p.sx, p.W, ci, fx);
-    src_coord(y, p.sy, p.H, ri, fy);
-    const int cj = min(ci + 1, p.W - 1), rj = min(ri + 1, p.H - 1);
-    const unsigned char* src = p.gray + (int64_t)blockIdx.z * p.gray_stride;
-    const int d = cj - ci;                              // 1, or 0 at the right border
-    const bool words_ok = (p.W & 3) == 0 && (p.gray_stride & 3) == 0 && ((uintptr_t)p.gray & 3) == 0;
-    float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;  // vertical accumulators of the four sample points
-
-    if (KSZ > 0 && words_ok && ci - r >= 0 && ci + 1 + r < p.W && ri - r >= 0 && ri + 1 + r < p.H) {
-        // ---- interior, tap count known at compile time: everything unrolled ----------------------
-        constexpr int KS = KSZ > 0 ? KSZ : 1;
-        constexpr int RR = KS / 2;
-        constexpr int NW = (KS + 1 + 3) / 4;            // aligned words that hold the KS+1 window bytes
-        float tp[KS];
-#pragma unroll
-        for (int j = 0; j < KS; ++j) tp[j] = s_taps[j];
-        const int off = (ci - RR) & 3;
-        const unsigned sh = (unsigned)off * 8u;
-        const unsigned char* base = src + (int64_t)(ri - RR) * p.W + (ci - RR - off);
-#pragma unroll
-        for (int q = 0; q <= KS; ++q) {                 // source rows ri-RR .. ri+1+RR
-            const unsigned* wp = reinterpret_cast<const unsigned*>(base + (int64_t)q * p.W);
-            unsigned wv[NW + 1];
-#pragma unroll
-            for (int i = 0; i <= NW; ++i) wv[i] = wp[i];
-            float ha = 0.f, hb = 0.f;
-#pragma unroll
-            for (int j = 0; j <= KS; ++j) {
-                // byte j of the window = byte (off + j) of the word sequence
-                const unsigned lo = wv[j >> 2], hi = wv[(j >> 2) + 1];
-                const unsigned al = __funnelshift_r(lo, hi, sh);         // word whose byte 0 is window byte 4*(j>>2)
-                const float b = (float)((al >> ((j & 3) * 8)) & 255u);
-                if (j < KS) ha = fmaf(tp[j], b, ha);
-                if (j >= 1) hb = fmaf(tp[j - 1], b, hb);
-            }
-            if (q < KS) { b00 = fmaf(tp[q < KS ? q : 0], ha, b00); b01 = fmaf(tp[q < KS ? q : 0], hb, b01); }
-            if (q >= 1) { b10 = fmaf(tp[q - 1], ha, b10); b11 = fmaf(tp[q - 1], hb, b11); }
-        }
-    } else {
-        // ---- borders / generic tap count: run-time loops; reflected indices only where needed ------
-        const int rows = rj - ri + ksz;                 // source rows ri-r .. rj+r
-        const bool cols_in = ci - r >= 0 && cj + r < p.W;
-        for (int q = 0; q < rows; ++q) {
-            const unsigned char* row = src + (int64_t)reflect101(ri - r + q, p.H) * p.W;
-            float ha = 0.f, hb = 0.f;
-            if (cols_in) {
-                const unsigned char* pa = row + ci - r;
-                for (int j = 0; j < ksz; ++j) {
-                    const float t = s_taps[j];
-                    ha = fmaf(t, (float)pa[j], ha);
-                    hb = fmaf(t, (float)pa[j + d], hb);       // d = 0 only on the last column, where hb = ha
-                }
-            } else {
-                for (int j = 0; j < ksz; ++j) {
-                    const float t = s_taps[j];
-                    ha = fmaf(t, (float)row[reflect101(ci - r + j, p.W)], ha);
-                    hb = fmaf(t, (float)row[reflect101(cj - r + j, p.W)], hb);
-                }
-            }
-            // this source row is tap q of sample row ri and tap q-(rj-ri) of sample row rj
-            if (q < ksz) { b00 = fmaf(s_taps[q], ha, b00); b01 = fmaf(s_taps[q], hb, b01); }
-            const int q2 = q - (rj - ri);
-            if (q2 >= 0) { b10 = fmaf(s_taps[q2], ha, b10); b11 = fmaf(s_taps[q2], hb, b11); }
-        }
-    }
-    (void)d;
-    const float top = b00 * (1.f - fx) + b01 * fx;
-    const float bot = b10 * (1.f - fx) + b11 * fx;
-    p.out[(int64_t)blockIdx.z * p.out_stride + (int64_t)y * p.w + x] = top * (1.f - fy) + bot * fy;
-}
-
-// ---------------------------------------------------------------------------
 // K2, lean tiled form for the down-sampled levels (tap count known at compile time).
 // A 256-thread CTA produces a 32x8 output tile:
 //   1  source window (8-bit) of the tile -> shared memory, aligned 32-bit loads in the
@@ -488,16 +398,18 @@ __global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const u
     };
     // G consecutive un-clamped rows starting at `first`: each row needs only one new horizontal sum
     auto load_I_run = [&](int first, float* dst) {
-        if (!FUSE3 || first < 0 || first + G > h) {
+        if constexpr (FUSE3) {
+            if (first >= 0 && first + G <= h) {
+                int hs[G + 2];
 #pragma unroll
-            for (int i = 0; i < G; ++i) dst[i] = load_I(first + i);
-            return;
+                for (int i = 0; i < G + 2; ++i) hs[i] = hsum(first - 1 + i);
+#pragma unroll
+                for (int i = 0; i < G; ++i) dst[i] = (float)(hs[i] + 2 * hs[i + 1] + hs[i + 2]) * 0.0625f;
+                return;
+            }
         }
-        int hs[G + 2];
 #pragma unroll
-        for (int i = 0; i < G + 2; ++i) hs[i] = hsum(first - 1 + i);
-#pragma unroll
-        for (int i = 0; i < G; ++i) dst[i] = (float)(hs[i] + 2 * hs[i + 1] + hs[i + 2]) * 0.0625f;
+        for (int i = 0; i < G; ++i) dst[i] = load_I(first + i);
     };
 
     float v[2 * N + G];                                // I(rows r-N .. r+G-1+N) of the current group
