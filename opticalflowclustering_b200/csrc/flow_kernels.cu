@@ -883,7 +883,6 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
     constexpr int K = 2 * R + 1;
     constexpr int CW = TW + 2 * R;                       // halo'd columns
     constexpr int CP = (CW + 3) / 4 * 4 + 4;             // hand-over pitch (room for the 128-bit over-read)
-    constexpr int SEG = TW / 4;                          // 4-pixel solver tasks per row
     constexpr int RING = (K * 5 * CW + 3) / 4 * 4;       // keeps the hand-over buffer 16-byte aligned
     static_assert(NT >= CW, "one thread per halo column");
     static_assert(G % 2 == 0, "the tap double buffer alternates by row parity");
