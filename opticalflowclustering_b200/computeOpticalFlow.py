@@ -27,7 +27,7 @@ def magnitude_csv_text(means) -> str:
     return "\n".join(lines) + "\n"
 
 
-def run(input_path, chunk_frames: int = 9):
+def run(input_path, chunk_frames: int = 17):
     import cv2 as cv
     cap = cv.VideoCapture(input_path)
     if not cap.isOpened():
@@ -42,29 +42,28 @@ def run(input_path, chunk_frames: int = 9):
     print("Type1:", first_frame.dtype)
     pipe = ClipPipeline(w, h, chunk_frames=chunk_frames, draw_lines=False)
     means = []
-    buf = [first_frame]
-    frameNum = 0
-    done = False
-    while not done:
-        while len(buf) < chunk_frames:
-            ret, frame = cap.read()
-            if not ret:
-                done = True
-                break
-            buf.append(frame)
-        if len(buf) < 2:
-            break
-        frames = torch.from_numpy(np.stack(buf)).cuda(non_blocking=True)
-        P = pipe.run_chunk(frames)
-        viz = pipe.viz[:P].cpu().numpy()
-        mag = (pipe.mag_sum[:P] / float(w * h)).cpu().numpy()
-        for p in range(P):
+    state = {"n": 0}
+
+    def frames():
+        yield first_frame
+        while True:
+            ok, frame = cap.read()
+            if not ok:
+                return
+            yield frame
+
+    def on_pairs(first_pair, res):
+        viz = res["viz"].numpy()
+        mag = res["mean_magnitude"].numpy()
+        for p in range(len(mag)):
             print("Average Magnitude of optical flow ", np.float32(mag[p]))
             means.append(mag[p])
             writer.write(viz[p])
-            frameNum += 1
-            print("Number of VideoFrames processed", frameNum, "/", number_of_videoFrames)
-        buf = [buf[-1]]                                  # one-frame halo: prev_gray of the next chunk
+            state["n"] += 1
+            print("Number of VideoFrames processed", state["n"], "/", number_of_videoFrames)
+
+    # decode -> pinned staging -> upload on a copy stream while the previous chunk computes
+    pipe.process_stream(frames(), on_pairs=on_pairs, want_viz=True)
     with open(input_path + '_opticalFlow.csv', 'w', newline='') as f:
         f.write(magnitude_csv_text(means))
     try:

@@ -159,8 +159,20 @@ __global__ void __launch_bounds__(256) flow_encode_kernel(VizParams p) {
         if (threadIdx.x == 0) {
             double t = 0.0;
             for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_part[i];
-            atomicAdd(p.mag_sum + frame, t);
+            // order-independent accumulation: the CTA's (deterministic) partial is added as 36.28 fixed
+            // point, so the frame sum does not depend on which CTA gets there first; the word is turned
+            // into a double by mag_sum_finalize_kernel.  A frame's sum of |flow| stays far below 2^35.
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.mag_sum) + frame,
+                      (unsigned long long)(t * 268435456.0 + 0.5));
         }
+    }
+}
+
+__global__ void mag_sum_finalize_kernel(double* mag_sum, int n_frames) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_frames) {
+        const unsigned long long fx = reinterpret_cast<unsigned long long*>(mag_sum)[i];
+        mag_sum[i] = (double)fx * (1.0 / 268435456.0);
     }
 }
 
@@ -205,6 +217,10 @@ int launch_flow_encode(const VizParams& p, int n_frames, void* stream) {
     ProfScope prof(PK_ENCODE, stream);
     OFC_LAUNCH(flow_encode_kernel, dim3(bx, n_frames), dim3(256), 0, stream, p);
     OFC_CHECK_LAUNCH("flow_encode");
+    if (p.mag_sum) {
+        OFC_LAUNCH(mag_sum_finalize_kernel, dim3(cdiv(n_frames, 128)), dim3(128), 0, stream, p.mag_sum, n_frames);
+        OFC_CHECK_LAUNCH("mag_sum_finalize");
+    }
     return OFC_OK;
 }
 

@@ -110,6 +110,98 @@ class ClipPipeline:
             P = self.run_chunk(chunk, carry=not first)
             avg[t:t + P] = self.avg_hue[:P].cpu()
             km[t:t + P] = self.km_hue[:P].cpu()
-            mag[t:t + P] = (self.mag_sum[:P] / float(self.H * self.W)).cpu()
+            mag[t:t + P] = self.mag_sum[:P].cpu() / float(self.H * self.W)     # IEEE division on the host
             t += P
         return {"avg_hue": avg, "km_hue": km, "mean_magnitude": mag}
+
+    def seed(self, first_frame):
+        """Start a stream: ``first_frame`` (BGR uint8 [H,W,3], host or device) becomes ``prev_gray``
+        (the reference's ``ComputeOpticalFLow.__init__``, computeOpticalFlowModule.py:7-16)."""
+        import numpy as np
+        f = torch.from_numpy(np.ascontiguousarray(first_frame)) if isinstance(first_frame, np.ndarray) else first_frame
+        f = f.to(self.device).contiguous()
+        if tuple(f.shape) != (self.H, self.W, 3) or f.dtype != torch.uint8:
+            raise ValueError("first_frame must be uint8 [H,W,3] of the pipeline's size")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ofc_bgr2gray(_ptr(f), _ptr(self.gray), self.H * self.W, _stream_ptr()))
+        self._last_gray_index = 0
+
+    def process_stream(self, frames, on_pairs=None, want_viz: bool = False, nbuf: int = 3):
+        """Streaming ingest: ``frames`` is any iterable of host BGR uint8 frames
+        ``[H,W,3]`` (e.g. a ``cv2.VideoCapture`` read loop).  Frames are packed into pinned staging
+        chunks and uploaded on a copy stream while the previous chunk computes; results come back
+        through pinned buffers.  ``on_pairs(first_pair_index, result_dict)`` is called per chunk with
+        host tensors ``avg_hue [p,cells]``, ``km_hue [p,cells]``, ``mean_magnitude [p]`` (and ``viz
+        [p,H,W,3]`` when ``want_viz``); without a callback the chunks are concatenated and returned."""
+        import numpy as np
+        P = self.F - 1
+        dev = self.device
+        pin = [torch.empty((P, self.H, self.W, 3), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+        stage = [torch.empty((P, self.H, self.W, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+        out_avg = [torch.empty((P, self.cells), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+        out_km = [torch.empty((P, self.cells), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+        out_mag = [torch.empty(P, dtype=torch.float64).pin_memory() for _ in range(nbuf)]
+        out_viz = [torch.empty((P, self.H, self.W, 3), dtype=torch.uint8).pin_memory() for _ in range(nbuf)] if want_viz else None
+        done = [None] * nbuf                      # event after which slot b's results are on the host / its buffers free
+        pending = []                              # (slot, first_pair, n_pairs) in flight
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        collected = []
+
+        def deliver(upto_all=False):
+            while pending and (upto_all or len(pending) >= nbuf - 1):
+                b, first, n = pending.pop(0)
+                done[b].synchronize()
+                res = {"avg_hue": out_avg[b][:n].clone(), "km_hue": out_km[b][:n].clone(),
+                       "mean_magnitude": out_mag[b][:n].clone() / float(self.H * self.W)}
+                if want_viz:
+                    res["viz"] = out_viz[b][:n].clone()
+                if on_pairs is not None:
+                    on_pairs(first, res)
+                else:
+                    collected.append(res)
+
+        def submit(b, n, first_pair):
+            up = torch.cuda.Event()
+            with torch.cuda.stream(copy_stream):
+                stage[b][:n].copy_(pin[b][:n], non_blocking=True)
+                up.record(copy_stream)
+            main.wait_event(up)
+            self.run_chunk(stage[b][:n], carry=True)
+            out_avg[b][:n].copy_(self.avg_hue[:n], non_blocking=True)
+            out_km[b][:n].copy_(self.km_hue[:n], non_blocking=True)
+            out_mag[b][:n].copy_(self.mag_sum[:n], non_blocking=True)
+            if want_viz:
+                out_viz[b][:n].copy_(self.viz[:n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            done[b] = ev
+            pending.append((b, first_pair, n))
+
+        it = iter(frames)
+        try:
+            self.seed(next(it))
+        except StopIteration:
+            raise ValueError("empty frame stream")
+        b, fill, n_pairs = 0, 0, 0
+        for fr in it:
+            if fill == 0 and done[b] is not None:
+                deliver()                          # make sure slot b's previous use has been handed over
+                done[b].synchronize()
+            pin[b][fill].copy_(torch.from_numpy(np.ascontiguousarray(fr)))
+            fill += 1
+            if fill == P:
+                submit(b, P, n_pairs)
+                n_pairs += P
+                b, fill = (b + 1) % nbuf, 0
+        if fill:
+            submit(b, fill, n_pairs)
+            n_pairs += fill
+        deliver(upto_all=True)
+        if on_pairs is not None:
+            return n_pairs
+        if not collected:
+            return {"avg_hue": torch.empty((0, self.cells), dtype=torch.uint8),
+                    "km_hue": torch.empty((0, self.cells), dtype=torch.uint8),
+                    "mean_magnitude": torch.empty(0, dtype=torch.float64)}
+        return {k: torch.cat([c[k] for c in collected]) for k in collected[0]}

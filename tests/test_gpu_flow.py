@@ -214,6 +214,14 @@ def test_pipeline_chunking_invariance_and_oracle(ofc):
     assert torch.equal(torch.cat(got), a["avg_hue"])
     with pytest.raises(ValueError):
         ClipPipeline(W, H, chunk_frames=4, rows=6, cols=8).run_chunk(dev_clip[0:2], carry=True)
+    # streaming ingest from a host frame iterator (pinned staging + copy stream) gives the same rows
+    st = ClipPipeline(W, H, chunk_frames=3, rows=6, cols=8).process_stream(iter(clip.numpy()))
+    for k in a:
+        assert torch.equal(a[k], st[k]), k
+    seen = []
+    n = ClipPipeline(W, H, chunk_frames=4, rows=6, cols=8).process_stream(
+        (f for f in clip.numpy()), on_pairs=lambda first, res: seen.append((first, res["viz"].shape[0])), want_viz=True)
+    assert n == T - 1 and seen == [(0, 3), (3, 3)]
     pipe = ClipPipeline(W, H, chunk_frames=T, rows=6, cols=8)
     pipe.run_chunk(clip.cuda())
     flow = pipe.flow.cpu().numpy()
