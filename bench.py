@@ -182,6 +182,17 @@ def kmeans_cosine_extras(dev, peak):
         nbytes = 2 * (N * D * X.element_size()) + 2 * 4 * N          # both kernels read X once and touch the labels
         out["kmeans_iter_" + name] = {"ms": ms, "rows_per_s": N / (ms / 1e3), "gb_s": nbytes / (ms / 1e3) / 1e9,
                                       "frac_of_hbm_peak": nbytes / (ms / 1e3) / 1e9 / peak}
+    # the reference's per-cell KMeans(n_clusters=8) over one 1080p frame (350 cells x 5852 px x 4 channels),
+    # k-means++ seeding included, as ONE device-resident launch (kmeans.lloyd_cells)
+    cells = torch.randint(0, 256, (350, 76 * 77, 4), generator=g).to(torch.uint8).to(dev)
+    km.lloyd_cells(cells, 8, seed=1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, _, _, n_it, _ = km.lloyd_cells(cells, 8, seed=1)
+    e1.record()
+    torch.cuda.synchronize()
+    out["per_cell_kmeans_k8_1080p_frame"] = {"ms": e0.elapsed_time(e1), "mean_lloyd_iterations": float(n_it.float().mean().item()),
+                                             "cells": 350, "rows_per_cell": 76 * 77}
     # host link: what a pinned 50 MB upload (one step's frames) achieves on this box
     hbuf = torch.empty(50 * 1024 * 1024, dtype=torch.uint8).pin_memory()
     dbuf = torch.empty_like(hbuf, device=dev)

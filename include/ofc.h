@@ -172,6 +172,17 @@ int ofc_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, i
                         const int32_t* labels, const double* centres_old, double* sums, int64_t* counts,
                         int raw_sums, const uint8_t* active, void* stream);
 
+/* Whole Lloyd runs on the device, one CTA per problem: the reference's per-cell fits
+ * (KMeans(n_clusters=k).fit on every grid cell of a frame, KmeanGrids.py:376-392) in ONE launch --
+ * column statistics, seeding, all iterations, relocation, sklearn's stopping rule, closing E-step.
+ * X u8 [batch][n][d], d <= 8, k <= 64, n <= 2^20.  init [batch][k][d] (float64) gives the same labels /
+ * centres / n_iter as the stepwise calls above; init == NULL seeds with k-means++ (sklearn's procedure,
+ * counter-based random stream from `seed`; workspace >= batch*n*8 bytes).  counts = members per cluster
+ * of the final labels (the reference's bincount of predict(), KmeanGrids.py:304-307). */
+int ofc_kmeans_cells(const uint8_t* X, int batch, int64_t n, int d, int k, const double* init, uint64_t seed,
+                     int max_iter, double tol, int32_t* labels, double* centres, double* inertia,
+                     int32_t* n_iter, int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
 /* image_dict ROIs (KmeanGrids.py:85,113) + preprocess_image (:269-286) for every cell:
  * out u8 [n_frames][rows*cols][ (H/rows)*(W/cols) ][4] = (c0, c1, c2, alpha).  draw_lines:
  * white row 0 / column 0 as at the reference's k-means stage; swap_rb:

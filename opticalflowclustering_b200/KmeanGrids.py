@@ -123,21 +123,53 @@ def cluster_colors(image, n_clusters, image_path, csv_file, init=None, random_st
     return c, hsv0[0][0][0]
 
 
+def cluster_cells_batched(rois, n_clusters, seed=0):
+    """preprocess_image + KMeans(n_clusters) + dominant cluster + rint + hue for a list of equal-sized BGR
+    ROIs in one upload and three launches (cell gather/threshold, per-cell Lloyd runs with k-means++
+    seeding, 8-bit HSV) instead of one sklearn fit per cell (KmeanGrids.py:382-392).  Returns
+    ``(centres_rint float64 [B,4], hues uint8 [B])``.  The ROIs themselves are left untouched (the
+    reference thresholds them in place, Q4, which no output depends on)."""
+    import ctypes as C
+
+    from . import _lib
+    from .flow import _ptr, _stream_ptr
+    stack = np.ascontiguousarray(np.stack(rois))                       # [B, h, w, 3]
+    B, h, w = stack.shape[:3]
+    dev = to_device_u8(stack.reshape(B * h, w, 3))
+    cells = torch.empty((B, h * w, 4), dtype=torch.uint8, device=dev.device)
+    with torch.cuda.device(dev.device):
+        # the stack is one tall image cut into B x 1 cells: threshold + alpha for all of them at once
+        _lib.check(_lib.lib().ofc_grid_extract_cells(_ptr(dev), 1, B * h, w, B, 1, 0, _ck.THRESHOLD, 0, _ptr(cells),
+                                                     _stream_ptr()))
+    labels, centres, inertia, n_iter, counts = _km.lloyd_cells(cells, n_clusters, seed=seed)
+    # largest cluster first; equal shares keep index order like the reference's stable sort (:317)
+    top = torch.argmax((counts == counts.max(dim=1, keepdim=True).values).to(torch.uint8), dim=1)
+    c = torch.round(centres[torch.arange(B, device=centres.device), top])           # np.rint: half to even
+    bgr = c[:, :3].to(torch.uint8).contiguous()
+    hsv = torch.empty_like(bgr)
+    with torch.cuda.device(dev.device):
+        _lib.check(_lib.lib().ofc_bgr2hsv(_ptr(bgr), _ptr(hsv), C.c_int64(B), _stream_ptr()))
+    return c.cpu().numpy(), hsv[:, 0].cpu().numpy()
+
+
 def frame_hues(frame_key, cell_names, n_clusters, random_state=None):
     """Hue per listed cell of one processed frame, in the order given, as the loop of
     KmeanGrids.py:382-392 computes them (``cell_names`` are the file stems found under
     ``<dir>/<frame>/``; the reference uses them only as ``image_dict`` keys, :384-385).
-    ``n_clusters == 1`` reads the GPU grid pass of that frame; k > 1 takes the ROI from
-    ``image_dict``, preprocesses it and runs the Lloyd kernels (k-means++ seeding)."""
+    ``n_clusters == 1`` reads the GPU grid pass of that frame; k > 1 clusters all listed cells of the
+    frame in one batched device run (:func:`cluster_cells_batched`)."""
     fn = get_number(str(frame_key))
+    keys = [f'{str(frame_key)}/{name}' for name in cell_names]
+    rois = [image_dict[key] for key in keys]            # KeyError like the reference if the frame was not processed
+    if n_clusters == 1 and fn in frame_results and all(str(nm).isdigit() and 1 <= int(nm) <= len(frame_results[fn]['km_hue'])
+                                                       for nm in cell_names):
+        return [int(frame_results[fn]['km_hue'][int(nm) - 1]) for nm in cell_names]
+    if rois and all(r.shape == rois[0].shape for r in rois):
+        seed = random_state if isinstance(random_state, int) else 0
+        _, hues = cluster_cells_batched(rois, n_clusters, seed=seed)
+        return [int(h) for h in hues]
     hues = []
-    for name in cell_names:
-        key = f'{str(frame_key)}/{name}'
-        image = image_dict[key]                         # KeyError like the reference if the frame was not processed
-        if n_clusters == 1 and fn in frame_results and str(name).isdigit() \
-                and 1 <= int(name) <= len(frame_results[fn]['km_hue']):
-            hues.append(int(frame_results[fn]['km_hue'][int(name) - 1]))
-            continue
+    for key, image in zip(keys, rois):
         processed = preprocess_image(image)
         _, hue = cluster_colors(processed, n_clusters, key, os.devnull, random_state=random_state)
         hues.append(int(hue))

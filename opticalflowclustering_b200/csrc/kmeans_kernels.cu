@@ -422,6 +422,375 @@ __global__ void __launch_bounds__(1024) kmeans_relocate_kernel(const T* Xall, in
 }
 
 // ---------------------------------------------------------------------------
+// Whole Lloyd runs on the device: one CTA per problem, for the reference's per-cell fits
+// (350 small uint8 problems per frame, KmeanGrids.py:376-392).  Column statistics, optional
+// k-means++ seeding, every E-step / M-step, empty-cluster relocation, the stopping rule of
+// sklearn's _kmeans_single_lloyd and the final E-step + inertia all happen inside the kernel,
+// so a frame's fits cost one launch and no host round trip.  Same arithmetic as the stepwise
+// kernels above (same fma chains, exact integer sums), hence the same labels / centres / n_iter
+// as kmeans.lloyd() for the same initial centres.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+struct KmCellsParams {
+    const unsigned char* X;      // [batch][n][d]
+    int n, d, k;
+    const double* init;          // [batch][k][d] or null (k-means++)
+    unsigned long long seed;
+    int max_iter;
+    double tol;
+    int32_t* labels;             // [batch][n]
+    double* centres;             // [batch][k][d]
+    double* inertia;             // [batch]
+    int32_t* n_iter;             // [batch]
+    long long* counts;           // [batch][k] members of the final labels
+    double* scratch;             // [batch][n] (k-means++ only)
+};
+
+template <int DP>
+__global__ void __launch_bounds__(256) kmeans_cells_kernel(KmCellsParams p) {
+    OFC_DYN_SMEM(double, sm);
+    const int n = p.n, d = p.d, k = p.k, b = blockIdx.x, tid = threadIdx.x;
+    double* cc = sm;                              // [k][d] centred centres
+    double* c2 = cc + k * d;                      // [k]
+    double* cnew = c2 + k;                        // [k][d]
+    double* shift = cnew + k * d;                 // [k]
+    double* mean = shift + k;                     // [d]
+    double* s_red = mean + d;                     // [8]
+    unsigned* s_sum = reinterpret_cast<unsigned*>(s_red + 8);   // [k][d]
+    int* s_cnt = reinterpret_cast<int*>(s_sum + k * d);         // [k]
+    __shared__ unsigned long long s_stat[16];     // sum x, sum x^2 per dim (d <= 8)
+    __shared__ double s_tol, s_val[8];
+    __shared__ long long s_idx[8], s_pick;
+    __shared__ int s_any, s_heavy, s_stop, s_changed;     // one word per decision: no reuse between barriers
+    const unsigned char* X = p.X + (int64_t)b * n * d;
+    int32_t* labels = p.labels + (int64_t)b * n;
+
+    auto load_x = [&](int i, double (&x)[DP]) {
+        const unsigned char* row = X + (int64_t)i * d;
+        if (DP == 4 && d == 4) {
+            const uchar4 q = *reinterpret_cast<const uchar4*>(row);
+            x[0] = (double)q.x; x[1] = (double)q.y; x[2] = (double)q.z; x[3] = (double)q.w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < DP; ++t) x[t] = t < d ? (double)row[t] : 0.0;
+        }
+    };
+    auto block_sum = [&](double v) -> double {       // fixed order; result in every thread
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = v;
+        __syncthreads();
+        double tsum = 0.0;
+        for (int w = 0; w < 8; ++w) tsum += s_red[w];
+        __syncthreads();
+        return tsum;
+    };
+
+    // ---- column statistics: mean, tolerance ------------------------------------------------
+    if (tid < 16) s_stat[tid] = 0ull;
+    __syncthreads();
+    {
+        unsigned long long sx[DP], sxx[DP];
+#pragma unroll
+        for (int t = 0; t < DP; ++t) { sx[t] = 0ull; sxx[t] = 0ull; }
+        for (int i = tid; i < n; i += 256) {
+            double x[DP];
+            load_x(i, x);
+#pragma unroll
+            for (int t = 0; t < DP; ++t) {
+                const unsigned long long v = (unsigned long long)x[t];
+                sx[t] += v; sxx[t] += v * v;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < DP; ++t) {
+            if (t < d) {
+                atomicAdd(&s_stat[t], sx[t]);
+                atomicAdd(&s_stat[8 + t], sxx[t]);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double vs = 0.0;
+        for (int t = 0; t < d; ++t) {
+            mean[t] = (double)s_stat[t] / (double)n;
+            const unsigned long long num = (unsigned long long)n * s_stat[8 + t] - s_stat[t] * s_stat[t];   // exact for n <= 2^20
+            vs += (double)num / ((double)n * (double)n);
+        }
+        s_tol = vs / (double)d * p.tol;
+    }
+    __syncthreads();
+
+    // ---- initial centres ----------------------------------------------------------------------
+    if (p.init) {
+        for (int e = tid; e < k * d; e += 256) cc[e] = p.init[(int64_t)b * k * d + e] - mean[e % d];
+    } else {
+        // k-means++ (sklearn/_kmeans.py:181-268): first centre uniform, then 2+int(log k) candidates per step
+        // drawn in proportion to the squared distance to the closest chosen centre, keeping the candidate with
+        // the lowest potential.  Distances are exact (integers); the random stream is a counter-based hash of
+        // (seed, problem, draw), not numpy's -- the reference leaves random_state unset.
+        double* closest = p.scratch + (int64_t)b * n;
+        const int trials = 2 + (int)log((double)k);
+        unsigned long long ctr = splitmix64(p.seed ^ (0xD1B54A32D192ED03ull * (unsigned long long)(b + 1)));
+        auto uniform = [&]() -> double { ctr = splitmix64(ctr); return (double)(ctr >> 11) * (1.0 / 9007199254740992.0); };
+        auto dist_to = [&](int i, int c) -> double {
+            const unsigned char* a = X + (int64_t)i * d;
+            const unsigned char* q = X + (int64_t)c * d;
+            double s = 0.0;
+            for (int t = 0; t < d; ++t) { const double df = (double)a[t] - (double)q[t]; s += df * df; }
+            return s;
+        };
+        int first = (int)(uniform() * (double)n);
+        if (first >= n) first = n - 1;
+        for (int t = tid; t < d; t += 256) cc[t] = (double)X[(int64_t)first * d + t] - mean[t];
+        double part = 0.0;
+        for (int i = tid; i < n; i += 256) { const double v = dist_to(i, first); closest[i] = v; part += v; }
+        double pot = block_sum(part);
+        const int chunk = (n + 255) / 256;               // contiguous ranges for the cumulative sum
+        for (int c = 1; c < k; ++c) {
+            double best_pot = 0.0;
+            int best = -1;
+            for (int tr = 0; tr < trials; ++tr) {
+                const double r = uniform() * pot;          // same value in every thread
+                // searchsorted(cumsum(closest), r): thread-range sums, then the owner scans its range
+                const int lo = tid * chunk, hi = min(n, lo + chunk);
+                double loc = 0.0;
+                for (int i = lo; i < hi; ++i) loc += closest[i];
+                // running sum over the 256 range sums by one thread (k is small, n moderate)
+                __shared__ double s_part[256];
+                s_part[tid] = loc;
+                __syncthreads();
+                if (tid == 0) {
+                    double run = 0.0;
+                    long long cand = n - 1;
+                    for (int q = 0; q < 256; ++q) {
+                        const double nxt = run + s_part[q];
+                        if (r < nxt || q == 255) {
+                            const int l2 = q * chunk, h2 = min(n, l2 + chunk);
+                            double acc = run;
+                            cand = h2 > l2 ? h2 - 1 : n - 1;
+                            for (int i = l2; i < h2; ++i) { acc += closest[i]; if (r < acc) { cand = i; break; } }
+                            break;
+                        }
+                        run = nxt;
+                    }
+                    if (cand > n - 1) cand = n - 1;
+                    s_pick = cand;
+                }
+                __syncthreads();
+                const int cand = (int)s_pick;
+                double pp = 0.0;
+                for (int i = tid; i < n; i += 256) pp += fmin(closest[i], dist_to(i, cand));
+                const double cp = block_sum(pp);
+                if (best < 0 || cp < best_pot) { best_pot = cp; best = cand; }
+            }
+            for (int i = tid; i < n; i += 256) closest[i] = fmin(closest[i], dist_to(i, best));
+            for (int t = tid; t < d; t += 256) cc[c * d + t] = (double)X[(int64_t)best * d + t] - mean[t];
+            pot = best_pot;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+
+    // ---- Lloyd iterations --------------------------------------------------------------------------
+    auto e_step_label = [&](const double (&x)[DP]) -> int {
+        double xc[DP];
+#pragma unroll
+        for (int t = 0; t < DP; ++t) xc[t] = t < d ? x[t] - mean[t] : 0.0;
+        double bestd = 0.0;
+        int label = 0;
+        for (int j = 0; j < k; ++j) {
+            const double* c = cc + j * d;
+            double dot = 0.0;
+#pragma unroll
+            for (int t = 0; t < DP; ++t)
+                if (t < d) dot = fma(xc[t], c[t], dot);
+            const double dist = fma(-2.0, dot, c2[j]);
+            if (j == 0 || dist < bestd) { bestd = dist; label = j; }
+        }
+        return label;
+    };
+    bool strict = false;
+    int iters = 0;
+    for (int it = 0; it < p.max_iter; ++it) {
+        for (int j = tid; j < k; j += 256) {
+            double sq = 0.0;
+            for (int t = 0; t < d; ++t) sq = fma(cc[j * d + t], cc[j * d + t], sq);
+            c2[j] = sq;
+            s_cnt[j] = 0;
+        }
+        for (int e = tid; e < k * d; e += 256) s_sum[e] = 0u;
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        int changed = 0;
+        for (int i = tid; i < n; i += 256) {
+            double x[DP];
+            load_x(i, x);
+            const int label = e_step_label(x);
+            if (it == 0 || labels[i] != label) ++changed;
+            labels[i] = label;
+#pragma unroll
+            for (int t = 0; t < DP; ++t)
+                if (t < d) atomicAdd(&s_sum[label * d + t], (unsigned)x[t]);
+            atomicAdd(&s_cnt[label], 1);
+        }
+        if (changed) atomicAdd(&s_changed, changed);
+        __syncthreads();
+        // empty clusters take the farthest points (distance to the old centre of their label)
+        if (tid == 0) {
+            int any = 0;
+            for (int j = 0; j < k; ++j) any |= s_cnt[j] == 0;
+            s_any = any;
+        }
+        __syncthreads();
+        if (s_any) {
+            long long* taken = reinterpret_cast<long long*>(cnew);     // scratch until the centre update
+            int n_taken = 0;
+            for (int e = 0; e < k; ++e) {
+                if (s_cnt[e] != 0) continue;
+                double bv = -1.0;
+                long long bi = -1;
+                for (int i = tid; i < n; i += 256) {
+                    bool tk = false;
+                    for (int q = 0; q < n_taken; ++q) tk |= taken[q] == i;
+                    if (tk) continue;
+                    double x[DP];
+                    load_x(i, x);
+                    const double* c = cc + labels[i] * d;
+                    double v = 0.0;
+                    for (int t = 0; t < d; ++t) { const double df = (x[t] - mean[t]) - c[t]; v = fma(df, df, v); }
+                    if (v > bv) { bv = v; bi = i; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+                }
+                if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+                __syncthreads();
+                if (tid == 0) {
+                    double v = -1.0;
+                    long long idx = -1;
+                    for (int w = 0; w < 8; ++w)
+                        if (s_idx[w] >= 0 && (idx < 0 || s_val[w] > v || (s_val[w] == v && s_idx[w] < idx))) { v = s_val[w]; idx = s_idx[w]; }
+                    if (n_taken == 0 && !(v > 0.0)) idx = -1;
+                    s_pick = idx;
+                    if (idx >= 0) {
+                        taken[n_taken] = idx;
+                        const int old = labels[idx];
+                        for (int t = 0; t < d; ++t) {
+                            const unsigned xv = X[idx * d + t];
+                            s_sum[old * d + t] -= xv;
+                            s_sum[e * d + t] = xv;
+                        }
+                        s_cnt[e] = 1;
+                        s_cnt[old] -= 1;
+                    }
+                }
+                __syncthreads();
+                if (s_pick < 0) break;
+                ++n_taken;
+            }
+            __syncthreads();
+        }
+        // centres, shift
+        if (tid == 0) {
+            int heavy = 0;
+            for (int j = 1; j < k; ++j) if (s_cnt[j] > s_cnt[heavy]) heavy = j;
+            s_heavy = heavy;
+        }
+        __syncthreads();
+        for (int j = tid; j < k; j += 256) {
+            const int srcj = s_cnt[j] > 0 ? j : s_heavy;
+            const double wgt = (double)s_cnt[srcj];
+            double ss = 0.0;
+            for (int t = 0; t < d; ++t) {
+                double v = (double)s_sum[srcj * d + t] / wgt;
+                v -= mean[t];
+                const double df = v - cc[j * d + t];
+                ss = fma(df, df, ss);
+                cnew[j * d + t] = v;
+            }
+            const double sr = sqrt(ss);
+            shift[j] = sr * sr;
+        }
+        __syncthreads();
+        for (int e = tid; e < k * d; e += 256) cc[e] = cnew[e];
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int j = 0; j < k; ++j) tot += shift[j];
+            int stop = 0;
+            if (s_changed == 0) stop = 2;                 // labels repeated: strict convergence
+            else if (tot <= s_tol) stop = 1;
+            s_stop = stop;
+        }
+        __syncthreads();
+        iters = it + 1;
+        if (s_stop) { strict = s_stop == 2; break; }
+    }
+    (void)strict;   // the closing E-step below is idempotent for a strict stop (kmeans.lloyd does the same)
+
+    // ---- closing E-step on the final centres, inertia, member counts ------------------------------
+    for (int j = tid; j < k; j += 256) {
+        double sq = 0.0;
+        for (int t = 0; t < d; ++t) sq = fma(cc[j * d + t], cc[j * d + t], sq);
+        c2[j] = sq;
+        s_cnt[j] = 0;
+    }
+    __syncthreads();
+    double inert = 0.0;
+    for (int i = tid; i < n; i += 256) {
+        double x[DP];
+        load_x(i, x);
+        const int label = e_step_label(x);
+        labels[i] = label;
+        atomicAdd(&s_cnt[label], 1);
+        const double* c = cc + label * d;
+        double sq = 0.0;
+#pragma unroll
+        for (int t = 0; t < DP; ++t)
+            if (t < d) { const double df = (x[t] - mean[t]) - c[t]; sq = fma(df, df, sq); }
+        inert += sq;
+    }
+    const double tot_inertia = block_sum(inert);
+    __syncthreads();
+    for (int e = tid; e < k * d; e += 256) p.centres[(int64_t)b * k * d + e] = cc[e] + mean[e % d];
+    for (int j = tid; j < k; j += 256) p.counts[(int64_t)b * k + j] = s_cnt[j];
+    if (tid == 0) {
+        p.inertia[b] = tot_inertia;
+        p.n_iter[b] = iters;
+    }
+}
+
+int launch_kmeans_cells(const unsigned char* X, int batch, int64_t n, int d, int k, const double* init,
+                        unsigned long long seed, int max_iter, double tol, int32_t* labels, double* centres,
+                        double* inertia, int32_t* n_iter, long long* counts, double* scratch, void* stream) {
+    if (batch <= 0) return OFC_OK;
+    KmCellsParams p;
+    p.X = X; p.n = (int)n; p.d = d; p.k = k; p.init = init; p.seed = seed; p.max_iter = max_iter; p.tol = tol;
+    p.labels = labels; p.centres = centres; p.inertia = inertia; p.n_iter = n_iter; p.counts = counts; p.scratch = scratch;
+    const size_t smem = (size_t)(2 * k * d + 2 * k + d + 8) * sizeof(double) + (size_t)k * d * sizeof(unsigned) + (size_t)k * sizeof(int);
+    ProfScope prof(PK_KMEANS, stream);
+    if (d <= 4) {
+        if (smem > 48 * 1024) OFC_CUDA(cudaFuncSetAttribute(kmeans_cells_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OFC_LAUNCH(kmeans_cells_kernel<4>, dim3(batch), dim3(256), smem, stream, p);
+    } else {
+        if (smem > 48 * 1024) OFC_CUDA(cudaFuncSetAttribute(kmeans_cells_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OFC_LAUNCH(kmeans_cells_kernel<8>, dim3(batch), dim3(256), smem, stream, p);
+    }
+    OFC_CHECK_LAUNCH("kmeans_cells");
+    return OFC_OK;
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 int kmeans_assign_grid(int64_t n) {

@@ -50,6 +50,9 @@ int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d
                            int raw_sums, const unsigned char* active, void* stream);
 int launch_inertia_reduce(const double* partial, int parts, int batch, double* inertia, const unsigned char* active,
                           void* stream);
+int launch_kmeans_cells(const unsigned char* X, int batch, int64_t n, int d, int k, const double* init,
+                        unsigned long long seed, int max_iter, double tol, int32_t* labels, double* centres,
+                        double* inertia, int32_t* n_iter, long long* counts, double* scratch, void* stream);
 int kmeans_assign_grid(int64_t n);
 int kmeans_sums_splits(int64_t n, int batch);
 

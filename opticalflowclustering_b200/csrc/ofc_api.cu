@@ -604,6 +604,22 @@ int ofc_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, i
     return launch_kmeans_relocate(X, dtype, batch, n, d, k, mean, labels, centres_old, sums, (long long*)counts, raw_sums, active, stream);
 }
 
+int ofc_kmeans_cells(const uint8_t* X, int batch, int64_t n, int d, int k, const double* init, uint64_t seed, int max_iter,
+                     double tol, int32_t* labels, double* centres, double* inertia, int32_t* n_iter, int64_t* counts,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    OFC_REQUIRE(batch >= 0 && n >= 1 && n <= (1 << 20) && d >= 1 && d <= 8 && k >= 1 && k <= 64 && max_iter >= 0,
+                "unsupported shape for the per-cell kernel: n=%lld d=%d k=%d", (long long)n, d, k);
+    OFC_REQUIRE(n >= k, "n_samples=%lld should be >= n_clusters=%d.", (long long)n, k);
+    if (batch == 0) return OFC_OK;
+    OFC_REQUIRE(X && labels && centres && inertia && n_iter && counts, "null buffer");
+    if (!init && (!workspace || workspace_bytes < (size_t)batch * n * sizeof(double))) {
+        set_error("k-means++ seeding needs %zu bytes of workspace", (size_t)batch * n * sizeof(double));
+        return OFC_ERR_WORKSPACE;
+    }
+    return launch_kmeans_cells(X, batch, n, d, k, init, seed, max_iter, tol, labels, centres, inertia, n_iter,
+                               (long long*)counts, (double*)workspace, stream);
+}
+
 int ofc_grid_extract_cells(const uint8_t* bgr, int n_frames, int height, int width, int rows, int cols,
                            int draw_lines, int threshold, int swap_rb, uint8_t* out, void* stream) {
     OFC_REQUIRE(n_frames >= 0 && height > 0 && width > 0, "bad sizes");

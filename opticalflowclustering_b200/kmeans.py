@@ -288,6 +288,45 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
     return final, out_centres, inertia, n_iter_t
 
 
+def lloyd_cells(X, n_clusters: int, init=None, seed: int = 0, max_iter: int = 300, tol: float = 1e-4,
+                _lib_override=None):
+    """All Lloyd runs of a batch of small uint8 problems in ONE kernel launch (one CTA per problem): the
+    reference's per-cell ``KMeans(n_clusters=k).fit`` loop over a frame's grid cells
+    (KmeanGrids.py:376-392).  X uint8 ``[B, n, d]`` (d <= 8, k <= 64).  ``init`` ``[B,k,d]`` / ``[k,d]``
+    gives the results of :func:`lloyd`; ``init=None`` seeds every problem with k-means++ from ``seed``.
+
+    Returns ``(labels int32 [B,n], centres float64 [B,k,d], inertia [B], n_iter int32 [B], counts int64 [B,k])``
+    on X's device; ``counts`` are the member counts of the final labels."""
+    Xb, single = _as_batch(X, _target_device(X, _lib_override))
+    if Xb.dtype != torch.uint8:
+        raise TypeError("lloyd_cells takes uint8 rows (the reference's pixels)")
+    ctx = _Ctx(Xb.device, _lib_override)
+    B, n, d = (int(v) for v in Xb.shape)
+    k = int(n_clusters)
+    dev = Xb.device
+    init_t = None
+    if init is not None:
+        init_t = torch.as_tensor(np.asarray(init) if not isinstance(init, torch.Tensor) else init)
+        init_t = init_t.to(device=dev, dtype=torch.float64)
+        if init_t.dim() == 2:
+            init_t = init_t.unsqueeze(0).expand(B, -1, -1)
+        init_t = init_t.contiguous()
+        if tuple(init_t.shape) != (B, k, d):
+            raise ValueError(f"init shape {tuple(init_t.shape)} does not match ({B}, {k}, {d})")
+    labels = torch.empty((B, n), dtype=torch.int32, device=dev)
+    centres = torch.empty((B, k, d), dtype=torch.float64, device=dev)
+    inertia = torch.empty(B, dtype=torch.float64, device=dev)
+    n_iter = torch.empty(B, dtype=torch.int32, device=dev)
+    counts = torch.empty((B, k), dtype=torch.int64, device=dev)
+    ws = torch.empty(B * n if init_t is None else 1, dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.ofc_kmeans_cells(_ptr(Xb), B, C.c_int64(n), d, k, _ptr(init_t), C.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                       int(max_iter), C.c_double(float(tol)), _ptr(labels), _ptr(centres), _ptr(inertia),
+                                       _ptr(n_iter), _ptr(counts), _ptr(ws), C.c_size_t(ws.numel() * 8), ctx.stream()))
+    if single:
+        return labels[0], centres[0], inertia[0], n_iter[0], counts[0]
+    return labels, centres, inertia, n_iter, counts
+
+
 def predict(X, centres, _lib_override=None):
     """``KMeans.predict``: E-step on the un-centred rows (_kmeans.py:1075-1107)."""
     Xb, single = _as_batch(X, _target_device(X, _lib_override))

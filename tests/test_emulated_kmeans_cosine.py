@@ -98,6 +98,38 @@ def test_empty_cluster_relocation(L):
     assert abs(float(inertia) - w[2]) <= 1e-9 * w[2]
 
 
+def test_lloyd_cells_device_loop_equals_stepwise(L):
+    """one-launch per-cell kernel == the stepwise host loop == the oracle, for the same initial centres"""
+    rng = np.random.default_rng(31)
+    B, n, d, k = 6, 900, 4, 4
+    cen = rng.uniform(10, 240, (B, k, d))
+    X = np.clip(np.rint(cen[np.arange(B)[:, None], rng.integers(k, size=(B, n))] + rng.normal(0, 10, (B, n, d))), 0, 255).astype(np.uint8)
+    init = X[:, :k].astype(np.float64)
+    init[2, 1] = init[2, 0]                                  # duplicated centre -> an empty cluster gets relocated
+    lab, cen_d, inertia, n_iter, counts = km.lloyd_cells(X, k, init=init, _lib_override=L)
+    l2, c2, i2, n2 = km.lloyd(X, init, _lib_override=L)
+    assert torch.equal(lab, l2) and torch.equal(cen_d, c2) and (n_iter.long() == n2).all()
+    assert ((inertia - i2).abs() <= 1e-12 * i2).all()
+    for b in range(B):
+        w = K.kmeans_fit(X[b], init[b])
+        assert (lab[b].numpy() == w[0]).all() and int(n_iter[b]) == w[3]
+        assert (counts[b].numpy() == np.bincount(w[0], minlength=k)).all()
+
+
+def test_lloyd_cells_kmeanspp_seeding(L):
+    rng = np.random.default_rng(32)
+    X = np.clip(np.rint(np.concatenate([rng.normal(50, 5, (300, 4)), rng.normal(130, 5, (300, 4)), rng.normal(210, 5, (300, 4))])), 0, 255)
+    X = np.stack([X.astype(np.uint8), X[::-1].astype(np.uint8)])
+    a = km.lloyd_cells(X, 3, seed=7, _lib_override=L)
+    b = km.lloyd_cells(X, 3, seed=7, _lib_override=L)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))                      # deterministic in the seed
+    lab, cen_d, inertia, n_iter, counts = a
+    assert sorted(counts[0].tolist()) == [300, 300, 300] and sorted(counts[1].tolist()) == [300, 300, 300]
+    assert np.allclose(np.sort(cen_d[0].numpy()[:, 0]), [50, 130, 210], atol=1.5)
+    with pytest.raises(Exception):
+        km.lloyd_cells(X[:, :2], 3, _lib_override=L)                         # n < k
+
+
 def test_k1_is_the_mean_and_matches_g2_rint(L):
     z = np.load(os.path.join(GOLDEN, "g23_cells.npz"))
     cells = z["cells"][0, :40]                              # 40 cells of one frame, 51x51x3

@@ -152,6 +152,44 @@ def test_kmeangrids_frame_hues_and_outcsv(km, tmp_path):
     assert rows[0][0] == "cell_0" and rows[0][-1] == "cell_349" and len(rows) == 3 and rows[1] == [str(h) for h in hues]
 
 
+def test_lloyd_cells_one_launch_vs_oracle(km):
+    """per-cell device-resident Lloyd runs (one launch for all cells) == oracle with the same initial centres"""
+    z = np.load(os.path.join(GOLDEN, "g23_cells.npz"))
+    cells = z["cells"][:2].reshape(-1, 51, 51, 3)
+    X = np.stack([G.preprocess_image(c.copy()).reshape(-1, 4) for c in cells])
+    # cells with fewer distinct rows than clusters are degenerate: which point an empty cluster takes is then
+    # decided by rounding noise of sklearn's centred sums (all distances are "zero"), not by the algorithm
+    X = X[[i for i, x in enumerate(X) if len(np.unique(x, axis=0)) >= 8]][:48]
+    assert len(X) >= 20
+    init = np.stack([np.unique(x, axis=0)[[0, len(np.unique(x, axis=0)) // 3, 2 * len(np.unique(x, axis=0)) // 3, -1]] for x in X]).astype(np.float64)
+    lab, cen, inertia, n_iter, counts = km.lloyd_cells(X, 4, init=init)
+    for b in range(len(X)):
+        w = K.kmeans_fit(X[b], init[b])
+        assert (lab[b].cpu().numpy() == w[0]).all() and int(n_iter[b]) == w[3]
+        assert np.abs(cen[b].cpu().numpy() - w[1]).max() < 1e-9
+        assert abs(float(inertia[b]) - w[2]) <= 1e-9 * max(w[2], 1.0)
+        assert (counts[b].cpu().numpy() == np.bincount(w[0], minlength=4)).all()
+
+
+def test_kmeangrids_k2_batched_dominant_hue(km):
+    """k = 2 through KmeanGrids.frame_hues: cells painted with a 70/30 mix of two flat colours -> the dominant
+    colour's hue, whatever the k-means++ draw"""
+    from opticalflowclustering_b200 import KmeanGrids as kg
+    rng = np.random.default_rng(8)
+    kg.image_dict.clear()
+    kg.frame_results.clear()
+    want = []
+    for c in range(1, 21):
+        major = rng.integers(60, 255, 3)
+        minor = (major.astype(int) + 120) % 200 + 40
+        roi = np.empty((40, 40, 3), np.uint8)
+        roi[:] = major
+        roi[:12] = minor                                                   # 30 % of the pixels
+        kg.image_dict[f"5/{c}"] = roi
+        want.append(int(V.bgr2hsv_u8(major.astype(np.uint8)[None, None])[0, 0, 0]))
+    assert kg.frame_hues("5", [str(c) for c in range(1, 21)], 2) == want
+
+
 def test_drawgrids_csv_row(km, tmp_path):
     from opticalflowclustering_b200 import drawGridsAndOutputCSV as dg
     rng = np.random.default_rng(6)
