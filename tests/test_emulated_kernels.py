@@ -83,3 +83,38 @@ def test_emu_grid_quad_path_and_ragged_grid():
 def test_emu_unsupported_flags():
     with pytest.raises(RuntimeError, match="flags"):
         E.Plan(64, 64, flags=256)
+
+
+@pytest.mark.parametrize("env", [{"OFC_STRIP_MIN_W": "1", "OFC_ITER_TMEM": "1"},            # ring in TMEM + cp.async landing
+                                 {"OFC_STRIP_MIN_W": "1", "OFC_ITER_TMEM": "0"},            # ring in smem, register taps
+                                 {"OFC_ITER_VARIANT": "1"}])                               # square tiles everywhere
+def test_emu_production_iteration_kernels_on_small_frames(env):
+    """The strip-walk kernels normally only see levels wider than 512 px; the dispatch switches are read once
+    per process, so a child process forces them onto small odd-sized frames (partial strips, strips that
+    stick out of the frame, ragged last row groups) and compares with cv2's golden flow / the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, numpy as np
+sys.path.insert(0, os.getcwd())
+from tests.emu import emu_lib as E
+from oracle import farneback_np as FB
+from opticalflowclustering_b200.synthetic import synthetic_clip
+z = np.load("tests/golden/flow_96x128.npz")
+flow = E.Plan(128, 96, max_frames=3).sequence(z["gray"])
+for p in range(2):
+    e = np.linalg.norm(flow[p] - z["flow"][p], axis=-1)
+    assert e.mean() < 2e-6 and e.max() < 1e-4, (p, e.mean(), e.max())
+for (H, W) in [(61, 250), (101, 150)]:
+    g = E.bgr2gray(synthetic_clip(2, H, W, seed=H).numpy())
+    f = E.Plan(W, H, max_frames=2).sequence(g)[0]
+    ref = FB.calc_optical_flow_farneback(g[0], g[1])
+    e = np.linalg.norm(f - ref, axis=-1)
+    assert e.mean() < 2e-6 and e.max() < 2e-4, (H, W, e.mean(), e.max())
+print("ok")
+'''
+    e = dict(os.environ)
+    e.update(env)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
