@@ -183,6 +183,30 @@ int ofc_kmeans_cells(const uint8_t* X, int batch, int64_t n, int d, int k, const
                      int max_iter, double tol, int32_t* labels, double* centres, double* inertia,
                      int32_t* n_iter, int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- k-means, dense corner on the tensor cores --------------------------------
+ * The same sklearn E-step / M-step (KmeanGrids.py:299-304, color_kmeans.py:65-78;
+ * _k_means_lloyd.pyx:160-213) for ONE float32 problem whose distance step is a real GEMM
+ * (d >= 32, d % 4 == 0, 2 <= k <= 8192; the 1M x D sweep of BASELINE configs[4]).
+ * ofc_kmeans_tc_prepare: Xc = float32(x - float32(mean)) (KMeans.fit centres float32 data in
+ *   float32, _kmeans.py:1487-1493; mean nullable) and xnorm[i] = |Xc_i|; once per fit.
+ * ofc_kmeans_tc_assign: TF32 tcgen05 distance GEMM (TMA-fed, accumulators in tensor memory) as a
+ *   filter + float32 re-evaluation of every row whose two best distances are closer than the TF32
+ *   error bound: labels are bit-identical to ofc_kmeans_assign(OFC_F32) on Xc.  n_changed /
+ *   inertia as there (nullable); n_rechecked (nullable, device u32) = rows re-evaluated.
+ * ofc_kmeans_tc_sums: M-step over a label-sorted member list (stable counting sort, float64 sums
+ *   in ascending row order per cluster; deterministic, no floating-point atomics).
+ * All three share one workspace of ofc_kmeans_tc_workspace_bytes(n, d, k) bytes. */
+size_t ofc_kmeans_tc_workspace_bytes(int64_t n, int d, int k);
+int ofc_kmeans_tc_prepare(const float* X, const double* mean /* [d] */, int64_t n, int d,
+                          float* Xc /* [n][d] */, float* xnorm /* [n] */, void* stream);
+int ofc_kmeans_tc_assign(const float* Xc, const float* xnorm, int64_t n, int d, int k,
+                         const double* centres /* [k][d] */, int32_t* labels, const int32_t* prev_labels,
+                         uint64_t* n_changed, double* inertia, uint32_t* n_rechecked,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int ofc_kmeans_tc_sums(const float* Xc, int64_t n, int d, int k, const int32_t* labels,
+                       double* sums /* [k][d] */, int64_t* counts /* [k] */,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* image_dict ROIs (KmeanGrids.py:85,113) + preprocess_image (:269-286) for every cell:
  * out u8 [n_frames][rows*cols][ (H/rows)*(W/cols) ][4] = (c0, c1, c2, alpha).  draw_lines:
  * white row 0 / column 0 as at the reference's k-means stage; swap_rb:

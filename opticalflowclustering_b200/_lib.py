@@ -42,6 +42,10 @@ SIGNATURES = {
     "ofc_kmeans_centres": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_kmeans_relocate": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "ofc_kmeans_cells": (_i, [_vp, _i, _i64, _i, _i, _vp, C.c_uint64, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_tc_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "ofc_kmeans_tc_prepare": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "ofc_kmeans_tc_assign": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_tc_sums": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_grid_extract_cells": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ofc_sliding_cosine": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
     "ofc_row_cosine": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),

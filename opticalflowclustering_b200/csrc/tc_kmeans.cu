@@ -1,0 +1,731 @@
+// k-means for the dense corner (float32 rows, d >= 32, k >= 16): the E-step's distance matrix
+// is a real GEMM there (2 n k d flop against n d bytes), so it runs on the
+// 5th-generation tensor cores; the M-step walks a label-sorted (CSR) member list.
+//
+// Replaces, for that shape, the arithmetic behind the reference's
+//   clt = KMeans(n_clusters = k); clt.fit(X); clt.predict(X)
+// (reference k-means-color-clustering/KmeanGrids.py:299-304, color_kmeans.py:65-78): scikit-learn's
+// Lloyd E-step  label = first strict minimum over j of ||c_j||^2 - 2 x.c_j  (_k_means_lloyd.pyx:196-213).
+//
+// E-step (kmeans_assign_tc_kernel), one persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer: 128 x 32 float tiles of the rows (A) and BN x 32 tiles of the centres (B)
+//               into a 4-stage shared-memory ring (128-byte swizzle, mbarrier complete_tx);
+//   warp 1      one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) with the
+//               128 x BN float32 accumulator in tensor memory; two accumulators (2 x BN <= 512 columns)
+//               so the epilogue of one tile overlaps the MMAs of the next;
+//   warps 2..5  epilogue: tcgen05.ld of the accumulator (one row per thread), dist = c2 - 2 acc, running
+//               first/second/third minimum per row.
+// TF32 keeps 10 mantissa bits, so the tensor-core distances only FILTER: a row whose two best
+// distances are further apart than a rigorous bound on the TF32 error keeps its arg-min; every other
+// row is appended to a list and re-evaluated by kmeans_assign_fix_kernel in exactly the float32
+// arithmetic of kmeans_assign_generic_kernel (two candidates when only two centres are inside the
+// bound, all k otherwise).  Labels are therefore bit-identical to the CUDA-core float32 path.
+//
+// GPU only (no host-side emulation: tests/emu skips tc_*.cu).
+#include <cuda.h>
+#include "ofc_common.cuh"
+#include "../../include/ofc.h"
+
+namespace ofc {
+namespace {
+
+constexpr int BM = 128;          // rows per tile (= TMEM lanes)
+constexpr int BK = 32;           // floats per shared-memory row: 128 bytes = one swizzle atom
+constexpr int STAGES = 4;
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+    int64_t n;
+    int d, k;
+    const float* c2;             // [k] squared norms of the float32 centres
+    const float* xnorm;          // [n] row norms
+    const float* cmax;           // [1] largest centre norm
+    float tol_scale;             // bound on |TF32 distance difference error| / (|x| cmax)
+    int32_t* labels;
+    int4* amb;                   // [n] (row, best, second, full?) of rows to re-evaluate
+    unsigned* amb_count;
+    unsigned* error_flag;
+};
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must not hang the GPU -- after ~4 s the kernel flags the error and traps.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, unsigned* error_flag) {
+    unsigned ok = 0;
+    long long t0 = 0;
+    for (unsigned spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((spin & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) {
+                if (error_flag) atomicExch(error_flag, 1u + bar);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile, rows of 128 bytes, 128-byte swizzle (what TMA writes with SWIZZLE_128B):
+// 8-row groups 1024 bytes apart (SBO), LBO unused, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_desc_sw128(unsigned addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    constexpr unsigned A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+    // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
+    constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2]
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * STAGES + 4);
+    const unsigned bar0 = smem_addr(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mtiles = (int)((p.n + BM - 1) / BM);
+    const int n_ntiles = (p.k + BN - 1) / BN;
+    const int n_ktiles = (p.d + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            unsigned it = 0;
+            for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x)
+                for (int nt = 0; nt < n_ntiles; ++nt)
+                    for (int kt = 0; kt < n_ktiles; ++kt, ++it) {
+                        const int s = it % STAGES;
+                        const unsigned ph = (it / STAGES) & 1u;
+                        mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag);
+                        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                        const unsigned a_dst = smem_addr(smem + (size_t)s * STAGE_BYTES);
+                        tma_load_2d(a_dst, &tmA, full_bar(s), kt * BK, mt * BM);
+                        tma_load_2d(a_dst + A_BYTES, &tmB, full_bar(s), kt * BK, nt * BN);
+                    }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            unsigned it = 0, unit = 0;
+            for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x)
+                for (int nt = 0; nt < n_ntiles; ++nt, ++unit) {
+                    const unsigned acc = unit & 1u, aph = (unit >> 1) & 1u;
+                    mbar_wait(tempty_bar(acc), aph ^ 1u, p.error_flag);
+                    tc_fence_after();
+                    const unsigned tmem_d = tmem_base + acc * BN;
+                    for (int kt = 0; kt < n_ktiles; ++kt, ++it) {
+                        const int s = it % STAGES;
+                        const unsigned ph = (it / STAGES) & 1u;
+                        mbar_wait(full_bar(s), ph, p.error_flag);
+                        tc_fence_after();
+                        const unsigned a_addr = smem_addr(smem + (size_t)s * STAGE_BYTES);
+                        const uint64_t adesc = make_desc_sw128(a_addr), bdesc = make_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                        for (int k4 = 0; k4 < BK / 8; ++k4)      // 8 floats = 32 bytes per MMA: +2 in 16-byte units
+                            umma_tf32(tmem_d, adesc + 2u * k4, bdesc + 2u * k4, IDESC, (kt | k4) != 0);
+                        umma_commit(empty_bar(s));               // frees the stage once these MMAs have read it
+                    }
+                    umma_commit(tfull_bar(acc));
+                }
+        }
+    } else {
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        const float cmax = __ldg(p.cmax);
+        unsigned unit = 0;
+        for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+            float m1 = __int_as_float(0x7f800000), m2 = m1, m3 = m1;
+            int a1 = 0, a2 = 0;
+            for (int nt = 0; nt < n_ntiles; ++nt, ++unit) {
+                const unsigned acc = unit & 1u, aph = (unit >> 1) & 1u;
+                mbar_wait(tfull_bar(acc), aph, p.error_flag);
+                tc_fence_after();
+                const unsigned trow = tmem_base + acc * BN + ((unsigned)(q * 32) << 16);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int j0 = nt * BN + c * 32;
+                    if (j0 >= p.k) break;
+                    float v[32];
+                    tmem_ld32(trow + c * 32, v);
+                    const int jn = p.k - j0 < 32 ? p.k - j0 : 32;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        if (jj < jn) {
+                            const float dist = fmaf(-2.f, v[jj], __ldg(p.c2 + j0 + jj));
+                            if (dist < m1) { m3 = m2; m2 = m1; a2 = a1; m1 = dist; a1 = j0 + jj; }
+                            else if (dist < m2) { m3 = m2; m2 = dist; a2 = j0 + jj; }
+                            else if (dist < m3) { m3 = dist; }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+            }
+            const int64_t row = (int64_t)mt * BM + q * 32 + lane;
+            if (row < p.n) {
+                const float tol = p.tol_scale * __ldg(p.xnorm + row) * cmax;
+                p.labels[row] = a1;
+                if (!(m2 - m1 > tol)) {
+                    const unsigned pos = atomicAdd(p.amb_count, 1u);
+                    p.amb[pos] = make_int4((int)row, a1, a2, !(m3 - m1 > tol) ? 1 : 0);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// one float32 distance in the arithmetic of kmeans_assign_generic_kernel<float, float>: lanes stride over
+// the features, xor-tree reduction, dist = fma(-2, dot, c2)
+__device__ __forceinline__ float exact_dist(const float* __restrict__ row, const float* __restrict__ c, float c2, int d, int lane) {
+    float part = 0.f;
+    for (int t = lane; t < d; t += 32) part = fmaf(row[t], c[t], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    return fmaf(-2.f, part, c2);
+}
+
+// rows the tensor-core filter could not decide: one warp per row
+__global__ void __launch_bounds__(256) kmeans_assign_fix_kernel(const float* __restrict__ X, int d, int k,
+                                                                const float* __restrict__ C, const float* __restrict__ c2,
+                                                                const int4* __restrict__ amb, const unsigned* __restrict__ amb_count,
+                                                                int32_t* __restrict__ labels) {
+    const int lane = threadIdx.x & 31;
+    const unsigned n_amb = *amb_count;
+    for (unsigned e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n_amb; e += gridDim.x * 8) {
+        const int4 a = amb[e];
+        const float* row = X + (int64_t)a.x * d;
+        int label;
+        if (!a.w) {
+            const int lo = a.y < a.z ? a.y : a.z, hi = a.y < a.z ? a.z : a.y;
+            const float dlo = exact_dist(row, C + (int64_t)lo * d, c2[lo], d, lane);
+            const float dhi = exact_dist(row, C + (int64_t)hi * d, c2[hi], d, lane);
+            label = dhi < dlo ? hi : lo;
+        } else {
+            float best = 0.f;
+            label = 0;
+            for (int j = 0; j < k; ++j) {
+                const float dist = exact_dist(row, C + (int64_t)j * d, c2[j], d, lane);
+                if (j == 0 || dist < best) { best = dist; label = j; }
+            }
+        }
+        if (lane == 0) labels[a.x] = label;
+    }
+}
+
+// centres f64 -> f32 copy (the B operand)
+__global__ void centres_to_f32_kernel(const double* __restrict__ c, float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (float)c[i];
+}
+// c2[j] in the order of kmeans_c2_kernel(as_float): sequential fma chain over the features
+__global__ void centres_c2_kernel(const float* __restrict__ c, float* __restrict__ c2, int d, int k) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    const float* r = c + (int64_t)j * d;
+    float s = 0.f;
+    for (int t = 0; t < d; ++t) s = fmaf(r[t], r[t], s);
+    c2[j] = s;
+}
+__global__ void __launch_bounds__(1024) centres_cmax_kernel(const float* __restrict__ c2, int k, float* __restrict__ cmax,
+                                                             unsigned* __restrict__ amb_count) {
+    __shared__ float s[32];
+    float m = 0.f;
+    for (int j = threadIdx.x; j < k; j += 1024) m = fmaxf(m, c2[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) m = fmaxf(m, s[w]);
+        *cmax = sqrtf(m);
+        *amb_count = 0u;
+    }
+}
+
+// Xc = float32(x - float32 mean) (KMeans.fit centres float32 data in float32, _kmeans.py:1487-1493) and the
+// row norms the tensor-core filter's error bound needs; one warp per row
+__global__ void __launch_bounds__(256) prepare_rows_kernel(const float* __restrict__ X, const double* __restrict__ mean, int64_t n,
+                                                           int d, float* __restrict__ Xc, float* __restrict__ xnorm) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * 8) {
+        const float* row = X + i * d;
+        float* out = Xc + i * d;
+        float s = 0.f;
+        for (int t = lane; t < d; t += 32) {
+            const float v = row[t] - (mean ? (float)mean[t] : 0.f);
+            out[t] = v;
+            s = fmaf(v, v, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) xnorm[i] = sqrtf(s);
+    }
+}
+
+__global__ void __launch_bounds__(256) labels_changed_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t n,
+                                                             unsigned long long* __restrict__ n_changed) {
+    unsigned c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) c += a[i] != b[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_changed, (unsigned long long)c);     // integers: order-free
+}
+
+// inertia partials: sum over the rows of a CTA of ||x - c_label||^2 (float32 per row like the assign kernels,
+// float64 across rows), one warp per row, fixed order inside the CTA; folded in CTA order afterwards
+__global__ void __launch_bounds__(256) inertia_rows_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ C,
+                                                           const int32_t* __restrict__ labels, double* __restrict__ partial) {
+    __shared__ double s_w[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + warp; i < n; i += (int64_t)gridDim.x * 8) {
+        const float* row = X + i * d;
+        const float* c = C + (int64_t)labels[i] * d;
+        float sq = 0.f;
+        for (int t = lane; t < d; t += 32) { const float df = row[t] - c[t]; sq = fmaf(df, df, sq); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        acc += (double)sq;
+    }
+    if (lane == 0) s_w[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void fold_partials_kernel(const double* __restrict__ partial, int parts, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < parts; ++i) s += partial[i];
+        *out = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// M-step over a label-sorted member list (deterministic, no floating-point atomics).
+//   1  csr_hist:    one warp per chunk of 1024 consecutive rows counts its labels (shared-memory table)
+//   2  csr_scan:    per cluster, running start of every chunk's members; clusters laid end to end;
+//                   every cluster's list is cut into segments of SEG members
+//   3  csr_scatter: the same walk as (1) writes the row indices -- ascending inside every cluster
+//   4  seg_sums:    grid (segment, 128-feature tile): float64 sums of the segment's rows, in list order
+//   5  seg_fold:    sums[j][t] = the cluster's segment partials in order; counts[j]
+// ---------------------------------------------------------------------------
+constexpr int CHUNK = 1024;
+constexpr int SEG = 512;
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) csr_walk_kernel(const int32_t* __restrict__ labels, int64_t n, int k, unsigned* __restrict__ table,
+                                                       int32_t* __restrict__ order) {
+    extern __shared__ unsigned s_cnt[];              // [8][k]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t chunk = (int64_t)blockIdx.x * 8 + warp;
+    const int64_t lo = chunk * CHUNK;
+    unsigned* cnt = s_cnt + (size_t)warp * k;
+    unsigned* tab = table + chunk * k;
+    if (lo < n) {
+        for (int j = lane; j < k; j += 32) cnt[j] = SCATTER ? tab[j] : 0u;
+    }
+    __syncwarp();
+    if (lo >= n) return;
+    const int64_t hi = lo + CHUNK < n ? lo + CHUNK : n;
+    for (int64_t base = lo; base < hi; base += 32) {
+        const int64_t i = base + lane;
+        const bool ok = i < hi;
+        const int l = ok ? labels[i] : -1 - lane;                        // distinct dummies for idle lanes
+        const unsigned peers = __match_any_sync(0xffffffffu, l);
+        const int leader = __ffs(peers) - 1;
+        unsigned start = 0;
+        if (ok && lane == leader) { start = cnt[l]; cnt[l] = start + __popc(peers); }
+        start = __shfl_sync(0xffffffffu, start, leader);
+        if (SCATTER && ok) order[start + __popc(peers & ((1u << lane) - 1u))] = (int32_t)i;
+        __syncwarp();
+    }
+    if (!SCATTER)
+        for (int j = lane; j < k; j += 32) tab[j] = cnt[j];
+}
+
+// table[chunk][j] (counts) -> absolute start of chunk's members of cluster j in `order`; counts[j];
+// seg_info[s] = (cluster, begin, end) for every segment; seg_first[j] = first segment of cluster j.
+// One CTA: G = 1024 / k thread groups split the chunk range (G = 1 for k >= 1024).
+__global__ void __launch_bounds__(1024) csr_scan_kernel(unsigned* __restrict__ table, int64_t n_chunks, int k, long long* __restrict__ counts,
+                                                        int* __restrict__ seg_first, int4* __restrict__ seg_info, int* __restrict__ n_segs) {
+    extern __shared__ unsigned s_scan[];             // [G][k] group totals, [k] cluster offsets, [k] first segments
+    const int G = k >= 1024 ? 1 : 1024 / k;
+    unsigned* s_tot = s_scan;
+    unsigned* s_off = s_scan + (size_t)G * k;
+    unsigned* s_seg = s_off + k;
+    const int64_t per = (n_chunks + G - 1) / G;
+    for (int e = threadIdx.x; e < G * k; e += 1024) {
+        const int g = e / k, j = e - g * k;
+        const int64_t c0 = g * per, c1 = c0 + per < n_chunks ? c0 + per : n_chunks;
+        unsigned run = 0;
+        for (int64_t c = c0; c < c1; ++c) run += table[c * k + j];
+        s_tot[e] = run;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += 1024) {
+        unsigned run = 0;
+        for (int g = 0; g < G; ++g) { const unsigned v = s_tot[g * k + j]; s_tot[g * k + j] = run; run += v; }
+        counts[j] = run;
+        s_off[j] = run;                              // cluster size for now
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned off = 0, segs = 0;
+        for (int j = 0; j < k; ++j) {
+            const unsigned c = s_off[j];
+            s_off[j] = off; off += c;
+            s_seg[j] = segs; seg_first[j] = (int)segs; segs += (c + SEG - 1) / SEG;
+        }
+        seg_first[k] = (int)segs;
+        *n_segs = (int)segs;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < G * k; e += 1024) {
+        const int g = e / k, j = e - g * k;
+        const int64_t c0 = g * per, c1 = c0 + per < n_chunks ? c0 + per : n_chunks;
+        unsigned run = s_off[j] + s_tot[e];
+        for (int64_t c = c0; c < c1; ++c) { const unsigned v = table[c * k + j]; table[c * k + j] = run; run += v; }
+    }
+    for (int j = threadIdx.x; j < k; j += 1024) {
+        const unsigned off = s_off[j], c = (unsigned)counts[j];
+        const unsigned ns = (c + SEG - 1) / SEG;
+        for (unsigned s = 0; s < ns; ++s) {
+            const unsigned b = off + s * SEG, e = (s + 1) * SEG < c ? off + (s + 1) * SEG : off + c;
+            seg_info[s_seg[j] + s] = make_int4(j, (int)b, (int)e, 0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) seg_sums_kernel(const float* __restrict__ X, int d, const int32_t* __restrict__ order,
+                                                       const int4* __restrict__ seg_info, const int* __restrict__ n_segs,
+                                                       double* __restrict__ partial) {
+    const int t = blockIdx.y * 128 + threadIdx.x;
+    for (int s = blockIdx.x; s < *n_segs; s += gridDim.x) {
+        const int4 si = seg_info[s];
+        double acc = 0.0;
+        if (t < d) {
+            int m = si.y;
+            for (; m + 4 <= si.z; m += 4) {
+                const float v0 = X[(int64_t)order[m] * d + t], v1 = X[(int64_t)order[m + 1] * d + t];
+                const float v2 = X[(int64_t)order[m + 2] * d + t], v3 = X[(int64_t)order[m + 3] * d + t];
+                acc += (double)v0; acc += (double)v1; acc += (double)v2; acc += (double)v3;
+            }
+            for (; m < si.z; ++m) acc += (double)X[(int64_t)order[m] * d + t];
+            partial[(int64_t)s * d + t] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) seg_fold_kernel(const double* __restrict__ partial, int d, const int* __restrict__ seg_first,
+                                                       double* __restrict__ sums) {
+    const int j = blockIdx.x, t = blockIdx.y * 128 + threadIdx.x;
+    if (t >= d) return;
+    double s = 0.0;
+    for (int g = seg_first[j]; g < seg_first[j + 1]; ++g) s += partial[(int64_t)g * d + t];
+    sums[(int64_t)j * d + t] = s;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_rows_map(CUtensorMap* map, const float* base, int64_t rows, int d, int box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) {
+            set_error("cuTensorMapEncodeTiled is not available from the driver");
+            return OFC_ERR_CUDA;
+        }
+        fn = (EncodeTiledFn)sym;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)d * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return OFC_ERR_CUDA; }
+    return OFC_OK;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        n = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    }
+    return n;
+}
+
+struct TcLayout {
+    size_t off_c32, off_c2, off_cmax, off_count, off_err, off_amb, off_part, off_table, off_order, off_segfirst, off_seginfo,
+        off_nsegs, off_segpart, total;
+    int64_t n_chunks, max_segs;
+    int parts;
+};
+TcLayout tc_layout(int64_t n, int d, int k) {
+    TcLayout w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    w.n_chunks = (n + CHUNK - 1) / CHUNK;
+    w.max_segs = n / SEG + k + 1;
+    w.parts = 148 * 8;
+    w.off_c32 = take((size_t)k * d * 4);
+    w.off_c2 = take((size_t)k * 4);
+    w.off_cmax = take(4);
+    w.off_count = take(4);
+    w.off_err = take(4);
+    w.off_amb = take((size_t)n * 16);
+    w.off_part = take((size_t)w.parts * 8);
+    w.off_table = take((size_t)(w.n_chunks + 8) * k * 4);
+    w.off_order = take((size_t)n * 4);
+    w.off_segfirst = take((size_t)(k + 1) * 4);
+    w.off_seginfo = take((size_t)w.max_segs * 16);
+    w.off_nsegs = take(4);
+    w.off_segpart = take((size_t)w.max_segs * d * 8);
+    w.total = off;
+    return w;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, void* stream) {
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int64_t mtiles = (p.n + BM - 1) / BM;
+    const int grid = (int)(mtiles < sm_count() ? mtiles : sm_count());
+    kmeans_assign_tc_kernel<BN><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+    OFC_CHECK_LAUNCH("kmeans_assign_tc");
+    return OFC_OK;
+}
+
+int tc_shape_ok(int64_t n, int d, int k) {
+    if (n < 1 || n > 0x7fffffffll) { set_error("tensor-core k-means: n=%lld outside [1, 2^31)", (long long)n); return OFC_ERR_UNSUPPORTED; }
+    if (d < 32 || (d & 3)) { set_error("tensor-core k-means needs d >= 32 and d %% 4 == 0 (d=%d)", d); return OFC_ERR_UNSUPPORTED; }
+    if (k < 2 || k > 8192) { set_error("tensor-core k-means needs 2 <= k <= 8192 (k=%d)", k); return OFC_ERR_UNSUPPORTED; }
+    return OFC_OK;
+}
+
+}  // namespace
+}  // namespace ofc
+
+using namespace ofc;
+
+extern "C" {
+
+size_t ofc_kmeans_tc_workspace_bytes(int64_t n, int d, int k) {
+    if (n <= 0 || d <= 0 || k <= 0) return 0;
+    return tc_layout(n, d, k).total;
+}
+
+int ofc_kmeans_tc_prepare(const float* X, const double* mean, int64_t n, int d, float* Xc, float* xnorm, void* stream) {
+    OFC_REQUIRE(X && Xc && xnorm && n >= 1 && d >= 1, "bad arguments");
+    int64_t g = (n + 7) / 8;
+    if (g > 148 * 16) g = 148 * 16;
+    ProfScope prof(PK_KMEANS, stream);
+    prepare_rows_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(X, mean, n, d, Xc, xnorm);
+    OFC_CHECK_LAUNCH("prepare_rows");
+    return OFC_OK;
+}
+
+int ofc_kmeans_tc_assign(const float* Xc, const float* xnorm, int64_t n, int d, int k, const double* centres, int32_t* labels,
+                         const int32_t* prev_labels, uint64_t* n_changed, double* inertia, uint32_t* n_rechecked,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = tc_shape_ok(n, d, k);
+    if (rc != OFC_OK) return rc;
+    OFC_REQUIRE(Xc && xnorm && centres && labels, "null buffer");
+    OFC_REQUIRE(((uintptr_t)Xc & 15) == 0, "rows must be 16-byte aligned");
+    const TcLayout w = tc_layout(n, d, k);
+    if (!workspace || workspace_bytes < w.total) { set_error("tensor-core k-means workspace too small: %zu < %zu", workspace_bytes, w.total); return OFC_ERR_WORKSPACE; }
+    OFC_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+    char* ws = (char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* c32 = (float*)(ws + w.off_c32);
+    float* c2 = (float*)(ws + w.off_c2);
+    float* cmax = (float*)(ws + w.off_cmax);
+    unsigned* count = (unsigned*)(ws + w.off_count);
+    unsigned* err = (unsigned*)(ws + w.off_err);
+    ProfScope prof(PK_KMEANS, stream);
+    const int64_t kd = (int64_t)k * d;
+    centres_to_f32_kernel<<<(int)((kd + 255) / 256 < 1184 ? (kd + 255) / 256 : 1184), 256, 0, st>>>(centres, c32, kd);
+    OFC_CHECK_LAUNCH("centres_to_f32");
+    centres_c2_kernel<<<cdiv(k, 128), 128, 0, st>>>(c32, c2, d, k);
+    OFC_CHECK_LAUNCH("centres_c2");
+    centres_cmax_kernel<<<1, 1024, 0, st>>>(c2, k, cmax, count);
+    OFC_CHECK_LAUNCH("centres_cmax");
+    OFC_CUDA(cudaMemsetAsync(err, 0, 4, st));
+
+    const int BN = k <= 64 ? 64 : (k <= 128 ? 128 : 256);
+    CUtensorMap tmA, tmB;
+    rc = encode_rows_map(&tmA, Xc, n, d, BM);
+    if (rc != OFC_OK) return rc;
+    rc = encode_rows_map(&tmB, c32, k, d, BN);
+    if (rc != OFC_OK) return rc;
+    TcParams p;
+    p.n = n; p.d = d; p.k = k; p.c2 = c2; p.xnorm = xnorm; p.cmax = cmax;
+    // per distance: 2 |x.c| (2^-9 TF32 operand truncation + d 2^-23 accumulation); two distances; x1.5 margin
+    p.tol_scale = 1.5f * 4.f * (1.f / 512.f + (float)d * (1.f / 8388608.f));
+    p.labels = labels; p.amb = (int4*)(ws + w.off_amb); p.amb_count = count; p.error_flag = err;
+    if (BN == 64) rc = launch_tc<64>(tmA, tmB, p, stream);
+    else if (BN == 128) rc = launch_tc<128>(tmA, tmB, p, stream);
+    else rc = launch_tc<256>(tmA, tmB, p, stream);
+    if (rc != OFC_OK) return rc;
+    kmeans_assign_fix_kernel<<<sm_count() * 4, 256, 0, st>>>(Xc, d, k, c32, c2, (const int4*)(ws + w.off_amb), count, labels);
+    OFC_CHECK_LAUNCH("kmeans_assign_fix");
+    if (n_rechecked) OFC_CUDA(cudaMemcpyAsync(n_rechecked, count, 4, cudaMemcpyDeviceToDevice, st));
+    if (n_changed) {
+        OFC_CUDA(cudaMemsetAsync(n_changed, 0, 8, st));
+        if (prev_labels) {
+            int64_t g = (n + 255) / 256;
+            if (g > 148 * 8) g = 148 * 8;
+            labels_changed_kernel<<<(int)g, 256, 0, st>>>(labels, prev_labels, n, (unsigned long long*)n_changed);
+            OFC_CHECK_LAUNCH("labels_changed");
+        }
+    }
+    if (inertia) {
+        int64_t g = (n + 7) / 8;
+        if (g > w.parts) g = w.parts;
+        inertia_rows_kernel<<<(int)g, 256, 0, st>>>(Xc, n, d, c32, labels, (double*)(ws + w.off_part));
+        OFC_CHECK_LAUNCH("inertia_rows");
+        fold_partials_kernel<<<1, 32, 0, st>>>((const double*)(ws + w.off_part), (int)g, inertia);
+        OFC_CHECK_LAUNCH("fold_partials");
+    }
+    return OFC_OK;
+}
+
+int ofc_kmeans_tc_sums(const float* Xc, int64_t n, int d, int k, const int32_t* labels, double* sums, int64_t* counts,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = tc_shape_ok(n, d, k);
+    if (rc != OFC_OK) return rc;
+    OFC_REQUIRE(Xc && labels && sums && counts, "null buffer");
+    const TcLayout w = tc_layout(n, d, k);
+    if (!workspace || workspace_bytes < w.total) { set_error("tensor-core k-means workspace too small: %zu < %zu", workspace_bytes, w.total); return OFC_ERR_WORKSPACE; }
+    char* ws = (char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* table = (unsigned*)(ws + w.off_table);
+    int32_t* order = (int32_t*)(ws + w.off_order);
+    int* seg_first = (int*)(ws + w.off_segfirst);
+    int4* seg_info = (int4*)(ws + w.off_seginfo);
+    int* n_segs = (int*)(ws + w.off_nsegs);
+    double* partial = (double*)(ws + w.off_segpart);
+    ProfScope prof(PK_KMEANS, stream);
+    const int walk_ctas = (int)((w.n_chunks + 7) / 8);
+    const size_t walk_smem = (size_t)8 * k * 4;
+    static size_t walk_conf = 0;
+    if (walk_smem > 48 * 1024 && walk_smem > walk_conf) {
+        OFC_CUDA(cudaFuncSetAttribute(csr_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+        OFC_CUDA(cudaFuncSetAttribute(csr_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+        walk_conf = walk_smem;
+    }
+    csr_walk_kernel<false><<<walk_ctas, 256, walk_smem, st>>>(labels, n, k, table, nullptr);
+    OFC_CHECK_LAUNCH("csr_hist");
+    const size_t scan_smem = ((size_t)(k >= 1024 ? 1 : 1024 / k) * k + 2 * (size_t)k) * 4;
+    static size_t scan_conf = 0;
+    if (scan_smem > 48 * 1024 && scan_smem > scan_conf) {
+        OFC_CUDA(cudaFuncSetAttribute(csr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+        scan_conf = scan_smem;
+    }
+    csr_scan_kernel<<<1, 1024, scan_smem, st>>>(table, w.n_chunks, k, (long long*)counts, seg_first, seg_info, n_segs);
+    OFC_CHECK_LAUNCH("csr_scan");
+    csr_walk_kernel<true><<<walk_ctas, 256, walk_smem, st>>>(labels, n, k, table, order);
+    OFC_CHECK_LAUNCH("csr_scatter");
+    const int dt = cdiv(d, 128);
+    int64_t gx = w.max_segs;
+    const int64_t cap = (int64_t)sm_count() * 32 / dt + 1;
+    if (gx > cap) gx = cap;
+    seg_sums_kernel<<<dim3((unsigned)gx, dt), 128, 0, st>>>(Xc, d, order, seg_info, n_segs, partial);
+    OFC_CHECK_LAUNCH("seg_sums");
+    seg_fold_kernel<<<dim3(k, dt), 128, 0, st>>>(partial, d, seg_first, sums);
+    OFC_CHECK_LAUNCH("seg_fold");
+    return OFC_OK;
+}
+
+}  // extern "C"

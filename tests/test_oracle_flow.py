@@ -35,6 +35,34 @@ def test_oracle_flow_vs_live_cv2(kw):
     assert epe.mean() < 2e-6 and epe.max() < 2e-4, (epe.mean(), epe.max())
 
 
+@pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")
+@pytest.mark.parametrize("flags,kw", [(256, dict()), (4, dict()), (260, dict(winsize=9)),
+                                      (4, dict(pyr_scale=0.6, levels=2, winsize=11)), (256, dict(winsize=21, levels=1))])
+def test_oracle_flow_flags_vs_live_cv2(flags, kw):
+    """OPTFLOW_FARNEBACK_GAUSSIAN (256) and OPTFLOW_USE_INITIAL_FLOW (4)"""
+    import cv2
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    clip = synthetic_clip(3, 101, 150, seed=9).numpy()
+    g = np.stack([V.bgr2gray(f) for f in clip])
+    a = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2)
+    a.update(kw)
+    init = cv2.calcOpticalFlowFarneback(g[0], g[1], None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    ref = cv2.calcOpticalFlowFarneback(g[1], g[2], init.copy(), a["pyr_scale"], a["levels"], a["winsize"],
+                                       a["iterations"], a["poly_n"], a["poly_sigma"], flags)
+    mine = FB.calc_optical_flow_farneback(g[1], g[2], init.copy(), flags=flags, **a)
+    epe = np.linalg.norm(mine - ref, axis=-1)
+    assert epe.mean() < 2e-6 and epe.max() < 2e-4, (epe.mean(), epe.max())
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")
+@pytest.mark.parametrize("shape", [(96, 128, 48, 64), (135, 240, 34, 60), (101, 150, 25, 38), (77, 131, 39, 66)])
+def test_oracle_resize_area_vs_live_cv2(shape):
+    import cv2
+    h, w, dh, dw = shape
+    f = (np.random.default_rng(1).standard_normal((h, w, 2)) * 3).astype(np.float32)
+    assert (FB.resize_area_f32(f, dw, dh) == cv2.resize(f, (dw, dh), interpolation=cv2.INTER_AREA)).all()
+
+
 def test_pyramid_plan_levels_plus_one():
     # Q1: levels=3 means 4 scales; cvRound sizes; ksize 19/9/3/3 at 1080p
     plan = FB.pyramid_plan(1920, 1080, 0.5, 3)
