@@ -48,8 +48,13 @@ int ofc_profile_end(float* ms_by_kind, int* launches_by_kind, int n_kinds);
  * winsize, iterations, poly_n, poly_sigma, flags)
  *   reference: computeOpticalFlowModule.py:20-22, computeOpticalFlow.py:99-101.
  * A plan fixes the frame size and parameters (pyramid geometry, filter taps,
- * workspace layout) for up to `max_frames` frames per call.  flags must be 0
- * (box window, no initial flow) -> OFC_ERR_UNSUPPORTED otherwise. */
+ * workspace layout) for up to `max_frames` frames per call.  flags: 0 (box window,
+ * the reference's literal), OFC_FLOW_GAUSSIAN (cv2.OPTFLOW_FARNEBACK_GAUSSIAN: Gaussian
+ * window of winsize | 1 taps, any odd winsize <= 65) and/or OFC_FLOW_USE_INITIAL_FLOW
+ * (cv2.OPTFLOW_USE_INITIAL_FLOW, through ofc_farneback_pair_init); anything else ->
+ * OFC_ERR_UNSUPPORTED. */
+#define OFC_FLOW_USE_INITIAL_FLOW 4
+#define OFC_FLOW_GAUSSIAN 256
 typedef struct ofc_flow_plan ofc_flow_plan;
 
 int ofc_flow_plan_create(ofc_flow_plan** plan, int width, int height, int max_frames,
@@ -82,6 +87,12 @@ int ofc_farneback_sequence(const ofc_flow_plan* plan, const uint8_t* gray, int n
 int ofc_farneback_pair(const ofc_flow_plan* plan, const uint8_t* prev, const uint8_t* next,
                        float* flow, uint32_t* minmax,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* the cv2 call with flags & OPTFLOW_USE_INITIAL_FLOW: init_flow f32[H][W][2] seeds the coarsest
+ * pyramid level (cv::resize INTER_AREA, times the level's scale); plan created with that flag */
+int ofc_farneback_pair_init(const ofc_flow_plan* plan, const uint8_t* prev, const uint8_t* next,
+                            const float* init_flow, float* flow, uint32_t* minmax,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- 8-bit colour ---------------------------------------------------------
  * cv.cvtColor(frame, COLOR_BGR2GRAY)        computeOpticalFlowModule.py:16,19 */
@@ -187,23 +198,25 @@ int ofc_kmeans_cells(const uint8_t* X, int batch, int64_t n, int d, int k, const
  * The same sklearn E-step / M-step (KmeanGrids.py:299-304, color_kmeans.py:65-78;
  * _k_means_lloyd.pyx:160-213) for ONE float32 problem whose distance step is a real GEMM
  * (d >= 32, d % 4 == 0, 2 <= k <= 8192; the 1M x D sweep of BASELINE configs[4]).
- * ofc_kmeans_tc_prepare: Xc = float32(x - float32(mean)) (KMeans.fit centres float32 data in
- *   float32, _kmeans.py:1487-1493; mean nullable) and xnorm[i] = |Xc_i|; once per fit.
- * ofc_kmeans_tc_assign: TF32 tcgen05 distance GEMM (TMA-fed, accumulators in tensor memory) as a
- *   filter + float32 re-evaluation of every row whose two best distances are closer than the TF32
- *   error bound: labels are bit-identical to ofc_kmeans_assign(OFC_F32) on Xc.  n_changed /
- *   inertia as there (nullable); n_rechecked (nullable, device u32) = rows re-evaluated.
+ * ofc_kmeans_tc_prepare: xc = float32(x - float32(mean)) (KMeans.fit centres float32 data in
+ *   float32, _kmeans.py:1487-1493; mean nullable), stored split as Xh = its top 11 significant
+ *   bits (exact in TF32) and Xl = xc - Xh (exact), and xnorm[i] = |xc_i|; once per fit.
+ * ofc_kmeans_tc_assign: 3xTF32 tcgen05 distance GEMM (lo.hi + hi.lo + hi.hi; TMA-fed, accumulators
+ *   in tensor memory) as a filter + float32 re-evaluation of every row whose two best distances
+ *   are closer than the remaining error bound: labels are bit-identical to
+ *   ofc_kmeans_assign(OFC_F32) on xc.  n_changed / inertia as there (nullable); n_rechecked
+ *   (nullable, device u32) = rows re-evaluated.
  * ofc_kmeans_tc_sums: M-step over a label-sorted member list (stable counting sort, float64 sums
  *   in ascending row order per cluster; deterministic, no floating-point atomics).
  * All three share one workspace of ofc_kmeans_tc_workspace_bytes(n, d, k) bytes. */
 size_t ofc_kmeans_tc_workspace_bytes(int64_t n, int d, int k);
 int ofc_kmeans_tc_prepare(const float* X, const double* mean /* [d] */, int64_t n, int d,
-                          float* Xc /* [n][d] */, float* xnorm /* [n] */, void* stream);
-int ofc_kmeans_tc_assign(const float* Xc, const float* xnorm, int64_t n, int d, int k,
+                          float* Xh /* [n][d] */, float* Xl /* [n][d] */, float* xnorm /* [n] */, void* stream);
+int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, int64_t n, int d, int k,
                          const double* centres /* [k][d] */, int32_t* labels, const int32_t* prev_labels,
                          uint64_t* n_changed, double* inertia, uint32_t* n_rechecked,
                          void* workspace, size_t workspace_bytes, void* stream);
-int ofc_kmeans_tc_sums(const float* Xc, int64_t n, int d, int k, const int32_t* labels,
+int ofc_kmeans_tc_sums(const float* Xh, const float* Xl, int64_t n, int d, int k, const int32_t* labels,
                        double* sums /* [k][d] */, int64_t* counts /* [k] */,
                        void* workspace, size_t workspace_bytes, void* stream);
 

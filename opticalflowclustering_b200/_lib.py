@@ -30,6 +30,7 @@ SIGNATURES = {
     "ofc_flow_plan_buffer": (_i, [_vp, _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),
     "ofc_farneback_sequence": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "ofc_farneback_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_farneback_pair_init": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_bgr2gray": (_i, [_vp, _vp, _i64, _vp]),
     "ofc_bgr2hsv": (_i, [_vp, _vp, _i64, _vp]),
     "ofc_flow_minmax": (_i, [_vp, _i, _i64, _vp, _vp]),
@@ -43,9 +44,9 @@ SIGNATURES = {
     "ofc_kmeans_relocate": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "ofc_kmeans_cells": (_i, [_vp, _i, _i64, _i, _i, _vp, C.c_uint64, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_kmeans_tc_workspace_bytes": (_sz, [_i64, _i, _i]),
-    "ofc_kmeans_tc_prepare": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
-    "ofc_kmeans_tc_assign": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "ofc_kmeans_tc_sums": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_tc_prepare": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
+    "ofc_kmeans_tc_assign": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_tc_sums": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_grid_extract_cells": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ofc_sliding_cosine": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
     "ofc_row_cosine": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),

@@ -1302,6 +1302,181 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
 #endif
 }
 
+// ---------------------------------------------------------------------------
+// OPTFLOW_FARNEBACK_GAUSSIAN (cv2 flag 256; FarnebackUpdateFlow_GaussianBlur): the same fused
+// iteration with a separable Gaussian window of 2R+1 taps instead of the box.  Square tiles
+// (32 x 16 outputs + R halo), R at run time.  OpenCV's order of operations is kept: vertical pass
+// first, symmetric pairs added before the multiply, float32 throughout without contraction, rows and
+// columns replicated at the border (M evaluated at the clamped coordinate), solve in float64.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void eval_update_matrix(const IterParams& p, const float4* __restrict__ RA0, const float* __restrict__ RB0,
+                                                   const float4* __restrict__ RA1, const float* __restrict__ RB1,
+                                                   const float2* __restrict__ fin, int gx, int gy, float (&m)[5]) {
+    const int w = p.w, h = p.h;
+    const float2 fl = load_flow(p, fin, gx, gy);
+    const float dx = fl.x, dy = fl.y;
+    float fx = (float)gx + dx, fy = (float)gy + dy;
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    fx -= (float)x1; fy -= (float)y1;
+    const int64_t o0 = (int64_t)gy * w + gx;
+    const float4 a = RA0[o0];
+    const float b = RB0[o0];
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy, a00 = (1.f - fx) * (1.f - fy);
+        const int64_t o1 = (int64_t)y1 * w + x1;
+        const float4 q00 = RA1[o1], q01 = RA1[o1 + 1], q10 = RA1[o1 + w], q11 = RA1[o1 + w + 1];
+        const float s00 = RB1[o1], s01 = RB1[o1 + 1], s10 = RB1[o1 + w], s11 = RB1[o1 + w + 1];
+        r2 = a00 * q00.x + a01 * q01.x + a10 * q10.x + a11 * q11.x;
+        r3 = a00 * q00.y + a01 * q01.y + a10 * q10.y + a11 * q11.y;
+        r4 = a00 * q00.z + a01 * q01.z + a10 * q10.z + a11 * q11.z;
+        r5 = a00 * q00.w + a01 * q01.w + a10 * q10.w + a11 * q11.w;
+        r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
+        r4 = (a.z + r4) * 0.5f;
+        r5 = (a.w + r5) * 0.5f;
+        r6 = (b + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = a.z; r5 = a.w; r6 = b * 0.5f;
+    }
+    r2 = (a.x - r2) * 0.5f;
+    r3 = (a.y - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if ((unsigned)(gx - 5) >= (unsigned)(w - 10) || (unsigned)(gy - 5) >= (unsigned)(h - 10)) {
+        const float sc = (gx < 5 ? p.border[gx] : 1.f) * (gx >= w - 5 ? p.border[w - gx - 1] : 1.f) *
+                         (gy < 5 ? p.border[gy] : 1.f) * (gy >= h - 5 ? p.border[h - gy - 1] : 1.f);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    m[0] = r4 * r4 + r6 * r6;
+    m[1] = (r4 + r5) * r6;
+    m[2] = r5 * r5 + r6 * r6;
+    m[3] = r4 * r2 + r6 * r3;
+    m[4] = r6 * r2 + r5 * r3;
+}
+
+__global__ void __launch_bounds__(256) flow_iter_gauss_kernel(IterParams p, GaussWindow gw) {
+    constexpr int TW = 32, TH = 16, NT = 256;
+    const int R = gw.r;
+    const int MW = TW + 2 * R, MH = TH + 2 * R;
+    OFC_DYN_SMEM(float, sm);                       // M [5][MH][MW], then V [5][TH][MW]
+    float* sv = sm + 5 * MH * MW;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, pair = blockIdx.z;
+    const int w = p.w, h = p.h;
+    const float4* RA0 = p.RA + (int64_t)pair * p.r_stride;
+    const float* RB0 = p.RB + (int64_t)pair * p.r_stride;
+    const float4* RA1 = RA0 + p.r_next;
+    const float* RB1 = RB0 + p.r_next;
+    const float2* fin = p.flow_in ? p.flow_in + (int64_t)pair * p.flow_in_stride : nullptr;
+    for (int i = tid; i < MH * MW; i += NT) {
+        const int my = i / MW, mx = i - my * MW;
+        float m[5];
+        eval_update_matrix(p, RA0, RB0, RA1, RB1, fin, clampi(x0 - R + mx, 0, w - 1), clampi(y0 - R + my, 0, h - 1), m);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) sm[(c * MH + my) * MW + mx] = m[c];
+    }
+    __syncthreads();
+    for (int i = tid; i < 5 * TH * MW; i += NT) {
+        const int c = i / (TH * MW), r = i - c * TH * MW, ty = r / MW, mx = r - ty * MW;
+        const float* col = sm + (c * MH + ty + R) * MW + mx;
+        float v = __fmul_rn(col[0], gw.k[0]);
+        for (int t = 1; t <= R; ++t) v = __fadd_rn(v, __fmul_rn(__fadd_rn(col[t * MW], col[-t * MW]), gw.k[t]));
+        sv[i] = v;
+    }
+    __syncthreads();
+    float lmin = 3.402823466e38f, lmax = 0.f;
+    for (int i = tid; i < TH * TW; i += NT) {
+        const int ty = i / TW, tx = i - ty * TW;
+        const int gx = x0 + tx, gy = y0 + ty;
+        if (gx >= w || gy >= h) continue;
+        float S[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float* row = sv + (c * TH + ty) * MW + tx + R;
+            float v = __fmul_rn(row[0], gw.k[0]);
+            for (int t = 1; t <= R; ++t) v = __fadd_rn(v, __fmul_rn(__fadd_rn(row[t], row[-t]), gw.k[t]));
+            S[c] = v;
+        }
+        const double g11 = S[0], g12 = S[1], g22 = S[2], h1 = S[3], h2 = S[4];
+        const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+        const float2 res = make_float2((float)((g11 * h2 - g12 * h1) * idet), (float)((g22 * h1 - g12 * h2) * idet));
+        p.flow_out[(int64_t)pair * p.flow_out_stride + (int64_t)gy * w + gx] = res;
+        if (p.minmax) {
+            const float m = sqrtf(__fmaf_rn(res.x, res.x, __fmul_rn(res.y, res.y)));
+            lmin = fminf(lmin, m);
+            lmax = fmaxf(lmax, m);
+        }
+    }
+    if (p.minmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(p.minmax + 2 * pair, __float_as_uint(lmin));
+            atomicMax(p.minmax + 2 * pair + 1, __float_as_uint(lmax));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// OPTFLOW_USE_INITIAL_FLOW (cv2 flag 4): the caller's full-resolution flow seeds the coarsest level
+// through cv::resize(INTER_AREA) times the level's scale.  One thread per output pixel walks the
+// area tables in OpenCV's order (whole-number ratios: float32 box sum in row-major order times
+// 1/area; fractional ratios: per source row a float32 weighted row sum, then times the row weight).
+// ---------------------------------------------------------------------------
+struct AreaSpan { int first, mid0, mid1, last; float wf, wm, wl; };     // first/last = -1 when absent
+__device__ __forceinline__ AreaSpan area_span(int dx, double scale, int ssize) {
+    AreaSpan a;
+    const double f1 = dx * scale, f2 = f1 + scale;
+    const double cell = fmin(scale, (double)ssize - f1);
+    int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+    s2 = min(s2, ssize - 1);
+    s1 = min(s1, s2);
+    a.first = (s1 - f1 > 1e-3) ? s1 - 1 : -1;
+    a.wf = (float)((s1 - f1) / cell);
+    a.mid0 = s1; a.mid1 = s2;
+    a.wm = (float)(1.0 / cell);
+    a.last = (f2 - s2 > 1e-3) ? s2 : -1;
+    a.wl = (float)(fmin(fmin(f2 - s2, 1.0), cell) / cell);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) flow_area_seed_kernel(const float2* __restrict__ src, int64_t src_stride, int W, int H,
+                                                             float2* __restrict__ dst, int64_t dst_stride, int w, int h, float mul) {
+    const int dx = blockIdx.x * 32 + (threadIdx.x & 31), dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (dx >= w || dy >= h) return;
+    const float2* S = src + (int64_t)blockIdx.z * src_stride;
+    const double sx = (double)W / w, sy = (double)H / h;
+    const int ix = (int)nearbyint(sx), iy = (int)nearbyint(sy);
+    float ax = 0.f, ay = 0.f;
+    if (fabs(sx - ix) < 2.2e-16 && fabs(sy - iy) < 2.2e-16) {
+        for (int a = 0; a < iy; ++a)
+            for (int b = 0; b < ix; ++b) {
+                const float2 v = S[(int64_t)(dy * iy + a) * W + dx * ix + b];
+                ax = __fadd_rn(ax, v.x); ay = __fadd_rn(ay, v.y);
+            }
+        const float inv = (float)(1.0 / (ix * iy));
+        ax = __fmul_rn(ax, inv); ay = __fmul_rn(ay, inv);
+    } else {
+        const AreaSpan cx = area_span(dx, sx, W), cy = area_span(dy, sy, H);
+        auto row_sum = [&](int yy, float beta) {
+            const float2* r = S + (int64_t)yy * W;
+            float bx = 0.f, by = 0.f;
+            if (cx.first >= 0) { bx = __fadd_rn(bx, __fmul_rn(r[cx.first].x, cx.wf)); by = __fadd_rn(by, __fmul_rn(r[cx.first].y, cx.wf)); }
+            for (int xx = cx.mid0; xx < cx.mid1; ++xx) { bx = __fadd_rn(bx, __fmul_rn(r[xx].x, cx.wm)); by = __fadd_rn(by, __fmul_rn(r[xx].y, cx.wm)); }
+            if (cx.last >= 0) { bx = __fadd_rn(bx, __fmul_rn(r[cx.last].x, cx.wl)); by = __fadd_rn(by, __fmul_rn(r[cx.last].y, cx.wl)); }
+            ax = __fadd_rn(ax, __fmul_rn(bx, beta)); ay = __fadd_rn(ay, __fmul_rn(by, beta));
+        };
+        if (cy.first >= 0) row_sum(cy.first, cy.wf);
+        for (int yy = cy.mid0; yy < cy.mid1; ++yy) row_sum(yy, cy.wm);
+        if (cy.last >= 0) row_sum(cy.last, cy.wl);
+    }
+    dst[(int64_t)blockIdx.z * dst_stride + (int64_t)dy * w + dx] = make_float2(__fmul_rn(ax, mul), __fmul_rn(ay, mul));
+}
+
 __global__ void minmax_init_kernel(unsigned* mm, int n_pairs) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_pairs) {
@@ -1534,7 +1709,32 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
     return launch_strip_r<7, 64, 96, 4, 5>(p, n_pairs, stream);
 }
 
-int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scratch, void* stream) {
+int launch_flow_area_seed(const float2* src, int64_t src_stride, int W, int H, float2* dst, int64_t dst_stride, int w, int h,
+                          float mul, int n_pairs, void* stream) {
+    ProfScope prof(PK_UPSAMPLE, stream);
+    OFC_LAUNCH(flow_area_seed_kernel, dim3(cdiv(w, 32), cdiv(h, 8), n_pairs), dim3(256), 0, stream, src, src_stride, W, H, dst,
+               dst_stride, w, h, mul);
+    OFC_CHECK_LAUNCH("flow_area_seed");
+    return OFC_OK;
+}
+
+static int launch_iter_gauss(const IterParams& p, const GaussWindow& gw, int n_pairs, void* stream) {
+    const int MW = 32 + 2 * gw.r, MH = 16 + 2 * gw.r;
+    const size_t smem = (size_t)5 * (MH + 16) * MW * sizeof(float);
+    if (smem > 200 * 1024) { set_error("Gaussian window of %d taps needs too much shared memory", 2 * gw.r + 1); return OFC_ERR_UNSUPPORTED; }
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        OFC_CUDA(cudaFuncSetAttribute(flow_iter_gauss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
+    OFC_LAUNCH(flow_iter_gauss_kernel, dim3(cdiv(p.w, 32), cdiv(p.h, 16), n_pairs), dim3(256), smem, stream, p, gw);
+    OFC_CHECK_LAUNCH("flow_iter_gauss");
+    return OFC_OK;
+}
+
+int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scratch, void* stream, const GaussWindow* gw) {
+    if (gw) return launch_iter_gauss(p, *gw, n_pairs, stream);
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("OFC_ITER_VARIANT"); variant = e ? atoi(e) : 0; }
     // winsize 15 (the reference's literal) on the wide levels runs the strip-walk kernel; the small

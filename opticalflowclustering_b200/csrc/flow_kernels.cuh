@@ -48,13 +48,23 @@ struct IterParams {
     double blur_scale;           // 1 / winsize^2
 };
 
+// OPTFLOW_FARNEBACK_GAUSSIAN window: k[0] centre tap, k[i] the tap at distance i (2r+1 taps)
+struct GaussWindow {
+    int r;
+    float k[33];
+};
+
 int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* stream);
 // gray != null: full-resolution level with the fixed 3-tap pre-filter; I is produced from the 8-bit
 // frame inside the expansion kernel (and written to I_out as a by-product)
 int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, const unsigned char* gray, int64_t gray_stride,
                    float* I_out, void* stream);
 // scratch: a flow-sized buffer [n_pairs][h][w] the launch may overwrite (up-sampled input flow)
-int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scratch, void* stream);
+// gw != null: Gaussian window (cv2 flag 256) instead of the winsize x winsize box
+int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scratch, void* stream, const GaussWindow* gw = nullptr);
+// cv::resize(INTER_AREA) of full-resolution flow fields to a coarser level, times mul (cv2 flag 4)
+int launch_flow_area_seed(const float2* src, int64_t src_stride, int W, int H, float2* dst, int64_t dst_stride, int w, int h,
+                          float mul, int n_pairs, void* stream);
 int launch_minmax_init(unsigned* mm, int n_pairs, void* stream);
 
 }  // namespace ofc

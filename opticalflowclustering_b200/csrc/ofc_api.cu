@@ -72,6 +72,8 @@ struct ofc_flow_plan {
     double pyr_scale;
     int levels, winsize, iterations, poly_n;
     double poly_sigma;
+    int flags;                       // OFC_FLOW_USE_INITIAL_FLOW | OFC_FLOW_GAUSSIAN
+    ofc::GaussWindow gauss;          // window taps when OFC_FLOW_GAUSSIAN
     int keep_level0_I;               // also materialise I of the full-resolution level (fused away by default)
     // Side stream for the per-frame work (pre-filter + polynomial expansion), so that the large
     // full-resolution expansion overlaps the small, latency-bound iterations of the coarse levels.
@@ -146,8 +148,14 @@ static int prepare_poly(int n, double sigma, PolyParams& pp) {
 }
 
 static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t gray_stride, int n_frames,
-                         float* flow, uint32_t* minmax, void* workspace, size_t workspace_bytes, void* stream) {
+                         float* flow, uint32_t* minmax, void* workspace, size_t workspace_bytes, void* stream,
+                         const float* init_flow = nullptr) {
     OFC_REQUIRE(pl != nullptr, "null plan");
+    if ((pl->flags & OFC_FLOW_USE_INITIAL_FLOW) && !init_flow) {
+        set_error("the plan was created with OPTFLOW_USE_INITIAL_FLOW: call ofc_farneback_pair_init with the initial flow");
+        return OFC_ERR_INVALID;
+    }
+    if (!(pl->flags & OFC_FLOW_USE_INITIAL_FLOW)) init_flow = nullptr;
     OFC_REQUIRE(n_frames >= 2 && n_frames <= pl->max_frames, "n_frames=%d outside [2, %d]", n_frames, pl->max_frames);
     OFC_REQUIRE(gray && flow && workspace, "null buffer");
     if (workspace_bytes < pl->workspace_bytes) {
@@ -214,7 +222,17 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
             ip.border[0] = 0.14f; ip.border[1] = 0.14f; ip.border[2] = 0.4472f; ip.border[3] = 0.4472f; ip.border[4] = 0.4472f;
             ip.blur_scale = 1.0 / ((double)pl->winsize * pl->winsize);
             ip.upsample = 0; ip.wc = ip.hc = 0; ip.usx = ip.usy = 1.0; ip.flow_mul = 1.0;
-            if (it == 0) {
+            if (it == 0 && l == 0 && init_flow) {
+                // cv2 flag 4: resize(flow0, INTER_AREA) * scale seeds the coarsest level (other ping-pong buffer)
+                double scale = 1.0;
+                for (int i = 0; i < L.k; ++i) scale *= pl->pyr_scale;
+                float2* seed = (float2*)(ws + L.off_flow[1]);
+                int rc = launch_flow_area_seed((const float2*)init_flow, (int64_t)pl->W * pl->H, pl->W, pl->H, seed, npx, L.w, L.h,
+                                               (float)scale, n_pairs, stream);
+                if (rc != OFC_OK) return rc;
+                ip.flow_in = seed;
+                ip.flow_in_stride = npx;
+            } else if (it == 0) {
                 ip.flow_in = prev_flow;
                 ip.flow_in_stride = (int64_t)prev_w * prev_h;
                 if (prev_flow) {
@@ -232,7 +250,8 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
             ip.flow_out_stride = npx;
             ip.minmax = last ? minmax : nullptr;
             g_prof_level = nl - 1 - l;
-            int rc = launch_flow_iter(ip, pl->winsize, n_pairs, (float2*)(ws + L.off_flow[(it & 1) ^ 1]), stream);
+            int rc = launch_flow_iter(ip, pl->winsize, n_pairs, (float2*)(ws + L.off_flow[(it & 1) ^ 1]), stream,
+                                      (pl->flags & OFC_FLOW_GAUSSIAN) ? &pl->gauss : nullptr);
             if (rc != OFC_OK) return rc;
         }
         prev_flow = (const float2*)(ws + L.off_flow[(pl->iterations - 1) & 1]);
@@ -279,8 +298,8 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
                          int poly_n, double poly_sigma, int flags) {
     OFC_REQUIRE(out != nullptr, "null plan pointer");
     *out = nullptr;
-    if (flags != 0) {
-        set_error("flags=%d unsupported: only 0 (box window, no initial flow); there is no CPU fallback", flags);
+    if (flags & ~(OFC_FLOW_USE_INITIAL_FLOW | OFC_FLOW_GAUSSIAN)) {
+        set_error("flags=%d unsupported: OPTFLOW_USE_INITIAL_FLOW (4) and OPTFLOW_FARNEBACK_GAUSSIAN (256) are the only flags", flags);
         return OFC_ERR_UNSUPPORTED;
     }
     OFC_REQUIRE(width >= 16 && height >= 16, "frame %dx%d too small", width, height);
@@ -293,6 +312,8 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
     pl->W = width; pl->H = height; pl->max_frames = max_frames;
     pl->pyr_scale = pyr_scale; pl->levels = levels; pl->winsize = winsize;
     pl->iterations = iterations; pl->poly_n = poly_n; pl->poly_sigma = poly_sigma;
+    pl->flags = flags;
+    memset(&pl->gauss, 0, sizeof(pl->gauss));
     pl->d_taps = nullptr;
     pl->keep_level0_I = 0;
     pl->side = nullptr;
@@ -301,7 +322,22 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
     int rc = prepare_poly(poly_n, poly_sigma, pl->poly);
     if (rc != OFC_OK) { delete pl; return rc; }
     if (poly_n != 5 && poly_n != 7) { set_error("poly_n=%d unsupported (5 or 7)", poly_n); delete pl; return OFC_ERR_UNSUPPORTED; }
-    {   // winsize instantiations (see launch_flow_iter)
+    if (flags & OFC_FLOW_GAUSSIAN) {
+        // FarnebackUpdateFlow_GaussianBlur: 2m+1 taps, sigma = m * 0.3, normalised in double, stored as float
+        const int m = winsize / 2;
+        if (m > 32) { set_error("winsize=%d unsupported with OPTFLOW_FARNEBACK_GAUSSIAN (<= 65)", winsize); delete pl; return OFC_ERR_UNSUPPORTED; }
+        const double sigma = m * 0.3;
+        double kk[33];
+        double sum = 1.0;
+        kk[0] = 1.0;
+        for (int i = 1; i <= m; ++i) {
+            const float t = (float)exp(-i * i / (2 * sigma * sigma));
+            kk[i] = t;
+            sum += (double)t * 2;
+        }
+        pl->gauss.r = m;
+        for (int i = 0; i <= m; ++i) pl->gauss.k[i] = (float)(kk[i] * (1.0 / sum));
+    } else {   // winsize instantiations (see launch_flow_iter)
         int r = winsize / 2;
         if (!((r >= 2 && r <= 7) || r == 10 || r == 12)) {
             set_error("winsize=%d unsupported (odd 5..15, 21, 25)", winsize);
@@ -442,6 +478,15 @@ int ofc_farneback_pair(const ofc_flow_plan* plan, const uint8_t* prev, const uin
     if (!plan) { set_error("null plan"); return OFC_ERR_INVALID; }
     OFC_REQUIRE(prev && next, "null frame");
     return run_farneback(plan, prev, (int64_t)(next - prev), 2, flow, minmax, workspace, workspace_bytes, stream);
+}
+
+int ofc_farneback_pair_init(const ofc_flow_plan* plan, const uint8_t* prev, const uint8_t* next, const float* init_flow,
+                            float* flow, uint32_t* minmax, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!plan) { set_error("null plan"); return OFC_ERR_INVALID; }
+    OFC_REQUIRE(prev && next && init_flow, "null frame / initial flow");
+    OFC_REQUIRE(plan->flags & OFC_FLOW_USE_INITIAL_FLOW, "the plan was created without OPTFLOW_USE_INITIAL_FLOW");
+    OFC_REQUIRE(((uintptr_t)init_flow & 7) == 0, "initial flow must be 8-byte aligned");
+    return run_farneback(plan, prev, (int64_t)(next - prev), 2, flow, minmax, workspace, workspace_bytes, stream, init_flow);
 }
 
 int ofc_bgr2gray(const uint8_t* bgr, uint8_t* gray, int64_t n_pixels, void* stream) {

@@ -8,21 +8,25 @@
 // Lloyd E-step  label = first strict minimum over j of ||c_j||^2 - 2 x.c_j  (_k_means_lloyd.pyx:196-213).
 //
 // E-step (kmeans_assign_tc_kernel), one persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer: 128 x 32 float tiles of the rows (A) and BN x 32 tiles of the centres (B)
-//               into a 4-stage shared-memory ring (128-byte swizzle, mbarrier complete_tx);
+//   warp 0      TMA producer: 128 x 32 float tiles of the rows (A hi, A lo) and BN x 32 tiles of the centres
+//               (B hi, B lo) into a shared-memory ring (128-byte swizzle, mbarrier complete_tx);
 //   warp 1      one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) with the
 //               128 x BN float32 accumulator in tensor memory; two accumulators (2 x BN <= 512 columns)
 //               so the epilogue of one tile overlaps the MMAs of the next;
 //   warps 2..5  epilogue: tcgen05.ld of the accumulator (one row per thread), dist = c2 - 2 acc, running
 //               first/second/third minimum per row.
-// TF32 keeps 10 mantissa bits, so the tensor-core distances only FILTER: a row whose two best
-// distances are further apart than a rigorous bound on the TF32 error keeps its arg-min; every other
-// row is appended to a list and re-evaluated by kmeans_assign_fix_kernel in exactly the float32
-// arithmetic of kmeans_assign_generic_kernel (two candidates when only two centres are inside the
-// bound, all k otherwise).  Labels are therefore bit-identical to the CUDA-core float32 path.
+// TF32 keeps 10 mantissa bits, so every operand is split once into hi = its top 11 significant bits
+// and lo = the exact remainder (x = hi + lo, both float32), and x.c is formed as lo.hi + hi.lo + hi.hi
+// -- three MMAs per step ("3xTF32"), the hi parts exact in TF32 whatever the hardware does with the low
+// bits.  What is left (the lo.lo term, the TF32 image of the lo parts, float32 accumulation) is bounded
+// by (2^-19 + d 2^-23) |x| |c| per dot product, and the tensor-core distances only FILTER: a row whose
+// two best distances are further apart than that bound keeps its arg-min; every other row is appended
+// to a list and re-evaluated by kmeans_assign_fix_kernel in exactly the float32 arithmetic of
+// kmeans_assign_generic_kernel (the two or three centres inside the bound; all k when there are more).  Labels are therefore bit-identical to the CUDA-core float32 path.
 //
 // GPU only (no host-side emulation: tests/emu skips tc_*.cu).
 #include <cuda.h>
+#include <stdlib.h>
 #include "ofc_common.cuh"
 #include "../../include/ofc.h"
 
@@ -31,7 +35,6 @@ namespace {
 
 constexpr int BM = 128;          // rows per tile (= TMEM lanes)
 constexpr int BK = 32;           // floats per shared-memory row: 128 bytes = one swizzle atom
-constexpr int STAGES = 4;
 constexpr int TC_THREADS = 192;
 
 struct TcParams {
@@ -42,7 +45,7 @@ struct TcParams {
     const float* cmax;           // [1] largest centre norm
     float tol_scale;             // bound on |TF32 distance difference error| / (|x| cmax)
     int32_t* labels;
-    int4* amb;                   // [n] (row, best, second, full?) of rows to re-evaluate
+    int4* amb;                   // [n] (row, best, second, third | candidates << 16) of rows to re-evaluate
     unsigned* amb_count;
     unsigned* error_flag;
 };
@@ -122,10 +125,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(unsigned addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <int BN> struct TcCfg {
+    static constexpr unsigned A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+};
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
-    constexpr unsigned A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, TcParams p) {
+    constexpr unsigned A_BYTES = TcCfg<BN>::A_BYTES, B_BYTES = TcCfg<BN>::B_BYTES, STAGE_BYTES = TcCfg<BN>::STAGE_BYTES;
+    constexpr int STAGES = TcCfg<BN>::STAGES;
     // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
     constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -169,8 +180,10 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag);
                         mbar_expect_tx(full_bar(s), STAGE_BYTES);
                         const unsigned a_dst = smem_addr(smem + (size_t)s * STAGE_BYTES);
-                        tma_load_2d(a_dst, &tmA, full_bar(s), kt * BK, mt * BM);
-                        tma_load_2d(a_dst + A_BYTES, &tmB, full_bar(s), kt * BK, nt * BN);
+                        tma_load_2d(a_dst, &tmAh, full_bar(s), kt * BK, mt * BM);
+                        tma_load_2d(a_dst + A_BYTES, &tmAl, full_bar(s), kt * BK, mt * BM);
+                        tma_load_2d(a_dst + 2 * A_BYTES, &tmBh, full_bar(s), kt * BK, nt * BN);
+                        tma_load_2d(a_dst + 2 * A_BYTES + B_BYTES, &tmBl, full_bar(s), kt * BK, nt * BN);
                     }
         }
     } else if (warp == 1) {
@@ -188,10 +201,14 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         mbar_wait(full_bar(s), ph, p.error_flag);
                         tc_fence_after();
                         const unsigned a_addr = smem_addr(smem + (size_t)s * STAGE_BYTES);
-                        const uint64_t adesc = make_desc_sw128(a_addr), bdesc = make_desc_sw128(a_addr + A_BYTES);
+                        const uint64_t ah = make_desc_sw128(a_addr), al = make_desc_sw128(a_addr + A_BYTES);
+                        const uint64_t bh = make_desc_sw128(a_addr + 2 * A_BYTES), bl = make_desc_sw128(a_addr + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                        for (int k4 = 0; k4 < BK / 8; ++k4)      // 8 floats = 32 bytes per MMA: +2 in 16-byte units
-                            umma_tf32(tmem_d, adesc + 2u * k4, bdesc + 2u * k4, IDESC, (kt | k4) != 0);
+                        for (int k4 = 0; k4 < BK / 8; ++k4) {    // 8 floats = 32 bytes per MMA: +2 in 16-byte units
+                            umma_tf32(tmem_d, al + 2u * k4, bh + 2u * k4, IDESC, (kt | k4) != 0);
+                            umma_tf32(tmem_d, ah + 2u * k4, bl + 2u * k4, IDESC, 1u);
+                            umma_tf32(tmem_d, ah + 2u * k4, bh + 2u * k4, IDESC, 1u);
+                        }
                         umma_commit(empty_bar(s));               // frees the stage once these MMAs have read it
                     }
                     umma_commit(tfull_bar(acc));
@@ -202,8 +219,9 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const float cmax = __ldg(p.cmax);
         unsigned unit = 0;
         for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-            float m1 = __int_as_float(0x7f800000), m2 = m1, m3 = m1;
-            int a1 = 0, a2 = 0;
+            // the four smallest distances of the row (ties keep the lower index first) and where they are
+            float m1 = __int_as_float(0x7f800000), m2 = m1, m3 = m1, m4 = m1;
+            int a1 = 0, a2 = 0, a3 = 0;
             for (int nt = 0; nt < n_ntiles; ++nt, ++unit) {
                 const unsigned acc = unit & 1u, aph = (unit >> 1) & 1u;
                 mbar_wait(tfull_bar(acc), aph, p.error_flag);
@@ -215,14 +233,21 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     if (j0 >= p.k) break;
                     float v[32];
                     tmem_ld32(trow + c * 32, v);
-                    const int jn = p.k - j0 < 32 ? p.k - j0 : 32;
+                    const float4* c2v = reinterpret_cast<const float4*>(p.c2 + j0);   // padded with +inf past k
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        if (jj < jn) {
-                            const float dist = fmaf(-2.f, v[jj], __ldg(p.c2 + j0 + jj));
-                            if (dist < m1) { m3 = m2; m2 = m1; a2 = a1; m1 = dist; a1 = j0 + jj; }
-                            else if (dist < m2) { m3 = m2; m2 = dist; a2 = j0 + jj; }
-                            else if (dist < m3) { m3 = dist; }
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 cc = __ldg(c2v + g4);
+                        const float cj[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float dist = fmaf(-2.f, v[g4 * 4 + e], cj[e]);
+                            if (dist < m4) {
+                                const int j = j0 + g4 * 4 + e;
+                                if (dist < m1) { m4 = m3; m3 = m2; a3 = a2; m2 = m1; a2 = a1; m1 = dist; a1 = j; }
+                                else if (dist < m2) { m4 = m3; m3 = m2; a3 = a2; m2 = dist; a2 = j; }
+                                else if (dist < m3) { m4 = m3; m3 = dist; a3 = j; }
+                                else m4 = dist;
+                            }
                         }
                     }
                 }
@@ -235,8 +260,10 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 const float tol = p.tol_scale * __ldg(p.xnorm + row) * cmax;
                 p.labels[row] = a1;
                 if (!(m2 - m1 > tol)) {
+                    // candidates inside the bound: 2, 3, or (0) too many to list -> all k are re-evaluated
+                    const int ncand = (m3 - m1 > tol) ? 2 : ((m4 - m1 > tol) ? 3 : 0);
                     const unsigned pos = atomicAdd(p.amb_count, 1u);
-                    p.amb[pos] = make_int4((int)row, a1, a2, !(m3 - m1 > tol) ? 1 : 0);
+                    p.amb[pos] = make_int4((int)row, a1, a2, a3 | (ncand << 16));
                 }
             }
         }
@@ -251,16 +278,17 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
 // one float32 distance in the arithmetic of kmeans_assign_generic_kernel<float, float>: lanes stride over
 // the features, xor-tree reduction, dist = fma(-2, dot, c2)
-__device__ __forceinline__ float exact_dist(const float* __restrict__ row, const float* __restrict__ c, float c2, int d, int lane) {
+__device__ __forceinline__ float exact_dist(const float* __restrict__ rh, const float* __restrict__ rl, const float* __restrict__ c,
+                                            float c2, int d, int lane) {
     float part = 0.f;
-    for (int t = lane; t < d; t += 32) part = fmaf(row[t], c[t], part);
+    for (int t = lane; t < d; t += 32) part = fmaf(rh[t] + rl[t], c[t], part);       // hi + lo is the row, exactly
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     return fmaf(-2.f, part, c2);
 }
 
 // rows the tensor-core filter could not decide: one warp per row
-__global__ void __launch_bounds__(256) kmeans_assign_fix_kernel(const float* __restrict__ X, int d, int k,
+__global__ void __launch_bounds__(256) kmeans_assign_fix_kernel(const float* __restrict__ Xh, const float* __restrict__ Xl, int d, int k,
                                                                 const float* __restrict__ C, const float* __restrict__ c2,
                                                                 const int4* __restrict__ amb, const unsigned* __restrict__ amb_count,
                                                                 int32_t* __restrict__ labels) {
@@ -268,18 +296,29 @@ __global__ void __launch_bounds__(256) kmeans_assign_fix_kernel(const float* __r
     const unsigned n_amb = *amb_count;
     for (unsigned e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n_amb; e += gridDim.x * 8) {
         const int4 a = amb[e];
-        const float* row = X + (int64_t)a.x * d;
+        const float* rh = Xh + (int64_t)a.x * d;
+        const float* rl = Xl + (int64_t)a.x * d;
         int label;
-        if (!a.w) {
-            const int lo = a.y < a.z ? a.y : a.z, hi = a.y < a.z ? a.z : a.y;
-            const float dlo = exact_dist(row, C + (int64_t)lo * d, c2[lo], d, lane);
-            const float dhi = exact_dist(row, C + (int64_t)hi * d, c2[hi], d, lane);
-            label = dhi < dlo ? hi : lo;
+        const int ncand = a.w >> 16;
+        if (ncand) {
+            // first strict minimum in ascending centre order over the listed candidates
+            int c0 = a.y, c1 = a.z, c2i = ncand == 3 ? (a.w & 0xffff) : 0x7fffffff, t;
+            if (c1 < c0) { t = c0; c0 = c1; c1 = t; }
+            if (c2i < c1) { t = c1; c1 = c2i; c2i = t; }
+            if (c1 < c0) { t = c0; c0 = c1; c1 = t; }
+            float best = exact_dist(rh, rl, C + (int64_t)c0 * d, c2[c0], d, lane);
+            label = c0;
+            const float d1 = exact_dist(rh, rl, C + (int64_t)c1 * d, c2[c1], d, lane);
+            if (d1 < best) { best = d1; label = c1; }
+            if (ncand == 3) {
+                const float d2 = exact_dist(rh, rl, C + (int64_t)c2i * d, c2[c2i], d, lane);
+                if (d2 < best) { best = d2; label = c2i; }
+            }
         } else {
             float best = 0.f;
             label = 0;
             for (int j = 0; j < k; ++j) {
-                const float dist = exact_dist(row, C + (int64_t)j * d, c2[j], d, lane);
+                const float dist = exact_dist(rh, rl, C + (int64_t)j * d, c2[j], d, lane);
                 if (j == 0 || dist < best) { best = dist; label = j; }
             }
         }
@@ -287,14 +326,27 @@ __global__ void __launch_bounds__(256) kmeans_assign_fix_kernel(const float* __r
     }
 }
 
-// centres f64 -> f32 copy (the B operand)
-__global__ void centres_to_f32_kernel(const double* __restrict__ c, float* __restrict__ out, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (float)c[i];
+// hi = the top 11 significant bits (exact in TF32), lo = the exact remainder
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    lo = v - hi;
+}
+// centres f64 -> f32 copy and its hi / lo split (the B operands)
+__global__ void centres_to_f32_kernel(const double* __restrict__ c, float* __restrict__ out, float* __restrict__ hi, float* __restrict__ lo,
+                                      int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = (float)c[i];
+        out[i] = v;
+        split_tf32(v, hi[i], lo[i]);
+    }
 }
 // c2[j] in the order of kmeans_c2_kernel(as_float): sequential fma chain over the features
-__global__ void centres_c2_kernel(const float* __restrict__ c, float* __restrict__ c2, int d, int k) {
+__global__ void centres_c2_kernel(const float* __restrict__ c, float* __restrict__ c2, int d, int k, int k_pad) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= k) return;
+    if (j >= k) {
+        if (j < k_pad) c2[j] = __int_as_float(0x7f800000);       // past the last centre: never the minimum
+        return;
+    }
     const float* r = c + (int64_t)j * d;
     float s = 0.f;
     for (int t = 0; t < d; ++t) s = fmaf(r[t], r[t], s);
@@ -316,18 +368,17 @@ __global__ void __launch_bounds__(1024) centres_cmax_kernel(const float* __restr
     }
 }
 
-// Xc = float32(x - float32 mean) (KMeans.fit centres float32 data in float32, _kmeans.py:1487-1493) and the
-// row norms the tensor-core filter's error bound needs; one warp per row
+// xc = float32(x - float32 mean) (KMeans.fit centres float32 data in float32, _kmeans.py:1487-1493), stored as
+// its hi / lo split, and the row norms the tensor-core filter's error bound needs; one warp per row
 __global__ void __launch_bounds__(256) prepare_rows_kernel(const float* __restrict__ X, const double* __restrict__ mean, int64_t n,
-                                                           int d, float* __restrict__ Xc, float* __restrict__ xnorm) {
+                                                           int d, float* __restrict__ Xh, float* __restrict__ Xl, float* __restrict__ xnorm) {
     const int lane = threadIdx.x & 31;
     for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * 8) {
         const float* row = X + i * d;
-        float* out = Xc + i * d;
         float s = 0.f;
         for (int t = lane; t < d; t += 32) {
             const float v = row[t] - (mean ? (float)mean[t] : 0.f);
-            out[t] = v;
+            split_tf32(v, Xh[i * d + t], Xl[i * d + t]);
             s = fmaf(v, v, s);
         }
 #pragma unroll
@@ -347,16 +398,18 @@ __global__ void __launch_bounds__(256) labels_changed_kernel(const int32_t* __re
 
 // inertia partials: sum over the rows of a CTA of ||x - c_label||^2 (float32 per row like the assign kernels,
 // float64 across rows), one warp per row, fixed order inside the CTA; folded in CTA order afterwards
-__global__ void __launch_bounds__(256) inertia_rows_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ C,
+__global__ void __launch_bounds__(256) inertia_rows_kernel(const float* __restrict__ Xh, const float* __restrict__ Xl, int64_t n, int d,
+                                                           const float* __restrict__ C,
                                                            const int32_t* __restrict__ labels, double* __restrict__ partial) {
     __shared__ double s_w[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * 8 + warp; i < n; i += (int64_t)gridDim.x * 8) {
-        const float* row = X + i * d;
+        const float* rh = Xh + i * d;
+        const float* rl = Xl + i * d;
         const float* c = C + (int64_t)labels[i] * d;
         float sq = 0.f;
-        for (int t = lane; t < d; t += 32) { const float df = row[t] - c[t]; sq = fmaf(df, df, sq); }
+        for (int t = lane; t < d; t += 32) { const float df = (rh[t] + rl[t]) - c[t]; sq = fmaf(df, df, sq); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         acc += (double)sq;
@@ -473,7 +526,8 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(unsigned* __restrict__ t
     }
 }
 
-__global__ void __launch_bounds__(128) seg_sums_kernel(const float* __restrict__ X, int d, const int32_t* __restrict__ order,
+__global__ void __launch_bounds__(128) seg_sums_kernel(const float* __restrict__ Xh, const float* __restrict__ Xl, int d,
+                                                       const int32_t* __restrict__ order,
                                                        const int4* __restrict__ seg_info, const int* __restrict__ n_segs,
                                                        double* __restrict__ partial) {
     const int t = blockIdx.y * 128 + threadIdx.x;
@@ -483,11 +537,13 @@ __global__ void __launch_bounds__(128) seg_sums_kernel(const float* __restrict__
         if (t < d) {
             int m = si.y;
             for (; m + 4 <= si.z; m += 4) {
-                const float v0 = X[(int64_t)order[m] * d + t], v1 = X[(int64_t)order[m + 1] * d + t];
-                const float v2 = X[(int64_t)order[m + 2] * d + t], v3 = X[(int64_t)order[m + 3] * d + t];
-                acc += (double)v0; acc += (double)v1; acc += (double)v2; acc += (double)v3;
+                const int64_t o0 = (int64_t)order[m] * d + t, o1 = (int64_t)order[m + 1] * d + t;
+                const int64_t o2 = (int64_t)order[m + 2] * d + t, o3 = (int64_t)order[m + 3] * d + t;
+                const float h0 = Xh[o0], h1 = Xh[o1], h2 = Xh[o2], h3 = Xh[o3];
+                const float l0 = Xl[o0], l1 = Xl[o1], l2 = Xl[o2], l3 = Xl[o3];
+                acc += (double)(h0 + l0); acc += (double)(h1 + l1); acc += (double)(h2 + l2); acc += (double)(h3 + l3);
             }
-            for (; m < si.z; ++m) acc += (double)X[(int64_t)order[m] * d + t];
+            for (; m < si.z; ++m) { const int64_t o = (int64_t)order[m] * d + t; acc += (double)(Xh[o] + Xl[o]); }
             partial[(int64_t)s * d + t] = acc;
         }
     }
@@ -543,7 +599,7 @@ int sm_count() {
 }
 
 struct TcLayout {
-    size_t off_c32, off_c2, off_cmax, off_count, off_err, off_amb, off_part, off_table, off_order, off_segfirst, off_seginfo,
+    size_t off_c32, off_ch, off_cl, off_c2, off_cmax, off_count, off_err, off_amb, off_part, off_table, off_order, off_segfirst, off_seginfo,
         off_nsegs, off_segpart, total;
     int64_t n_chunks, max_segs;
     int parts;
@@ -556,7 +612,9 @@ TcLayout tc_layout(int64_t n, int d, int k) {
     w.max_segs = n / SEG + k + 1;
     w.parts = 148 * 8;
     w.off_c32 = take((size_t)k * d * 4);
-    w.off_c2 = take((size_t)k * 4);
+    w.off_ch = take((size_t)k * d * 4);
+    w.off_cl = take((size_t)k * d * 4);
+    w.off_c2 = take((size_t)(k + 512) * 4);
     w.off_cmax = take(4);
     w.off_count = take(4);
     w.off_err = take(4);
@@ -573,8 +631,9 @@ TcLayout tc_layout(int64_t n, int d, int k) {
 }
 
 template <int BN>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, void* stream) {
-    constexpr size_t smem = (size_t)STAGES * (BM * BK * 4 + BN * BK * 4) + 1024 + 256;
+int launch_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh, const CUtensorMap& tmBl, const TcParams& p,
+              void* stream) {
+    constexpr size_t smem = TcCfg<BN>::SMEM;
     static bool configured = false;
     if (!configured) {
         OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -582,7 +641,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
     }
     const int64_t mtiles = (p.n + BM - 1) / BM;
     const int grid = (int)(mtiles < sm_count() ? mtiles : sm_count());
-    kmeans_assign_tc_kernel<BN><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+    kmeans_assign_tc_kernel<BN><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmAh, tmAl, tmBh, tmBl, p);
     OFC_CHECK_LAUNCH("kmeans_assign_tc");
     return OFC_OK;
 }
@@ -606,59 +665,63 @@ size_t ofc_kmeans_tc_workspace_bytes(int64_t n, int d, int k) {
     return tc_layout(n, d, k).total;
 }
 
-int ofc_kmeans_tc_prepare(const float* X, const double* mean, int64_t n, int d, float* Xc, float* xnorm, void* stream) {
-    OFC_REQUIRE(X && Xc && xnorm && n >= 1 && d >= 1, "bad arguments");
+int ofc_kmeans_tc_prepare(const float* X, const double* mean, int64_t n, int d, float* Xh, float* Xl, float* xnorm, void* stream) {
+    OFC_REQUIRE(X && Xh && Xl && xnorm && n >= 1 && d >= 1, "bad arguments");
     int64_t g = (n + 7) / 8;
     if (g > 148 * 16) g = 148 * 16;
     ProfScope prof(PK_KMEANS, stream);
-    prepare_rows_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(X, mean, n, d, Xc, xnorm);
+    prepare_rows_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(X, mean, n, d, Xh, Xl, xnorm);
     OFC_CHECK_LAUNCH("prepare_rows");
     return OFC_OK;
 }
 
-int ofc_kmeans_tc_assign(const float* Xc, const float* xnorm, int64_t n, int d, int k, const double* centres, int32_t* labels,
+int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, int64_t n, int d, int k, const double* centres, int32_t* labels,
                          const int32_t* prev_labels, uint64_t* n_changed, double* inertia, uint32_t* n_rechecked,
                          void* workspace, size_t workspace_bytes, void* stream) {
     int rc = tc_shape_ok(n, d, k);
     if (rc != OFC_OK) return rc;
-    OFC_REQUIRE(Xc && xnorm && centres && labels, "null buffer");
-    OFC_REQUIRE(((uintptr_t)Xc & 15) == 0, "rows must be 16-byte aligned");
+    OFC_REQUIRE(Xh && Xl && xnorm && centres && labels, "null buffer");
+    OFC_REQUIRE(((uintptr_t)Xh & 15) == 0 && ((uintptr_t)Xl & 15) == 0, "rows must be 16-byte aligned");
     const TcLayout w = tc_layout(n, d, k);
     if (!workspace || workspace_bytes < w.total) { set_error("tensor-core k-means workspace too small: %zu < %zu", workspace_bytes, w.total); return OFC_ERR_WORKSPACE; }
     OFC_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     char* ws = (char*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     float* c32 = (float*)(ws + w.off_c32);
+    float* ch = (float*)(ws + w.off_ch);
+    float* cl = (float*)(ws + w.off_cl);
     float* c2 = (float*)(ws + w.off_c2);
     float* cmax = (float*)(ws + w.off_cmax);
     unsigned* count = (unsigned*)(ws + w.off_count);
     unsigned* err = (unsigned*)(ws + w.off_err);
     ProfScope prof(PK_KMEANS, stream);
     const int64_t kd = (int64_t)k * d;
-    centres_to_f32_kernel<<<(int)((kd + 255) / 256 < 1184 ? (kd + 255) / 256 : 1184), 256, 0, st>>>(centres, c32, kd);
+    centres_to_f32_kernel<<<(int)((kd + 255) / 256 < 1184 ? (kd + 255) / 256 : 1184), 256, 0, st>>>(centres, c32, ch, cl, kd);
     OFC_CHECK_LAUNCH("centres_to_f32");
-    centres_c2_kernel<<<cdiv(k, 128), 128, 0, st>>>(c32, c2, d, k);
+    centres_c2_kernel<<<cdiv(k + 256, 128), 128, 0, st>>>(c32, c2, d, k, k + 256);
     OFC_CHECK_LAUNCH("centres_c2");
     centres_cmax_kernel<<<1, 1024, 0, st>>>(c2, k, cmax, count);
     OFC_CHECK_LAUNCH("centres_cmax");
     OFC_CUDA(cudaMemsetAsync(err, 0, 4, st));
 
     const int BN = k <= 64 ? 64 : (k <= 128 ? 128 : 256);
-    CUtensorMap tmA, tmB;
-    rc = encode_rows_map(&tmA, Xc, n, d, BM);
-    if (rc != OFC_OK) return rc;
-    rc = encode_rows_map(&tmB, c32, k, d, BN);
+    CUtensorMap tmAh, tmAl, tmBh, tmBl;
+    rc = encode_rows_map(&tmAh, Xh, n, d, BM);
+    if (rc == OFC_OK) rc = encode_rows_map(&tmAl, Xl, n, d, BM);
+    if (rc == OFC_OK) rc = encode_rows_map(&tmBh, ch, k, d, BN);
+    if (rc == OFC_OK) rc = encode_rows_map(&tmBl, cl, k, d, BN);
     if (rc != OFC_OK) return rc;
     TcParams p;
     p.n = n; p.d = d; p.k = k; p.c2 = c2; p.xnorm = xnorm; p.cmax = cmax;
-    // per distance: 2 |x.c| (2^-9 TF32 operand truncation + d 2^-23 accumulation); two distances; x1.5 margin
-    p.tol_scale = 1.5f * 4.f * (1.f / 512.f + (float)d * (1.f / 8388608.f));
+    // per distance: 2 |x| |c| (2^-19 split remainder + d 2^-23 accumulation); two distances; x1.5 margin
+    static const float tol_mul = getenv("OFC_TC_TOL_MUL") ? (float)atof(getenv("OFC_TC_TOL_MUL")) : 1.5f;
+    p.tol_scale = tol_mul * 4.f * (1.f / 524288.f + (float)d * (1.f / 8388608.f));
     p.labels = labels; p.amb = (int4*)(ws + w.off_amb); p.amb_count = count; p.error_flag = err;
-    if (BN == 64) rc = launch_tc<64>(tmA, tmB, p, stream);
-    else if (BN == 128) rc = launch_tc<128>(tmA, tmB, p, stream);
-    else rc = launch_tc<256>(tmA, tmB, p, stream);
+    if (BN == 64) rc = launch_tc<64>(tmAh, tmAl, tmBh, tmBl, p, stream);
+    else if (BN == 128) rc = launch_tc<128>(tmAh, tmAl, tmBh, tmBl, p, stream);
+    else rc = launch_tc<256>(tmAh, tmAl, tmBh, tmBl, p, stream);
     if (rc != OFC_OK) return rc;
-    kmeans_assign_fix_kernel<<<sm_count() * 4, 256, 0, st>>>(Xc, d, k, c32, c2, (const int4*)(ws + w.off_amb), count, labels);
+    kmeans_assign_fix_kernel<<<sm_count() * 4, 256, 0, st>>>(Xh, Xl, d, k, c32, c2, (const int4*)(ws + w.off_amb), count, labels);
     OFC_CHECK_LAUNCH("kmeans_assign_fix");
     if (n_rechecked) OFC_CUDA(cudaMemcpyAsync(n_rechecked, count, 4, cudaMemcpyDeviceToDevice, st));
     if (n_changed) {
@@ -673,7 +736,7 @@ int ofc_kmeans_tc_assign(const float* Xc, const float* xnorm, int64_t n, int d, 
     if (inertia) {
         int64_t g = (n + 7) / 8;
         if (g > w.parts) g = w.parts;
-        inertia_rows_kernel<<<(int)g, 256, 0, st>>>(Xc, n, d, c32, labels, (double*)(ws + w.off_part));
+        inertia_rows_kernel<<<(int)g, 256, 0, st>>>(Xh, Xl, n, d, c32, labels, (double*)(ws + w.off_part));
         OFC_CHECK_LAUNCH("inertia_rows");
         fold_partials_kernel<<<1, 32, 0, st>>>((const double*)(ws + w.off_part), (int)g, inertia);
         OFC_CHECK_LAUNCH("fold_partials");
@@ -681,11 +744,11 @@ int ofc_kmeans_tc_assign(const float* Xc, const float* xnorm, int64_t n, int d, 
     return OFC_OK;
 }
 
-int ofc_kmeans_tc_sums(const float* Xc, int64_t n, int d, int k, const int32_t* labels, double* sums, int64_t* counts,
+int ofc_kmeans_tc_sums(const float* Xh, const float* Xl, int64_t n, int d, int k, const int32_t* labels, double* sums, int64_t* counts,
                        void* workspace, size_t workspace_bytes, void* stream) {
     int rc = tc_shape_ok(n, d, k);
     if (rc != OFC_OK) return rc;
-    OFC_REQUIRE(Xc && labels && sums && counts, "null buffer");
+    OFC_REQUIRE(Xh && Xl && labels && sums && counts, "null buffer");
     const TcLayout w = tc_layout(n, d, k);
     if (!workspace || workspace_bytes < w.total) { set_error("tensor-core k-means workspace too small: %zu < %zu", workspace_bytes, w.total); return OFC_ERR_WORKSPACE; }
     char* ws = (char*)workspace;
@@ -721,7 +784,7 @@ int ofc_kmeans_tc_sums(const float* Xc, int64_t n, int d, int k, const int32_t* 
     int64_t gx = w.max_segs;
     const int64_t cap = (int64_t)sm_count() * 32 / dt + 1;
     if (gx > cap) gx = cap;
-    seg_sums_kernel<<<dim3((unsigned)gx, dt), 128, 0, st>>>(Xc, d, order, seg_info, n_segs, partial);
+    seg_sums_kernel<<<dim3((unsigned)gx, dt), 128, 0, st>>>(Xh, Xl, d, order, seg_info, n_segs, partial);
     OFC_CHECK_LAUNCH("seg_sums");
     seg_fold_kernel<<<dim3(k, dt), 128, 0, st>>>(partial, d, seg_first, sums);
     OFC_CHECK_LAUNCH("seg_fold");

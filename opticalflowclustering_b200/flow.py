@@ -15,6 +15,8 @@ import torch
 from . import _lib
 
 _vp = C.c_void_p
+OPTFLOW_USE_INITIAL_FLOW = 4          # cv2.OPTFLOW_USE_INITIAL_FLOW
+OPTFLOW_FARNEBACK_GAUSSIAN = 256      # cv2.OPTFLOW_FARNEBACK_GAUSSIAN
 
 
 def _stream_ptr() -> _vp:
@@ -103,13 +105,25 @@ class FarnebackPlan:
         return flow
 
     def pair(self, prev: torch.Tensor, nxt: torch.Tensor, flow: torch.Tensor | None = None,
-             minmax: torch.Tensor | None = None):
+             minmax: torch.Tensor | None = None, init_flow: torch.Tensor | None = None):
+        """One pair, the literal cv2 call.  ``init_flow`` f32 [H,W,2] (CUDA) is required when the plan was
+        created with cv2.OPTFLOW_USE_INITIAL_FLOW (4) and seeds the coarsest level."""
         for g in (prev, nxt):
             if tuple(g.shape) != (self.height, self.width) or g.dtype != torch.uint8 or not g.is_cuda:
                 raise ValueError("prev/next must be CUDA uint8 [H,W] of the plan's size")
         prev, nxt = prev.contiguous(), nxt.contiguous()
         if flow is None:
             flow = torch.empty((self.height, self.width, 2), dtype=torch.float32, device=self.device)
+        if self.params[6] & OPTFLOW_USE_INITIAL_FLOW:
+            if (init_flow is None or tuple(init_flow.shape) != (self.height, self.width, 2) or init_flow.dtype != torch.float32
+                    or not init_flow.is_cuda):
+                raise ValueError("OPTFLOW_USE_INITIAL_FLOW needs init_flow: CUDA float32 [H,W,2] of the plan's size")
+            init_flow = init_flow.contiguous()
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().ofc_farneback_pair_init(self._ptr, _ptr(prev), _ptr(nxt), _ptr(init_flow), _ptr(flow),
+                                                              _ptr(minmax), _ptr(self.workspace), self.workspace_bytes,
+                                                              _stream_ptr()))
+            return flow
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ofc_farneback_pair(self._ptr, _ptr(prev), _ptr(nxt), _ptr(flow), _ptr(minmax),
                                                      _ptr(self.workspace), self.workspace_bytes, _stream_ptr()))
@@ -144,7 +158,9 @@ def calc_optical_flow_farneback(prev, next, flow=None, pyr_scale=0.5, levels=3, 
 
     ``prev`` / ``next``: single-channel uint8 images of equal size, numpy or
     torch (CUDA).  Returns float32 ``[H, W, 2]`` of the same kind as the input.
-    ``flags`` other than 0 raise NotImplementedError (no CPU fallback).
+    ``flags``: 0 (the reference's literal), ``cv2.OPTFLOW_FARNEBACK_GAUSSIAN`` (256) and/or
+    ``cv2.OPTFLOW_USE_INITIAL_FLOW`` (4, ``flow`` is then the initial flow, float32 ``[H, W, 2]``);
+    any other bit raises NotImplementedError (no CPU fallback).
     """
     as_numpy = not isinstance(prev, torch.Tensor)
     p = to_device_u8(prev)
@@ -153,7 +169,13 @@ def calc_optical_flow_farneback(prev, next, flow=None, pyr_scale=0.5, levels=3, 
         raise ValueError("prev and next must be single-channel images of equal size")
     params = (float(pyr_scale), int(levels), int(winsize), int(iterations), int(poly_n), float(poly_sigma), int(flags))
     plan = _cached_plan(int(p.shape[1]), int(p.shape[0]), params, p.device)
-    out = plan.pair(p, n)
+    init = None
+    if int(flags) & OPTFLOW_USE_INITIAL_FLOW:
+        if flow is None:
+            raise ValueError("OPTFLOW_USE_INITIAL_FLOW needs the initial flow in `flow`")
+        init = flow if isinstance(flow, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(flow, dtype=np.float32))
+        init = init.to(device=p.device, dtype=torch.float32)
+    out = plan.pair(p, n, init_flow=init)
     if as_numpy:
         res = out.cpu().numpy()
         if isinstance(flow, np.ndarray) and flow.shape == res.shape and flow.dtype == res.dtype:

@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from fractions import Fraction
 
 import numpy as np
@@ -98,7 +99,9 @@ def _as_batch(X, device=None):
 class LloydState:
     """Buffers of one batched Lloyd run (all on the data's device)."""
 
-    def __init__(self, ctx: _Ctx, X: torch.Tensor, k: int):
+    def __init__(self, ctx: _Ctx, X: torch.Tensor, k: int, ws_k: int | None = None):
+        """``ws_k``: cluster count the stepwise workspace is sized for (1 when the tensor-core path does
+        the E/M steps and only the column statistics run through the stepwise kernels)."""
         self.ctx, self.X, self.k = ctx, X, int(k)
         self.B, self.n, self.d = (int(s) for s in X.shape)
         self.dtype = _DT[X.dtype]
@@ -106,7 +109,7 @@ class LloydState:
         lib = ctx.lib
         lib.ofc_kmeans_workspace_bytes.restype = C.c_size_t
         lib.ofc_kmeans_workspace_bytes.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int]
-        self.ws_bytes = int(lib.ofc_kmeans_workspace_bytes(self.B, self.n, self.d, max(self.k, 1)))
+        self.ws_bytes = int(lib.ofc_kmeans_workspace_bytes(self.B, self.n, self.d, max(self.k if ws_k is None else int(ws_k), 1)))
         self.ws = torch.empty(max(self.ws_bytes, 256), dtype=torch.uint8, device=dev)
         self.labels = [torch.full((self.B, self.n), -1, dtype=torch.int32, device=dev) for _ in range(2)]
         # one flat fp64 buffer so a single all-reduce moves sums, counts and n_changed together
@@ -143,6 +146,48 @@ class LloydState:
         c.check(c.lib.ofc_kmeans_relocate(_ptr(self.X), self.dtype, self.B, C.c_int64(self.n), self.d, self.k, _ptr(mean),
                                           _ptr(labels), _ptr(centres_old), _ptr(sums), _ptr(counts), int(raw_sums),
                                           _ptr(active), c.stream()))
+
+
+class TensorCoreSteps:
+    """E-step / M-step of ONE float32 problem on the tensor-core path (libofc's ofc_kmeans_tc_*): the
+    centred rows are split once into TF32-exact hi parts and exact remainders; every E-step is a
+    3xTF32 tcgen05 distance GEMM used as a filter plus a float32 re-evaluation of the near-ties, so
+    the labels are those of the float32 CUDA-core E-step; the M-step walks a label-sorted member list."""
+
+    @staticmethod
+    def usable(st: "LloydState", lib_override) -> bool:
+        return (lib_override is None and st.X.is_cuda and st.dtype == 1 and st.B == 1 and st.d > 32 and st.d % 4 == 0
+                and 2 <= st.k <= 4096 and st.n < 2 ** 31 and os.environ.get("OFC_KMEANS_TC", "1") != "0")
+
+    def __init__(self, st: "LloydState", mean: torch.Tensor):
+        self.st = st
+        c = st.ctx
+        dev = st.X.device
+        n, d, k = st.n, st.d, st.k
+        self.Xh = torch.empty((n, d), dtype=torch.float32, device=dev)
+        self.Xl = torch.empty((n, d), dtype=torch.float32, device=dev)
+        self.xnorm = torch.empty(n, dtype=torch.float32, device=dev)
+        self.ws_bytes = int(c.lib.ofc_kmeans_tc_workspace_bytes(C.c_int64(n), d, k))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.n_rechecked = torch.zeros(1, dtype=torch.int32, device=dev)
+        c.check(c.lib.ofc_kmeans_tc_prepare(_ptr(st.X), _ptr(mean), C.c_int64(n), d, _ptr(self.Xh), _ptr(self.Xl),
+                                            _ptr(self.xnorm), c.stream()))
+
+    def assign(self, centres, labels, prev=None, n_changed=None, inertia=None):
+        st, c = self.st, self.st.ctx
+        c.check(c.lib.ofc_kmeans_tc_assign(_ptr(self.Xh), _ptr(self.Xl), _ptr(self.xnorm), C.c_int64(st.n), st.d, st.k,
+                                           _ptr(centres), _ptr(labels), _ptr(prev), _ptr(n_changed), _ptr(inertia),
+                                           _ptr(self.n_rechecked), _ptr(self.ws), C.c_size_t(self.ws_bytes), c.stream()))
+
+    def sums_(self, labels, sums, counts):
+        st, c = self.st, self.st.ctx
+        c.check(c.lib.ofc_kmeans_tc_sums(_ptr(self.Xh), _ptr(self.Xl), C.c_int64(st.n), st.d, st.k, _ptr(labels), _ptr(sums),
+                                         _ptr(counts), _ptr(self.ws), C.c_size_t(self.ws_bytes), c.stream()))
+
+
+def _tc_wanted(Xb, k, lib_override) -> bool:
+    return (lib_override is None and Xb.is_cuda and Xb.dtype == torch.float32 and Xb.shape[0] == 1 and Xb.shape[2] > 32
+            and Xb.shape[2] % 4 == 0 and 2 <= k <= 4096 and os.environ.get("OFC_KMEANS_TC", "1") != "0")
 
 
 def _all_reduce(t, group):
@@ -209,7 +254,7 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
     k = int(init.shape[1])
     if init.shape[0] != B or init.shape[2] != d:
         raise ValueError(f"init shape {tuple(init.shape)} does not match X {tuple(Xb.shape)}")
-    st = LloydState(ctx, Xb, k)
+    st = LloydState(ctx, Xb, k, ws_k=1 if _tc_wanted(Xb, k, _lib_override) else None)
     mean, var, n_tot = column_mean_var(st, group)
     if int(n_tot.min().item()) < k:
         raise ValueError(f"n_samples={int(n_tot.min().item())} should be >= n_clusters={k}.")   # _kmeans.py:876-879
@@ -222,6 +267,8 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
     if st.dtype == 1:
         centres = centres.to(torch.float32).to(torch.float64).contiguous()
     centres_old = torch.empty_like(centres)
+    # dense float32 corner (d > 32): E/M steps on the tensor-core path, same labels as the float32 kernels
+    tc = TensorCoreSteps(st, mean[0].contiguous()) if TensorCoreSteps.usable(st, _lib_override) else None
 
     active = torch.ones(B, dtype=torch.uint8, device=Xb.device)
     active_h = np.ones(B, bool)
@@ -231,9 +278,13 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
     cur = 0
     for it in range(max_iter):
         lab, lab_old = st.labels[cur], st.labels[cur ^ 1]
-        st.assign(mean, centres, lab, prev=lab_old, n_changed=st.n_changed, active=active)
-        # uint8: raw (exact integer) sums; floats: sums of the centred rows like sklearn
-        st.sums_(None if is_u8 else mean, lab, st.sums, st.counts, k, active=active)
+        if tc is not None:
+            tc.assign(centres, lab, prev=lab_old, n_changed=st.n_changed)
+            tc.sums_(lab, st.sums, st.counts)
+        else:
+            st.assign(mean, centres, lab, prev=lab_old, n_changed=st.n_changed, active=active)
+            # uint8: raw (exact integer) sums; floats: sums of the centred rows like sklearn
+            st.sums_(None if is_u8 else mean, lab, st.sums, st.counts, k, active=active)
         if group is not None:
             st.red[:, :kd] = st.sums.view(B, kd)
             st.red[:, kd:kd + k] = st.counts.to(torch.float64)
@@ -277,7 +328,10 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
     # strict stops already hold the labels of the final centres; the rest get one more E-step
     # (_kmeans.py:745-755).  Re-running it for everyone is idempotent for the strict ones and
     # yields the inertia of the final (centres, labels) in the same pass.
-    st.assign(mean, centres, final, inertia=st.inertia)
+    if tc is not None:
+        tc.assign(centres, final, inertia=st.inertia)
+    else:
+        st.assign(mean, centres, final, inertia=st.inertia)
     inertia = st.inertia.clone()
     if group is not None:
         _all_reduce(inertia, group)

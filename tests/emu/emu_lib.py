@@ -91,6 +91,15 @@ class Plan:
                                             C.c_size_t(self.ws_bytes), C.c_void_p(0)))
         return (flow, mm) if want_minmax else flow
 
+    def pair_init(self, prev, nxt, init_flow):
+        """cv2 flag OPTFLOW_USE_INITIAL_FLOW: init_flow f32 [H,W,2]"""
+        g = np.ascontiguousarray(np.stack([prev, nxt]), np.uint8)
+        init = np.ascontiguousarray(init_flow, np.float32)
+        flow = np.zeros((self.H, self.W, 2), np.float32)
+        _check(lib().ofc_farneback_pair_init(self.ptr, _p(g[0]), _p(g[1]), _p(init), _p(flow), C.c_void_p(0), _p(self.ws),
+                                             C.c_size_t(self.ws_bytes), C.c_void_p(0)))
+        return flow
+
     def __del__(self):
         try:
             lib().ofc_flow_plan_destroy(self.ptr)

@@ -82,7 +82,27 @@ def test_emu_grid_quad_path_and_ragged_grid():
 
 def test_emu_unsupported_flags():
     with pytest.raises(RuntimeError, match="flags"):
-        E.Plan(64, 64, flags=256)
+        E.Plan(64, 64, flags=8)
+    with pytest.raises(RuntimeError, match="INITIAL_FLOW"):          # a flag-4 plan needs the initial flow
+        E.Plan(64, 64, flags=4).sequence(np.zeros((2, 64, 64), np.uint8))
+
+
+@pytest.mark.parametrize("flags,kw", [(256, dict()), (256, dict(winsize=9, levels=1)), (4, dict()),
+                                      (260, dict(pyr_scale=0.6, levels=2, winsize=11))])
+def test_emu_flow_flags_vs_oracle(flags, kw):
+    """OPTFLOW_FARNEBACK_GAUSSIAN (Gaussian window kernel) and OPTFLOW_USE_INITIAL_FLOW
+    (INTER_AREA seed of the coarsest level) against the cv2-pinned oracle"""
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    clip = synthetic_clip(3, 77, 131, seed=4).numpy()
+    g = np.stack([V.bgr2gray(f) for f in clip])
+    a = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2)
+    a.update(kw)
+    init = FB.calc_optical_flow_farneback(g[0], g[1])
+    ref = FB.calc_optical_flow_farneback(g[1], g[2], init.copy(), flags=flags, **a)
+    plan = E.Plan(131, 77, flags=flags, **a)
+    got = plan.pair_init(g[1], g[2], init) if flags & 4 else plan.sequence(g[1:3])[0]
+    epe = np.linalg.norm(got - ref, axis=-1)
+    assert epe.mean() <= 5e-6 and epe.max() <= 1e-3, (epe.mean(), epe.max())
 
 
 @pytest.mark.parametrize("env", [{"OFC_STRIP_MIN_W": "1", "OFC_ITER_TMEM": "1"},            # ring in TMEM + cp.async landing

@@ -94,11 +94,38 @@ def test_cv2_signature_drop_in(ofc, kw):
         assert e.mean() <= MEAN_EPE and e.max() <= MAX_EPE, (kw, e.mean(), e.max())
 
 
+@pytest.mark.parametrize("flags,kw", [(256, dict()), (256, dict(winsize=21, levels=1)), (4, dict()),
+                                      (260, dict(pyr_scale=0.6, levels=2, winsize=11))])
+def test_flow_flags_vs_oracle_and_cv2(ofc, flags, kw):
+    """cv2.OPTFLOW_FARNEBACK_GAUSSIAN (256) and cv2.OPTFLOW_USE_INITIAL_FLOW (4) through the
+    cv2-signature call; bar as for flags=0 (mean EPE <= 5e-6 px, max <= 1e-3 px)"""
+    from opticalflowclustering_b200.flow import calc_optical_flow_farneback
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    clip = synthetic_clip(3, 270, 480, seed=21).numpy()
+    g = np.stack([V.bgr2gray(f) for f in clip])
+    a = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2)
+    a.update(kw)
+    init = calc_optical_flow_farneback(g[0], g[1], None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    got = calc_optical_flow_farneback(g[1], g[2], init.copy(), a["pyr_scale"], a["levels"], a["winsize"], a["iterations"],
+                                      a["poly_n"], a["poly_sigma"], flags)
+    ref = FB.calc_optical_flow_farneback(g[1], g[2], init.copy(), flags=flags, **a)
+    e = _epe(got, ref)
+    assert e.mean() <= MEAN_EPE and e.max() <= MAX_EPE, (flags, kw, e.mean(), e.max())
+    if have_cv2():
+        import cv2
+        ref2 = cv2.calcOpticalFlowFarneback(g[1], g[2], init.copy(), a["pyr_scale"], a["levels"], a["winsize"],
+                                            a["iterations"], a["poly_n"], a["poly_sigma"], flags)
+        e = _epe(got, ref2)
+        assert e.mean() <= MEAN_EPE and e.max() <= MAX_EPE, (flags, kw, e.mean(), e.max())
+
+
 def test_unsupported_flags_raise(ofc):
     from opticalflowclustering_b200.flow import calc_optical_flow_farneback
     g = np.zeros((64, 64), np.uint8)
     with pytest.raises(NotImplementedError):
-        calc_optical_flow_farneback(g, g, None, 0.5, 3, 15, 3, 5, 1.2, 256)      # OPTFLOW_FARNEBACK_GAUSSIAN
+        calc_optical_flow_farneback(g, g, None, 0.5, 3, 15, 3, 5, 1.2, 8)        # not a Farneback flag
+    with pytest.raises(ValueError):
+        calc_optical_flow_farneback(g, g, None, 0.5, 3, 15, 3, 5, 1.2, 4)        # OPTFLOW_USE_INITIAL_FLOW without a flow
     with pytest.raises(ValueError):
         calc_optical_flow_farneback(g, g[:32], None, 0.5, 3, 15, 3, 5, 1.2, 0)
 

@@ -17,7 +17,7 @@ def P(t):
     return vp(t.data_ptr()) if t is not None else vp(0)
 
 
-def run(n, d, k, seed=0, timing=False, blobs=True):
+def run(n, d, k, seed=0, timing=False, blobs=True, ties=False):
     dev = torch.device("cuda")
     g = torch.Generator(device=dev).manual_seed(seed)
     if blobs:
@@ -27,13 +27,20 @@ def run(n, d, k, seed=0, timing=False, blobs=True):
         X = torch.rand((n, d), device=dev, generator=g) * 255
     X = X.float().contiguous()
     mean = X.double().mean(0).float().double().contiguous()
-    Xc = torch.empty_like(X)
+    Xh = torch.empty_like(X)
+    Xl = torch.empty_like(X)
     xnorm = torch.empty(n, dtype=torch.float32, device=dev)
     st = vp(torch.cuda.current_stream().cuda_stream)
-    _lib.check(L.ofc_kmeans_tc_prepare(P(X), P(mean), n, d, P(Xc), P(xnorm), st))
-    ref_Xc = X - mean.float()
-    assert torch.equal(Xc, ref_Xc), "prepare: centred rows differ"
+    _lib.check(L.ofc_kmeans_tc_prepare(P(X), P(mean), n, d, P(Xh), P(Xl), P(xnorm), st))
+    Xc = X - mean.float()
+    assert torch.equal(Xh + Xl, Xc), "prepare: hi + lo is not the centred row"
+    assert int((Xh.view(torch.int32) & 0x1fff).abs().max().item()) == 0, "prepare: hi part has low bits"
     centres = Xc[:k].double().contiguous()                       # init = first k rows (centred)
+    if ties:                                                     # duplicated / nearly duplicated centres
+        h = k // 2
+        centres[h:2 * h] = centres[:h]
+        centres[h:h + h // 2] += 1e-6 * torch.randn((h // 2, d), device=dev, generator=g, dtype=torch.float64)
+        centres = centres.float().double().contiguous()
     wsb = int(L.ofc_kmeans_tc_workspace_bytes(n, d, k))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     labels = torch.full((n,), -1, dtype=torch.int32, device=dev)
@@ -41,7 +48,7 @@ def run(n, d, k, seed=0, timing=False, blobs=True):
     n_changed = torch.zeros(1, dtype=torch.int64, device=dev)
     inertia = torch.zeros(1, dtype=torch.float64, device=dev)
     nre = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(L.ofc_kmeans_tc_assign(P(Xc), P(xnorm), n, d, k, P(centres), P(labels), P(prev), P(n_changed), P(inertia),
+    _lib.check(L.ofc_kmeans_tc_assign(P(Xh), P(Xl), P(xnorm), n, d, k, P(centres), P(labels), P(prev), P(n_changed), P(inertia),
                                       P(nre), P(ws), wsb, st))
     torch.cuda.synchronize()
     # reference: generic float32 kernel on the centred rows
@@ -63,7 +70,7 @@ def run(n, d, k, seed=0, timing=False, blobs=True):
     # M-step
     sums = torch.empty((k, d), dtype=torch.float64, device=dev)
     counts = torch.empty(k, dtype=torch.int64, device=dev)
-    _lib.check(L.ofc_kmeans_tc_sums(P(Xc), n, d, k, P(labels), P(sums), P(counts), P(ws), wsb, st))
+    _lib.check(L.ofc_kmeans_tc_sums(P(Xh), P(Xl), n, d, k, P(labels), P(sums), P(counts), P(ws), wsb, st))
     torch.cuda.synchronize()
     cnt_ref = torch.bincount(labels.long(), minlength=k)
     sums_ref = torch.zeros((k, d), dtype=torch.float64, device=dev).index_add_(0, labels.long(), Xc.double())
@@ -73,9 +80,9 @@ def run(n, d, k, seed=0, timing=False, blobs=True):
     print(f"   M-step: count mismatches {cnt_bad}, max |sum diff| {err:.3e} (scale {scale:.3e})", flush=True)
     ok = ok and cnt_bad == 0 and err <= 1e-9 * max(scale, 1.0)
     if timing:
-        for name, fn in (("tc_assign", lambda: L.ofc_kmeans_tc_assign(P(Xc), P(xnorm), n, d, k, P(centres), P(labels), vp(0), vp(0),
+        for name, fn in (("tc_assign", lambda: L.ofc_kmeans_tc_assign(P(Xh), P(Xl), P(xnorm), n, d, k, P(centres), P(labels), vp(0), vp(0),
                                                                      vp(0), vp(0), P(ws), wsb, st)),
-                         ("tc_sums", lambda: L.ofc_kmeans_tc_sums(P(Xc), n, d, k, P(labels), P(sums), P(counts), P(ws), wsb, st))):
+                         ("tc_sums", lambda: L.ofc_kmeans_tc_sums(P(Xh), P(Xl), n, d, k, P(labels), P(sums), P(counts), P(ws), wsb, st))):
             for _ in range(2):
                 fn()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -91,12 +98,16 @@ def run(n, d, k, seed=0, timing=False, blobs=True):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 4 and sys.argv[1] == "one":
+        sys.exit(0 if run(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), timing=True) else 1)
     shapes = [(1000, 32, 8), (4096, 64, 64), (5000, 100, 40), (20000, 128, 300), (100000, 64, 256), (50000, 512, 1024),
               (3001, 36, 2)]
     ok = True
     for (n, d, k) in shapes:
         ok = run(n, d, k) and ok
     ok = run(20000, 64, 64, blobs=False) and ok
+    ok = run(30000, 96, 128, ties=True) and ok
+    ok = run(30000, 256, 512, ties=True, blobs=False) and ok
     if len(sys.argv) > 1 and sys.argv[1] == "time":
         for (n, d, k) in [(1000000, 64, 256), (1000000, 128, 1024), (1000000, 512, 256), (200000, 2048, 1024)]:
             ok = run(n, d, k, timing=True) and ok
