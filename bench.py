@@ -182,6 +182,47 @@ def kmeans_cosine_extras(dev, peak):
         nbytes = 2 * (N * D * X.element_size()) + 2 * 4 * N          # both kernels read X once and touch the labels
         out["kmeans_iter_" + name] = {"ms": ms, "rows_per_s": N / (ms / 1e3), "gb_s": nbytes / (ms / 1e3) / 1e9,
                                       "frac_of_hbm_peak": nbytes / (ms / 1e3) / 1e9 / peak}
+    # dense corner of configs[4] (float32, d > 32): one Lloyd iteration on the tensor-core path -- 3xTF32 tcgen05
+    # E-step (filter + float32 re-evaluation of near-ties) and the CSR M-step.  `tflops` counts the 2 N k D flop of the
+    # distance GEMM once; the tensor cores execute three TF32 MMAs per product term (`tf32_tflops`), whose peak is
+    # half the measured bf16 one.
+    bf16_peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            bf16_peak = float(json.load(f).get("bf16_tflops"))
+    except Exception:
+        pass
+    for name, (N, D, K) in {"f32_d64_k256": (1_000_000, 64, 256), "f32_d512_k256": (1_000_000, 512, 256),
+                            "f32_d128_k1024": (1_000_000, 128, 1024)}.items():
+        gd = torch.Generator(device=dev).manual_seed(1)
+        cen = torch.rand((K, D), device=dev, generator=gd) * 8
+        X = (cen[torch.randint(0, K, (N,), device=dev, generator=gd)] + torch.randn((N, D), device=dev, generator=gd)).float()
+        ctx = km._Ctx(dev)
+        st = km.LloydState(ctx, X.unsqueeze(0).contiguous(), K, ws_k=1)
+        mean = X.double().mean(0).float().double().contiguous()
+        tc = km.TensorCoreSteps(st, mean)
+        centres = (X[:K].double() - mean).unsqueeze(0).contiguous()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_assign = t_sums = 0.0
+        for it in range(6):
+            ev[0].record()
+            tc.assign(centres, st.labels[0], prev=st.labels[1], n_changed=st.n_changed)
+            ev[1].record()
+            tc.sums_(st.labels[0], st.sums, st.counts)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 1:
+                t_assign += ev[0].elapsed_time(ev[1]) / 5
+                t_sums += ev[1].elapsed_time(ev[2]) / 5
+        flop = 2.0 * N * K * D
+        rec = {"ms_assign": t_assign, "ms_sums": t_sums, "rows_per_s": N / ((t_assign + t_sums) / 1e3),
+               "tflops": flop / (t_assign / 1e3) / 1e12, "tf32_tflops": 3 * flop / (t_assign / 1e3) / 1e12,
+               "rechecked_rows": int(tc.n_rechecked.item()),
+               "sums_gb_s": (2 * N * D * 4 + 8 * N) / (t_sums / 1e3) / 1e9}
+        if bf16_peak:
+            rec["tf32_frac_of_peak"] = rec["tf32_tflops"] / (bf16_peak / 2)
+        out["kmeans_iter_tc_" + name] = rec
+        del tc, st, X
     # the reference's per-cell KMeans(n_clusters=8) over one 1080p frame (350 cells x 5852 px x 4 channels),
     # k-means++ seeding included, as ONE device-resident launch (kmeans.lloyd_cells)
     cells = torch.randint(0, 256, (350, 76 * 77, 4), generator=g).to(torch.uint8).to(dev)

@@ -219,9 +219,16 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
         const float cmax = __ldg(p.cmax);
         unsigned unit = 0;
         for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-            // the four smallest distances of the row (ties keep the lower index first) and where they are
-            float m1 = __int_as_float(0x7f800000), m2 = m1, m3 = m1, m4 = m1;
-            int a1 = 0, a2 = 0, a3 = 0;
+            // Running minimum (first strict minimum in centre order) plus a four-deep history of every distance
+            // that came within the row's error bound of the running minimum: whatever ends within the bound of
+            // the FINAL minimum is in that history unless it was pushed out while still eligible (`lost`).
+            const int64_t row = (int64_t)mt * BM + q * 32 + lane;
+            const float tol = p.tol_scale * __ldg(p.xnorm + (row < p.n ? row : p.n - 1)) * cmax;
+            float m1 = __int_as_float(0x7f800000), thr = m1;
+            int a1 = 0;
+            float h0 = m1, h1 = m1, h2 = m1, h3 = m1;
+            int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+            bool lost = false;
             for (int nt = 0; nt < n_ntiles; ++nt, ++unit) {
                 const unsigned acc = unit & 1u, aph = (unit >> 1) & 1u;
                 mbar_wait(tfull_bar(acc), aph, p.error_flag);
@@ -241,12 +248,12 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float dist = fmaf(-2.f, v[g4 * 4 + e], cj[e]);
-                            if (dist < m4) {
+                            if (dist <= thr) {
                                 const int j = j0 + g4 * 4 + e;
-                                if (dist < m1) { m4 = m3; m3 = m2; a3 = a2; m2 = m1; a2 = a1; m1 = dist; a1 = j; }
-                                else if (dist < m2) { m4 = m3; m3 = m2; a3 = a2; m2 = dist; a2 = j; }
-                                else if (dist < m3) { m4 = m3; m3 = dist; a3 = j; }
-                                else m4 = dist;
+                                const float out = h3;
+                                h3 = h2; i3 = i2; h2 = h1; i2 = i1; h1 = h0; i1 = i0; h0 = dist; i0 = j;
+                                if (dist < m1) { m1 = dist; a1 = j; thr = dist + tol; }
+                                lost = lost || out <= thr;
                             }
                         }
                     }
@@ -255,15 +262,19 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
-            const int64_t row = (int64_t)mt * BM + q * 32 + lane;
             if (row < p.n) {
-                const float tol = p.tol_scale * __ldg(p.xnorm + row) * cmax;
                 p.labels[row] = a1;
-                if (!(m2 - m1 > tol)) {
-                    // candidates inside the bound: 2, 3, or (0) too many to list -> all k are re-evaluated
-                    const int ncand = (m3 - m1 > tol) ? 2 : ((m4 - m1 > tol) ? 3 : 0);
+                // the other centres inside the bound of the final minimum
+                int cand[4], nc = 0;
+                if (i0 != a1 && h0 <= thr) cand[nc++] = i0;
+                if (i1 != a1 && h1 <= thr) cand[nc++] = i1;
+                if (i2 != a1 && h2 <= thr) cand[nc++] = i2;
+                if (i3 != a1 && h3 <= thr) cand[nc++] = i3;
+                if (nc > 0 || lost || !(m1 < __int_as_float(0x7f800000))) {
+                    // 2 or 3 candidates are listed; otherwise (0) all k centres are re-evaluated
+                    const int ncand = (lost || nc > 2 || nc == 0) ? 0 : nc + 1;
                     const unsigned pos = atomicAdd(p.amb_count, 1u);
-                    p.amb[pos] = make_int4((int)row, a1, a2, a3 | (ncand << 16));
+                    p.amb[pos] = make_int4((int)row, a1, nc > 0 ? cand[0] : 0, (nc > 1 ? cand[1] : 0) | (ncand << 16));
                 }
             }
         }
@@ -278,26 +289,31 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
 
 // one float32 distance in the arithmetic of kmeans_assign_generic_kernel<float, float>: lanes stride over
 // the features, xor-tree reduction, dist = fma(-2, dot, c2)
-__device__ __forceinline__ float exact_dist(const float* __restrict__ rh, const float* __restrict__ rl, const float* __restrict__ c,
-                                            float c2, int d, int lane) {
+__device__ __forceinline__ float exact_dist(const float* __restrict__ x, const float* __restrict__ c, float c2, int d, int lane) {
     float part = 0.f;
-    for (int t = lane; t < d; t += 32) part = fmaf(rh[t] + rl[t], c[t], part);       // hi + lo is the row, exactly
+    for (int t = lane; t < d; t += 32) part = fmaf(x[t], c[t], part);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     return fmaf(-2.f, part, c2);
 }
 
-// rows the tensor-core filter could not decide: one warp per row
+// rows the tensor-core filter could not decide: one warp per row; the row (hi + lo, exactly the centred
+// float32 row) is staged once in the warp's slice of shared memory when it fits
 __global__ void __launch_bounds__(256) kmeans_assign_fix_kernel(const float* __restrict__ Xh, const float* __restrict__ Xl, int d, int k,
                                                                 const float* __restrict__ C, const float* __restrict__ c2,
                                                                 const int4* __restrict__ amb, const unsigned* __restrict__ amb_count,
-                                                                int32_t* __restrict__ labels) {
-    const int lane = threadIdx.x & 31;
+                                                                int32_t* __restrict__ labels, float* __restrict__ row_ws, int use_smem) {
+    OFC_DYN_SMEM(float, s_rows);                     // [8][d] when use_smem
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned n_amb = *amb_count;
-    for (unsigned e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n_amb; e += gridDim.x * 8) {
+    float* x = use_smem ? s_rows + (size_t)warp * d : row_ws + ((size_t)blockIdx.x * 8 + warp) * d;
+    for (unsigned e = blockIdx.x * 8 + warp; e < n_amb; e += gridDim.x * 8) {
         const int4 a = amb[e];
         const float* rh = Xh + (int64_t)a.x * d;
         const float* rl = Xl + (int64_t)a.x * d;
+        __syncwarp();
+        for (int t = lane; t < d; t += 32) x[t] = rh[t] + rl[t];
+        __syncwarp();
         int label;
         const int ncand = a.w >> 16;
         if (ncand) {
@@ -306,19 +322,19 @@ __global__ void __launch_bounds__(256) kmeans_assign_fix_kernel(const float* __r
             if (c1 < c0) { t = c0; c0 = c1; c1 = t; }
             if (c2i < c1) { t = c1; c1 = c2i; c2i = t; }
             if (c1 < c0) { t = c0; c0 = c1; c1 = t; }
-            float best = exact_dist(rh, rl, C + (int64_t)c0 * d, c2[c0], d, lane);
+            float best = exact_dist(x, C + (int64_t)c0 * d, c2[c0], d, lane);
             label = c0;
-            const float d1 = exact_dist(rh, rl, C + (int64_t)c1 * d, c2[c1], d, lane);
+            const float d1 = exact_dist(x, C + (int64_t)c1 * d, c2[c1], d, lane);
             if (d1 < best) { best = d1; label = c1; }
             if (ncand == 3) {
-                const float d2 = exact_dist(rh, rl, C + (int64_t)c2i * d, c2[c2i], d, lane);
+                const float d2 = exact_dist(x, C + (int64_t)c2i * d, c2[c2i], d, lane);
                 if (d2 < best) { best = d2; label = c2i; }
             }
         } else {
             float best = 0.f;
             label = 0;
             for (int j = 0; j < k; ++j) {
-                const float dist = exact_dist(rh, rl, C + (int64_t)j * d, c2[j], d, lane);
+                const float dist = exact_dist(x, C + (int64_t)j * d, c2[j], d, lane);
                 if (j == 0 || dist < best) { best = dist; label = j; }
             }
         }
@@ -600,7 +616,7 @@ int sm_count() {
 
 struct TcLayout {
     size_t off_c32, off_ch, off_cl, off_c2, off_cmax, off_count, off_err, off_amb, off_part, off_table, off_order, off_segfirst, off_seginfo,
-        off_nsegs, off_segpart, total;
+        off_nsegs, off_segpart, off_fixrows, total;
     int64_t n_chunks, max_segs;
     int parts;
 };
@@ -626,6 +642,7 @@ TcLayout tc_layout(int64_t n, int d, int k) {
     w.off_seginfo = take((size_t)w.max_segs * 16);
     w.off_nsegs = take(4);
     w.off_segpart = take((size_t)w.max_segs * d * 8);
+    w.off_fixrows = take((size_t)148 * 4 * 8 * d * 4);
     w.total = off;
     return w;
 }
@@ -721,7 +738,18 @@ int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, i
     else if (BN == 128) rc = launch_tc<128>(tmAh, tmAl, tmBh, tmBl, p, stream);
     else rc = launch_tc<256>(tmAh, tmAl, tmBh, tmBl, p, stream);
     if (rc != OFC_OK) return rc;
-    kmeans_assign_fix_kernel<<<sm_count() * 4, 256, 0, st>>>(Xh, Xl, d, k, c32, c2, (const int4*)(ws + w.off_amb), count, labels);
+    {
+        const size_t fix_smem = (size_t)8 * d * 4;
+        const int use_smem = fix_smem <= 200 * 1024;
+        static size_t fix_conf = 0;
+        if (use_smem && fix_smem > 48 * 1024 && fix_smem > fix_conf) {
+            OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fix_smem));
+            fix_conf = fix_smem;
+        }
+        const int fix_ctas = sm_count() < 148 ? sm_count() * 4 : 148 * 4;
+        kmeans_assign_fix_kernel<<<fix_ctas, 256, use_smem ? fix_smem : 0, st>>>(Xh, Xl, d, k, c32, c2, (const int4*)(ws + w.off_amb),
+                                                                                 count, labels, (float*)(ws + w.off_fixrows), use_smem);
+    }
     OFC_CHECK_LAUNCH("kmeans_assign_fix");
     if (n_rechecked) OFC_CUDA(cudaMemcpyAsync(n_rechecked, count, 4, cudaMemcpyDeviceToDevice, st));
     if (n_changed) {

@@ -161,6 +161,27 @@ def main():
         cases[name + "_predict"] = km.predict(X).astype(np.int32)
     np.savez_compressed(f"{HERE}/kmeans_sklearn.npz", **cases)
     print("kmeans goldens ok")
+    make_dense_kmeans_golden()
+
+
+def make_dense_kmeans_golden():
+    """float32 rows with d > 32 (the tensor-core path of the build): sklearn 1.9.0 KMeans(init=first k rows, n_init=1).
+    Separate file so the older fixtures stay byte-identical; X is regenerated from the seed by the test."""
+    from sklearn.cluster import KMeans
+    cases = {}
+    for name, (N, D, k, seed) in {"f32_d64_k32": (6000, 64, 32, 11), "f32_d96_k40": (5000, 96, 40, 12)}.items():
+        rng = np.random.default_rng(seed)
+        cen = rng.uniform(0, 8, (k, D))
+        X = (cen[rng.integers(k, size=N)] + rng.normal(0, 1, (N, D))).astype(np.float32)
+        init = X[:k].copy()
+        km = KMeans(n_clusters=k, init=init, n_init=1).fit(X)
+        cases[name + "_shape"] = np.array([N, D, k, seed])
+        cases[name + "_labels"] = km.labels_.astype(np.int32)
+        cases[name + "_centers"] = km.cluster_centers_
+        cases[name + "_inertia"] = np.float64(km.inertia_)
+        cases[name + "_niter"] = np.int64(km.n_iter_)
+    np.savez_compressed(f"{HERE}/kmeans_sklearn_dense.npz", **cases)
+    print("dense kmeans goldens ok")
 
 
 if __name__ == "__main__":

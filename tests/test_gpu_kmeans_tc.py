@@ -1,0 +1,75 @@
+"""GPU parity tests of the tensor-core k-means path (csrc/tc_kmeans.cu: 3xTF32 tcgen05 E-step + CSR M-step),
+called through the C-ABI.  Bars: labels bit-identical to the float32 CUDA-core E-step on the same centred
+rows (the tensor cores only filter; near-ties are re-evaluated in float32), counts exact, float64 sums equal to
+an index_add restatement; whole fits against scikit-learn 1.9.0 goldens (float32 data: >= 99.95 % labels,
+inertia within 1e-5 relative -- the bar of the existing float32 case)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def tc():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    spec = importlib.util.spec_from_file_location("tc_check", os.path.join(ROOT, "tools", "tc_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("shape", [(1000, 36, 2), (4096, 64, 64), (5000, 100, 40), (20000, 128, 300), (50000, 512, 1024),
+                                   (100000, 64, 256)])
+def test_tc_steps_equal_float32_kernels(tc, shape):
+    """ragged n (not a multiple of 128), d not a multiple of 32, k not a multiple of the 64/128/256 centre tile"""
+    assert tc.run(*shape)
+
+
+def test_tc_steps_uniform_data_and_tied_centres(tc):
+    """unclustered data (every distance close) and duplicated / 1e-6-perturbed centres: every row is a near-tie
+    and must come out of the float32 re-evaluation with the lowest-index rule"""
+    assert tc.run(20000, 64, 64, blobs=False)
+    assert tc.run(30000, 96, 128, ties=True)
+    assert tc.run(30000, 256, 512, ties=True, blobs=False)
+
+
+@pytest.mark.parametrize("name", ["f32_d64_k32", "f32_d96_k40"])
+def test_lloyd_dense_float32_vs_sklearn_golden(name):
+    from opticalflowclustering_b200 import kmeans
+    z = np.load(os.path.join(GOLDEN, "kmeans_sklearn_dense.npz"))
+    N, D, k, seed = (int(v) for v in z[name + "_shape"])
+    rng = np.random.default_rng(seed)                       # same stream as tests/golden/make_golden.py
+    cen = rng.uniform(0, 8, (k, D))
+    X = (cen[rng.integers(k, size=N)] + rng.normal(0, 1, (N, D))).astype(np.float32)
+    labels, centres, inertia, n_iter = kmeans.kmeans_fit(X, X[:k].copy())
+    assert (labels == z[name + "_labels"]).mean() > 0.9995
+    assert np.abs(centres - z[name + "_centers"]).max() < 1e-2
+    assert abs(inertia - float(z[name + "_inertia"])) <= 1e-5 * float(z[name + "_inertia"])
+    assert n_iter == int(z[name + "_niter"])
+
+
+def test_lloyd_tensor_core_path_on_off(monkeypatch):
+    """the same fit through the stepwise float32 kernels (OFC_KMEANS_TC=0) and through the tensor-core path"""
+    from opticalflowclustering_b200 import kmeans
+    g = torch.Generator().manual_seed(5)
+    cen = torch.rand((40, 96), generator=g) * 6
+    X = (cen[torch.randint(0, 40, (30000,), generator=g)] + torch.randn((30000, 96), generator=g)).float().cuda()
+    init = X[:40].double()
+    monkeypatch.setenv("OFC_KMEANS_TC", "0")
+    l0, c0, i0, n0 = kmeans.lloyd(X, init)
+    monkeypatch.setenv("OFC_KMEANS_TC", "1")
+    l1, c1, i1, n1 = kmeans.lloyd(X, init)
+    l2, c2, i2, n2 = kmeans.lloyd(X, init)
+    assert torch.equal(l1, l2) and torch.equal(c1, c2) and float(i1) == float(i2)          # deterministic
+    assert int(n0) == int(n1)
+    assert (l0 == l1).float().mean().item() > 0.9995
+    assert (c0 - c1).abs().max().item() < 1e-4
+    assert abs(float(i0) - float(i1)) <= 1e-6 * float(i0)

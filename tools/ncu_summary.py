@@ -32,6 +32,8 @@ KEYS = [
     "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "smsp__inst_executed.sum",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warp_latency_per_inst_issued.ratio", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+    "lts__t_bytes.sum", "sm__cycles_elapsed.avg",
 ]
 UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0,
               "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
@@ -78,10 +80,14 @@ def launch_shares(path):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
-    md = [f"# ncu summary `{tag}`", "",
-          "Captured on a B200 through `gpurun` with `tools/gpu_profile.sh` (command: `python tools/profile_step.py`,",
-          "3 steps of the 1080p pipeline, 9 frames = 8 pairs per step).  ncu times are cold-cache and serialised:",
-          "compare SHARES with bench.py's CUDA-event breakdown, not absolutes.", ""]
+    note = os.environ.get("OFC_PROFILE_NOTE")
+    md = [f"# ncu summary `{tag}`", ""]
+    if note:
+        md += [note, ""]
+    else:
+        md += ["Captured on a B200 through `gpurun` with `tools/gpu_profile.sh` (command: `python tools/profile_step.py`,",
+               "3 steps of the 1080p pipeline, 9 frames = 8 pairs per step).  ncu times are cold-cache and serialised:",
+               "compare SHARES with bench.py's CUDA-event breakdown, not absolutes.", ""]
     lc = os.path.join(OUT, "launches.csv")
     if os.path.exists(lc):
         shutil.copy(lc, os.path.join(PROF, f"{tag}_launches.csv"))
@@ -107,7 +113,9 @@ def main():
                    f"warps active {d.get('sm__warps_active.avg.pct_of_peak_sustained_active', 0):.1f} %, "
                    f"{int(d.get('launch__registers_per_thread', 0))} regs/thread, "
                    f"{d.get('smsp__inst_executed.sum', 0) / 1e6:.1f} M warp instructions, "
-                   f"L2 hit {d.get('lts__t_sector_hit_rate.pct', 0):.1f} %"]
+                   f"L2 hit {d.get('lts__t_sector_hit_rate.pct', 0):.1f} %"
+                   + (f", tensor pipe active {d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']:.1f} %"
+                      if 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active' in d else "")]
         md.append("")
         if name.startswith("flow_iter") and rows:
             d = max(rows, key=lambda r: r.get("gpu__time_duration.sum", 0.0))     # the full-resolution launch
