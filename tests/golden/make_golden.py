@@ -162,6 +162,7 @@ def main():
     np.savez_compressed(f"{HERE}/kmeans_sklearn.npz", **cases)
     print("kmeans goldens ok")
     make_dense_kmeans_golden()
+    make_seeded_kmeans_golden()
 
 
 def make_dense_kmeans_golden():
@@ -186,3 +187,26 @@ def make_dense_kmeans_golden():
 
 if __name__ == "__main__":
     main()
+
+
+def make_seeded_kmeans_golden():
+    """KMeans(n_clusters=k, random_state=int) -- k-means++ seeding with sklearn's RNG call sequence
+    followed by Lloyd -- on uint8 rows (a blob set and one 1080p grid cell's worth of pixels, k = 8 as `-c 8`)."""
+    from sklearn.cluster import KMeans, kmeans_plusplus
+    cases = {}
+    rng = np.random.default_rng(0)
+    cen = rng.uniform(20, 230, (5, 4))
+    blobs = np.clip(np.rint(cen[rng.integers(5, size=3000)] + rng.normal(0, 10, (3000, 4))), 0, 255).astype(np.uint8)
+    cell = rng.integers(0, 256, (76 * 77, 4), dtype=np.uint8)
+    for name, (X, k, rs) in {"blobs_k5_rs0": (blobs, 5, 0), "blobs_k5_rs42": (blobs, 5, 42), "cell_k8_rs3": (cell, 8, 3)}.items():
+        km = KMeans(n_clusters=k, random_state=rs).fit(X)
+        _, idx = kmeans_plusplus(X.astype(np.float64), k, random_state=rs)
+        cases[name + "_X"] = X
+        cases[name + "_k_rs"] = np.array([k, rs])
+        cases[name + "_seed_idx"] = idx.astype(np.int64)
+        cases[name + "_labels"] = km.labels_.astype(np.int32)
+        cases[name + "_centers"] = km.cluster_centers_
+        cases[name + "_inertia"] = np.float64(km.inertia_)
+        cases[name + "_niter"] = np.int64(km.n_iter_)
+    np.savez_compressed(f"{HERE}/kmeans_sklearn_seeded.npz", **cases)
+    print("seeded kmeans goldens ok")

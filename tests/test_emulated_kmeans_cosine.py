@@ -154,6 +154,21 @@ def test_kmeans_class_api(L):
         km.KMeans(n_clusters=5, _lib_override=L).fit(X[:3])
 
 
+@pytest.mark.parametrize("name", ["blobs_k5_rs0", "blobs_k5_rs42", "cell_k8_rs3"])
+def test_kmeans_random_state_reproduces_sklearn(L, name):
+    """KMeans(n_clusters=k, random_state=int) end to end -- k-means++ with sklearn's RNG call
+    sequence (same seed indices), then Lloyd: labels, n_iter bit-exact, centres / inertia to rounding"""
+    z = np.load(os.path.join(GOLDEN, "kmeans_sklearn_seeded.npz"))
+    X = z[name + "_X"]
+    k, rs = (int(v) for v in z[name + "_k_rs"])
+    _, idx = km.kmeans_plusplus(X, k, random_state=rs, _lib_override=L)
+    assert (idx == z[name + "_seed_idx"]).all()
+    clt = km.KMeans(n_clusters=k, random_state=rs, _lib_override=L).fit(X)
+    assert (clt.labels_ == z[name + "_labels"]).all() and clt.n_iter_ == int(z[name + "_niter"])
+    assert np.abs(clt.cluster_centers_ - z[name + "_centers"]).max() < 1e-9
+    assert abs(clt.inertia_ - float(z[name + "_inertia"])) <= 1e-9 * float(z[name + "_inertia"])
+
+
 def test_sliding_cosine_goldens(L):
     short = _hue_col(os.path.join(GOLDEN, "bounce.csv"))
     for name, want_sim, want_frame in [("601_3_3_cropped.csv", 0.91448231723348, 24),

@@ -46,6 +46,21 @@ def test_kmeans_fit_vs_sklearn_golden(km, name):
     assert abs(inertia - float(z[name + "_inertia"])) <= 1e-5 * float(z[name + "_inertia"])
 
 
+@pytest.mark.parametrize("name", ["blobs_k5_rs0", "blobs_k5_rs42", "cell_k8_rs3"])
+def test_kmeans_random_state_reproduces_sklearn(km, name):
+    """KMeans(n_clusters=k, random_state=int) end to end against sklearn 1.9.0 (the reference's
+    call with a seed): same k-means++ seed indices, labels and n_iter bit-exact"""
+    z = np.load(os.path.join(GOLDEN, "kmeans_sklearn_seeded.npz"))
+    X = z[name + "_X"]
+    k, rs = (int(v) for v in z[name + "_k_rs"])
+    _, idx = km.kmeans_plusplus(X, k, random_state=rs)
+    assert (idx == z[name + "_seed_idx"]).all()
+    clt = km.KMeans(n_clusters=k, random_state=rs).fit(X)
+    assert (clt.labels_ == z[name + "_labels"]).all() and clt.n_iter_ == int(z[name + "_niter"])
+    assert np.abs(clt.cluster_centers_ - z[name + "_centers"]).max() < 1e-9
+    assert abs(clt.inertia_ - float(z[name + "_inertia"])) <= 1e-9 * float(z[name + "_inertia"])
+
+
 def test_kmeans_large_n_properties(km):
     """1M x 4 uint8 rows, k = 8: too slow for the numpy oracle in full, so check (a) labels equal
     an independent fp64 torch restatement of the E-step on the final centres, (b) centres are the
