@@ -164,24 +164,31 @@ def kmeans_cosine_extras(dev, peak):
     from opticalflowclustering_b200 import kmeans as km
     out = {}
     g = torch.Generator().manual_seed(0)
-    for name, (N, D, K, dt) in {"u8_d4_k8": (1_000_000, 4, 8, torch.uint8), "u8_d350_k8": (200_000, 350, 8, torch.uint8),
+    for name, (N, D, K, dt) in {"u8_d4_k8": (1_000_000, 4, 8, torch.uint8), "u8_d4_k8_64M": (64_000_000, 4, 8, torch.uint8),
+                                "u8_d16_k8_16M": (16_000_000, 16, 8, torch.uint8), "u8_d350_k8": (200_000, 350, 8, torch.uint8),
                                 "f32_d32_k16": (1_000_000, 32, 16, torch.float32)}.items():
-        X = torch.randint(0, 180, (N, D), generator=g).to(dt).to(dev)
+        X = torch.randint(0, 180, (N, D), device=dev, dtype=torch.uint8).to(dt)          # generated on the device
         ctx = km._Ctx(dev)
         st = km.LloydState(ctx, X.unsqueeze(0).contiguous(), K)
         centres = X[:K].double().unsqueeze(0).contiguous()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fused = st.step_supported()          # uint8 rows with small [k][d]: E-step + exact sums in one pass over X
         for it in range(6):
             if it == 1:
                 e0.record()
-            st.assign(None, centres, st.labels[0])
-            st.sums_(None, st.labels[0], st.sums, st.counts, K)
+            if fused:
+                st.step(None, centres, st.labels[it & 1], st.labels[(it & 1) ^ 1], st.n_changed, st.sums, st.counts)
+            else:
+                st.assign(None, centres, st.labels[0])
+                st.sums_(None, st.labels[0], st.sums, st.counts, K)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        nbytes = 2 * (N * D * X.element_size()) + 2 * 4 * N          # both kernels read X once and touch the labels
+        # algorithmic bytes: X once + labels written (+ previous labels read by the fused step);
+        # the two-kernel form reads X and the labels a second time
+        nbytes = (N * D * X.element_size() + 2 * 4 * N) if fused else (2 * (N * D * X.element_size()) + 2 * 4 * N)
         out["kmeans_iter_" + name] = {"ms": ms, "rows_per_s": N / (ms / 1e3), "gb_s": nbytes / (ms / 1e3) / 1e9,
-                                      "frac_of_hbm_peak": nbytes / (ms / 1e3) / 1e9 / peak}
+                                      "frac_of_hbm_peak": nbytes / (ms / 1e3) / 1e9 / peak, "fused_step": bool(fused), "rows": N}
     # dense corner of configs[4] (float32, d > 32): one Lloyd iteration on the tensor-core path -- 3xTF32 tcgen05
     # E-step (filter + float32 re-evaluation of near-ties) and the CSR M-step.  `tflops` counts the 2 N k D flop of the
     # distance GEMM once; the tensor cores execute three TF32 MMAs per product term (`tf32_tflops`), whose peak is

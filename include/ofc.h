@@ -166,6 +166,16 @@ int ofc_kmeans_sums(const void* X, int dtype, int batch, int64_t n, int d, int k
                     double* sums /* [batch][k][d] */, int64_t* counts /* [batch][k] */, const uint8_t* active,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* E-step and M-step sums of one Lloyd iteration in ONE pass over X, for the reference's own shape: uint8 rows
+ * (pixels, hues) with d <= 32 whose [k][d] integer accumulators fit shared memory (ofc_kmeans_step_supported).
+ * Same labels / n_changed as ofc_kmeans_assign and the same (exact integer) raw sums / counts as ofc_kmeans_sums
+ * with mean = NULL; `mean` only centres the rows for the distance, as in ofc_kmeans_assign. */
+int ofc_kmeans_step_supported(int dtype, int d, int k);
+int ofc_kmeans_step(const void* X, int dtype, int batch, int64_t n, int d, int k,
+                    const double* mean, const double* centres, int32_t* labels, const int32_t* prev_labels,
+                    uint64_t* n_changed, double* sums /* [batch][k][d] */, int64_t* counts /* [batch][k] */,
+                    const uint8_t* active, void* workspace, size_t workspace_bytes, void* stream);
+
 /* centres[b][j] = sums/counts (use_reciprocal: sums * (1/count) as sklearn's _average_centers)
  * minus mean_sub (nullable); empty clusters copy the heaviest cluster; shift_tot[b] =
  * sum_j ||new_j - old_j||^2 (_k_means_common.pyx:274-311).  centres: old in, new out. */

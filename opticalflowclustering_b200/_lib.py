@@ -40,6 +40,8 @@ SIGNATURES = {
     "ofc_kmeans_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "ofc_kmeans_assign": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_kmeans_sums": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_step_supported": (_i, [_i, _i, _i]),
+    "ofc_kmeans_step": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_kmeans_centres": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_kmeans_relocate": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "ofc_kmeans_cells": (_i, [_vp, _i, _i64, _i, _i, _vp, C.c_uint64, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -270,6 +270,97 @@ __global__ void __launch_bounds__(256) kmeans_sums_kernel(KmSumsParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// One Lloyd iteration in ONE pass for the reference's own shape -- uint8 rows with a handful of
+// features and clusters (pixels: d = 4, hues per frame: d <= 32): E-step exactly as
+// kmeans_assign_small_kernel, and in the same pass every thread adds its row to a thread-private
+// integer accumulator [k][d] (+ member count) in shared memory, laid out [slot][thread] so no two
+// threads ever share a word or a bank.  The sums are exact integers, so the CTA reduction and the
+// fold over CTAs give the same bits as kmeans_sums_kernel in any order; X is read once per
+// iteration instead of twice and no floating-point atomic exists anywhere.
+// ---------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256) kmeans_step_u8_kernel(KmAssignParams p, double* __restrict__ partial,
+                                                             long long* __restrict__ cnt_partial) {
+    OFC_DYN_SMEM(unsigned char, raw);
+    const int b = blockIdx.y, tid = threadIdx.x, d = p.d, k = p.k;
+    if (p.active && !p.active[b]) return;
+    double* sc = reinterpret_cast<double*>(raw);              // [k][d]
+    double* sc2 = sc + (size_t)k * d;                          // [k]
+    double* smean = sc2 + k;                                   // [d]
+    unsigned* acc = reinterpret_cast<unsigned*>(smean + d);    // [k*d + k][256]
+    const int slots = k * d + k;
+    const double* cen = p.centres + (int64_t)b * k * d;
+    for (int i = tid; i < k * d; i += 256) sc[i] = cen[i];
+    for (int i = tid; i < d; i += 256) smean[i] = p.mean ? p.mean[(int64_t)b * d + i] : 0.0;
+    for (int s = 0; s < slots; ++s) acc[s * 256 + tid] = 0u;
+    __syncthreads();
+    for (int j = tid; j < k; j += 256) {
+        double s = 0.0;
+        for (int t = 0; t < d; ++t) s = fma(sc[j * d + t], sc[j * d + t], s);
+        sc2[j] = s;
+    }
+    __syncthreads();
+    const unsigned char* X = reinterpret_cast<const unsigned char*>(p.X) + (int64_t)b * p.n * d;
+    int32_t* labels = p.labels + (int64_t)b * p.n;
+    const int32_t* prev = p.prev_labels ? p.prev_labels + (int64_t)b * p.n : nullptr;
+    unsigned changed = 0;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < p.n; base += (int64_t)gridDim.x * 256) {
+        const int64_t i = base + tid;
+        if (i < p.n) {
+            unsigned xr[DP];
+            double x[DP];
+            const unsigned char* row = X + i * d;
+            if (DP == 4 && d == 4) {
+                const uchar4 q = *reinterpret_cast<const uchar4*>(row);
+                xr[0] = q.x; xr[1] = q.y; xr[2] = q.z; xr[3] = q.w;
+            } else {
+#pragma unroll
+                for (int t = 0; t < DP; ++t) xr[t] = t < d ? row[t] : 0u;
+            }
+#pragma unroll
+            for (int t = 0; t < DP; ++t) x[t] = t < d ? (double)xr[t] - smean[t] : 0.0;
+            double best = 0.0;
+            int label = 0;
+            for (int j = 0; j < k; ++j) {
+                const double* c = sc + j * d;
+                double dot = 0.0;
+#pragma unroll
+                for (int t = 0; t < DP; ++t)
+                    if (t < d) dot = fma(x[t], c[t], dot);
+                const double dist = fma(-2.0, dot, sc2[j]);
+                if (j == 0 || dist < best) { best = dist; label = j; }
+            }
+            labels[i] = label;
+            if (prev && prev[i] != label) ++changed;
+            unsigned* a = acc + (size_t)label * d * 256 + tid;
+#pragma unroll
+            for (int t = 0; t < DP; ++t)
+                if (t < d) a[t * 256] += xr[t];
+            acc[(size_t)(k * d + label) * 256 + tid] += 1u;
+        }
+    }
+    __syncthreads();
+    // CTA totals: warp w folds slots w, w + 8, ... (integers: any order gives the same bits)
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int s = warp; s < slots; s += 8) {
+        unsigned long long v = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += acc[s * 256 + q * 32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+            if (s < k * d) partial[((int64_t)b * gridDim.x + blockIdx.x) * k * d + s] = (double)v;
+            else cnt_partial[((int64_t)b * gridDim.x + blockIdx.x) * k + (s - k * d)] = (long long)v;
+        }
+    }
+    if (p.n_changed && prev) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+        if (lane == 0 && changed) atomicAdd(p.n_changed + b, (unsigned long long)changed);
+    }
+}
+
 // sums[b][j][t] = sum over splits (in split order) of the partials; counts likewise
 __global__ void kmeans_fold_kernel(const double* partial, const long long* cnt_partial, int splits, int k, int d,
                                    double* sums, long long* counts, const unsigned char* active) {
@@ -856,6 +947,49 @@ int launch_kmeans_assign(KmAssignParams p, int batch, double* c2_ws, void* strea
     else if (p.dtype == DT_F32) OFC_LAUNCH((kmeans_assign_generic_kernel<float, float>), grid, dim3(256), 0, stream, p);
     else OFC_LAUNCH((kmeans_assign_generic_kernel<double, double>), grid, dim3(256), 0, stream, p);
     OFC_CHECK_LAUNCH("kmeans_assign_generic");
+    return OFC_OK;
+}
+
+// grid of the fused uint8 step: every thread's 32-bit accumulators must hold 255 * its rows
+int kmeans_step_grid(int64_t n, int batch) {
+    int64_t tiles = (n + 255) / 256;
+    int64_t cap = (148 * 4 + batch - 1) / batch;
+    if (cap < 1) cap = 1;
+    int64_t g = tiles < cap ? tiles : cap;
+    const int64_t need = (n + (int64_t)256 * 8000000 - 1) / ((int64_t)256 * 8000000);   // <= 8M rows per thread
+    if (g < need) g = need;
+    return (int)(g < 1 ? 1 : g);
+}
+
+size_t kmeans_step_smem(int d, int k) { return ((size_t)k * d + k + d) * 8 + ((size_t)k * d + k) * 256 * 4; }
+
+int launch_kmeans_step_u8(KmAssignParams p, int batch, double* partial, long long* cnt_partial, double* sums, long long* counts,
+                          void* stream) {
+    if (batch <= 0 || p.n <= 0) return OFC_OK;
+    if (batch > 65535) { set_error("batch=%d exceeds 65535", batch); return OFC_ERR_UNSUPPORTED; }
+    const size_t smem = kmeans_step_smem(p.d, p.k);
+    if (p.d > 32 || smem > 200 * 1024) { set_error("fused k-means step: shape d=%d k=%d does not fit shared memory", p.d, p.k); return OFC_ERR_UNSUPPORTED; }
+    const int grid = kmeans_step_grid(p.n, batch);
+    ProfScope prof(PK_KMEANS, stream);
+#define OFC_KM_STEP(DPV)                                                                                                  \
+    {                                                                                                                     \
+        static size_t conf = 0;                                                                                           \
+        if (smem > 48 * 1024 && smem > conf) {                                                                            \
+            OFC_CUDA(cudaFuncSetAttribute(kmeans_step_u8_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            conf = smem;                                                                                                  \
+        }                                                                                                                 \
+        OFC_LAUNCH(kmeans_step_u8_kernel<DPV>, dim3(grid, batch), dim3(256), smem, stream, p, partial, cnt_partial);      \
+    }
+    if (p.d <= 4) OFC_KM_STEP(4)
+    else if (p.d <= 8) OFC_KM_STEP(8)
+    else if (p.d <= 16) OFC_KM_STEP(16)
+    else OFC_KM_STEP(32)
+#undef OFC_KM_STEP
+    OFC_CHECK_LAUNCH("kmeans_step_u8");
+    const int64_t kd = (int64_t)p.k * p.d;
+    OFC_LAUNCH(kmeans_fold_kernel, dim3((unsigned)((kd + 255) / 256), batch), dim3(256), 0, stream, partial, cnt_partial, grid, p.k,
+               p.d, sums, counts, p.active);
+    OFC_CHECK_LAUNCH("kmeans_fold");
     return OFC_OK;
 }
 

@@ -42,6 +42,11 @@ struct KmSumsParams {
 
 int launch_kmeans_assign(KmAssignParams p, int batch, double* c2_ws, void* stream);
 int launch_kmeans_sums(const KmSumsParams& p, int batch, double* sums, long long* counts, void* stream);
+// fused E-step + M-step sums for uint8 rows whose [k][d] accumulators fit shared memory (one pass over X)
+int kmeans_step_grid(int64_t n, int batch);
+size_t kmeans_step_smem(int d, int k);
+int launch_kmeans_step_u8(KmAssignParams p, int batch, double* partial, long long* cnt_partial, double* sums, long long* counts,
+                          void* stream);
 int launch_kmeans_centres(int batch, int d, int k, const double* sums, const long long* counts, const double* mean_sub,
                           int use_reciprocal, double* centres, double* shift_tot, double* shift_ws,
                           const unsigned char* active, void* stream);

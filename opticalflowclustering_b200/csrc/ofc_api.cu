@@ -566,8 +566,11 @@ KmWorkspace km_layout(int batch, int64_t n, int d, int k) {
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     w.off_c2 = take((size_t)batch * k * 8);
     w.off_inertia = take((size_t)batch * w.parts * 8);
-    w.off_partial = take((size_t)batch * w.splits * k * d * 8);
-    w.off_cnt = take((size_t)batch * w.splits * k * 8);
+    // per-CTA partials of the M-step kernel (splits) or of the fused uint8 step (its own grid)
+    const int step_grid = kmeans_step_grid(n, batch);
+    const int parts = w.splits > step_grid ? w.splits : step_grid;
+    w.off_partial = take((size_t)batch * parts * k * d * 8);
+    w.off_cnt = take((size_t)batch * parts * k * 8);
     w.off_shift = take((size_t)batch * k * 8);
     w.total = off;
     return w;
@@ -625,6 +628,32 @@ int ofc_kmeans_sums(const void* X, int dtype, int batch, int64_t n, int d, int k
     p.partial = (double*)(ws + w.off_partial); p.cnt_partial = (long long*)(ws + w.off_cnt);
     p.splits = w.splits; p.dt = w.dt; p.kt = w.kt; p.active = active;
     return launch_kmeans_sums(p, batch, sums, (long long*)counts, stream);
+}
+
+int ofc_kmeans_step_supported(int dtype, int d, int k) {
+    return dtype == OFC_U8 && d >= 1 && d <= 32 && k >= 1 && kmeans_step_smem(d, k) <= 200 * 1024;
+}
+
+int ofc_kmeans_step(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const double* centres,
+                    int32_t* labels, const int32_t* prev_labels, uint64_t* n_changed, double* sums, int64_t* counts,
+                    const uint8_t* active, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = km_check(X, dtype, batch, n, d, k);
+    if (rc != OFC_OK) return rc;
+    if (!ofc_kmeans_step_supported(dtype, d, k)) {
+        set_error("fused k-means step needs uint8 rows, d <= 32 and [k][d] accumulators that fit shared memory (dtype=%d d=%d k=%d)", dtype, d, k);
+        return OFC_ERR_UNSUPPORTED;
+    }
+    if (batch == 0 || n == 0) return OFC_OK;
+    OFC_REQUIRE(centres && labels && sums && counts, "null buffer");
+    KmWorkspace w = km_layout(batch, n, d, k);
+    if (!workspace || workspace_bytes < w.total) { set_error("k-means workspace too small: %zu < %zu", workspace_bytes, w.total); return OFC_ERR_WORKSPACE; }
+    char* ws = (char*)workspace;
+    KmAssignParams p;
+    p.X = X; p.dtype = dtype; p.n = n; p.d = d; p.k = k; p.mean = mean; p.centres = centres; p.c2 = nullptr;
+    p.labels = labels; p.prev_labels = prev_labels; p.n_changed = (unsigned long long*)n_changed;
+    p.inertia_partial = nullptr; p.min_dist = nullptr; p.active = active;
+    if (n_changed) OFC_CUDA(cudaMemsetAsync(n_changed, 0, sizeof(uint64_t) * batch, (cudaStream_t)stream));
+    return launch_kmeans_step_u8(p, batch, (double*)(ws + w.off_partial), (long long*)(ws + w.off_cnt), sums, (long long*)counts, stream);
 }
 
 int ofc_kmeans_centres(int batch, int d, int k, const double* sums, const int64_t* counts, const double* mean_sub,

@@ -129,6 +129,18 @@ class LloydState:
                                         _ptr(inertia), _ptr(min_dist), _ptr(active), _ptr(self.ws),
                                         C.c_size_t(self.ws.numel()), c.stream()))
 
+    def step_supported(self) -> bool:
+        """uint8 rows whose [k][d] accumulators fit shared memory: E-step + M-step sums in one pass"""
+        lib = self.ctx.lib
+        return (os.environ.get("OFC_KMEANS_FUSED", "1") != "0" and hasattr(lib, "ofc_kmeans_step_supported")
+                and bool(lib.ofc_kmeans_step_supported(self.dtype, self.d, self.k)))
+
+    def step(self, mean, centres, labels, prev, n_changed, sums, counts, active=None):
+        c = self.ctx
+        c.check(c.lib.ofc_kmeans_step(_ptr(self.X), self.dtype, self.B, C.c_int64(self.n), self.d, self.k, _ptr(mean),
+                                      _ptr(centres), _ptr(labels), _ptr(prev), _ptr(n_changed), _ptr(sums), _ptr(counts),
+                                      _ptr(active), _ptr(self.ws), C.c_size_t(self.ws.numel()), c.stream()))
+
     def sums_(self, mean, labels, sums, counts, k, square=0, active=None):
         c = self.ctx
         c.check(c.lib.ofc_kmeans_sums(_ptr(self.X), self.dtype, self.B, C.c_int64(self.n), self.d, int(k), _ptr(mean),
@@ -270,6 +282,8 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
     # dense float32 corner (d > 32): E/M steps on the tensor-core path, same labels as the float32 kernels
     tc = TensorCoreSteps(st, mean[0].contiguous()) if TensorCoreSteps.usable(st, _lib_override) else None
 
+    fused = tc is None and is_u8 and st.step_supported()
+
     active = torch.ones(B, dtype=torch.uint8, device=Xb.device)
     active_h = np.ones(B, bool)
     strict = np.zeros(B, bool)
@@ -281,6 +295,8 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
         if tc is not None:
             tc.assign(centres, lab, prev=lab_old, n_changed=st.n_changed)
             tc.sums_(lab, st.sums, st.counts)
+        elif fused:
+            st.step(mean, centres, lab, lab_old, st.n_changed, st.sums, st.counts, active=active)
         else:
             st.assign(mean, centres, lab, prev=lab_old, n_changed=st.n_changed, active=active)
             # uint8: raw (exact integer) sums; floats: sums of the centred rows like sklearn

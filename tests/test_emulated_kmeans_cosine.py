@@ -169,6 +169,19 @@ def test_kmeans_random_state_reproduces_sklearn(L, name):
     assert abs(clt.inertia_ - float(z[name + "_inertia"])) <= 1e-9 * float(z[name + "_inertia"])
 
 
+@pytest.mark.parametrize("shape", [(5000, 4, 8, 1), (3001, 7, 5, 3), (1500, 32, 4, 1)])
+def test_fused_uint8_step_equals_two_kernel_iteration(L, shape, monkeypatch):
+    """ofc_kmeans_step (E-step + exact integer sums in one pass) against ofc_kmeans_assign + ofc_kmeans_sums"""
+    n, d, k, B = shape
+    X = np.random.default_rng(1).integers(0, 256, (B, n, d), dtype=np.uint8)
+    init = X[:, :k].astype(np.float64)
+    monkeypatch.setenv("OFC_KMEANS_FUSED", "0")
+    a = km.lloyd(X, init, _lib_override=L)
+    monkeypatch.setenv("OFC_KMEANS_FUSED", "1")
+    b = km.lloyd(X, init, _lib_override=L)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
 def test_sliding_cosine_goldens(L):
     short = _hue_col(os.path.join(GOLDEN, "bounce.csv"))
     for name, want_sim, want_frame in [("601_3_3_cropped.csv", 0.91448231723348, 24),

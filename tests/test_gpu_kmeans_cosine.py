@@ -61,6 +61,20 @@ def test_kmeans_random_state_reproduces_sklearn(km, name):
     assert abs(clt.inertia_ - float(z[name + "_inertia"])) <= 1e-9 * float(z[name + "_inertia"])
 
 
+@pytest.mark.parametrize("shape", [(200000, 4, 8, 1), (30001, 7, 5, 3), (20000, 32, 4, 2), (5852, 4, 8, 350)])
+def test_fused_uint8_step_equals_two_kernel_iteration(km, shape, monkeypatch):
+    """ofc_kmeans_step (E-step + exact integer sums in one pass) against ofc_kmeans_assign + ofc_kmeans_sums:
+    labels, centres, inertia and n_iter bit-identical (the last shape is one 1080p frame's 350 cells)"""
+    n, d, k, B = shape
+    X = torch.from_numpy(np.random.default_rng(1).integers(0, 256, (B, n, d), dtype=np.uint8)).cuda()
+    init = X[:, :k].double()
+    monkeypatch.setenv("OFC_KMEANS_FUSED", "0")
+    a = km.lloyd(X, init, max_iter=12)
+    monkeypatch.setenv("OFC_KMEANS_FUSED", "1")
+    b = km.lloyd(X, init, max_iter=12)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
 def test_kmeans_large_n_properties(km):
     """1M x 4 uint8 rows, k = 8: too slow for the numpy oracle in full, so check (a) labels equal
     an independent fp64 torch restatement of the E-step on the final centres, (b) centres are the
