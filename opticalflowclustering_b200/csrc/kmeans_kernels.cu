@@ -16,6 +16,7 @@
 //
 // All kernels take a batch dimension (independent problems of equal shape): the
 // reference runs one fit per grid cell per frame (350 per frame).
+#include <stdlib.h>
 #include "ofc_common.cuh"
 #include "kmeans_kernels.cuh"
 
@@ -167,6 +168,75 @@ __global__ void __launch_bounds__(256) kmeans_assign_generic_kernel(KmAssignPara
                 W df = ((W)row[t] - (mean ? (W)mean[t] : (W)0)) - (W)c[t];
                 sq = fma_w<W>(df, df, sq);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) {
+                inert += (double)sq;
+                if (p.min_dist) p.min_dist[(int64_t)b * p.n + i] = (double)sq;
+            }
+        }
+    }
+    if (p.inertia_partial) {
+        double t = block_sum_256(inert, s_red);
+        if (tid == 0) p.inertia_partial[(int64_t)b * gridDim.x + blockIdx.x] = t;
+    }
+    if (p.n_changed && prev && lane == 0 && changed) atomicAdd(p.n_changed + b, (unsigned long long)changed);
+}
+
+// ---------------------------------------------------------------------------
+// E-step, medium shape (32 < d <= 32*NT, centres fit shared memory): one warp per point like the generic
+// kernel and in exactly its arithmetic order (lanes stride over the features, fma chain, xor-tree reduction),
+// but the centred row is loaded ONCE into registers and the centres (in the working precision) and their
+// norms live in shared memory -- X is read once per iteration and nothing else leaves the SM.
+// ---------------------------------------------------------------------------
+template <typename T, typename W, int NT>
+__global__ void __launch_bounds__(256) kmeans_assign_medium_kernel(KmAssignParams p) {
+    OFC_DYN_SMEM(unsigned char, raw);
+    W* sc = reinterpret_cast<W*>(raw);                        // [k][d]
+    W* sc2 = sc + (size_t)p.k * p.d;                           // [k]
+    __shared__ double s_red[8];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, d = p.d, k = p.k;
+    if (p.active && !p.active[b]) return;
+    const double* cen = p.centres + (int64_t)b * k * d;
+    const double* c2 = p.c2 + (int64_t)b * k;
+    for (int i = tid; i < k * d; i += 256) sc[i] = (W)cen[i];
+    for (int i = tid; i < k; i += 256) sc2[i] = (W)c2[i];
+    __syncthreads();
+    const double* mean = p.mean ? p.mean + (int64_t)b * d : nullptr;
+    W m[NT];
+#pragma unroll
+    for (int u = 0; u < NT; ++u) { const int t = lane + 32 * u; m[u] = (mean && t < d) ? (W)mean[t] : (W)0; }
+    const T* X = reinterpret_cast<const T*>(p.X) + (int64_t)b * p.n * d;
+    int32_t* labels = p.labels + (int64_t)b * p.n;
+    const int32_t* prev = p.prev_labels ? p.prev_labels + (int64_t)b * p.n : nullptr;
+    double inert = 0.0;
+    unsigned changed = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + warp; i < p.n; i += (int64_t)gridDim.x * 8) {
+        const T* row = X + i * d;
+        W x[NT];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) { const int t = lane + 32 * u; x[u] = t < d ? (W)row[t] - m[u] : (W)0; }
+        W best = (W)0;
+        int label = 0;
+        for (int j = 0; j < k; ++j) {
+            const W* c = sc + (size_t)j * d;
+            W part = (W)0;
+#pragma unroll
+            for (int u = 0; u < NT; ++u) { const int t = lane + 32 * u; if (t < d) part = fma_w<W>(x[u], c[t], part); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            const W dist = fma_w<W>((W)-2, part, sc2[j]);
+            if (j == 0 || dist < best) { best = dist; label = j; }
+        }
+        if (lane == 0) {
+            labels[i] = label;
+            if (prev && prev[i] != label) ++changed;
+        }
+        if (p.inertia_partial || p.min_dist) {
+            const W* c = sc + (size_t)label * d;
+            W sq = (W)0;
+#pragma unroll
+            for (int u = 0; u < NT; ++u) { const int t = lane + 32 * u; if (t < d) { const W df = x[u] - c[t]; sq = fma_w<W>(df, df, sq); } }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
             if (lane == 0) {
@@ -943,6 +1013,35 @@ int launch_kmeans_assign(KmAssignParams p, int batch, double* c2_ws, void* strea
     // (n+7)/8 >= (n+255)/256 and the cap above is larger, so clamping gives exactly that count
     const int parts = kmeans_assign_grid(p.n);
     if ((int)grid.x > parts) grid.x = parts;
+    // centres fit shared memory and the row fits a warp's registers: same arithmetic, X read once
+    static const int use_medium = getenv("OFC_KMEANS_MEDIUM") ? atoi(getenv("OFC_KMEANS_MEDIUM")) : 1;
+    const size_t msmem = ((size_t)p.k * p.d + p.k) * wsz;
+    if (use_medium && p.d <= 512 && msmem <= 200 * 1024) {
+#define OFC_KM_MED(TT, WW, NTV)                                                                                        \
+    {                                                                                                                  \
+        static size_t conf = 0;                                                                                        \
+        if (msmem > 48 * 1024 && msmem > conf) {                                                                       \
+            OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_medium_kernel<TT, WW, NTV>,                                    \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));                   \
+            conf = msmem;                                                                                              \
+        }                                                                                                              \
+        OFC_LAUNCH((kmeans_assign_medium_kernel<TT, WW, NTV>), grid, dim3(256), msmem, stream, p);                     \
+    }
+#define OFC_KM_MED_NT(TT, WW)                                                                                          \
+    {                                                                                                                  \
+        if (p.d <= 64) OFC_KM_MED(TT, WW, 2)                                                                           \
+        else if (p.d <= 128) OFC_KM_MED(TT, WW, 4)                                                                     \
+        else if (p.d <= 256) OFC_KM_MED(TT, WW, 8)                                                                     \
+        else OFC_KM_MED(TT, WW, 16)                                                                                    \
+    }
+        if (p.dtype == DT_U8) OFC_KM_MED_NT(unsigned char, double)
+        else if (p.dtype == DT_F32) OFC_KM_MED_NT(float, float)
+        else OFC_KM_MED_NT(double, double)
+#undef OFC_KM_MED_NT
+#undef OFC_KM_MED
+        OFC_CHECK_LAUNCH("kmeans_assign_medium");
+        return OFC_OK;
+    }
     if (p.dtype == DT_U8) OFC_LAUNCH((kmeans_assign_generic_kernel<unsigned char, double>), grid, dim3(256), 0, stream, p);
     else if (p.dtype == DT_F32) OFC_LAUNCH((kmeans_assign_generic_kernel<float, float>), grid, dim3(256), 0, stream, p);
     else OFC_LAUNCH((kmeans_assign_generic_kernel<double, double>), grid, dim3(256), 0, stream, p);
@@ -950,9 +1049,35 @@ int launch_kmeans_assign(KmAssignParams p, int batch, double* c2_ws, void* strea
     return OFC_OK;
 }
 
+// fold of the fused step's per-CTA partials: integers held exactly in float64, so a warp per element can
+// add them in any order (lanes stride over the CTAs, xor tree) and still give the bits of the serial fold
+__global__ void __launch_bounds__(256) kmeans_fold_exact_kernel(const double* __restrict__ partial, const long long* __restrict__ cnt_partial,
+                                                                int splits, int k, int d, double* __restrict__ sums,
+                                                                long long* __restrict__ counts, const unsigned char* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t e = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t kd = (int64_t)k * d;
+    if (e < kd) {
+        double s = 0.0;
+        for (int sp = lane; sp < splits; sp += 32) s += partial[((int64_t)b * splits + sp) * kd + e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sums[(int64_t)b * kd + e] = s;
+    } else if (e < kd + k) {
+        const int64_t j = e - kd;
+        long long c = 0;
+        for (int sp = lane; sp < splits; sp += 32) c += cnt_partial[((int64_t)b * splits + sp) * k + j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) counts[(int64_t)b * k + j] = c;
+    }
+}
+
 // grid of the fused uint8 step: every thread's 32-bit accumulators must hold 255 * its rows
 int kmeans_step_grid(int64_t n, int batch) {
-    int64_t tiles = (n + 255) / 256;
+    int64_t tiles = (n + 4095) / 4096;                 // >= 4096 rows per CTA: the zero / fold overhead stays small
     int64_t cap = (148 * 4 + batch - 1) / batch;
     if (cap < 1) cap = 1;
     int64_t g = tiles < cap ? tiles : cap;
@@ -987,9 +1112,9 @@ int launch_kmeans_step_u8(KmAssignParams p, int batch, double* partial, long lon
 #undef OFC_KM_STEP
     OFC_CHECK_LAUNCH("kmeans_step_u8");
     const int64_t kd = (int64_t)p.k * p.d;
-    OFC_LAUNCH(kmeans_fold_kernel, dim3((unsigned)((kd + 255) / 256), batch), dim3(256), 0, stream, partial, cnt_partial, grid, p.k,
-               p.d, sums, counts, p.active);
-    OFC_CHECK_LAUNCH("kmeans_fold");
+    OFC_LAUNCH(kmeans_fold_exact_kernel, dim3((unsigned)((kd + p.k + 7) / 8), batch), dim3(256), 0, stream, partial, cnt_partial, grid,
+               p.k, p.d, sums, counts, p.active);
+    OFC_CHECK_LAUNCH("kmeans_fold_exact");
     return OFC_OK;
 }
 

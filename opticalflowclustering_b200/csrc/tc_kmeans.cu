@@ -13,8 +13,9 @@
 //   warp 1      one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) with the
 //               128 x BN float32 accumulator in tensor memory; two accumulators (2 x BN <= 512 columns)
 //               so the epilogue of one tile overlaps the MMAs of the next;
-//   warps 2..5  epilogue: tcgen05.ld of the accumulator (one row per thread), dist = c2 - 2 acc, running
-//               first/second/third minimum per row.
+//   warps 2..9  epilogue: tcgen05.ld of the accumulator (one row per thread, two warp sets splitting the
+//               columns, next chunk in flight while one is scanned), dist = c2 - 2 acc, running minimum plus
+//               a short history of the near-minimum distances per row.
 // TF32 keeps 10 mantissa bits, so every operand is split once into hi = its top 11 significant bits
 // and lo = the exact remainder (x = hi + lo, both float32), and x.c is formed as lo.hi + hi.lo + hi.hi
 // -- three MMAs per step ("3xTF32"), the hi parts exact in TF32 whatever the hardware does with the low
@@ -35,7 +36,7 @@ namespace {
 
 constexpr int BM = 128;          // rows per tile (= TMEM lanes)
 constexpr int BK = 32;           // floats per shared-memory row: 128 bytes = one swizzle atom
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;      // TMA warp, MMA warp, 2 x 4 epilogue warps
 
 struct TcParams {
     int64_t n;
@@ -103,8 +104,8 @@ __device__ __forceinline__ void umma_commit(unsigned bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-    unsigned r[32];
+// issue only: the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -114,10 +115,8 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, rows of 128 bytes, 128-byte swizzle (what TMA writes with SWIZZLE_128B):
 // 8-row groups 1024 bytes apart (SBO), LBO unused, descriptor version 1 (sm_100).
@@ -128,7 +127,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128(unsigned addr) {
 template <int BN> struct TcCfg {
     static constexpr unsigned A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + 128 * 12 * 4;
 };
 
 template <int BN>
@@ -157,7 +156,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -215,17 +214,22 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
                 }
         }
     } else {
+        // Epilogue: warps 2..5 take the even 32-column chunks of every accumulator, warps 6..9 the odd ones (a warp
+        // may only read the TMEM lane quarter warp % 4, so the two sets cover the same 128 rows); each thread keeps a
+        // running minimum (first strict minimum in centre order) plus a four-deep history of every distance that
+        // came within the row's error bound of its running minimum: whatever ends within the bound of the FINAL
+        // minimum is in a history unless it was pushed out while still eligible (`lost`).  The odd set hands its
+        // state over through shared memory at the end of the row block and the even set decides.
         const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        const int half = warp >= 6 ? 1 : 0;
         const float cmax = __ldg(p.cmax);
+        float* xch = reinterpret_cast<float*>(tmem_slot + 4);     // [128][12] hand-over
         unsigned unit = 0;
         for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-            // Running minimum (first strict minimum in centre order) plus a four-deep history of every distance
-            // that came within the row's error bound of the running minimum: whatever ends within the bound of
-            // the FINAL minimum is in that history unless it was pushed out while still eligible (`lost`).
             const int64_t row = (int64_t)mt * BM + q * 32 + lane;
             const float tol = p.tol_scale * __ldg(p.xnorm + (row < p.n ? row : p.n - 1)) * cmax;
             float m1 = __int_as_float(0x7f800000), thr = m1;
-            int a1 = 0;
+            int a1 = 0x7fffffff;
             float h0 = m1, h1 = m1, h2 = m1, h3 = m1;
             int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
             bool lost = false;
@@ -234,12 +238,10 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
                 mbar_wait(tfull_bar(acc), aph, p.error_flag);
                 tc_fence_after();
                 const unsigned trow = tmem_base + acc * BN + ((unsigned)(q * 32) << 16);
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    const int j0 = nt * BN + c * 32;
-                    if (j0 >= p.k) break;
-                    float v[32];
-                    tmem_ld32(trow + c * 32, v);
+                // two register buffers, statically named: the next chunk of this warp is in flight while one is scanned
+                unsigned bufA[32], bufB[32];
+                constexpr int NCH = BN / 32;
+                auto scan = [&](const unsigned (&buf)[32], int j0) {
                     const float4* c2v = reinterpret_cast<const float4*>(p.c2 + j0);   // padded with +inf past k
 #pragma unroll
                     for (int g4 = 0; g4 < 8; ++g4) {
@@ -247,7 +249,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
                         const float cj[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float dist = fmaf(-2.f, v[g4 * 4 + e], cj[e]);
+                            const float dist = fmaf(-2.f, __uint_as_float(buf[g4 * 4 + e]), cj[e]);
                             if (dist <= thr) {
                                 const int j = j0 + g4 * 4 + e;
                                 const float out = h3;
@@ -257,19 +259,54 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
                             }
                         }
                     }
+                };
+                const int jt = nt * BN;
+                int c = half;
+                if (c < NCH && jt + c * 32 < p.k) tmem_ld32_issue(trow + c * 32, bufA);
+                tmem_ld_wait();
+#pragma unroll 1
+                while (c < NCH && jt + c * 32 < p.k) {
+                    if (c + 2 < NCH && jt + (c + 2) * 32 < p.k) tmem_ld32_issue(trow + (c + 2) * 32, bufB);
+                    scan(bufA, jt + c * 32);
+                    tmem_ld_wait();
+                    c += 2;
+                    if (!(c < NCH && jt + c * 32 < p.k)) break;
+                    if (c + 2 < NCH && jt + (c + 2) * 32 < p.k) tmem_ld32_issue(trow + (c + 2) * 32, bufA);
+                    scan(bufB, jt + c * 32);
+                    tmem_ld_wait();
+                    c += 2;
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
-            if (row < p.n) {
+            // hand-over of the odd set's state; named barrier 1 over the 256 epilogue threads
+            float* slot = xch + (q * 32 + lane) * 12;
+            if (half) {
+                slot[0] = m1; slot[1] = __int_as_float(a1); slot[2] = lost ? 1.f : 0.f;
+                slot[3] = h0; slot[4] = __int_as_float(i0); slot[5] = h1; slot[6] = __int_as_float(i1);
+                slot[7] = h2; slot[8] = __int_as_float(i2); slot[9] = h3; slot[10] = __int_as_float(i3);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (!half && row < p.n) {
+                const float om1 = slot[0];
+                const int oa1 = __float_as_int(slot[1]);
+                const float oh[4] = {slot[3], slot[5], slot[7], slot[9]};
+                const int oi[4] = {__float_as_int(slot[4]), __float_as_int(slot[6]), __float_as_int(slot[8]), __float_as_int(slot[10])};
+                lost = lost || slot[2] != 0.f;
+                // first strict minimum over both halves: the lower centre index wins a tie
+                if (om1 < m1 || (om1 == m1 && oa1 < a1)) { m1 = om1; a1 = oa1; }
+                thr = m1 + tol;
                 p.labels[row] = a1;
                 // the other centres inside the bound of the final minimum
-                int cand[4], nc = 0;
+                int cand[8], nc = 0;
                 if (i0 != a1 && h0 <= thr) cand[nc++] = i0;
                 if (i1 != a1 && h1 <= thr) cand[nc++] = i1;
                 if (i2 != a1 && h2 <= thr) cand[nc++] = i2;
                 if (i3 != a1 && h3 <= thr) cand[nc++] = i3;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (oi[u] != a1 && oh[u] <= thr) cand[nc++] = oi[u];
                 if (nc > 0 || lost || !(m1 < __int_as_float(0x7f800000))) {
                     // 2 or 3 candidates are listed; otherwise (0) all k centres are re-evaluated
                     const int ncand = (lost || nc > 2 || nc == 0) ? 0 : nc + 1;
@@ -277,6 +314,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
                     p.amb[pos] = make_int4((int)row, a1, nc > 0 ? cand[0] : 0, (nc > 1 ? cand[1] : 0) | (ncand << 16));
                 }
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // the slots are free for the next row block
         }
     }
     tc_fence_before();
