@@ -194,10 +194,10 @@ from tests.emu import emu_lib as E
 from opticalflowclustering_b200 import kmeans as km
 rng = np.random.default_rng(2)
 h = hashlib.sha256()
-for dt, (n, d, k, B) in [(np.uint8, (700, 350, 8, 1)), (np.float32, (600, 70, 9, 2)), (np.float64, (500, 130, 5, 1)),
-                         (np.uint8, (400, 33, 12, 1))]:
+for dt, (n, d, k, B) in [(np.uint8, (260, 350, 8, 1)), (np.float32, (300, 70, 9, 2)), (np.float64, (200, 130, 5, 1)),
+                         (np.uint8, (200, 33, 12, 1))]:
     X = (rng.integers(0, 256, (B, n, d)) if dt == np.uint8 else rng.normal(0, 3, (B, n, d))).astype(dt)
-    for t in km.lloyd(X, X[:, :k].astype(np.float64), max_iter=6, _lib_override=E.lib()):
+    for t in km.lloyd(X, X[:, :k].astype(np.float64), max_iter=4, _lib_override=E.lib()):
         h.update(t.cpu().numpy().tobytes())
 print(h.hexdigest())
 '''
