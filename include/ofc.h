@@ -48,7 +48,8 @@ int ofc_profile_end(float* ms_by_kind, int* launches_by_kind, int n_kinds);
  * winsize, iterations, poly_n, poly_sigma, flags)
  *   reference: computeOpticalFlowModule.py:20-22, computeOpticalFlow.py:99-101.
  * A plan fixes the frame size and parameters (pyramid geometry, filter taps,
- * workspace layout) for up to `max_frames` frames per call.  flags: 0 (box window,
+ * workspace layout) for up to `max_frames` frames per call.  winsize 4..65 (cv2's quirk kept: the window is
+ * 2 (winsize / 2) + 1 wide, the box sums are scaled by 1 / winsize^2), poly_n 5 or 7.  flags: 0 (box window,
  * the reference's literal), OFC_FLOW_GAUSSIAN (cv2.OPTFLOW_FARNEBACK_GAUSSIAN: Gaussian
  * window of winsize | 1 taps, any odd winsize <= 65) and/or OFC_FLOW_USE_INITIAL_FLOW
  * (cv2.OPTFLOW_USE_INITIAL_FLOW, through ofc_farneback_pair_init); anything else ->

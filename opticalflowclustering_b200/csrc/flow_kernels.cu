@@ -1398,7 +1398,7 @@ __global__ void __launch_bounds__(256) flow_iter_gauss_kernel(IterParams p, Gaus
             for (int t = 1; t <= R; ++t) v = __fadd_rn(v, __fmul_rn(__fadd_rn(row[t], row[-t]), gw.k[t]));
             S[c] = v;
         }
-        const double g11 = S[0], g12 = S[1], g22 = S[2], h1 = S[3], h2 = S[4];
+        const double g11 = S[0] * gw.scale, g12 = S[1] * gw.scale, g22 = S[2] * gw.scale, h1 = S[3] * gw.scale, h2 = S[4] * gw.scale;
         const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
         const float2 res = make_float2((float)((g11 * h2 - g12 * h1) * idet), (float)((g22 * h1 - g12 * h2) * idet));
         p.flow_out[(int64_t)pair * p.flow_out_stride + (int64_t)gy * w + gx] = res;
@@ -1763,9 +1763,16 @@ int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scra
         }
         case 10: return launch_iter_r<10, 32, 256, 2>(p, n_pairs, stream);
         case 12: return launch_iter_r<12, 32, 256, 2>(p, n_pairs, stream);
-        default:
-            set_error("winsize=%d unsupported (odd 5..15, 21, 25)", winsize);
-            return OFC_ERR_UNSUPPORTED;
+        default: {
+            // any other window: the run-time-radius kernel with unit taps (box sums in float32, scaled like OpenCV
+            // by 1 / winsize^2 -- the window itself is 2 (winsize / 2) + 1 wide)
+            if (winsize / 2 < 1 || winsize / 2 > 32) { set_error("winsize=%d unsupported (4..65)", winsize); return OFC_ERR_UNSUPPORTED; }
+            GaussWindow box;
+            box.r = winsize / 2;
+            for (int i = 0; i <= box.r; ++i) box.k[i] = 1.f;
+            box.scale = p.blur_scale;
+            return launch_iter_gauss(p, box, n_pairs, stream);
+        }
     }
 }
 

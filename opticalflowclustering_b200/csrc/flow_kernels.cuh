@@ -52,6 +52,7 @@ struct IterParams {
 struct GaussWindow {
     int r;
     float k[33];
+    double scale;                // applied to the window sums before the solve (1 for the Gaussian window)
 };
 
 int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* stream);

@@ -306,7 +306,7 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
     OFC_REQUIRE(max_frames >= 2, "max_frames must be >= 2");
     OFC_REQUIRE(pyr_scale > 0 && pyr_scale < 1, "pyr_scale must be in (0,1)");
     OFC_REQUIRE(levels >= 0 && iterations >= 1, "levels >= 0 and iterations >= 1 required");
-    OFC_REQUIRE(winsize >= 5 && (winsize & 1), "winsize must be odd and >= 5");
+    OFC_REQUIRE(winsize >= 4 && winsize <= 65, "winsize must be in [4, 65]");
     OFC_REQUIRE(poly_sigma > 0, "poly_sigma must be > 0");
     ofc_flow_plan* pl = new ofc_flow_plan();
     pl->W = width; pl->H = height; pl->max_frames = max_frames;
@@ -336,14 +336,11 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
             sum += (double)t * 2;
         }
         pl->gauss.r = m;
+        pl->gauss.scale = 1.0;
         for (int i = 0; i <= m; ++i) pl->gauss.k[i] = (float)(kk[i] * (1.0 / sum));
-    } else {   // winsize instantiations (see launch_flow_iter)
-        int r = winsize / 2;
-        if (!((r >= 2 && r <= 7) || r == 10 || r == 12)) {
-            set_error("winsize=%d unsupported (odd 5..15, 21, 25)", winsize);
-            delete pl; return OFC_ERR_UNSUPPORTED;
-        }
     }
+    // box window: radii 2..7, 10, 12 have unrolled kernels (launch_flow_iter), any other winsize in [4, 65] runs the
+    // run-time-radius kernel
     // pyramid: levels+1 scales, cropped while the coarse side stays >= 32
     int eff = 0;
     {

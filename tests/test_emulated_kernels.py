@@ -88,7 +88,9 @@ def test_emu_unsupported_flags():
 
 
 @pytest.mark.parametrize("flags,kw", [(256, dict()), (256, dict(winsize=9, levels=1)), (4, dict()),
-                                      (260, dict(pyr_scale=0.6, levels=2, winsize=11))])
+                                      (260, dict(pyr_scale=0.6, levels=2, winsize=11)),
+                                      (0, dict(winsize=10, levels=2, iterations=2)),     # even window: cv2's 1/winsize^2 quirk
+                                      (0, dict(winsize=17, levels=1, iterations=2))])    # no unrolled kernel: run-time radius
 def test_emu_flow_flags_vs_oracle(flags, kw):
     """OPTFLOW_FARNEBACK_GAUSSIAN (Gaussian window kernel) and OPTFLOW_USE_INITIAL_FLOW
     (INTER_AREA seed of the coarsest level) against the cv2-pinned oracle"""

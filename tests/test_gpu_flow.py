@@ -71,7 +71,8 @@ def test_flow_intermediates_vs_oracle(ofc):
 
 @pytest.mark.parametrize("kw", [dict(), dict(levels=1, winsize=9, iterations=2), dict(levels=5),
                                 dict(pyr_scale=0.6, levels=2, winsize=11, poly_n=7, poly_sigma=1.5),
-                                dict(winsize=21), dict(winsize=5, iterations=1)])
+                                dict(winsize=21), dict(winsize=5, iterations=1),
+                                dict(winsize=10), dict(winsize=17, levels=2), dict(winsize=33, levels=1), dict(winsize=4)])
 def test_cv2_signature_drop_in(ofc, kw):
     """calc_optical_flow_farneback(prev, next, None, ...) numpy in -> numpy out, odd size."""
     from opticalflowclustering_b200.flow import calc_optical_flow_farneback
