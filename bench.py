@@ -200,13 +200,15 @@ def kmeans_cosine_extras(dev, peak):
     except Exception:
         pass
     for name, (N, D, K) in {"f32_d64_k256": (1_000_000, 64, 256), "f32_d512_k256": (1_000_000, 512, 256),
-                            "f32_d128_k1024": (1_000_000, 128, 1024)}.items():
+                            "f32_d128_k1024": (1_000_000, 128, 1024), "u8_d352_k256": (1_000_000, 352, 256)}.items():
         gd = torch.Generator(device=dev).manual_seed(1)
-        cen = torch.rand((K, D), device=dev, generator=gd) * 8
-        X = (cen[torch.randint(0, K, (N,), device=dev, generator=gd)] + torch.randn((N, D), device=dev, generator=gd)).float()
+        is_u8 = name.startswith("u8")          # uint8 hue vectors: float64 semantics, tensor-core filter + float64 re-evaluation
+        cen = torch.rand((K, D), device=dev, generator=gd) * (200 if is_u8 else 8)
+        X = cen[torch.randint(0, K, (N,), device=dev, generator=gd)] + (12 if is_u8 else 1) * torch.randn((N, D), device=dev, generator=gd)
+        X = X.round().clamp(0, 255).to(torch.uint8) if is_u8 else X.float()
         ctx = km._Ctx(dev)
         st = km.LloydState(ctx, X.unsqueeze(0).contiguous(), K, ws_k=1)
-        mean = X.double().mean(0).float().double().contiguous()
+        mean = X.double().mean(0).contiguous() if is_u8 else X.double().mean(0).float().double().contiguous()
         tc = km.TensorCoreSteps(st, mean)
         centres = (X[:K].double() - mean).unsqueeze(0).contiguous()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -225,7 +227,7 @@ def kmeans_cosine_extras(dev, peak):
         rec = {"ms_assign": t_assign, "ms_sums": t_sums, "rows_per_s": N / ((t_assign + t_sums) / 1e3),
                "tflops": flop / (t_assign / 1e3) / 1e12, "tf32_tflops": 3 * flop / (t_assign / 1e3) / 1e12,
                "rechecked_rows": int(tc.n_rechecked.item()),
-               "sums_gb_s": (2 * N * D * 4 + 8 * N) / (t_sums / 1e3) / 1e9}
+               "sums_gb_s": ((N * D if is_u8 else 2 * N * D * 4) + 8 * N) / (t_sums / 1e3) / 1e9}
         if bf16_peak:
             rec["tf32_frac_of_peak"] = rec["tf32_tflops"] / (bf16_peak / 2)
         out["kmeans_iter_tc_" + name] = rec

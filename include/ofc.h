@@ -145,6 +145,8 @@ int ofc_draw_grid(uint8_t* bgr, int n_frames, int height, int width, int rows, i
 #define OFC_F64 2
 
 size_t ofc_kmeans_workspace_bytes(int batch, int64_t n, int d, int k);
+/* the (small) prefix of that workspace ofc_kmeans_assign and ofc_kmeans_centres need on their own */
+size_t ofc_kmeans_assign_workspace_bytes(int batch, int64_t n, int d, int k);
 
 /* E-step: labels[i] = first strict minimum over j of ||c_j||^2 - 2 (x_i - mean).c_j
  * (_k_means_lloyd.pyx:160-213).  mean [batch][d] (nullable) is subtracted from every
@@ -230,6 +232,19 @@ int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, i
 int ofc_kmeans_tc_sums(const float* Xh, const float* Xl, int64_t n, int d, int k, const int32_t* labels,
                        double* sums /* [k][d] */, int64_t* counts /* [k] */,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* The same for uint8 rows (the reference's pixels / hues, which sklearn works in float64): the split rows hold
+ * float32(x - mean) with the float64 column mean; the tensor-core filter's bound also covers that rounding, and
+ * every near-tie is re-evaluated on the ORIGINAL bytes in the float64 arithmetic of ofc_kmeans_assign(OFC_U8):
+ * labels bit-identical to it (and so to sklearn given the same centres).  ofc_kmeans_tc_sums_u8 sums the raw
+ * bytes (exact integers, what ofc_kmeans_sums gives for OFC_U8 with mean = NULL). */
+int ofc_kmeans_tc_prepare_u8(const uint8_t* X, const double* mean /* [d] */, int64_t n, int d,
+                             float* Xh, float* Xl, float* xnorm, void* stream);
+int ofc_kmeans_tc_assign_u8(const uint8_t* X, const double* mean, const float* Xh, const float* Xl, const float* xnorm,
+                            int64_t n, int d, int k, const double* centres, int32_t* labels,
+                            const int32_t* prev_labels, uint64_t* n_changed, uint32_t* n_rechecked,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int ofc_kmeans_tc_sums_u8(const uint8_t* X, int64_t n, int d, int k, const int32_t* labels,
+                          double* sums, int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 
 /* image_dict ROIs (KmeanGrids.py:85,113) + preprocess_image (:269-286) for every cell:
  * out u8 [n_frames][rows*cols][ (H/rows)*(W/cols) ][4] = (c0, c1, c2, alpha).  draw_lines:

@@ -38,6 +38,7 @@ SIGNATURES = {
     "ofc_grid_cells": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ofc_draw_grid": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
     "ofc_kmeans_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
+    "ofc_kmeans_assign_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "ofc_kmeans_assign": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_kmeans_sums": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_kmeans_step_supported": (_i, [_i, _i, _i]),
@@ -49,6 +50,9 @@ SIGNATURES = {
     "ofc_kmeans_tc_prepare": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
     "ofc_kmeans_tc_assign": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_kmeans_tc_sums": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_tc_prepare_u8": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
+    "ofc_kmeans_tc_assign_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_tc_sums_u8": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_grid_extract_cells": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ofc_sliding_cosine": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
     "ofc_row_cosine": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),

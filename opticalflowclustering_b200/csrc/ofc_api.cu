@@ -550,6 +550,7 @@ int ofc_draw_grid(uint8_t* bgr, int n_frames, int height, int width, int rows, i
 namespace {
 struct KmWorkspace {
     size_t off_c2, off_inertia, off_partial, off_cnt, off_shift, total;
+    size_t assign_total;         // the prefix ofc_kmeans_assign / ofc_kmeans_centres need (no M-step partials)
     int parts, splits, dt, kt;
 };
 KmWorkspace km_layout(int batch, int64_t n, int d, int k) {
@@ -563,6 +564,7 @@ KmWorkspace km_layout(int batch, int64_t n, int d, int k) {
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     w.off_c2 = take((size_t)batch * k * 8);
     w.off_inertia = take((size_t)batch * w.parts * 8);
+    w.assign_total = off;
     // per-CTA partials of the M-step kernel (splits) or of the fused uint8 step (its own grid)
     const int step_grid = kmeans_step_grid(n, batch);
     const int parts = w.splits > step_grid ? w.splits : step_grid;
@@ -577,6 +579,11 @@ KmWorkspace km_layout(int batch, int64_t n, int d, int k) {
 size_t ofc_kmeans_workspace_bytes(int batch, int64_t n, int d, int k) {
     if (batch <= 0 || n <= 0 || d <= 0 || k <= 0) return 0;
     return km_layout(batch, n, d, k).total;
+}
+
+size_t ofc_kmeans_assign_workspace_bytes(int batch, int64_t n, int d, int k) {
+    if (batch <= 0 || n <= 0 || d <= 0 || k <= 0) return 0;
+    return km_layout(batch, n, d, k).assign_total;
 }
 
 static int km_check(const void* X, int dtype, int batch, int64_t n, int d, int k) {
@@ -595,7 +602,7 @@ int ofc_kmeans_assign(const void* X, int dtype, int batch, int64_t n, int d, int
     if (batch == 0 || n == 0) return OFC_OK;
     OFC_REQUIRE(centres && labels, "null centres / labels");
     KmWorkspace w = km_layout(batch, n, d, k);
-    if (!workspace || workspace_bytes < w.total) { set_error("k-means workspace too small: %zu < %zu", workspace_bytes, w.total); return OFC_ERR_WORKSPACE; }
+    if (!workspace || workspace_bytes < w.assign_total) { set_error("k-means workspace too small: %zu < %zu", workspace_bytes, w.assign_total); return OFC_ERR_WORKSPACE; }
     char* ws = (char*)workspace;
     KmAssignParams p;
     p.X = X; p.dtype = dtype; p.n = n; p.d = d; p.k = k; p.mean = mean; p.centres = centres; p.c2 = nullptr;

@@ -45,6 +45,7 @@ struct TcParams {
     const float* xnorm;          // [n] row norms
     const float* cmax;           // [1] largest centre norm
     float tol_scale;             // bound on |TF32 distance difference error| / (|x| cmax)
+    float tol_c2;                // ... plus this times cmax^2 (rounding of the squared norms; uint8 path only)
     int32_t* labels;
     int4* amb;                   // [n] (row, best, second, third | candidates << 16) of rows to re-evaluate
     unsigned* amb_count;
@@ -227,7 +228,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
         unsigned unit = 0;
         for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
             const int64_t row = (int64_t)mt * BM + q * 32 + lane;
-            const float tol = p.tol_scale * __ldg(p.xnorm + (row < p.n ? row : p.n - 1)) * cmax;
+            const float tol = p.tol_scale * __ldg(p.xnorm + (row < p.n ? row : p.n - 1)) * cmax + p.tol_c2 * cmax * cmax;
             float m1 = __int_as_float(0x7f800000), thr = m1;
             int a1 = 0x7fffffff;
             float h0 = m1, h1 = m1, h2 = m1, h3 = m1;
@@ -385,6 +386,93 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     lo = v - hi;
 }
+
+// uint8 rows (worked in float64 by sklearn and by ofc_kmeans_assign(OFC_U8)): the same re-evaluation in the
+// float64 arithmetic of kmeans_assign_generic_kernel<unsigned char, double> on the ORIGINAL bytes
+__device__ __forceinline__ double exact_dist64(const double* __restrict__ x, const double* __restrict__ c, double c2, int d, int lane) {
+    double part = 0.0;
+    for (int t = lane; t < d; t += 32) part = fma(x[t], c[t], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    return fma(-2.0, part, c2);
+}
+
+__global__ void __launch_bounds__(256) kmeans_assign_fix_u8_kernel(const unsigned char* __restrict__ X, const double* __restrict__ mean, int d,
+                                                                   int k, const double* __restrict__ C, const double* __restrict__ c2,
+                                                                   const int4* __restrict__ amb, const unsigned* __restrict__ amb_count,
+                                                                   int32_t* __restrict__ labels, double* __restrict__ row_ws, int use_smem) {
+    OFC_DYN_SMEM(double, s_rows);                    // [8][d] when use_smem
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned n_amb = *amb_count;
+    double* x = use_smem ? s_rows + (size_t)warp * d : row_ws + ((size_t)blockIdx.x * 8 + warp) * d;
+    for (unsigned e = blockIdx.x * 8 + warp; e < n_amb; e += gridDim.x * 8) {
+        const int4 a = amb[e];
+        const unsigned char* row = X + (int64_t)a.x * d;
+        __syncwarp();
+        for (int t = lane; t < d; t += 32) x[t] = (double)row[t] - (mean ? mean[t] : 0.0);
+        __syncwarp();
+        int label;
+        const int ncand = a.w >> 16;
+        if (ncand) {
+            int c0 = a.y, c1 = a.z, c2i = ncand == 3 ? (a.w & 0xffff) : 0x7fffffff, t;
+            if (c1 < c0) { t = c0; c0 = c1; c1 = t; }
+            if (c2i < c1) { t = c1; c1 = c2i; c2i = t; }
+            if (c1 < c0) { t = c0; c0 = c1; c1 = t; }
+            double best = exact_dist64(x, C + (int64_t)c0 * d, c2[c0], d, lane);
+            label = c0;
+            const double d1 = exact_dist64(x, C + (int64_t)c1 * d, c2[c1], d, lane);
+            if (d1 < best) { best = d1; label = c1; }
+            if (ncand == 3) {
+                const double d2 = exact_dist64(x, C + (int64_t)c2i * d, c2[c2i], d, lane);
+                if (d2 < best) { best = d2; label = c2i; }
+            }
+        } else {
+            double best = 0.0;
+            label = 0;
+            for (int j = 0; j < k; ++j) {
+                const double dist = exact_dist64(x, C + (int64_t)j * d, c2[j], d, lane);
+                if (j == 0 || dist < best) { best = dist; label = j; }
+            }
+        }
+        if (lane == 0) labels[a.x] = label;
+    }
+}
+
+// c2 in float64 in the order of kmeans_c2_kernel (sequential fma chain) for the re-evaluation, and its float32
+// image (padded with +inf) for the tensor-core epilogue
+__global__ void centres_c2_f64_kernel(const double* __restrict__ c, double* __restrict__ c2d, float* __restrict__ c2f, int d, int k,
+                                      int k_pad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) {
+        if (j < k_pad) c2f[j] = __int_as_float(0x7f800000);
+        return;
+    }
+    const double* r = c + (int64_t)j * d;
+    double s = 0.0;
+    for (int t = 0; t < d; ++t) s = fma(r[t], r[t], s);
+    c2d[j] = s;
+    c2f[j] = (float)s;
+}
+
+// uint8 rows: xc = float32(x - mean) with the float64 column mean (KMeans.fit works uint8 data in float64)
+__global__ void __launch_bounds__(256) prepare_rows_u8_kernel(const unsigned char* __restrict__ X, const double* __restrict__ mean, int64_t n,
+                                                              int d, float* __restrict__ Xh, float* __restrict__ Xl,
+                                                              float* __restrict__ xnorm) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * 8) {
+        const unsigned char* row = X + i * d;
+        float s = 0.f;
+        for (int t = lane; t < d; t += 32) {
+            const float v = (float)((double)row[t] - (mean ? mean[t] : 0.0));
+            split_tf32(v, Xh[i * d + t], Xl[i * d + t]);
+            s = fmaf(v, v, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) xnorm[i] = sqrtf(s);
+    }
+}
+
 // centres f64 -> f32 copy and its hi / lo split (the B operands)
 __global__ void centres_to_f32_kernel(const double* __restrict__ c, float* __restrict__ out, float* __restrict__ hi, float* __restrict__ lo,
                                       int64_t n) {
@@ -580,6 +668,27 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(unsigned* __restrict__ t
     }
 }
 
+// uint8 rows: sums of the raw bytes (exact integers in float64, what ofc_kmeans_sums gives for OFC_U8)
+__global__ void __launch_bounds__(128) seg_sums_u8_kernel(const unsigned char* __restrict__ X, int d, const int32_t* __restrict__ order,
+                                                          const int4* __restrict__ seg_info, const int* __restrict__ n_segs,
+                                                          double* __restrict__ partial) {
+    const int t = blockIdx.y * 128 + threadIdx.x;
+    for (int s = blockIdx.x; s < *n_segs; s += gridDim.x) {
+        const int4 si = seg_info[s];
+        if (t < d) {
+            unsigned long long acc = 0;
+            int m = si.y;
+            for (; m + 4 <= si.z; m += 4) {
+                const unsigned v0 = X[(int64_t)order[m] * d + t], v1 = X[(int64_t)order[m + 1] * d + t];
+                const unsigned v2 = X[(int64_t)order[m + 2] * d + t], v3 = X[(int64_t)order[m + 3] * d + t];
+                acc += v0 + v1 + v2 + v3;
+            }
+            for (; m < si.z; ++m) acc += X[(int64_t)order[m] * d + t];
+            partial[(int64_t)s * d + t] = (double)acc;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) seg_sums_kernel(const float* __restrict__ Xh, const float* __restrict__ Xl, int d,
                                                        const int32_t* __restrict__ order,
                                                        const int4* __restrict__ seg_info, const int* __restrict__ n_segs,
@@ -653,7 +762,7 @@ int sm_count() {
 }
 
 struct TcLayout {
-    size_t off_c32, off_ch, off_cl, off_c2, off_cmax, off_count, off_err, off_amb, off_part, off_table, off_order, off_segfirst, off_seginfo,
+    size_t off_c32, off_ch, off_cl, off_c2, off_c2d, off_cmax, off_count, off_err, off_amb, off_part, off_table, off_order, off_segfirst, off_seginfo,
         off_nsegs, off_segpart, off_fixrows, total;
     int64_t n_chunks, max_segs;
     int parts;
@@ -669,6 +778,7 @@ TcLayout tc_layout(int64_t n, int d, int k) {
     w.off_ch = take((size_t)k * d * 4);
     w.off_cl = take((size_t)k * d * 4);
     w.off_c2 = take((size_t)(k + 512) * 4);
+    w.off_c2d = take((size_t)k * 8);
     w.off_cmax = take(4);
     w.off_count = take(4);
     w.off_err = take(4);
@@ -680,7 +790,7 @@ TcLayout tc_layout(int64_t n, int d, int k) {
     w.off_seginfo = take((size_t)w.max_segs * 16);
     w.off_nsegs = take(4);
     w.off_segpart = take((size_t)w.max_segs * d * 8);
-    w.off_fixrows = take((size_t)148 * 4 * 8 * d * 4);
+    w.off_fixrows = take((size_t)148 * 4 * 8 * d * 8);
     w.total = off;
     return w;
 }
@@ -730,9 +840,10 @@ int ofc_kmeans_tc_prepare(const float* X, const double* mean, int64_t n, int d, 
     return OFC_OK;
 }
 
-int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, int64_t n, int d, int k, const double* centres, int32_t* labels,
-                         const int32_t* prev_labels, uint64_t* n_changed, double* inertia, uint32_t* n_rechecked,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+// X8 != null: the rows are uint8 (worked in float64): float64 squared norms, float64 re-evaluation on the bytes
+static int tc_assign_impl(const float* Xh, const float* Xl, const float* xnorm, int64_t n, int d, int k, const double* centres,
+                          int32_t* labels, const int32_t* prev_labels, uint64_t* n_changed, double* inertia, uint32_t* n_rechecked,
+                          void* workspace, size_t workspace_bytes, void* stream, const uint8_t* X8, const double* mean8) {
     int rc = tc_shape_ok(n, d, k);
     if (rc != OFC_OK) return rc;
     OFC_REQUIRE(Xh && Xl && xnorm && centres && labels, "null buffer");
@@ -753,7 +864,9 @@ int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, i
     const int64_t kd = (int64_t)k * d;
     centres_to_f32_kernel<<<(int)((kd + 255) / 256 < 1184 ? (kd + 255) / 256 : 1184), 256, 0, st>>>(centres, c32, ch, cl, kd);
     OFC_CHECK_LAUNCH("centres_to_f32");
-    centres_c2_kernel<<<cdiv(k + 256, 128), 128, 0, st>>>(c32, c2, d, k, k + 256);
+    double* c2d = (double*)(ws + w.off_c2d);
+    if (X8) centres_c2_f64_kernel<<<cdiv(k + 256, 128), 128, 0, st>>>(centres, c2d, c2, d, k, k + 256);
+    else centres_c2_kernel<<<cdiv(k + 256, 128), 128, 0, st>>>(c32, c2, d, k, k + 256);
     OFC_CHECK_LAUNCH("centres_c2");
     centres_cmax_kernel<<<1, 1024, 0, st>>>(c2, k, cmax, count);
     OFC_CHECK_LAUNCH("centres_cmax");
@@ -771,12 +884,30 @@ int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, i
     // per distance: 2 |x| |c| (2^-19 split remainder + d 2^-23 accumulation); two distances; x1.5 margin
     static const float tol_mul = getenv("OFC_TC_TOL_MUL") ? (float)atof(getenv("OFC_TC_TOL_MUL")) : 1.5f;
     p.tol_scale = tol_mul * 4.f * (1.f / 524288.f + (float)d * (1.f / 8388608.f));
+    p.tol_c2 = 0.f;
+    if (X8) {
+        // against the float64 distance of the bytes: also the float32 rounding of the centred row and of the centres
+        // (2 x 2^-24 |x| |c| per dot product) and of the squared norms / the final fma (2^-24 (c2 + |dist|) each)
+        p.tol_scale = tol_mul * 4.f * (1.f / 524288.f + 1.f / 4194304.f + (float)d * (1.f / 8388608.f));
+        p.tol_c2 = tol_mul * 4.f * (1.f / 8388608.f);
+    }
     p.labels = labels; p.amb = (int4*)(ws + w.off_amb); p.amb_count = count; p.error_flag = err;
     if (BN == 64) rc = launch_tc<64>(tmAh, tmAl, tmBh, tmBl, p, stream);
     else if (BN == 128) rc = launch_tc<128>(tmAh, tmAl, tmBh, tmBl, p, stream);
     else rc = launch_tc<256>(tmAh, tmAl, tmBh, tmBl, p, stream);
     if (rc != OFC_OK) return rc;
-    {
+    const int fix_ctas = sm_count() < 148 ? sm_count() * 4 : 148 * 4;
+    if (X8) {
+        const size_t fix_smem = (size_t)8 * d * 8;
+        const int use_smem = fix_smem <= 200 * 1024;
+        static size_t fix_conf8 = 0;
+        if (use_smem && fix_smem > 48 * 1024 && fix_smem > fix_conf8) {
+            OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_fix_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fix_smem));
+            fix_conf8 = fix_smem;
+        }
+        kmeans_assign_fix_u8_kernel<<<fix_ctas, 256, use_smem ? fix_smem : 0, st>>>(X8, mean8, d, k, centres, c2d, (const int4*)(ws + w.off_amb),
+                                                                                    count, labels, (double*)(ws + w.off_fixrows), use_smem);
+    } else {
         const size_t fix_smem = (size_t)8 * d * 4;
         const int use_smem = fix_smem <= 200 * 1024;
         static size_t fix_conf = 0;
@@ -784,7 +915,6 @@ int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, i
             OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fix_smem));
             fix_conf = fix_smem;
         }
-        const int fix_ctas = sm_count() < 148 ? sm_count() * 4 : 148 * 4;
         kmeans_assign_fix_kernel<<<fix_ctas, 256, use_smem ? fix_smem : 0, st>>>(Xh, Xl, d, k, c32, c2, (const int4*)(ws + w.off_amb),
                                                                                  count, labels, (float*)(ws + w.off_fixrows), use_smem);
     }
@@ -810,11 +940,51 @@ int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, i
     return OFC_OK;
 }
 
+int ofc_kmeans_tc_assign(const float* Xh, const float* Xl, const float* xnorm, int64_t n, int d, int k, const double* centres, int32_t* labels,
+                         const int32_t* prev_labels, uint64_t* n_changed, double* inertia, uint32_t* n_rechecked,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    return tc_assign_impl(Xh, Xl, xnorm, n, d, k, centres, labels, prev_labels, n_changed, inertia, n_rechecked, workspace,
+                          workspace_bytes, stream, nullptr, nullptr);
+}
+
+int ofc_kmeans_tc_assign_u8(const uint8_t* X, const double* mean, const float* Xh, const float* Xl, const float* xnorm, int64_t n, int d,
+                            int k, const double* centres, int32_t* labels, const int32_t* prev_labels, uint64_t* n_changed,
+                            uint32_t* n_rechecked, void* workspace, size_t workspace_bytes, void* stream) {
+    OFC_REQUIRE(X != nullptr, "null rows");
+    return tc_assign_impl(Xh, Xl, xnorm, n, d, k, centres, labels, prev_labels, n_changed, nullptr, n_rechecked, workspace,
+                          workspace_bytes, stream, X, mean);
+}
+
+int ofc_kmeans_tc_prepare_u8(const uint8_t* X, const double* mean, int64_t n, int d, float* Xh, float* Xl, float* xnorm, void* stream) {
+    OFC_REQUIRE(X && Xh && Xl && xnorm && n >= 1 && d >= 1, "bad arguments");
+    int64_t g = (n + 7) / 8;
+    if (g > 148 * 16) g = 148 * 16;
+    ProfScope prof(PK_KMEANS, stream);
+    prepare_rows_u8_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(X, mean, n, d, Xh, Xl, xnorm);
+    OFC_CHECK_LAUNCH("prepare_rows_u8");
+    return OFC_OK;
+}
+
+static int tc_sums_impl(const float* Xh, const float* Xl, const uint8_t* X8, int64_t n, int d, int k, const int32_t* labels, double* sums,
+                        int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
 int ofc_kmeans_tc_sums(const float* Xh, const float* Xl, int64_t n, int d, int k, const int32_t* labels, double* sums, int64_t* counts,
                        void* workspace, size_t workspace_bytes, void* stream) {
+    OFC_REQUIRE(Xh && Xl, "null buffer");
+    return tc_sums_impl(Xh, Xl, nullptr, n, d, k, labels, sums, counts, workspace, workspace_bytes, stream);
+}
+
+int ofc_kmeans_tc_sums_u8(const uint8_t* X, int64_t n, int d, int k, const int32_t* labels, double* sums, int64_t* counts,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    OFC_REQUIRE(X != nullptr, "null buffer");
+    return tc_sums_impl(nullptr, nullptr, X, n, d, k, labels, sums, counts, workspace, workspace_bytes, stream);
+}
+
+static int tc_sums_impl(const float* Xh, const float* Xl, const uint8_t* X8, int64_t n, int d, int k, const int32_t* labels, double* sums,
+                        int64_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = tc_shape_ok(n, d, k);
     if (rc != OFC_OK) return rc;
-    OFC_REQUIRE(Xh && Xl && labels && sums && counts, "null buffer");
+    OFC_REQUIRE(labels && sums && counts, "null buffer");
     const TcLayout w = tc_layout(n, d, k);
     if (!workspace || workspace_bytes < w.total) { set_error("tensor-core k-means workspace too small: %zu < %zu", workspace_bytes, w.total); return OFC_ERR_WORKSPACE; }
     char* ws = (char*)workspace;
@@ -850,7 +1020,8 @@ int ofc_kmeans_tc_sums(const float* Xh, const float* Xl, int64_t n, int d, int k
     int64_t gx = w.max_segs;
     const int64_t cap = (int64_t)sm_count() * 32 / dt + 1;
     if (gx > cap) gx = cap;
-    seg_sums_kernel<<<dim3((unsigned)gx, dt), 128, 0, st>>>(Xh, Xl, d, order, seg_info, n_segs, partial);
+    if (X8) seg_sums_u8_kernel<<<dim3((unsigned)gx, dt), 128, 0, st>>>(X8, d, order, seg_info, n_segs, partial);
+    else seg_sums_kernel<<<dim3((unsigned)gx, dt), 128, 0, st>>>(Xh, Xl, d, order, seg_info, n_segs, partial);
     OFC_CHECK_LAUNCH("seg_sums");
     seg_fold_kernel<<<dim3(k, dt), 128, 0, st>>>(partial, d, seg_first, sums);
     OFC_CHECK_LAUNCH("seg_fold");

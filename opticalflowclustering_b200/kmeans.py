@@ -110,6 +110,11 @@ class LloydState:
         lib.ofc_kmeans_workspace_bytes.restype = C.c_size_t
         lib.ofc_kmeans_workspace_bytes.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int]
         self.ws_bytes = int(lib.ofc_kmeans_workspace_bytes(self.B, self.n, self.d, max(self.k if ws_k is None else int(ws_k), 1)))
+        if ws_k is not None and hasattr(lib, "ofc_kmeans_assign_workspace_bytes"):
+            # the E-step / centre kernels still run for all k clusters (final inertia, relocation, new centres)
+            lib.ofc_kmeans_assign_workspace_bytes.restype = C.c_size_t
+            lib.ofc_kmeans_assign_workspace_bytes.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int]
+            self.ws_bytes = max(self.ws_bytes, int(lib.ofc_kmeans_assign_workspace_bytes(self.B, self.n, self.d, max(self.k, 1))))
         self.ws = torch.empty(max(self.ws_bytes, 256), dtype=torch.uint8, device=dev)
         self.labels = [torch.full((self.B, self.n), -1, dtype=torch.int32, device=dev) for _ in range(2)]
         # one flat fp64 buffer so a single all-reduce moves sums, counts and n_changed together
@@ -161,15 +166,17 @@ class LloydState:
 
 
 class TensorCoreSteps:
-    """E-step / M-step of ONE float32 problem on the tensor-core path (libofc's ofc_kmeans_tc_*): the
+    """E-step / M-step of ONE float32 or uint8 problem on the tensor-core path (libofc's ofc_kmeans_tc_*): the
     centred rows are split once into TF32-exact hi parts and exact remainders; every E-step is a
-    3xTF32 tcgen05 distance GEMM used as a filter plus a float32 re-evaluation of the near-ties, so
-    the labels are those of the float32 CUDA-core E-step; the M-step walks a label-sorted member list."""
+    3xTF32 tcgen05 distance GEMM used as a filter plus a re-evaluation of the near-ties in the working
+    precision (float32 rows: float32; uint8 rows: float64 on the original bytes), so the labels are those
+    of the CUDA-core E-step; the M-step walks a label-sorted member list (uint8: exact integer sums)."""
 
     @staticmethod
     def usable(st: "LloydState", lib_override) -> bool:
-        return (lib_override is None and st.X.is_cuda and st.dtype == 1 and st.B == 1 and st.d > 32 and st.d % 4 == 0
-                and 2 <= st.k <= 4096 and st.n < 2 ** 31 and os.environ.get("OFC_KMEANS_TC", "1") != "0")
+        return (lib_override is None and st.X.is_cuda and st.dtype in (0, 1) and st.B == 1 and st.d > 32 and st.d % 4 == 0
+                and 2 <= st.k <= 4096 and st.n < 2 ** 31 and _tc_worth_it(st.dtype, st.d, st.k)
+                and os.environ.get("OFC_KMEANS_TC", "1") != "0")
 
     def __init__(self, st: "LloydState", mean: torch.Tensor):
         self.st = st
@@ -182,24 +189,46 @@ class TensorCoreSteps:
         self.ws_bytes = int(c.lib.ofc_kmeans_tc_workspace_bytes(C.c_int64(n), d, k))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.n_rechecked = torch.zeros(1, dtype=torch.int32, device=dev)
-        c.check(c.lib.ofc_kmeans_tc_prepare(_ptr(st.X), _ptr(mean), C.c_int64(n), d, _ptr(self.Xh), _ptr(self.Xl),
-                                            _ptr(self.xnorm), c.stream()))
+        self.u8 = st.dtype == 0
+        self.mean = mean
+        prep = c.lib.ofc_kmeans_tc_prepare_u8 if self.u8 else c.lib.ofc_kmeans_tc_prepare
+        c.check(prep(_ptr(st.X), _ptr(mean), C.c_int64(n), d, _ptr(self.Xh), _ptr(self.Xl), _ptr(self.xnorm), c.stream()))
 
     def assign(self, centres, labels, prev=None, n_changed=None, inertia=None):
         st, c = self.st, self.st.ctx
+        if self.u8:
+            c.check(c.lib.ofc_kmeans_tc_assign_u8(_ptr(st.X), _ptr(self.mean), _ptr(self.Xh), _ptr(self.Xl), _ptr(self.xnorm),
+                                                  C.c_int64(st.n), st.d, st.k, _ptr(centres), _ptr(labels), _ptr(prev),
+                                                  _ptr(n_changed), _ptr(self.n_rechecked), _ptr(self.ws),
+                                                  C.c_size_t(self.ws_bytes), c.stream()))
+            if inertia is not None:
+                # inertia of the final (centres, labels): the float64 CUDA-core E-step (idempotent on the labels)
+                st.assign(self.mean.view(1, -1), centres, labels, inertia=inertia)
+            return
         c.check(c.lib.ofc_kmeans_tc_assign(_ptr(self.Xh), _ptr(self.Xl), _ptr(self.xnorm), C.c_int64(st.n), st.d, st.k,
                                            _ptr(centres), _ptr(labels), _ptr(prev), _ptr(n_changed), _ptr(inertia),
                                            _ptr(self.n_rechecked), _ptr(self.ws), C.c_size_t(self.ws_bytes), c.stream()))
 
     def sums_(self, labels, sums, counts):
         st, c = self.st, self.st.ctx
+        if self.u8:         # raw (exact integer) sums like the stepwise uint8 path
+            c.check(c.lib.ofc_kmeans_tc_sums_u8(_ptr(st.X), C.c_int64(st.n), st.d, st.k, _ptr(labels), _ptr(sums), _ptr(counts),
+                                                _ptr(self.ws), C.c_size_t(self.ws_bytes), c.stream()))
+            return
         c.check(c.lib.ofc_kmeans_tc_sums(_ptr(self.Xh), _ptr(self.Xl), C.c_int64(st.n), st.d, st.k, _ptr(labels), _ptr(sums),
                                          _ptr(counts), _ptr(self.ws), C.c_size_t(self.ws_bytes), c.stream()))
 
 
+def _tc_worth_it(dtype: int, d: int, k: int) -> bool:
+    """float32 rows: always past d = 32.  uint8 rows pay 8 bytes per element for the split copy, so the tensor cores
+    are only used where the float64 CUDA-core E-step is the bottleneck (k * d large)."""
+    return dtype == 1 or k * d >= 4096
+
+
 def _tc_wanted(Xb, k, lib_override) -> bool:
-    return (lib_override is None and Xb.is_cuda and Xb.dtype == torch.float32 and Xb.shape[0] == 1 and Xb.shape[2] > 32
-            and Xb.shape[2] % 4 == 0 and 2 <= k <= 4096 and os.environ.get("OFC_KMEANS_TC", "1") != "0")
+    return (lib_override is None and Xb.is_cuda and Xb.dtype in (torch.float32, torch.uint8) and Xb.shape[0] == 1
+            and Xb.shape[2] > 32 and Xb.shape[2] % 4 == 0 and 2 <= k <= 4096
+            and _tc_worth_it(_DT[Xb.dtype], int(Xb.shape[2]), k) and os.environ.get("OFC_KMEANS_TC", "1") != "0")
 
 
 def _all_reduce(t, group):

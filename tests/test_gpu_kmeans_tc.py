@@ -41,6 +41,33 @@ def test_tc_steps_uniform_data_and_tied_centres(tc):
     assert tc.run(30000, 256, 512, ties=True, blobs=False)
 
 
+@pytest.mark.parametrize("shape", [(3000, 36, 8), (20000, 352, 8), (50000, 128, 256), (30000, 352, 1024)])
+def test_tc_steps_uint8_equal_float64_kernels(tc, shape):
+    """uint8 rows: labels bit-identical to the float64 CUDA-core E-step (hence to sklearn given the centres),
+    integer sums and counts exact"""
+    assert tc.run_u8(*shape)
+
+
+def test_tc_steps_uint8_tied_centres(tc):
+    assert tc.run_u8(20000, 64, 128, ties=True)
+
+
+def test_lloyd_uint8_dense_tensor_core_path_on_off(monkeypatch):
+    """whole uint8 fits (hue vectors per frame: d = 352, k = 64) through the float64 kernels and the tensor-core
+    path: everything bit-identical, because both E-steps give the same labels and the sums are exact integers"""
+    from opticalflowclustering_b200 import kmeans
+    g = torch.Generator().manual_seed(8)
+    cen = torch.rand((64, 352), generator=g) * 150 + 20
+    X = (cen[torch.randint(0, 64, (20000,), generator=g)] + 10 * torch.randn((20000, 352), generator=g))
+    X = X.round().clamp(0, 255).to(torch.uint8).cuda()
+    init = X[:64].double()
+    monkeypatch.setenv("OFC_KMEANS_TC", "0")
+    a = kmeans.lloyd(X, init)
+    monkeypatch.setenv("OFC_KMEANS_TC", "1")
+    b = kmeans.lloyd(X, init)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
 @pytest.mark.parametrize("name", ["f32_d64_k32", "f32_d96_k40"])
 def test_lloyd_dense_float32_vs_sklearn_golden(name):
     from opticalflowclustering_b200 import kmeans
