@@ -196,6 +196,14 @@ int ofc_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, i
                         const int32_t* labels, const double* centres_old, double* sums, int64_t* counts,
                         int raw_sums, const uint8_t* active, void* stream);
 
+/* Row-sharded data (one shard per GPU): the search half of that relocation.  out_val / out_idx [batch][n_far] =
+ * this shard's n_far farthest rows (squared distance to the old centre of their label; largest first, lowest
+ * index on ties; idx -1 past the shard's size).  The host merges the ranks' lists and applies the moves to the
+ * all-reduced sums (opticalflowclustering_b200/kmeans.py, _relocate_across_ranks). */
+int ofc_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
+                          const int32_t* labels, const double* centres_old, int n_far,
+                          double* out_val, int64_t* out_idx, void* stream);
+
 /* Whole Lloyd runs on the device, one CTA per problem: the reference's per-cell fits
  * (KMeans(n_clusters=k).fit on every grid cell of a frame, KmeanGrids.py:376-392) in ONE launch --
  * column statistics, seeding, all iterations, relocation, sklearn's stopping rule, closing E-step.

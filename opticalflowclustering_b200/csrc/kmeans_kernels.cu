@@ -582,6 +582,58 @@ __global__ void __launch_bounds__(1024) kmeans_relocate_kernel(const T* Xall, in
     }
 }
 
+// The search half of the relocation for row-sharded data: this rank's n_far farthest rows
+// (squared distance to the old centre of their label, same arithmetic and tie rule as kmeans_relocate_kernel:
+// largest first, lowest index on ties).  The host merges the ranks' lists and applies the moves to the
+// all-reduced sums.  One CTA of 1024 threads per problem.
+template <typename T>
+__global__ void __launch_bounds__(1024) kmeans_far_points_kernel(const T* Xall, int64_t n, int d, int k, const double* mean_all,
+                                                                  const int32_t* labels_all, const double* centres_all, int n_far,
+                                                                  double* out_val, long long* out_idx) {
+    OFC_DYN_SMEM(long long, s_taken);                  // [n_far]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const T* X = Xall + (int64_t)b * n * d;
+    const int32_t* labels = labels_all + (int64_t)b * n;
+    const double* cen = centres_all + (int64_t)b * k * d;
+    const double* mean = mean_all ? mean_all + (int64_t)b * d : nullptr;
+    __shared__ double s_val[32];
+    __shared__ long long s_idx[32];
+    for (int e = 0; e < n_far; ++e) {
+        double bv = -1.0;
+        long long bi = -1;
+        for (int64_t i = tid; i < n; i += 1024) {
+            bool taken = false;
+            for (int q = 0; q < e; ++q) taken |= s_taken[q] == i;
+            if (taken) continue;
+            const double* c = cen + (int64_t)labels[i] * d;
+            double v = 0.0;
+            for (int t = 0; t < d; ++t) {
+                const double df = ((double)X[i * d + t] - (mean ? mean[t] : 0.0)) - c[t];
+                v = fma(df, df, v);
+            }
+            if (v > bv) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double v = -1.0;
+            long long idx = -1;
+            for (int w = 0; w < 32; ++w)
+                if (s_idx[w] >= 0 && (idx < 0 || s_val[w] > v || (s_val[w] == v && s_idx[w] < idx))) { v = s_val[w]; idx = s_idx[w]; }
+            s_taken[e] = idx;
+            out_val[(int64_t)b * n_far + e] = v;
+            out_idx[(int64_t)b * n_far + e] = idx;
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Whole Lloyd runs on the device: one CTA per problem, for the reference's per-cell fits
 // (350 small uint8 problems per frame, KmeanGrids.py:376-392).  Column statistics, optional
@@ -1178,6 +1230,25 @@ int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d
         OFC_LAUNCH(kmeans_relocate_kernel<double>, dim3(batch), dim3(1024), smem, stream, (const double*)X, n, d, k, mean, labels,
                    centres_old, sums, counts, raw_sums, active);
     OFC_CHECK_LAUNCH("kmeans_relocate");
+    return OFC_OK;
+}
+
+int launch_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
+                             const double* centres_old, int n_far, double* out_val, long long* out_idx, void* stream) {
+    if (batch <= 0 || n_far <= 0) return OFC_OK;
+    ProfScope prof(PK_KMEANS, stream);
+    const size_t smem = (size_t)n_far * sizeof(long long);
+    if (smem > 40 * 1024) { set_error("n_far=%d too large", n_far); return OFC_ERR_UNSUPPORTED; }
+    if (dtype == DT_U8)
+        OFC_LAUNCH(kmeans_far_points_kernel<unsigned char>, dim3(batch), dim3(1024), smem, stream, (const unsigned char*)X, n, d, k, mean,
+                   labels, centres_old, n_far, out_val, out_idx);
+    else if (dtype == DT_F32)
+        OFC_LAUNCH(kmeans_far_points_kernel<float>, dim3(batch), dim3(1024), smem, stream, (const float*)X, n, d, k, mean, labels,
+                   centres_old, n_far, out_val, out_idx);
+    else
+        OFC_LAUNCH(kmeans_far_points_kernel<double>, dim3(batch), dim3(1024), smem, stream, (const double*)X, n, d, k, mean, labels,
+                   centres_old, n_far, out_val, out_idx);
+    OFC_CHECK_LAUNCH("kmeans_far_points");
     return OFC_OK;
 }
 

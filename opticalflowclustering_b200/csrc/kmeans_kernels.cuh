@@ -53,6 +53,8 @@ int launch_kmeans_centres(int batch, int d, int k, const double* sums, const lon
 int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                            const int32_t* labels, const double* centres_old, double* sums, long long* counts,
                            int raw_sums, const unsigned char* active, void* stream);
+int launch_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
+                             const double* centres_old, int n_far, double* out_val, long long* out_idx, void* stream);
 int launch_inertia_reduce(const double* partial, int parts, int batch, double* inertia, const unsigned char* active,
                           void* stream);
 int launch_kmeans_cells(const unsigned char* X, int batch, int64_t n, int d, int k, const double* init,

@@ -231,6 +231,52 @@ def _tc_wanted(Xb, k, lib_override) -> bool:
             and _tc_worth_it(_DT[Xb.dtype], int(Xb.shape[2]), k) and os.environ.get("OFC_KMEANS_TC", "1") != "0")
 
 
+def _relocate_across_ranks(st: "LloydState", mean, labels, centres_old, sums, counts, raw_sums: bool, group, row_offset: int):
+    """Empty-cluster relocation (_k_means_common.pyx:167-211) for row-sharded data, on the all-reduced sums / counts:
+    every rank lists its farthest rows (ofc_kmeans_far_points: the single-GPU kernel's arithmetic and tie rule),
+    the lists are all-gathered, and every rank applies the same moves -- each empty cluster, in index order, takes
+    the globally farthest remaining row (ties: lowest global row index).  Same result as one GPU on the whole set."""
+    import torch.distributed as dist
+    c = st.ctx
+    world = dist.get_world_size(group)
+    B, k, d = st.B, st.k, st.d
+    counts_h = counts.cpu().numpy()
+    n_far = int((counts_h == 0).sum(axis=1).max())
+    dev = st.X.device
+    val = torch.full((B, n_far), -1.0, dtype=torch.float64, device=dev)
+    idx = torch.full((B, n_far), -1, dtype=torch.int64, device=dev)
+    if st.n > 0:
+        c.check(c.lib.ofc_kmeans_far_points(_ptr(st.X), st.dtype, B, C.c_int64(st.n), d, k, _ptr(mean), _ptr(labels), _ptr(centres_old),
+                                            n_far, _ptr(val), _ptr(idx), c.stream()))
+    safe = idx.clamp(min=0)
+    rows = torch.gather(st.X, 1, safe.unsqueeze(-1).expand(B, n_far, d)).to(torch.float64)
+    if not raw_sums and mean is not None:
+        rows = rows - mean.unsqueeze(1)
+    lab = torch.gather(labels, 1, safe).to(torch.float64)
+    gidx = torch.where(idx >= 0, idx + row_offset, idx).to(torch.float64)
+    pay = torch.cat([val.unsqueeze(-1), gidx.unsqueeze(-1), lab.unsqueeze(-1), rows], dim=-1).contiguous()   # [B, n_far, 3 + d]
+    allpay = [torch.empty_like(pay) for _ in range(world)]
+    dist.all_gather(allpay, pay, group=group)
+    allpay = torch.cat(allpay, dim=1).cpu().numpy()                                                         # [B, world * n_far, 3 + d]
+    sums_h, changed = sums.cpu().numpy(), False
+    for b in range(B):
+        cand = [r for r in allpay[b] if r[1] >= 0]
+        cand.sort(key=lambda r: (-r[0], r[1]))
+        empties = [j for j in range(k) if counts_h[b, j] == 0]
+        if not empties or not cand or not (cand[0][0] > 0.0):
+            continue                                         # np.max(distances) == 0: nothing to do
+        for e, r in zip(empties, cand):
+            old = int(r[2])
+            sums_h[b, old] -= r[3:]
+            sums_h[b, e] = r[3:]
+            counts_h[b, e] = 1
+            counts_h[b, old] -= 1
+            changed = True
+    if changed:
+        sums.copy_(torch.from_numpy(sums_h))
+        counts.copy_(torch.from_numpy(counts_h))
+
+
 def _all_reduce(t, group):
     import torch.distributed as dist
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
@@ -296,6 +342,13 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
     if init.shape[0] != B or init.shape[2] != d:
         raise ValueError(f"init shape {tuple(init.shape)} does not match X {tuple(Xb.shape)}")
     st = LloydState(ctx, Xb, k, ws_k=1 if _tc_wanted(Xb, k, _lib_override) else None)
+    row_offset = 0
+    if group is not None:
+        # global index of this rank's first row (ranks hold consecutive row ranges): the tie rule of the relocation
+        import torch.distributed as dist
+        ns = [torch.zeros(1, dtype=torch.int64, device=Xb.device) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(ns, torch.tensor([n], dtype=torch.int64, device=Xb.device), group=group)
+        row_offset = sum(int(t.item()) for t in ns[:dist.get_rank(group)])
     mean, var, n_tot = column_mean_var(st, group)
     if int(n_tot.min().item()) < k:
         raise ValueError(f"n_samples={int(n_tot.min().item())} should be >= n_clusters={k}.")   # _kmeans.py:876-879
@@ -339,7 +392,7 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
             st.counts.copy_(st.red[:, kd:kd + k].to(torch.int64))
             st.n_changed.copy_(st.red[:, kd + k].to(torch.int64))
             if bool((st.counts == 0).any().item()):
-                raise NotImplementedError("empty-cluster relocation across ranks is not implemented")
+                _relocate_across_ranks(st, mean, lab, centres, st.sums, st.counts, is_u8, group, row_offset)
         else:
             st.relocate(mean, lab, centres, st.sums, st.counts, is_u8, active=active)
         centres_old.copy_(centres)

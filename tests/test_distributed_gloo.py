@@ -31,7 +31,17 @@ def _case():
     return X, X[:k].astype(np.float64)
 
 
-def _worker(rank, world, port, out_dir):
+def _case_empty():
+    """initial centres with two far-away outliers: both go empty in the first E-step and must be relocated"""
+    rng = np.random.default_rng(22)
+    n, d, k = 2500, 4, 6
+    cen = rng.uniform(60, 120, (4, d))
+    X = np.clip(np.rint(cen[rng.integers(4, size=n)] + rng.normal(0, 9, (n, d))), 0, 255).astype(np.uint8)
+    init = np.concatenate([X[:4].astype(np.float64), np.full((2, d), 250.0) + np.arange(2)[:, None]])
+    return X, init
+
+
+def _worker(rank, world, port, out_dir, case="plain"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -39,7 +49,7 @@ def _worker(rank, world, port, out_dir):
     from opticalflowclustering_b200 import kmeans as km
     from opticalflowclustering_b200.sharding import shard_range
     from tests.emu import emu_lib as E
-    X, init = _case()
+    X, init = _case() if case == "plain" else _case_empty()
     lo, hi = shard_range(len(X), rank, world)
     labels, centres, inertia, n_iter = km.lloyd(X[lo:hi], init, group=dist.group.WORLD, _lib_override=E.lib())
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), labels=labels.numpy(), centres=centres.numpy(),
@@ -62,6 +72,25 @@ def test_sharded_lloyd_equals_single_rank(tmp_path):
         assert (g["centres"] == c1.numpy()).all()          # bit-identical across world sizes
         assert int(g["n_iter"]) == int(n1)
         assert abs(float(g["inertia"]) - float(i1)) <= 1e-12 * float(i1)
+
+
+def test_sharded_lloyd_relocates_empty_clusters_like_single_rank(tmp_path):
+    """the relocation of empty clusters across ranks (global farthest rows, merged on the host)
+    gives the single-rank result bit for bit"""
+    from tests.emu import emu_lib as E
+    E.build()
+    from opticalflowclustering_b200 import kmeans as km
+    from oracle import kmeans_np as K
+    X, init = _case_empty()
+    l1, c1, i1, n1 = km.lloyd(X, init, _lib_override=E.lib())
+    ref = K.kmeans_fit(X, init)                              # the relocation really happens and matches sklearn's rule
+    assert (l1.numpy() == ref[0]).all() and int(n1) == ref[3]
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path), "empty"), nprocs=2, join=True)
+    got = [np.load(tmp_path / f"r{r}.npz") for r in range(2)]
+    assert (np.concatenate([g["labels"] for g in got]) == l1.numpy()).all()
+    for g in got:
+        assert (g["centres"] == c1.numpy()).all() and int(g["n_iter"]) == int(n1)
 
 
 def test_shard_ranges_cover_with_halo():
