@@ -1082,8 +1082,11 @@ int launch_kmeans_assign(KmAssignParams p, int batch, double* c2_ws, void* strea
 #define OFC_KM_MED_NT(TT, WW)                                                                                          \
     {                                                                                                                  \
         if (p.d <= 64) OFC_KM_MED(TT, WW, 2)                                                                           \
+        else if (p.d <= 96) OFC_KM_MED(TT, WW, 3)                                                                      \
         else if (p.d <= 128) OFC_KM_MED(TT, WW, 4)                                                                     \
+        else if (p.d <= 192) OFC_KM_MED(TT, WW, 6)                                                                     \
         else if (p.d <= 256) OFC_KM_MED(TT, WW, 8)                                                                     \
+        else if (p.d <= 384) OFC_KM_MED(TT, WW, 12)                                                                    \
         else OFC_KM_MED(TT, WW, 16)                                                                                    \
     }
         if (p.dtype == DT_U8) OFC_KM_MED_NT(unsigned char, double)
