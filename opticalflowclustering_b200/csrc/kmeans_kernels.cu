@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256) kmeans_sums_kernel(KmSumsParams p) {
 // fold over CTAs give the same bits as kmeans_sums_kernel in any order; X is read once per
 // iteration instead of twice and no floating-point atomic exists anywhere.
 // ---------------------------------------------------------------------------
-template <int DP>
+template <int DP, int KREG>
 __global__ void __launch_bounds__(256) kmeans_step_u8_kernel(KmAssignParams p, double* __restrict__ partial,
                                                              long long* __restrict__ cnt_partial) {
     OFC_DYN_SMEM(unsigned char, raw);
@@ -375,6 +375,15 @@ __global__ void __launch_bounds__(256) kmeans_step_u8_kernel(KmAssignParams p, d
     int32_t* labels = p.labels + (int64_t)b * p.n;
     const int32_t* prev = p.prev_labels ? p.prev_labels + (int64_t)b * p.n : nullptr;
     unsigned changed = 0;
+    double creg[KREG > 0 ? KREG : 1][DP], c2reg[KREG > 0 ? KREG : 1];
+    if (KREG > 0) {
+#pragma unroll
+        for (int j = 0; j < KREG; ++j) {
+            c2reg[j] = j < k ? sc2[j] : 0.0;
+#pragma unroll
+            for (int t = 0; t < DP; ++t) creg[j][t] = j < k ? sc[j * d + t] : 0.0;
+        }
+    }
     for (int64_t base = (int64_t)blockIdx.x * 256; base < p.n; base += (int64_t)gridDim.x * 256) {
         const int64_t i = base + tid;
         if (i < p.n) {
@@ -392,14 +401,28 @@ __global__ void __launch_bounds__(256) kmeans_step_u8_kernel(KmAssignParams p, d
             for (int t = 0; t < DP; ++t) x[t] = t < d ? (double)xr[t] - smean[t] : 0.0;
             double best = 0.0;
             int label = 0;
-            for (int j = 0; j < k; ++j) {
-                const double* c = sc + j * d;
-                double dot = 0.0;
+            if (KREG > 0) {
+                // the reference's pixel shape (d = 4, k <= 8): centres and norms live in registers
 #pragma unroll
-                for (int t = 0; t < DP; ++t)
-                    if (t < d) dot = fma(x[t], c[t], dot);
-                const double dist = fma(-2.0, dot, sc2[j]);
-                if (j == 0 || dist < best) { best = dist; label = j; }
+                for (int j = 0; j < KREG; ++j) {
+                    if (j < k) {
+                        double dot = 0.0;
+#pragma unroll
+                        for (int t = 0; t < DP; ++t) dot = fma(x[t], creg[j][t], dot);
+                        const double dist = fma(-2.0, dot, c2reg[j]);
+                        if (j == 0 || dist < best) { best = dist; label = j; }
+                    }
+                }
+            } else {
+                for (int j = 0; j < k; ++j) {
+                    const double* c = sc + j * d;
+                    double dot = 0.0;
+#pragma unroll
+                    for (int t = 0; t < DP; ++t)
+                        if (t < d) dot = fma(x[t], c[t], dot);
+                    const double dist = fma(-2.0, dot, sc2[j]);
+                    if (j == 0 || dist < best) { best = dist; label = j; }
+                }
             }
             labels[i] = label;
             if (prev && prev[i] != label) ++changed;
@@ -1151,19 +1174,20 @@ int launch_kmeans_step_u8(KmAssignParams p, int batch, double* partial, long lon
     if (p.d > 32 || smem > 200 * 1024) { set_error("fused k-means step: shape d=%d k=%d does not fit shared memory", p.d, p.k); return OFC_ERR_UNSUPPORTED; }
     const int grid = kmeans_step_grid(p.n, batch);
     ProfScope prof(PK_KMEANS, stream);
-#define OFC_KM_STEP(DPV)                                                                                                  \
+#define OFC_KM_STEP(DPV, KR)                                                                                                \
     {                                                                                                                     \
         static size_t conf = 0;                                                                                           \
         if (smem > 48 * 1024 && smem > conf) {                                                                            \
-            OFC_CUDA(cudaFuncSetAttribute(kmeans_step_u8_kernel<DPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            OFC_CUDA(cudaFuncSetAttribute((kmeans_step_u8_kernel<DPV, KR>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             conf = smem;                                                                                                  \
         }                                                                                                                 \
-        OFC_LAUNCH(kmeans_step_u8_kernel<DPV>, dim3(grid, batch), dim3(256), smem, stream, p, partial, cnt_partial);      \
+        OFC_LAUNCH((kmeans_step_u8_kernel<DPV, KR>), dim3(grid, batch), dim3(256), smem, stream, p, partial, cnt_partial); \
     }
-    if (p.d <= 4) OFC_KM_STEP(4)
-    else if (p.d <= 8) OFC_KM_STEP(8)
-    else if (p.d <= 16) OFC_KM_STEP(16)
-    else OFC_KM_STEP(32)
+    if (p.d == 4 && p.k <= 8) OFC_KM_STEP(4, 8)
+    else if (p.d <= 4) OFC_KM_STEP(4, 0)
+    else if (p.d <= 8) OFC_KM_STEP(8, 0)
+    else if (p.d <= 16) OFC_KM_STEP(16, 0)
+    else OFC_KM_STEP(32, 0)
 #undef OFC_KM_STEP
     OFC_CHECK_LAUNCH("kmeans_step_u8");
     const int64_t kd = (int64_t)p.k * p.d;
