@@ -1183,7 +1183,10 @@ int launch_kmeans_step_u8(KmAssignParams p, int batch, double* partial, long lon
         }                                                                                                                 \
         OFC_LAUNCH((kmeans_step_u8_kernel<DPV, KR>), dim3(grid, batch), dim3(256), smem, stream, p, partial, cnt_partial); \
     }
-    if (p.d == 4 && p.k <= 8) OFC_KM_STEP(4, 8)
+    // (register-resident centres, KREG = 8, measured slower at d = 4, k = 8: 1.15 vs 0.75 ms per 64 M rows -- the
+    // 64 extra registers cost more occupancy than the shared-memory broadcasts they save)
+    static const int kreg = getenv("OFC_KMEANS_STEP_KREG") ? atoi(getenv("OFC_KMEANS_STEP_KREG")) : 0;
+    if (kreg && p.d == 4 && p.k <= 8) OFC_KM_STEP(4, 8)
     else if (p.d <= 4) OFC_KM_STEP(4, 0)
     else if (p.d <= 8) OFC_KM_STEP(8, 0)
     else if (p.d <= 16) OFC_KM_STEP(16, 0)
