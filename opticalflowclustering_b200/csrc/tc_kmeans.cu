@@ -50,6 +50,8 @@ struct TcParams {
     int4* amb;                   // [n] (row, best, second, third | candidates << 16) of rows to re-evaluate
     unsigned* amb_count;
     unsigned* error_flag;
+    int stages;                  // ring depth (centre-resident form: row stages only)
+    unsigned tile_bytes;         // shared memory taken by the operand tiles (ring [+ resident centres])
 };
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -128,27 +130,34 @@ __device__ __forceinline__ uint64_t make_desc_sw128(unsigned addr) {
 template <int BN> struct TcCfg {
     static constexpr unsigned A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + 128 * 12 * 4;
 };
 
-template <int BN>
+// BRES (k <= BN and few K-steps): the centre tiles (hi and lo, every K-step) are loaded ONCE and stay resident in
+// shared memory; the ring then only carries the rows, a third of the bytes per row block -- the small-d corner is
+// bound by the latency of refilling the ring, not by the tensor cores.
+constexpr int MAX_STAGES = 8;
+
+template <int BN, bool BRES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                         const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, TcParams p) {
-    constexpr unsigned A_BYTES = TcCfg<BN>::A_BYTES, B_BYTES = TcCfg<BN>::B_BYTES, STAGE_BYTES = TcCfg<BN>::STAGE_BYTES;
-    constexpr int STAGES = TcCfg<BN>::STAGES;
+    constexpr unsigned A_BYTES = TcCfg<BN>::A_BYTES, B_BYTES = TcCfg<BN>::B_BYTES;
+    constexpr unsigned STAGE_BYTES = BRES ? 2 * A_BYTES : TcCfg<BN>::STAGE_BYTES;
+    const int STAGES = p.stages;
     // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
     constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2]
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * STAGES + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.tile_bytes);
+    // bars: full[MAX_STAGES], empty[MAX_STAGES], tfull[2], tempty[2], bfull
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * MAX_STAGES + 5);
     const unsigned bar0 = smem_addr(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + 2 + a); };
+    const unsigned bfull_bar = bar0 + 8u * (2 * MAX_STAGES + 4);
+    unsigned char* bres = smem + (size_t)STAGES * STAGE_BYTES;          // resident centre tiles (BRES)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_mtiles = (int)((p.n + BM - 1) / BM);
@@ -158,6 +167,7 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        mbar_init(bfull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -171,6 +181,14 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
 
     if (warp == 0) {
         if (lane == 0) {
+            if (BRES) {
+                mbar_expect_tx(bfull_bar, (unsigned)n_ktiles * 2u * B_BYTES);
+                for (int kt = 0; kt < n_ktiles; ++kt) {
+                    const unsigned b_dst = smem_addr(bres + (size_t)kt * 2 * B_BYTES);
+                    tma_load_2d(b_dst, &tmBh, bfull_bar, kt * BK, 0);
+                    tma_load_2d(b_dst + B_BYTES, &tmBl, bfull_bar, kt * BK, 0);
+                }
+            }
             unsigned it = 0;
             for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x)
                 for (int nt = 0; nt < n_ntiles; ++nt)
@@ -182,13 +200,16 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
                         const unsigned a_dst = smem_addr(smem + (size_t)s * STAGE_BYTES);
                         tma_load_2d(a_dst, &tmAh, full_bar(s), kt * BK, mt * BM);
                         tma_load_2d(a_dst + A_BYTES, &tmAl, full_bar(s), kt * BK, mt * BM);
-                        tma_load_2d(a_dst + 2 * A_BYTES, &tmBh, full_bar(s), kt * BK, nt * BN);
-                        tma_load_2d(a_dst + 2 * A_BYTES + B_BYTES, &tmBl, full_bar(s), kt * BK, nt * BN);
+                        if (!BRES) {
+                            tma_load_2d(a_dst + 2 * A_BYTES, &tmBh, full_bar(s), kt * BK, nt * BN);
+                            tma_load_2d(a_dst + 2 * A_BYTES + B_BYTES, &tmBl, full_bar(s), kt * BK, nt * BN);
+                        }
                     }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             unsigned it = 0, unit = 0;
+            if (BRES) { mbar_wait(bfull_bar, 0u, p.error_flag); tc_fence_after(); }
             for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x)
                 for (int nt = 0; nt < n_ntiles; ++nt, ++unit) {
                     const unsigned acc = unit & 1u, aph = (unit >> 1) & 1u;
@@ -202,7 +223,8 @@ kmeans_assign_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
                         tc_fence_after();
                         const unsigned a_addr = smem_addr(smem + (size_t)s * STAGE_BYTES);
                         const uint64_t ah = make_desc_sw128(a_addr), al = make_desc_sw128(a_addr + A_BYTES);
-                        const uint64_t bh = make_desc_sw128(a_addr + 2 * A_BYTES), bl = make_desc_sw128(a_addr + 2 * A_BYTES + B_BYTES);
+                        const unsigned b_addr = BRES ? smem_addr(bres + (size_t)kt * 2 * B_BYTES) : a_addr + 2 * A_BYTES;
+                        const uint64_t bh = make_desc_sw128(b_addr), bl = make_desc_sw128(b_addr + B_BYTES);
 #pragma unroll
                         for (int k4 = 0; k4 < BK / 8; ++k4) {    // 8 floats = 32 bytes per MMA: +2 in 16-byte units
                             umma_tf32(tmem_d, al + 2u * k4, bh + 2u * k4, IDESC, (kt | k4) != 0);
@@ -795,20 +817,40 @@ TcLayout tc_layout(int64_t n, int d, int k) {
     return w;
 }
 
-template <int BN>
-int launch_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh, const CUtensorMap& tmBl, const TcParams& p,
-              void* stream) {
-    constexpr size_t smem = TcCfg<BN>::SMEM;
-    static bool configured = false;
-    if (!configured) {
-        OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+template <int BN, bool BRES>
+int launch_tc_form(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh, const CUtensorMap& tmBl, const TcParams& p,
+                   void* stream) {
+    const size_t smem = (size_t)p.tile_bytes + 1024 + 256 + 128 * 12 * 4;
+    static size_t configured = 0;
+    if (smem > configured) {
+        OFC_CUDA(cudaFuncSetAttribute((kmeans_assign_tc_kernel<BN, BRES>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
     const int64_t mtiles = (p.n + BM - 1) / BM;
     const int grid = (int)(mtiles < sm_count() ? mtiles : sm_count());
-    kmeans_assign_tc_kernel<BN><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmAh, tmAl, tmBh, tmBl, p);
+    kmeans_assign_tc_kernel<BN, BRES><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmAh, tmAl, tmBh, tmBl, p);
     OFC_CHECK_LAUNCH("kmeans_assign_tc");
     return OFC_OK;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh, const CUtensorMap& tmBl, TcParams p,
+              void* stream) {
+    // centre-resident form when one centre tile covers all k and the resident tiles leave room for >= 2 row stages
+    static const int want_bres = getenv("OFC_TC_BRES") ? atoi(getenv("OFC_TC_BRES")) : 1;
+    const int n_ktiles = (p.d + BK - 1) / BK;
+    const size_t bres_bytes = (size_t)n_ktiles * 2 * TcCfg<BN>::B_BYTES;
+    const size_t budget = 200 * 1024;
+    if (want_bres && p.k <= BN && bres_bytes + 2 * (2 * TcCfg<BN>::A_BYTES) <= budget) {
+        int st = (int)((budget - bres_bytes) / (2 * TcCfg<BN>::A_BYTES));
+        if (st > MAX_STAGES) st = MAX_STAGES;
+        p.stages = st;
+        p.tile_bytes = (unsigned)((size_t)st * 2 * TcCfg<BN>::A_BYTES + bres_bytes);
+        return launch_tc_form<BN, true>(tmAh, tmAl, tmBh, tmBl, p, stream);
+    }
+    p.stages = TcCfg<BN>::STAGES;
+    p.tile_bytes = (unsigned)((size_t)TcCfg<BN>::STAGES * TcCfg<BN>::STAGE_BYTES);
+    return launch_tc_form<BN, false>(tmAh, tmAl, tmBh, tmBl, p, stream);
 }
 
 int tc_shape_ok(int64_t n, int d, int k) {
