@@ -88,16 +88,23 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
+    def sample_now(self):
+        """one sample from the calling thread (the timed loop calls it while the GPU is still working through the
+        enqueued steps, so a starved sampler thread cannot leave the record empty)"""
+        if not self.nv:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def _run(self):
         while not self._stop.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
+            self.sample_now()
             self._stop.wait(0.01)
 
     def start(self):
@@ -310,7 +317,10 @@ def main():
     e0.record()
     for i in range(args.warmup, args.warmup + args.steps):
         pipe.run_chunk(clip[starts[i]:starts[i] + F])
+        if i % 8 == 0:
+            sampler.sample_now()
     e1.record()
+    sampler.sample_now()
     barrier()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
