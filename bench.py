@@ -159,7 +159,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=_claim_stdout(), flush=True)
 
 
 def kmeans_cosine_extras(dev, peak):
@@ -275,8 +275,24 @@ def kmeans_cosine_extras(dev, peak):
     return out
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to stdout
+    under torchrun), so file descriptor 1 is pointed at stderr for the rest of the process and the JSON line goes to
+    a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -455,7 +471,7 @@ def main():
                              f"({pipe.plan.workspace_bytes / 1e6:.0f} MB workspace) are rewritten every step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels, "extras": extras,
-        }))
+        }), file=_claim_stdout(), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
