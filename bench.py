@@ -272,6 +272,33 @@ def kmeans_cosine_extras(dev, peak):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     out["row_cosine_u8_1Mx16"] = {"ms": ms, "rows_per_s": 1e6 / (ms / 1e3), "gb_s": (16e6 + 8e6) / (ms / 1e3) / 1e9}
+    # the rest of SURVEY 8(d)'s cosine sweep: a wide float32 row cosine (HBM-bound) and the sliding-window form of
+    # findCosineDifferentVectors.py (n = 16 over m = 1 M; the call includes its 8-byte result read-back)
+    Xw = torch.rand((1_000_000, 512), device=dev, dtype=torch.float32)
+    qw = torch.rand(512, dtype=torch.float64)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(6):
+        if it == 1:
+            e0.record()
+        cosm.row_cosine(Xw, qw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    nb = 1e6 * 512 * 4 + 8e6
+    out["row_cosine_f32_1Mx512"] = {"ms": ms, "rows_per_s": 1e6 / (ms / 1e3), "gb_s": nb / (ms / 1e3) / 1e9,
+                                    "frac_of_hbm_peak": nb / (ms / 1e3) / 1e9 / peak}
+    del Xw
+    short = torch.randint(0, 180, (16,), generator=g).double().to(dev)
+    long_ = torch.randint(0, 180, (1_000_000,), generator=g).double().to(dev)
+    cosm.sliding_cosine(short, long_)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        cosm.sliding_cosine(short, long_)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out["sliding_cosine_n16_m1M"] = {"ms": ms, "windows_per_s": (1e6 - 15) / (ms / 1e3), "gb_s": 16e6 / (ms / 1e3) / 1e9}
     return out
 
 
