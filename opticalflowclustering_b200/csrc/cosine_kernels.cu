@@ -112,7 +112,21 @@ __global__ void __launch_bounds__(256) row_cosine_kernel(const T* X, int64_t n, 
         double dot = 0.0, nx = 0.0;
         if (r < n) {
             const T* row = X + r * d;
-            for (int t = sub; t < d; t += lpr) {
+            // eight loads in flight per lane; the fma chains keep their order (t = sub, sub + lpr, ...), so the
+            // result is bit for bit what the one-load-at-a-time loop gives
+            int t = sub;
+            for (; t + 7 * lpr < d; t += 8 * lpr) {
+                T a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = row[t + u * lpr];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double v = (double)a[u];
+                    dot = fma(v, sq[t + u * lpr], dot);
+                    nx = fma(v, v, nx);
+                }
+            }
+            for (; t < d; t += lpr) {
                 const double v = (double)row[t];
                 dot = fma(v, sq[t], dot);
                 nx = fma(v, v, nx);
