@@ -100,3 +100,29 @@ def test_lloyd_tensor_core_path_on_off(monkeypatch):
     assert (l0 == l1).float().mean().item() > 0.9995
     assert (c0 - c1).abs().max().item() < 1e-4
     assert abs(float(i0) - float(i1)) <= 1e-6 * float(i0)
+
+
+def test_lloyd_dense_full_size_properties():
+    """BASELINE configs[4] scale (1 M x 64 float32 rows, k = 64) through the tensor-core path -- too large for the
+    oracle, so size-independent properties: (a) two runs are bit-identical, (b) the labels are the arg-min of an
+    independent float64 torch restatement on the final centres up to float32 near-ties, (c) run to a strict stop
+    (tol = 0) the centres are the member means, (d) inertia equals the direct sum."""
+    from opticalflowclustering_b200 import kmeans
+    g = torch.Generator(device="cuda").manual_seed(4)
+    N, D, K = 1_000_000, 64, 64
+    cen = torch.rand((K, D), device="cuda", generator=g) * 8
+    X = (cen[torch.randint(0, K, (N,), device="cuda", generator=g)] + torch.randn((N, D), device="cuda", generator=g)).float()
+    init = X[:K].double()
+    l1, c1, i1, n1 = kmeans.lloyd(X, init, tol=0.0)
+    l2, c2, i2, n2 = kmeans.lloyd(X, init, tol=0.0)
+    assert int(n1) < 300
+    assert torch.equal(l1, l2) and torch.equal(c1, c2) and float(i1) == float(i2) and int(n1) == int(n2)
+    Xd = X.double()
+    d2 = (c1 ** 2).sum(1)[None, :] - 2.0 * Xd @ c1.T
+    ref = d2.argmin(1).to(torch.int32)
+    assert (ref != l1).sum().item() <= 20                                    # float32 near-ties only (of 1 M rows)
+    sums = torch.zeros((K, D), dtype=torch.float64, device="cuda").index_add_(0, l1.long(), Xd)
+    cnt = torch.bincount(l1.long(), minlength=K).double()
+    assert ((sums / cnt[:, None]) - c1).abs().max().item() < 1e-5           # float32 centring / rounding of the centres
+    direct = ((Xd - c1[l1.long()]) ** 2).sum().item()
+    assert abs(direct - float(i1)) <= 1e-5 * direct
