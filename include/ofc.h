@@ -39,7 +39,8 @@ const char* ofc_last_error(void);
  * summed device time (ms) and the launch count.  Kinds: 0 bgr2gray, 1 prefilter,
  * 2 polyexp, 3 minmax_init, 4 flow_encode, 5 grid_cells, 6 flow_minmax,
  * 7 draw_grid, 8 kmeans, 9 cosine, 10 flow_upsample, 12+l flow_iter at pyramid level l (0 = full
- * resolution).  n_kinds must be >= 20.  Not thread-safe. */
+ * resolution).  n_kinds must be >= 20.  The record list is mutex-protected (launches from several host
+ * threads are all recorded); begin/end themselves are meant to be called from one thread. */
 int ofc_profile_begin(void);
 int ofc_profile_end(float* ms_by_kind, int* launches_by_kind, int n_kinds);
 
@@ -53,7 +54,10 @@ int ofc_profile_end(float* ms_by_kind, int* launches_by_kind, int n_kinds);
  * the reference's literal), OFC_FLOW_GAUSSIAN (cv2.OPTFLOW_FARNEBACK_GAUSSIAN: Gaussian
  * window of winsize | 1 taps, any odd winsize <= 65) and/or OFC_FLOW_USE_INITIAL_FLOW
  * (cv2.OPTFLOW_USE_INITIAL_FLOW, through ofc_farneback_pair_init); anything else ->
- * OFC_ERR_UNSUPPORTED. */
+ * OFC_ERR_UNSUPPORTED.
+ * Threading: a plan (its side stream, events and the workspace handed to its calls) must be used by ONE
+ * stream / host thread at a time; different plans are independent.  The shared-memory opt-in of every
+ * kernel is recorded per device, so one process may drive several GPUs. */
 #define OFC_FLOW_USE_INITIAL_FLOW 4
 #define OFC_FLOW_GAUSSIAN 256
 typedef struct ofc_flow_plan ofc_flow_plan;
@@ -111,6 +115,17 @@ int ofc_flow_minmax(const float* flow, int n_frames, int64_t n_pixels, uint32_t*
  * rounds in the scalar tail (last width % 32 pixels of each row). */
 int ofc_flow_to_bgr(const float* flow, int n_frames, int height, int width, const uint32_t* minmax,
                     uint8_t* bgr, double* mag_sum, void* stream);
+/* Same, additionally writing the reference's `mask` image (H, 255, V) that ComputeOpticalFLow keeps as an
+ * attribute (computeOpticalFlowModule.py:14-15, 28-31): hsv u8 [n_frames][H][W][3]. */
+int ofc_flow_to_hsv(const float* flow, int n_frames, int height, int width, const uint32_t* minmax,
+                    uint8_t* bgr, uint8_t* hsv, void* stream);
+/* ofc_flow_to_bgr + ofc_grid_cells in one kernel (one CTA per grid cell and frame): the visualisation is written
+ * once and never read back; the per-cell outputs are those of ofc_grid_cells (any of them may be NULL).
+ * Replaces computeOpticalFlowModule.py:25-33 followed by overlayGridAndComputeAvgColor (KmeanGrids.py:52-113)
+ * and the k = 1 colour cluster (:269-339) for every frame of the batch. */
+int ofc_flow_to_bgr_grid(const float* flow, int n_frames, int height, int width, const uint32_t* minmax, uint8_t* bgr,
+                         double* mag_sum, int rows, int cols, int draw_lines, int threshold, uint8_t* avg_bgr,
+                         uint8_t* avg_hue, uint8_t* km_centre, uint8_t* km_hue, void* stream);
 
 /* ---- grid-cell aggregation ------------------------------------------------
  * overlayGridAndComputeAvgColor (KmeanGrids.py:52-113,
@@ -185,6 +200,18 @@ int ofc_kmeans_step(const void* X, int dtype, int batch, int64_t n, int d, int k
 int ofc_kmeans_centres(int batch, int d, int k, const double* sums, const int64_t* counts,
                        const double* mean_sub, int use_reciprocal, double* centres, double* shift_tot,
                        const uint8_t* active, void* workspace, size_t workspace_bytes, void* stream);
+/* ofc_kmeans_centres + sklearn's stopping rule (_kmeans.py:705-758) on the device, so the Lloyd loop needs no
+ * device->host read per iteration: a problem stops when n_changed == 0 (labels repeated) or shift <= tol[b];
+ * it then clears active[b], sets just_done[b] (and, for batch > 1, its labels are copied from labels_cur into
+ * labels_other so both ping-pong buffers hold them).  n_iter[b] = iteration + 1 for every problem still running;
+ * *n_active += number of problems that continue (the host polls it asynchronously).  round_f32: store the
+ * centres rounded to float32 (float32 data).  NULL tol / n_changed / active / just_done / n_iter / n_active /
+ * labels_* skip the corresponding part. */
+int ofc_kmeans_update(int batch, int64_t n, int d, int k, const double* sums, const int64_t* counts, const double* mean_sub,
+                      int use_reciprocal, int round_f32, double* centres, double* shift_tot, const uint64_t* n_changed,
+                      const double* tol, int iteration, uint8_t* active, uint8_t* just_done, int32_t* n_iter,
+                      int32_t* n_active, const int32_t* labels_cur, int32_t* labels_other, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* Empty-cluster relocation on the sums/counts (_k_means_common.pyx:167-211): every empty
  * cluster, in index order, takes the point farthest from the (old) centre of its label.
@@ -214,6 +241,20 @@ int ofc_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d,
 int ofc_kmeans_cells(const uint8_t* X, int batch, int64_t n, int d, int k, const double* init, uint64_t seed,
                      int max_iter, double tol, int32_t* labels, double* centres, double* inertia,
                      int32_t* n_iter, int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The reference's main loop over one frame's cells, fused: image_dict ROI + preprocess_image
+ * (KmeanGrids.py:85,113,269-286: white row 0 / column 0 when draw_lines, channel < threshold -> 0, alpha) +
+ * KMeans(n_clusters=k).fit per cell (k-means++ from `seed`, problem index (first_frame + frame) * cells + cell,
+ * so results do not depend on how a clip is cut into calls) + largest cluster -> np.rint -> BGR2HSV hue
+ * (:288-339, :376-392), one CTA per cell, the cell's pixels staged once in shared memory.  k <= 16.
+ * Out (each may be NULL): dom_centre u8 [n_frames][cells][4], dom_hue u8 [n_frames][cells],
+ * centres f64 [n_frames][cells][k][4], counts i64 [n_frames][cells][k], n_iter i32 [n_frames][cells].
+ * Same numbers as ofc_grid_extract_cells + ofc_kmeans_cells(init = NULL, same seed) at first_frame = 0. */
+size_t ofc_grid_kmeans_cells_workspace_bytes(int n_frames, int height, int width, int rows, int cols, int k);
+int ofc_grid_kmeans_cells(const uint8_t* bgr, int n_frames, int height, int width, int rows, int cols, int draw_lines,
+                          int threshold, int swap_rb, int k, uint64_t seed, uint64_t first_frame, int max_iter, double tol,
+                          uint8_t* dom_centre, uint8_t* dom_hue, double* centres, int64_t* counts, int32_t* n_iter,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- k-means, dense corner on the tensor cores --------------------------------
  * The same sklearn E-step / M-step (KmeanGrids.py:299-304, color_kmeans.py:65-78;

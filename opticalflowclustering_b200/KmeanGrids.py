@@ -38,6 +38,12 @@ image_dict = {}
 #: per-frame GPU results keyed by frame number: {'avg_bgr','avg_hue','km_centre','km_hue'} numpy arrays
 frame_results = {}
 
+#: ``-c`` of the running command, set by :func:`main` before the video pass so that the per-cell fits for k > 1 run
+#: on the frame while it is still on the device (``frame_results[framNum]['km_hue_k']``); None = not known yet
+pending_clusters = None
+#: seed of the device-resident k-means++ streams (the reference leaves random_state unset)
+KMEANS_SEED = 0
+
 GRID_PARAMS = {'rows': 14, 'cols': 25, 'cell_width': 50, 'cell_height': 50}      # KmeanGrids.py:177
 
 preprocess_image = _ck.preprocess_image
@@ -70,6 +76,14 @@ def overlayGridAndComputeAvgColor(framNum, frame, grid_params, csv_file, inputVi
     dev = to_device_u8(frame)
     out = _grid.grid_cells(dev, rows, cols, draw_lines=True, threshold=_ck.THRESHOLD)
     frame_results[framNum] = {k: v[0].cpu().numpy() for k, v in out.items()}
+    if pending_clusters is not None and pending_clusters > 1:
+        # -c k > 1: the 350 KMeans(k) fits of this frame (KmeanGrids.py:376-392) in one launch on the uploaded frame;
+        # the white-line state and the < 30 threshold of the later host loop are applied inside the kernel
+        km = _grid.grid_kmeans_cells(dev, pending_clusters, rows, cols, draw_lines=True, threshold=_ck.THRESHOLD,
+                                     seed=KMEANS_SEED, first_frame=int(framNum))
+        frame_results[framNum]['km_k'] = int(pending_clusters)
+        frame_results[framNum]['km_hue_k'] = km['dom_hue'][0].cpu().numpy()
+        frame_results[framNum]['km_centre_k'] = km['dom_centre'][0].cpu().numpy()
     draw_grid_lines_host(frame, rows, cols)
     cell_idx = 0
     for y in range(rows):
@@ -164,6 +178,9 @@ def frame_hues(frame_key, cell_names, n_clusters, random_state=None):
     if n_clusters == 1 and fn in frame_results and all(str(nm).isdigit() and 1 <= int(nm) <= len(frame_results[fn]['km_hue'])
                                                        for nm in cell_names):
         return [int(frame_results[fn]['km_hue'][int(nm) - 1]) for nm in cell_names]
+    if (n_clusters > 1 and fn in frame_results and frame_results[fn].get('km_k') == n_clusters and random_state is None
+            and all(str(nm).isdigit() and 1 <= int(nm) <= len(frame_results[fn]['km_hue_k']) for nm in cell_names)):
+        return [int(frame_results[fn]['km_hue_k'][int(nm) - 1]) for nm in cell_names]
     if rois and all(r.shape == rois[0].shape for r in rois):
         seed = random_state if isinstance(random_state, int) else 0
         _, hues = cluster_cells_batched(rois, n_clusters, seed=seed)
@@ -207,6 +224,8 @@ def main(argv=None):
     gety = args.get('noyolo', True)
     getc = args.get('noyolo', True)                 # the reference reads 'noyolo' twice (:353-354)
     print('noyolo flag is set' if gety else 'noyolo flag is not set')
+    global pending_clusters
+    pending_clusters = int(args["clusters"])
     process_video("yolo_labels.txt", args['path'], gety, getc)
     dirs = args['dir']
     fr = 0

@@ -35,6 +35,8 @@ SIGNATURES = {
     "ofc_bgr2hsv": (_i, [_vp, _vp, _i64, _vp]),
     "ofc_flow_minmax": (_i, [_vp, _i, _i64, _vp, _vp]),
     "ofc_flow_to_bgr": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ofc_flow_to_hsv": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ofc_flow_to_bgr_grid": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "ofc_grid_cells": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ofc_draw_grid": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
     "ofc_kmeans_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
@@ -44,9 +46,14 @@ SIGNATURES = {
     "ofc_kmeans_step_supported": (_i, [_i, _i, _i]),
     "ofc_kmeans_step": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_kmeans_centres": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_kmeans_update": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                               _vp]),
     "ofc_kmeans_relocate": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "ofc_kmeans_far_points": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ofc_kmeans_cells": (_i, [_vp, _i, _i64, _i, _i, _vp, C.c_uint64, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_grid_kmeans_cells_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "ofc_grid_kmeans_cells": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.c_uint64, C.c_uint64, _i, _d, _vp, _vp, _vp, _vp,
+                                   _vp, _vp, _sz, _vp]),
     "ofc_kmeans_tc_workspace_bytes": (_sz, [_i64, _i, _i]),
     "ofc_kmeans_tc_prepare": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
     "ofc_kmeans_tc_assign": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

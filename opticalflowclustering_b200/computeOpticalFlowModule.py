@@ -21,11 +21,13 @@ class ComputeOpticalFLow:
         self._numpy = not isinstance(firstframe, torch.Tensor)
         if self._numpy:
             self.outputImg = np.zeros([self.height, 2 * self.width, 3], dtype=firstframe.dtype)
-            self.mask = np.zeros_like(firstframe)
-            self.mask[..., 1] = 255
+            self._mask0 = np.zeros_like(firstframe)
+            self._mask0[..., 1] = 255
         else:
             self.outputImg = None
-            self.mask = None
+            self._mask0 = torch.zeros_like(firstframe)
+            self._mask0[..., 1] = 255
+        self._mask = None                # HSV image of the latest pair, produced on demand (see `mask`)
         dev_frame = _flow.to_device_u8(firstframe)
         self._plan = _flow.FarnebackPlan(self.width, self.height, 2, 0.5, 3, 15, 3, 5, 1.2, 0, device=dev_frame.device)
         self._prev_gray = _flow.bgr2gray(dev_frame)
@@ -36,6 +38,18 @@ class ComputeOpticalFLow:
     def prev_gray(self):
         return self._prev_gray.cpu().numpy() if self._numpy else self._prev_gray
 
+    @property
+    def mask(self):
+        """The reference's ``self.mask`` (computeOpticalFlowModule.py:14-15, 28-31): HSV image with H = direction byte,
+        S = 255, V = min-max-normalised magnitude byte of the latest pair (all zero with S = 255 before the first
+        ``compute``).  ``compute`` itself only needs the BGR image, so the HSV bytes are produced on first access."""
+        if self.last_flow is None:
+            return self._mask0
+        if self._mask is None:
+            _, hsv = _flow.flow_to_bgr(self.last_flow.unsqueeze(0), self._minmax, want_hsv=True)
+            self._mask = hsv[0].cpu().numpy() if self._numpy else hsv[0]
+        return self._mask
+
     def compute(self, frame):
         dev_frame = _flow.to_device_u8(frame, self._prev_gray.device)
         gray = _flow.bgr2gray(dev_frame)
@@ -43,6 +57,7 @@ class ComputeOpticalFLow:
         bgr = _flow.flow_to_bgr(fl.unsqueeze(0), self._minmax)[0]
         self._prev_gray = gray
         self.last_flow = fl
+        self._mask = None
         if self._numpy:
             return bgr.cpu().numpy()
         return bgr

@@ -238,8 +238,7 @@ int launch_row_cosine(const void* X, int dtype, int64_t n, int d, const double* 
     ProfScope prof(PK_COSINE, stream);
 #define OFC_ROWCOS(TT)                                                                                         \
     {                                                                                                          \
-        if (smem > 48 * 1024)                                                                                  \
-            OFC_CUDA(cudaFuncSetAttribute(row_cosine_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        OFC_SMEM_OPTIN(row_cosine_kernel<TT>, smem);                                                           \
         OFC_LAUNCH(row_cosine_kernel<TT>, dim3((unsigned)blocks), dim3(256), smem, stream, (const TT*)X, n, d, q, lpr, out); \
     }
     if (dtype == DT_U8) OFC_ROWCOS(unsigned char)

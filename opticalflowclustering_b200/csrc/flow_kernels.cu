@@ -341,6 +341,176 @@ __global__ void __launch_bounds__(256) prefilter_tile_kernel(PrefilterParams p, 
 }
 
 // ---------------------------------------------------------------------------
+// K2, pyramid form (production when a level is an exact 1/S fraction of the frame, S = 2, 4, 8, 16 -- every
+// level of pyr_scale = 0.5 on frames whose sides divide): ALL such levels in one launch.
+//
+// With an exact ratio the resize samples sit at column S x + S/2 - 1/2, i.e. between source columns
+// ci = S x + S/2 - 1 and ci + 1 with weight 1/2 each (rows alike), so an output needs the blurred image at
+// a 2 x 2 block only.  A thread owns one output column and walks down the source rows of its row segment:
+//   * the CTA stages 8 (or S) source rows of its column range in shared memory as bytes (aligned words);
+//   * per source row the thread reads its KSZ + 1 window bytes as words and forms BOTH horizontal sums
+//     (columns ci and ci + 1) from the same registers, taps in ascending order like cv::sepFilter2D;
+//   * the row then feeds the vertical chains of the (at most three) output rows whose windows contain it --
+//     tap indices are compile-time because the walk is unrolled over one period of S rows -- again in
+//     ascending tap order, so every output is bit-identical to prefilter_tile_kernel's;
+//   * an output row is finished S rows after the next one started: lerp (weights 1/2), one coalesced store.
+// No per-tile prologue, no float64 coordinate math, every source byte converted once per output column pair
+// instead of once per tap, and three launches become one.
+// ---------------------------------------------------------------------------
+struct PyrLevel {
+    float* out;
+    int64_t out_stride;
+    const float* taps;
+    int w, h, S;
+    int blocks_x, segs, rows_per_seg, first_block;
+};
+struct PyrParams {
+    const unsigned char* gray;
+    int64_t gray_stride;
+    int W, H, n_levels;
+    PyrLevel lv[4];
+};
+constexpr int PYR_NT = 128;
+
+__device__ __forceinline__ float byte_to_float_sel(unsigned w, int t) {
+#ifndef OFC_EMULATE
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + t)) - 8388608.f;
+#else
+    return (float)((w >> (8 * t)) & 255u);
+#endif
+}
+
+template <int S, int KSZ>
+__device__ __forceinline__ void pyr_level(const PyrParams& p, const PyrLevel& L, int local_block, int frame, unsigned* srow) {
+    constexpr int NT = PYR_NT;
+    constexpr int RR = KSZ / 2;
+    constexpr int C0 = RR + 1 - S / 2;                          // tap index (first sample row) of group m's row 0 for output row m
+    constexpr int PH_END = KSZ - S - C0;                         // phase at which output row m - 1 receives its last tap
+    constexpr int A_OFF = ((S / 2 - 1 - RR) % 4 + 4) % 4;        // byte offset of thread 0's window in the staged row
+    constexpr int RB = S < 8 ? 8 : S;                            // source rows staged per barrier
+    constexpr int GB = RB / S;                                   // groups of S rows per staged batch
+    constexpr int PW = (S * (NT - 1) + A_OFF + KSZ + 1 + 3) / 4; // words per staged row
+    constexpr int NWD = S == 2 ? 2 : (A_OFF + KSZ + 1 + 3) / 4;  // words a thread reads per row
+    static_assert(PH_END >= 0 && PH_END < S && C0 < S && 2 * S + C0 > KSZ, "three output rows in flight");
+
+    const int t = threadIdx.x;
+    const int seg = local_block / L.blocks_x, bx = local_block - seg * L.blocks_x;
+    const int ox0 = bx * NT, x = ox0 + t;
+    const int oy0 = seg * L.rows_per_seg, oy1 = min(L.h, oy0 + L.rows_per_seg);
+    const int W = p.W, H = p.H;
+    const unsigned char* __restrict__ gray = p.gray + (int64_t)frame * p.gray_stride;
+    float* __restrict__ out = L.out + (int64_t)frame * L.out_stride;
+    const int cb = S * ox0 + S / 2 - 1 - RR - A_OFF;             // source column of staged byte 0 (a multiple of 4)
+    float tp[KSZ];
+#pragma unroll
+    for (int j = 0; j < KSZ; ++j) tp[j] = L.taps[j];
+    const int o = S * t + A_OFF;                                 // byte offset of this thread's window
+    const int wofs = o >> 2;
+    const int shift = (o & 3) * 8;                               // S >= 4: A_OFF * 8 for every thread
+
+    float acc[3][4];                                             // [slot: output row m+1, m, m-1][b00, b01, b10, b11]
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+
+    const int m_lo = oy0 - 1, n_groups = oy1 - oy0 + 2;
+    const int n_batches = (n_groups + GB - 1) / GB;
+    for (int bi = 0; bi < n_batches; ++bi) {
+        __syncthreads();                                         // the previous batch has been consumed
+        const int r0 = S * m_lo + bi * RB;
+        for (int idx = t; idx < RB * PW; idx += NT) {
+            const int lr = idx / PW, wc = idx - lr * PW;
+            const unsigned char* row = gray + (int64_t)reflect101(r0 + lr, H) * W;
+            const int gc = cb + 4 * wc;
+            unsigned v;
+            if (gc >= 0 && gc + 3 < W) {
+                v = *reinterpret_cast<const unsigned*>(row + gc);
+            } else {
+                v = (unsigned)row[reflect101(gc, W)] | ((unsigned)row[reflect101(gc + 1, W)] << 8) |
+                    ((unsigned)row[reflect101(gc + 2, W)] << 16) | ((unsigned)row[reflect101(gc + 3, W)] << 24);
+            }
+            srow[idx] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < GB; ++g) {
+            const int m = m_lo + bi * GB + g;
+#pragma unroll
+            for (int ph = 0; ph < S; ++ph) {
+                const unsigned* rw = srow + (g * S + ph) * PW + wofs;
+                unsigned wd[NWD];
+#pragma unroll
+                for (int q = 0; q < NWD; ++q) wd[q] = rw[q];
+                float ha = 0.f, hb = 0.f;
+                if (S == 2) {
+                    const unsigned v = __funnelshift_r(wd[0], wd[1], shift);
+                    float prev = byte_to_float_sel(v, 0);
+#pragma unroll
+                    for (int j = 0; j < KSZ; ++j) {
+                        const float nxt = byte_to_float_sel(v, j + 1);
+                        ha = fmaf(tp[j], prev, ha);
+                        hb = fmaf(tp[j], nxt, hb);
+                        prev = nxt;
+                    }
+                } else {
+                    float prev = byte_to_float_sel(wd[A_OFF >> 2], A_OFF & 3);
+#pragma unroll
+                    for (int j = 0; j < KSZ; ++j) {
+                        const float nxt = byte_to_float_sel(wd[(A_OFF + j + 1) >> 2], (A_OFF + j + 1) & 3);
+                        ha = fmaf(tp[j], prev, ha);
+                        hb = fmaf(tp[j], nxt, hb);
+                        prev = nxt;
+                    }
+                }
+#pragma unroll
+                for (int dl = -1; dl <= 1; ++dl) {
+                    const int j0 = S * dl + ph + C0;             // tap of this row for the first sample row of output m - dl
+                    const int slot = dl + 1;
+                    if (j0 >= 0 && j0 < KSZ) {
+                        acc[slot][0] = fmaf(tp[j0 < KSZ && j0 >= 0 ? j0 : 0], ha, acc[slot][0]);
+                        acc[slot][1] = fmaf(tp[j0 < KSZ && j0 >= 0 ? j0 : 0], hb, acc[slot][1]);
+                    }
+                    if (j0 - 1 >= 0 && j0 - 1 < KSZ) {
+                        acc[slot][2] = fmaf(tp[j0 - 1 >= 0 && j0 - 1 < KSZ ? j0 - 1 : 0], ha, acc[slot][2]);
+                        acc[slot][3] = fmaf(tp[j0 - 1 >= 0 && j0 - 1 < KSZ ? j0 - 1 : 0], hb, acc[slot][3]);
+                    }
+                }
+                if (ph == PH_END) {
+                    const int y = m - 1;
+                    if (y >= oy0 && y < oy1 && x < L.w) {
+                        const float fx = 0.5f, fy = 0.5f;
+                        const float top = acc[2][0] * (1.f - fx) + acc[2][1] * fx;
+                        const float bot = acc[2][2] * (1.f - fx) + acc[2][3] * fx;
+                        out[(int64_t)y * L.w + x] = top * (1.f - fy) + bot * fy;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[2][c] = acc[1][c]; acc[1][c] = acc[0][c]; acc[0][c] = 0.f; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PYR_NT) prefilter_pyr_kernel(PyrParams p) {
+    OFC_DYN_SMEM(unsigned, srow);
+    const int frame = blockIdx.y;
+    int b = blockIdx.x;
+    for (int l = 0; l < p.n_levels; ++l) {
+        const PyrLevel& L = p.lv[l];
+        const int nb = L.blocks_x * L.segs;
+        if (b < nb) {
+            switch (L.S) {
+                case 2: pyr_level<2, 3>(p, L, b, frame, srow); break;
+                case 4: pyr_level<4, 9>(p, L, b, frame, srow); break;
+                case 8: pyr_level<8, 19>(p, L, b, frame, srow); break;
+                default: pyr_level<16, 39>(p, L, b, frame, srow); break;
+            }
+            return;
+        }
+        b -= nb;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K3, strip-walk form (production): thread t owns column x0-N+t and walks down a
 // strip of rows with the 2N+G-row vertical window of I in registers; every G rows
 // the vertical results (r0,r1,r2) of G rows go through shared memory and the CTA
@@ -547,6 +717,16 @@ __global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const u
 //            iteration of level 0 -- the magnitude min/max the visualisation
 //            needs (warp-shuffle reduce + one atomic pair per warp).
 // ---------------------------------------------------------------------------
+// cv::resize(INTER_LINEAR) of the coarser level's flow at one pixel, times 1/pyr_scale: the ONE expression every
+// consumer uses (tile kernel, stand-alone up-sample kernel, fused strip walk), so they agree bit for bit
+__device__ __forceinline__ float2 bilerp_flow(float2 q00, float2 q01, float2 q10, float2 q11, float fx, float fy, double mul) {
+    const float ax = 1.f - fx, ay = 1.f - fy;
+    const float tx0 = q00.x * ax + q01.x * fx, tx1 = q10.x * ax + q11.x * fx;
+    const float ty0 = q00.y * ax + q01.y * fx, ty1 = q10.y * ax + q11.y * fx;
+    const float u = tx0 * ay + tx1 * fy, v = ty0 * ay + ty1 * fy;
+    return make_float2((float)((double)u * mul), (float)((double)v * mul));
+}
+
 __device__ __forceinline__ float2 load_flow(const IterParams& p, const float2* fin, int gx, int gy) {
     if (fin == nullptr) return make_float2(0.f, 0.f);
     if (!p.upsample) return fin[(int64_t)gy * p.w + gx];
@@ -556,11 +736,7 @@ __device__ __forceinline__ float2 load_flow(const IterParams& p, const float2* f
     int xj = min(xi + 1, p.wc - 1), yj = min(yi + 1, p.hc - 1);
     float2 q00 = fin[(int64_t)yi * p.wc + xi], q01 = fin[(int64_t)yi * p.wc + xj];
     float2 q10 = fin[(int64_t)yj * p.wc + xi], q11 = fin[(int64_t)yj * p.wc + xj];
-    float ax = 1.f - fx, ay = 1.f - fy;
-    float tx0 = q00.x * ax + q01.x * fx, tx1 = q10.x * ax + q11.x * fx;
-    float ty0 = q00.y * ax + q01.y * fx, ty1 = q10.y * ax + q11.y * fx;
-    float u = tx0 * ay + tx1 * fy, v = ty0 * ay + ty1 * fy;
-    return make_float2((float)((double)u * p.flow_mul), (float)((double)v * p.flow_mul));
+    return bilerp_flow(q00, q01, q10, q11, fx, fy, p.flow_mul);
 }
 
 template <int R, int TH, int NT, int MINB>
@@ -737,19 +913,16 @@ __global__ void __launch_bounds__(256) flow_upsample_kernel(IterParams p, float2
     const float2* fin = p.flow_in + (int64_t)blockIdx.z * p.flow_in_stride;
     float2* out = dst + (int64_t)blockIdx.z * dst_stride;
     const int xi = s_xi[tx], xj = min(xi + 1, p.wc - 1);
-    const float fx = s_fx[tx], ax = 1.f - fx;
+    const float fx = s_fx[tx];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int ly = ty + r * 4, gy = y0 + ly;
         if (gy >= p.h) break;
         const int yi = s_yi[ly], yj = min(yi + 1, p.hc - 1);
-        const float fy = s_fy[ly], ay = 1.f - fy;
+        const float fy = s_fy[ly];
         const float2 q00 = fin[yi * p.wc + xi], q01 = fin[yi * p.wc + xj];
         const float2 q10 = fin[yj * p.wc + xi], q11 = fin[yj * p.wc + xj];
-        const float tx0 = q00.x * ax + q01.x * fx, tx1 = q10.x * ax + q11.x * fx;
-        const float ty0 = q00.y * ax + q01.y * fx, ty1 = q10.y * ax + q11.y * fx;
-        const float u = tx0 * ay + tx1 * fy, v = ty0 * ay + ty1 * fy;
-        out[(int64_t)gy * p.w + gx] = make_float2((float)((double)u * p.flow_mul), (float)((double)v * p.flow_mul));
+        out[(int64_t)gy * p.w + gx] = bilerp_flow(q00, q01, q10, q11, fx, fy, p.flow_mul);
     }
 }
 
@@ -1102,7 +1275,9 @@ static inline void tmem_st8(unsigned taddr, const float (&v)[8]) { memcpy(&ofc_e
 static inline void tmem_wait_st() {}
 #endif
 
-template <int R, int TW, int NT, int G, bool MINMAX>
+// UPS: flow_in is the COARSER level's flow; every flow row is up-sampled on the fly (bilerp_flow, the expression of
+// flow_upsample_kernel), so the first iteration of a level needs no up-sample launch and no full-size scratch field.
+template <int R, int TW, int NT, int G, bool MINMAX, bool UPS>
 __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int n_cols, int64_t total_rows) {
     constexpr int K = 2 * R + 1;
     constexpr int CW = TW + 2 * R;
@@ -1196,13 +1371,29 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
         cp_async_commit();
     };
 
+    // flow of one (clamped) row at this thread's column
+    int ups_xi = 0, ups_xj = 0;
+    float ups_fx = 0.f;
+    if (UPS) {
+        src_coord(gx, p.usx, p.wc, ups_xi, ups_fx);
+        ups_xj = min(ups_xi + 1, p.wc - 1);
+    }
+    auto flow_at = [&](int row) -> float2 {
+        if (!UPS) return fin[row * w + gx];
+        int yi;
+        float fy;
+        src_coord(row, p.usy, p.hc, yi, fy);
+        const int yj = min(yi + 1, p.hc - 1);
+        const float2* r0p = fin + yi * p.wc;
+        const float2* r1p = fin + yj * p.wc;
+        return bilerp_flow(r0p[ups_xi], r0p[ups_xj], r1p[ups_xi], r1p[ups_xj], ups_fx, fy, p.flow_mul);
+    };
+
     // ---- prologue: flow of rows 0..3 in registers, requests for rows 0 and 1 ------------
     float2 fl[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int o = clampi(row0 + i, 0, h - 1) * w + gx;
-        fl[i] = (fin && live) ? fin[o] : make_float2(0.f, 0.f);
-    }
+    for (int i = 0; i < 4; ++i)
+        fl[i] = (fin && live) ? flow_at(clampi(row0 + i, 0, h - 1)) : make_float2(0.f, 0.f);
     request_row(clampi(row0, 0, h - 1), fl[0].x, fl[0].y, 0);
     request_row(clampi(row0 + 1, 0, h - 1), fl[1].x, fl[1].y, 1);
 
@@ -1217,7 +1408,7 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
                 request_row(clampi(row0 + ri + 2, 0, h - 1), fl[(i + 2) & 3].x, fl[(i + 2) & 3].y, l2);
             }
             const float dx = fl[i].x, dy = fl[i].y;
-            if (fin && live) fl[i] = fin[clampi(row0 + ri + 4, 0, h - 1) * w + gx];
+            if (fin && live) fl[i] = flow_at(clampi(row0 + ri + 4, 0, h - 1));
             // old ring row (leaves the window) -- TMEM read overlaps the wait for the landing zone
             float old[8];
             tmem_wait_st();                              // last row's ring store
@@ -1524,11 +1715,7 @@ int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* 
             ProfScope prof(PK_PREFILTER, stream);
 #define OFC_PF_TILE(KS)                                                                                                \
     {                                                                                                                  \
-        static size_t conf = 0;                                                                                        \
-        if (sm > 48 * 1024 && sm > conf) {                                                                             \
-            OFC_CUDA(cudaFuncSetAttribute(prefilter_tile_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-            conf = sm;                                                                                                 \
-        }                                                                                                              \
+        OFC_SMEM_OPTIN(prefilter_tile_kernel<KS>, sm);                                                                 \
         OFC_LAUNCH(prefilter_tile_kernel<KS>, g, dim3(256), sm, stream, p, in_rows, in_pitch);                          \
     }
             if (p.ksz == 3) OFC_PF_TILE(3)
@@ -1541,14 +1728,57 @@ int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* 
         }
     }
     dim3 grid(cdiv(p.w, p.tx), cdiv(p.h, p.ty), n_frames);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        OFC_CUDA(cudaFuncSetAttribute(prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    OFC_SMEM_OPTIN(prefilter_kernel, smem);
     ProfScope prof(PK_PREFILTER, stream);
     OFC_LAUNCH(prefilter_kernel, grid, dim3(256), smem, stream, p);
     OFC_CHECK_LAUNCH("prefilter");
+    return OFC_OK;
+}
+
+static size_t pyr_smem(int S, int ksz) {
+    const int RR = ksz / 2, A = ((S / 2 - 1 - RR) % 4 + 4) % 4, RB = S < 8 ? 8 : S;
+    const int PW = (S * (PYR_NT - 1) + A + ksz + 1 + 3) / 4;
+    return (size_t)RB * PW * 4;
+}
+
+int launch_prefilter_pyramid(const PrefilterParams* levels, const size_t* smem_fallback, int n_levels, int n_frames,
+                             bool* done, void* stream) {
+    (void)smem_fallback;
+    const int off = env_int("OFC_PREFILTER_PYR", 1) == 0;          // read per call: tests compare both forms in one process
+    PyrParams pp;
+    pp.n_levels = 0;
+    size_t smem = 0;
+    int blocks = 0;
+    for (int i = 0; i < n_levels; ++i) done[i] = false;
+    if (off || n_levels <= 0) return OFC_OK;
+    // heaviest levels (largest S) first: their CTAs start first
+    for (int pass = 16; pass >= 2; pass >>= 1) {
+        for (int i = 0; i < n_levels && pp.n_levels < 4; ++i) {
+            const PrefilterParams& p = levels[i];
+            if (p.identity3 || p.w <= 0) continue;
+            const int S = p.w > 0 ? p.W / p.w : 0;
+            if (S != pass || p.W != p.w * S || p.H != p.h * S) continue;
+            const int want_ksz = S == 2 ? 3 : (S == 4 ? 9 : (S == 8 ? 19 : 39));
+            if (p.ksz != want_ksz || (p.W & 3) || (p.gray_stride & 3) || ((uintptr_t)p.gray & 3)) continue;
+            if (p.H < 2 * S + p.ksz) continue;
+            if (pp.n_levels == 0) { pp.gray = p.gray; pp.gray_stride = p.gray_stride; pp.W = p.W; pp.H = p.H; }
+            PyrLevel& L = pp.lv[pp.n_levels++];
+            L.out = p.out; L.out_stride = p.out_stride; L.taps = p.taps; L.w = p.w; L.h = p.h; L.S = S;
+            L.blocks_x = cdiv(p.w, PYR_NT);
+            L.rows_per_seg = 128 / S < 8 ? 8 : 128 / S;
+            L.segs = cdiv(p.h, L.rows_per_seg);
+            L.first_block = blocks;
+            blocks += L.blocks_x * L.segs;
+            const size_t sm = pyr_smem(S, p.ksz);
+            if (sm > smem) smem = sm;
+            done[i] = true;
+        }
+    }
+    if (pp.n_levels == 0) return OFC_OK;
+    ProfScope prof(PK_PREFILTER, stream);
+    OFC_SMEM_OPTIN(prefilter_pyr_kernel, smem);
+    OFC_LAUNCH(prefilter_pyr_kernel, dim3(blocks, n_frames), dim3(PYR_NT), smem, stream, pp);
+    OFC_CHECK_LAUNCH("prefilter_pyr");
     return OFC_OK;
 }
 
@@ -1616,12 +1846,7 @@ static int launch_iter_r(const IterParams& p, int n_pairs, void* stream) {
     constexpr int P0 = (MW + 2 + 3) / 4 * 4;
     constexpr int PITCH = ((P0 / 4) % 2 == 0) ? P0 + 4 : P0;
     constexpr size_t smem = (size_t)5 * MH * PITCH * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        OFC_CUDA(cudaFuncSetAttribute(flow_iter_kernel<R, TH, NT, MINB>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    OFC_SMEM_OPTIN((flow_iter_kernel<R, TH, NT, MINB>), smem);
     dim3 grid(cdiv(p.w, 64), cdiv(p.h, TH), n_pairs);
     ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
     OFC_LAUNCH((flow_iter_kernel<R, TH, NT, MINB>), grid, dim3(NT), smem, stream, p);
@@ -1633,12 +1858,7 @@ template <int R, int TW, int NT, int G, int MINB, bool MINMAX>
 static int launch_strip_rm(const IterParams& p, int n_pairs, void* stream) {
     constexpr int K = 2 * R + 1, CW = TW + 2 * R, CP = (CW + 3) / 4 * 4 + 4;
     constexpr size_t smem = (size_t)((K * 5 * CW + 3) / 4 * 4 + G * 5 * CP) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        OFC_CUDA(cudaFuncSetAttribute(flow_iter_strip_kernel<R, TW, NT, G, MINB, MINMAX>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    OFC_SMEM_OPTIN((flow_iter_strip_kernel<R, TW, NT, G, MINB, MINMAX>), smem);
     // persistent grid: every SM holds as many CTAs as fit, each gets an equal share of the rows
     static int resident = 0;
     if (!resident) {
@@ -1662,24 +1882,20 @@ static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
                     : launch_strip_rm<R, TW, NT, G, MINB, false>(p, n_pairs, stream);
 }
 
-template <bool MINMAX>
+template <bool MINMAX, bool UPS>
 static int launch_tmem(const IterParams& p, int n_pairs, void* stream) {
     constexpr int R = 7, TW = 240, NT = 256, G = 4;
     constexpr int CW = TW + 2 * R, CP = (CW + 3) / 4 * 4 + 4, S = 3;
     constexpr size_t smem = (size_t)(G * 5 * CP) * 4 + (size_t)S * 4 * NT * 16 + (size_t)S * NT * 16 + (size_t)S * 4 * NT * 4 +
                             (size_t)S * NT * 4;
-    static bool configured = false;
-    if (!configured) {
-        OFC_CUDA(cudaFuncSetAttribute(flow_iter_tmem_kernel<R, TW, NT, G, MINMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    OFC_SMEM_OPTIN((flow_iter_tmem_kernel<R, TW, NT, G, MINMAX, UPS>), smem);
     const int cols = cdiv(p.w, TW);
     const int64_t total_rows = (int64_t)n_pairs * cols * p.h;
     int64_t ctas = (int64_t)num_sms() * 2;              // 2 CTAs per SM: 2 x 256 TMEM columns
     const int64_t max_ctas = (total_rows + 15) / 16;
     if (ctas > max_ctas) ctas = max_ctas;
     ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
-    OFC_LAUNCH((flow_iter_tmem_kernel<R, TW, NT, G, MINMAX>), dim3((unsigned)ctas), dim3(NT), smem, stream, p, cols, total_rows);
+    OFC_LAUNCH((flow_iter_tmem_kernel<R, TW, NT, G, MINMAX, UPS>), dim3((unsigned)ctas), dim3(NT), smem, stream, p, cols, total_rows);
     OFC_CHECK_LAUNCH("flow_iter_tmem");
     return OFC_OK;
 }
@@ -1688,6 +1904,11 @@ static int launch_tmem(const IterParams& p, int n_pairs, void* stream) {
 // it first into `scratch` (this level's other ping-pong buffer, not otherwise live on iteration 0).
 static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, void* stream) {
     IterParams p = p_in;
+    const int use_tmem0 = env_int("OFC_ITER_TMEM", 513), any_w0 = env_int("OFC_TMEM_ANYW", 1);
+    const bool tmem_path = use_tmem0 && (p.w >= use_tmem0 || p.w % 240 == 0) && (any_w0 || p.w % 240 == 0);
+    // the tensor-memory walk up-samples the coarser flow itself (OFC_FUSE_UPSAMPLE=0: separate launch as before)
+    if (p.upsample && tmem_path && env_int("OFC_FUSE_UPSAMPLE", 1) && (int64_t)p.wc * p.hc < ((int64_t)1 << 30))
+        return p.minmax ? launch_tmem<true, true>(p, n_pairs, stream) : launch_tmem<false, true>(p, n_pairs, stream);
     if (p.upsample) {
         dim3 g(cdiv(p.w, 64), cdiv(p.h, 16), n_pairs);
         {
@@ -1702,7 +1923,7 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
     static const int use_tmem = env_int("OFC_ITER_TMEM", 513);      // minimum level width; 0 = off
     // (OFC_TMEM_ANYW=0 restricts it to widths that are a multiple of its 240-column strips)
     static const int any_w = env_int("OFC_TMEM_ANYW", 1);
-    if (use_tmem && (p.w >= use_tmem || p.w % 240 == 0) && (any_w || p.w % 240 == 0)) return p.minmax ? launch_tmem<true>(p, n_pairs, stream) : launch_tmem<false>(p, n_pairs, stream);
+    if (use_tmem && (p.w >= use_tmem || p.w % 240 == 0) && (any_w || p.w % 240 == 0)) return p.minmax ? launch_tmem<true, false>(p, n_pairs, stream) : launch_tmem<false, false>(p, n_pairs, stream);
     static const int minb4 = env_int("OFC_STRIP_MINB4", 1);
     if (p.w > 512 && minb4) return launch_strip_r<7, 128, 160, 4, 4>(p, n_pairs, stream);
     if (p.w > 512) return launch_strip_r<7, 128, 160, 4, 3>(p, n_pairs, stream);
@@ -1722,11 +1943,7 @@ static int launch_iter_gauss(const IterParams& p, const GaussWindow& gw, int n_p
     const int MW = 32 + 2 * gw.r, MH = 16 + 2 * gw.r;
     const size_t smem = (size_t)5 * (MH + 16) * MW * sizeof(float);
     if (smem > 200 * 1024) { set_error("Gaussian window of %d taps needs too much shared memory", 2 * gw.r + 1); return OFC_ERR_UNSUPPORTED; }
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        OFC_CUDA(cudaFuncSetAttribute(flow_iter_gauss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    OFC_SMEM_OPTIN(flow_iter_gauss_kernel, smem);
     ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
     OFC_LAUNCH(flow_iter_gauss_kernel, dim3(cdiv(p.w, 32), cdiv(p.h, 16), n_pairs), dim3(256), smem, stream, p, gw);
     OFC_CHECK_LAUNCH("flow_iter_gauss");

@@ -56,6 +56,10 @@ struct GaussWindow {
 };
 
 int launch_prefilter(const PrefilterParams& p, int n_frames, size_t smem, void* stream);
+// all down-sampled levels whose size is an exact power-of-two fraction of the frame in ONE launch
+// (prefilter_pyr_kernel); done[i] is set for the levels it covered, the others go through launch_prefilter
+int launch_prefilter_pyramid(const PrefilterParams* levels, const size_t* smem_fallback, int n_levels, int n_frames,
+                             bool* done, void* stream);
 // gray != null: full-resolution level with the fixed 3-tap pre-filter; I is produced from the 8-bit
 // frame inside the expansion kernel (and written to I_out as a by-product)
 int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, const unsigned char* gray, int64_t gray_stride,

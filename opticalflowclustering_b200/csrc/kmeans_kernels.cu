@@ -522,6 +522,79 @@ __global__ void __launch_bounds__(256) kmeans_centres_kernel(int d, int k, const
 }
 
 // ---------------------------------------------------------------------------
+// End of one Lloyd iteration, entirely on the device: new centres (kmeans_centres_kernel's arithmetic),
+// optional float32 rounding of the stored centres, and sklearn's stopping rule (_kmeans.py:705-758) --
+// a problem stops when its labels repeated (n_changed == 0, "strict") or when the squared centre shift is
+// <= tol.  Stopped problems clear their `active` byte (every kernel skips them from then on) and raise
+// `just_done` (their labels are copied into both label buffers by kmeans_freeze_labels_kernel); the number
+// of problems still running is accumulated in *n_active, which the host reads asynchronously, a few
+// iterations behind, to know when to stop enqueuing.  One CTA per problem.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kmeans_update_kernel(int d, int k, const double* sums, const long long* counts,
+                                                            const double* mean_sub, int use_reciprocal, int round_f32,
+                                                            double* centres, double* shift_tot, double* shift_ws,
+                                                            const unsigned long long* n_changed, const double* tol, int it,
+                                                            unsigned char* active, unsigned char* just_done, int* n_iter,
+                                                            int* n_active) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (just_done && tid == 0) just_done[b] = 0;
+    if (active && !active[b]) return;
+    const double* S = sums + (int64_t)b * k * d;
+    const long long* Cn = counts + (int64_t)b * k;
+    double* C = centres + (int64_t)b * k * d;
+    double* sh = shift_ws + (int64_t)b * k;
+    __shared__ int s_heavy;
+    if (tid == 0) {
+        int best = 0;
+        for (int j = 1; j < k; ++j) if (Cn[j] > Cn[best]) best = j;
+        s_heavy = best;
+    }
+    __syncthreads();
+    const int heavy = s_heavy;
+    for (int j = tid; j < k; j += 256) {
+        const int src = Cn[j] > 0 ? j : heavy;
+        const double w = (double)Cn[src];
+        const double alpha = 1.0 / w;
+        double ss = 0.0;
+        for (int t = 0; t < d; ++t) {
+            double v = S[(int64_t)src * d + t];
+            v = use_reciprocal ? v * alpha : v / w;
+            if (mean_sub) v -= mean_sub[(int64_t)b * d + t];
+            const double df = v - C[(int64_t)j * d + t];
+            ss = fma(df, df, ss);
+            C[(int64_t)j * d + t] = round_f32 ? (double)(float)v : v;
+        }
+        const double s = sqrt(ss);
+        sh[j] = s * s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int j = 0; j < k; ++j) tot += sh[j];
+        if (shift_tot) shift_tot[b] = tot;
+        if (n_iter) n_iter[b] = it + 1;
+        bool stop = false;
+        if (n_changed && n_changed[b] == 0ull) stop = true;                 // labels repeated: strict convergence
+        else if (tol && tot <= tol[b]) stop = true;
+        if (stop) {
+            if (active) active[b] = 0;
+            if (just_done) just_done[b] = 1;
+        } else if (n_active) {
+            atomicAdd(n_active, 1);
+        }
+    }
+}
+
+// problems that stopped in this iteration keep the labels they stopped with in BOTH ping-pong buffers
+__global__ void __launch_bounds__(256) kmeans_freeze_labels_kernel(int64_t n, const unsigned char* just_done, const int32_t* cur,
+                                                                   int32_t* other) {
+    const int b = blockIdx.y;
+    if (!just_done[b]) return;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        other[(int64_t)b * n + i] = cur[(int64_t)b * n + i];
+}
+
+// ---------------------------------------------------------------------------
 // empty-cluster relocation (_k_means_common.pyx:167-211): each empty cluster, in
 // index order, takes the farthest remaining point (squared distance to the OLD
 // centre of its label); labels are left untouched.  One CTA of 1024 threads per
@@ -1016,10 +1089,10 @@ int launch_kmeans_cells(const unsigned char* X, int batch, int64_t n, int d, int
     const size_t smem = (size_t)(2 * k * d + 2 * k + d + 8) * sizeof(double) + (size_t)k * d * sizeof(unsigned) + (size_t)k * sizeof(int);
     ProfScope prof(PK_KMEANS, stream);
     if (d <= 4) {
-        if (smem > 48 * 1024) OFC_CUDA(cudaFuncSetAttribute(kmeans_cells_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OFC_SMEM_OPTIN(kmeans_cells_kernel<4>, smem);
         OFC_LAUNCH(kmeans_cells_kernel<4>, dim3(batch), dim3(256), smem, stream, p);
     } else {
-        if (smem > 48 * 1024) OFC_CUDA(cudaFuncSetAttribute(kmeans_cells_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OFC_SMEM_OPTIN(kmeans_cells_kernel<8>, smem);
         OFC_LAUNCH(kmeans_cells_kernel<8>, dim3(batch), dim3(256), smem, stream, p);
     }
     OFC_CHECK_LAUNCH("kmeans_cells");
@@ -1047,9 +1120,7 @@ template <typename T, typename W>
 static int assign_small_dispatch(const KmAssignParams& p, dim3 grid, size_t smem, void* stream) {
 #define OFC_KM_CASE(DPV)                                                                                     \
     {                                                                                                        \
-        if (smem > 48 * 1024)                                                                                \
-            OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_small_kernel<T, W, DPV>,                             \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        OFC_SMEM_OPTIN((kmeans_assign_small_kernel<T, W, DPV>), smem);                                       \
         OFC_LAUNCH((kmeans_assign_small_kernel<T, W, DPV>), grid, dim3(256), smem, stream, p);               \
     }
     if (p.d <= 4) OFC_KM_CASE(4)
@@ -1094,12 +1165,7 @@ int launch_kmeans_assign(KmAssignParams p, int batch, double* c2_ws, void* strea
     if (use_medium && p.d <= 512 && msmem <= 200 * 1024) {
 #define OFC_KM_MED(TT, WW, NTV)                                                                                        \
     {                                                                                                                  \
-        static size_t conf = 0;                                                                                        \
-        if (msmem > 48 * 1024 && msmem > conf) {                                                                       \
-            OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_medium_kernel<TT, WW, NTV>,                                    \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));                   \
-            conf = msmem;                                                                                              \
-        }                                                                                                              \
+        OFC_SMEM_OPTIN((kmeans_assign_medium_kernel<TT, WW, NTV>), msmem);                                             \
         OFC_LAUNCH((kmeans_assign_medium_kernel<TT, WW, NTV>), grid, dim3(256), msmem, stream, p);                     \
     }
 #define OFC_KM_MED_NT(TT, WW)                                                                                          \
@@ -1176,11 +1242,7 @@ int launch_kmeans_step_u8(KmAssignParams p, int batch, double* partial, long lon
     ProfScope prof(PK_KMEANS, stream);
 #define OFC_KM_STEP(DPV, KR)                                                                                                \
     {                                                                                                                     \
-        static size_t conf = 0;                                                                                           \
-        if (smem > 48 * 1024 && smem > conf) {                                                                            \
-            OFC_CUDA(cudaFuncSetAttribute((kmeans_step_u8_kernel<DPV, KR>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            conf = smem;                                                                                                  \
-        }                                                                                                                 \
+        OFC_SMEM_OPTIN((kmeans_step_u8_kernel<DPV, KR>), smem);                                                           \
         OFC_LAUNCH((kmeans_step_u8_kernel<DPV, KR>), dim3(grid, batch), dim3(256), smem, stream, p, partial, cnt_partial); \
     }
     // (register-resident centres, KREG = 8, measured slower at d = 4, k = 8: 1.15 vs 0.75 ms per 64 M rows -- the
@@ -1216,8 +1278,7 @@ int launch_kmeans_sums(const KmSumsParams& p, int batch, double* sums, long long
     ProfScope prof(PK_KMEANS, stream);
 #define OFC_KM_SUMS(TT)                                                                                      \
     {                                                                                                        \
-        if (smem > 48 * 1024)                                                                                \
-            OFC_CUDA(cudaFuncSetAttribute(kmeans_sums_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        OFC_SMEM_OPTIN(kmeans_sums_kernel<TT>, smem);                                                        \
         OFC_LAUNCH(kmeans_sums_kernel<TT>, grid, dim3(256), smem, stream, p);                                \
     }
     if (p.dtype == DT_U8) OFC_KM_SUMS(unsigned char)
@@ -1243,13 +1304,36 @@ int launch_kmeans_centres(int batch, int d, int k, const double* sums, const lon
     return OFC_OK;
 }
 
+int launch_kmeans_update(int batch, int d, int k, const double* sums, const long long* counts, const double* mean_sub,
+                         int use_reciprocal, int round_f32, double* centres, double* shift_tot, double* shift_ws,
+                         const unsigned long long* n_changed, const double* tol, int it, unsigned char* active,
+                         unsigned char* just_done, int* n_iter, int* n_active, int64_t n, const int32_t* labels_cur,
+                         int32_t* labels_other, void* stream) {
+    if (batch <= 0) return OFC_OK;
+    ProfScope prof(PK_KMEANS, stream);
+    OFC_LAUNCH(kmeans_update_kernel, dim3(batch), dim3(256), 0, stream, d, k, sums, counts, mean_sub, use_reciprocal, round_f32,
+               centres, shift_tot, shift_ws, n_changed, tol, it, active, just_done, n_iter, n_active);
+    OFC_CHECK_LAUNCH("kmeans_update");
+    if (batch > 1 && just_done && labels_cur && labels_other && n > 0) {
+        int64_t bx = (n + 255) / 256;
+        if (bx > 64) bx = 64;
+        OFC_LAUNCH(kmeans_freeze_labels_kernel, dim3((unsigned)bx, batch), dim3(256), 0, stream, n, just_done, labels_cur, labels_other);
+        OFC_CHECK_LAUNCH("kmeans_freeze_labels");
+    }
+    return OFC_OK;
+}
+
 int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                            const int32_t* labels, const double* centres_old, double* sums, long long* counts,
                            int raw_sums, const unsigned char* active, void* stream) {
     if (batch <= 0) return OFC_OK;
     ProfScope prof(PK_KMEANS, stream);
     const size_t smem = (size_t)k * sizeof(long long);
-    if (smem > 40 * 1024) { set_error("k=%d too large for the relocation kernel", k); return OFC_ERR_UNSUPPORTED; }
+    // the list of rows already given away is k words of shared memory: opt in past 48 KB (k <= 25 600)
+    if (smem > 200 * 1024) { set_error("k=%d too large for the relocation kernel (k <= 25600)", k); return OFC_ERR_UNSUPPORTED; }
+    OFC_SMEM_OPTIN(kmeans_relocate_kernel<unsigned char>, smem);
+    OFC_SMEM_OPTIN(kmeans_relocate_kernel<float>, smem);
+    OFC_SMEM_OPTIN(kmeans_relocate_kernel<double>, smem);
     if (dtype == DT_U8)
         OFC_LAUNCH(kmeans_relocate_kernel<unsigned char>, dim3(batch), dim3(1024), smem, stream, (const unsigned char*)X, n, d, k,
                    mean, labels, centres_old, sums, counts, raw_sums, active);

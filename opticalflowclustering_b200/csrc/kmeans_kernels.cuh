@@ -50,6 +50,11 @@ int launch_kmeans_step_u8(KmAssignParams p, int batch, double* partial, long lon
 int launch_kmeans_centres(int batch, int d, int k, const double* sums, const long long* counts, const double* mean_sub,
                           int use_reciprocal, double* centres, double* shift_tot, double* shift_ws,
                           const unsigned char* active, void* stream);
+int launch_kmeans_update(int batch, int d, int k, const double* sums, const long long* counts, const double* mean_sub,
+                         int use_reciprocal, int round_f32, double* centres, double* shift_tot, double* shift_ws,
+                         const unsigned long long* n_changed, const double* tol, int it, unsigned char* active,
+                         unsigned char* just_done, int* n_iter, int* n_active, int64_t n, const int32_t* labels_cur,
+                         int32_t* labels_other, void* stream);
 int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                            const int32_t* labels, const double* centres_old, double* sums, long long* counts,
                            int raw_sums, const unsigned char* active, void* stream);
@@ -60,6 +65,30 @@ int launch_inertia_reduce(const double* partial, int parts, int batch, double* i
 int launch_kmeans_cells(const unsigned char* X, int batch, int64_t n, int d, int k, const double* init,
                         unsigned long long seed, int max_iter, double tol, int32_t* labels, double* centres,
                         double* inertia, int32_t* n_iter, long long* counts, double* scratch, void* stream);
+// fast per-cell Lloyd runs for 4-channel uint8 rows, k <= 16 (cells_kmeans.cu)
+struct KmCellsFastParams {
+    const unsigned char* X;        // [batch][n][4] packed rows, or null when the cells are gathered from `bgr`
+    const unsigned char* bgr;      // [n_frames][H][W][3] flow visualisation (cell gather + preprocess_image fused in)
+    int64_t frame_stride;          // bytes between frames
+    int W, H, cols, cells, x_step, y_step, draw_lines, threshold, swap_rb;
+    int n, k;
+    const double* init;            // [batch][k][4] or null (k-means++ from `seed`)
+    unsigned long long seed, problem_offset;
+    int max_iter;
+    double tol;
+    int32_t* labels;               // [batch][n]      or null
+    double* centres;               // [batch][k][4]   or null
+    double* inertia;               // [batch]         or null
+    int32_t* n_iter;               // [batch]         or null
+    long long* counts;             // [batch][k]      or null
+    unsigned char* dom_centre;     // [batch][4] np.rint of the largest cluster's centre, or null
+    unsigned char* dom_hue;        // [batch]    BGR2HSV hue of its first three channels, or null
+    unsigned* closest_ws;          // [batch][n] k-means++ scratch when it does not fit shared memory
+    int closest_in_smem;           // set by the launcher
+};
+bool kmeans_cells_fast_supported(int64_t n, int d, int k);
+size_t kmeans_cells_fast_workspace(int batch, int64_t n, int k, bool seeding);
+int launch_kmeans_cells_fast(KmCellsFastParams p, int batch, void* stream);
 int kmeans_assign_grid(int64_t n);
 int kmeans_sums_splits(int64_t n, int batch);
 

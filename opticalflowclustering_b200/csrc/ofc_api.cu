@@ -6,6 +6,9 @@
 #include <string.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/ofc.h"
@@ -32,22 +35,45 @@ int check_cuda(cudaError_t e, const char* what) {
     return OFC_ERR_CUDA;
 }
 
+// per-(device, kernel) record of the dynamic shared memory already opted in to
+int smem_optin(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;
+    int dev = 0;
+    OFC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = done[std::make_pair(dev, kernel)];
+    if (bytes <= have) return OFC_OK;
+#ifndef OFC_EMULATE
+    OFC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+#endif
+    have = bytes;
+    return OFC_OK;
+}
+
 // ---- optional per-kernel event timing --------------------------------------
+// The records are process-global and mutex-protected; a scope remembers its own record index, so launches
+// from several host threads interleave without corrupting each other (their times then overlap, of course).
 struct ProfRec { int kind; cudaEvent_t a, b; };
 static bool g_prof_on = false;
+static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 int g_prof_level = 0;
 
-ProfScope::ProfScope(int kind_, void* stream_) : kind(kind_), stream(stream_), on(g_prof_on) {
+ProfScope::ProfScope(int kind_, void* stream_) : kind(kind_), stream(stream_), on(g_prof_on), index(-1) {
     if (!on) return;
     ProfRec r;
     r.kind = kind;
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { on = false; return; }
     cudaEventRecord(r.a, (cudaStream_t)stream);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    index = (int)g_prof.size();
     g_prof.push_back(r);
 }
 ProfScope::~ProfScope() {
-    if (on) cudaEventRecord(g_prof.back().b, (cudaStream_t)stream);
+    if (!on) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (index >= 0 && index < (int)g_prof.size()) cudaEventRecord(g_prof[index].b, (cudaStream_t)stream);
 }
 
 // cvRound: round half to even
@@ -178,9 +204,19 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         OFC_CUDA(cudaEventRecord(pl->ev_fork, (cudaStream_t)stream));
         OFC_CUDA(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
     }
+    // an early error return must not leave the side stream running behind the caller's back: whatever
+    // was enqueued there is joined into the caller's stream on every exit path
+    struct SideJoin {
+        cudaStream_t side, main; cudaEvent_t ev; bool armed;
+        ~SideJoin() { if (armed && cudaEventRecord(ev, side) == cudaSuccess) cudaStreamWaitEvent(main, ev, 0); }
+    } side_join{fork ? pl->side : nullptr, (cudaStream_t)stream, fork ? pl->ev_fork : cudaEvent_t(), fork};
+    // the pre-filter of every level that is an exact power-of-two fraction of the frame: one launch
+    std::vector<PrefilterParams> pfs(nl);
+    std::vector<size_t> pf_smem(nl);
+    std::vector<char> pf_done(nl, 0);
     for (int l = 0; l < nl; ++l) {
         const Level& L = pl->lv[l];
-        PrefilterParams pf;
+        PrefilterParams& pf = pfs[l];
         pf.gray = gray; pf.gray_stride = gray_stride;
         pf.out = (float*)(ws + L.off_I); pf.out_stride = (int64_t)L.w * L.h;
         pf.W = pl->W; pf.H = pl->H; pf.w = L.w; pf.h = L.h;
@@ -188,8 +224,17 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         pf.taps = pl->d_taps + L.taps_off;
         pf.identity3 = (L.sigma <= 0 && L.ksz == 3 && L.w == pl->W && L.h == pl->H) ? 1 : 0;
         pf.tx = L.tx; pf.ty = L.ty; pf.in_rows = L.in_rows; pf.in_pitch = L.in_pitch; pf.taps_pad = L.taps_pad;
+        pf_smem[l] = L.prefilter_smem;
+    }
+    {
+        int rc = launch_prefilter_pyramid(pfs.data(), pf_smem.data(), nl, n_frames, reinterpret_cast<bool*>(pf_done.data()), stream1);
+        if (rc != OFC_OK) return rc;
+    }
+    for (int l = 0; l < nl; ++l) {
+        const Level& L = pl->lv[l];
+        const PrefilterParams& pf = pfs[l];
         int rc = OFC_OK;
-        if (!pf.identity3) {
+        if (!pf.identity3 && !pf_done[l]) {
             rc = launch_prefilter(pf, n_frames, L.prefilter_smem, stream1);
             if (rc != OFC_OK) return rc;
         }
@@ -257,6 +302,7 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         prev_flow = (const float2*)(ws + L.off_flow[(pl->iterations - 1) & 1]);
         prev_w = L.w; prev_h = L.h;
     }
+    side_join.armed = false;          // every level's event has been waited for above
     return OFC_OK;
 }
 
@@ -269,6 +315,7 @@ extern "C" {
 int ofc_version(void) { return 100; }
 
 int ofc_profile_begin(void) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_prof.clear();
     g_prof_on = true;
@@ -277,6 +324,7 @@ int ofc_profile_begin(void) {
 
 int ofc_profile_end(float* ms_by_kind, int* launches_by_kind, int n_kinds) {
     g_prof_on = false;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     OFC_REQUIRE(ms_by_kind && launches_by_kind && n_kinds >= PK_COUNT, "need %d slots", (int)PK_COUNT);
     for (int i = 0; i < n_kinds; ++i) { ms_by_kind[i] = 0.f; launches_by_kind[i] = 0; }
     int rc = OFC_OK;
@@ -516,7 +564,44 @@ int ofc_flow_to_bgr(const float* flow, int n_frames, int height, int width, cons
     if (mag_sum) OFC_CUDA(cudaMemsetAsync(mag_sum, 0, sizeof(double) * n_frames, (cudaStream_t)stream));
     VizParams p;
     p.flow = (const float2*)flow; p.n_px = n_pixels; p.width = width; p.minmax = minmax; p.bgr = bgr; p.mag_sum = mag_sum;
+    p.hsv = nullptr;
     return launch_flow_encode(p, n_frames, stream);
+}
+
+int ofc_flow_to_hsv(const float* flow, int n_frames, int height, int width, const uint32_t* minmax, uint8_t* bgr, uint8_t* hsv,
+                    void* stream) {
+    OFC_REQUIRE(n_frames >= 0 && height >= 0 && width >= 0, "bad sizes");
+    const int64_t n_pixels = (int64_t)height * width;
+    if (n_frames == 0 || n_pixels == 0) return OFC_OK;
+    OFC_REQUIRE(flow && minmax && bgr && hsv, "null buffer");
+    OFC_REQUIRE(((uintptr_t)flow & 15) == 0 && ((uintptr_t)bgr & 3) == 0 && ((uintptr_t)hsv & 3) == 0,
+                "flow must be 16-byte, bgr / hsv 4-byte aligned");
+    VizParams p;
+    p.flow = (const float2*)flow; p.n_px = n_pixels; p.width = width; p.minmax = minmax; p.bgr = bgr; p.mag_sum = nullptr; p.hsv = hsv;
+    return launch_flow_encode(p, n_frames, stream);
+}
+
+int ofc_flow_to_bgr_grid(const float* flow, int n_frames, int height, int width, const uint32_t* minmax, uint8_t* bgr,
+                         double* mag_sum, int rows, int cols, int draw_lines, int threshold, uint8_t* avg_bgr, uint8_t* avg_hue,
+                         uint8_t* km_centre, uint8_t* km_hue, void* stream) {
+    OFC_REQUIRE(n_frames >= 0 && height > 0 && width > 0, "bad sizes");
+    OFC_REQUIRE(rows > 0 && cols > 0 && rows <= height && cols <= width, "grid %dx%d does not fit %dx%d", rows, cols, height, width);
+    OFC_REQUIRE(threshold >= 0 && threshold <= 255, "bad threshold");
+    if (n_frames == 0) return OFC_OK;
+    OFC_REQUIRE(flow && minmax && bgr, "null buffer");
+    OFC_REQUIRE(((uintptr_t)flow & 7) == 0, "flow must be 8-byte aligned");
+    if (mag_sum) OFC_CUDA(cudaMemsetAsync(mag_sum, 0, sizeof(double) * n_frames, (cudaStream_t)stream));
+    VizParams p;
+    p.flow = (const float2*)flow; p.n_px = (int64_t)height * width; p.width = width; p.minmax = minmax; p.bgr = bgr;
+    p.mag_sum = mag_sum; p.hsv = nullptr;
+    GridParams g;
+    g.bgr = bgr; g.frame_stride = (int64_t)height * width * 3;
+    g.W = width; g.H = height; g.rows = rows; g.cols = cols;
+    g.x_step = width / cols; g.y_step = height / rows;
+    OFC_REQUIRE((int64_t)g.x_step * g.y_step * 255 < (int64_t)1 << 32, "cell too large for 32-bit sums");
+    g.draw_lines = draw_lines; g.threshold = threshold;
+    g.avg_bgr = avg_bgr; g.avg_hue = avg_hue; g.km_centre = km_centre; g.km_hue = km_hue; g.km_sums = nullptr;
+    return launch_flow_encode_grid(p, g, n_frames, stream);
 }
 
 int ofc_grid_cells(const uint8_t* bgr, int n_frames, int height, int width, int rows, int cols,
@@ -672,6 +757,19 @@ int ofc_kmeans_centres(int batch, int d, int k, const double* sums, const int64_
                                  (double*)workspace, active, stream);
 }
 
+int ofc_kmeans_update(int batch, int64_t n, int d, int k, const double* sums, const int64_t* counts, const double* mean_sub,
+                      int use_reciprocal, int round_f32, double* centres, double* shift_tot, const uint64_t* n_changed,
+                      const double* tol, int iteration, uint8_t* active, uint8_t* just_done, int32_t* n_iter, int32_t* n_active,
+                      const int32_t* labels_cur, int32_t* labels_other, void* workspace, size_t workspace_bytes, void* stream) {
+    OFC_REQUIRE(batch >= 0 && d >= 1 && k >= 1 && n >= 0, "bad shape");
+    if (batch == 0) return OFC_OK;
+    OFC_REQUIRE(sums && counts && centres, "null buffer");
+    OFC_REQUIRE(workspace && workspace_bytes >= align_up((size_t)batch * k * 8, 256), "k-means workspace too small");
+    return launch_kmeans_update(batch, d, k, sums, (const long long*)counts, mean_sub, use_reciprocal, round_f32, centres, shift_tot,
+                                (double*)workspace, (const unsigned long long*)n_changed, tol, iteration, active, just_done, n_iter,
+                                n_active, n, labels_cur, labels_other, stream);
+}
+
 int ofc_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                         const int32_t* labels, const double* centres_old, double* sums, int64_t* counts,
                         int raw_sums, const uint8_t* active, void* stream) {
@@ -704,8 +802,58 @@ int ofc_kmeans_cells(const uint8_t* X, int batch, int64_t n, int d, int k, const
         set_error("k-means++ seeding needs %zu bytes of workspace", (size_t)batch * n * sizeof(double));
         return OFC_ERR_WORKSPACE;
     }
+    // the reference's own shape (4 channels, small k) runs the shared-memory / filtered form (cells_kmeans.cu):
+    // same labels, centres, n_iter, counts and inertia, bit for bit (OFC_CELLS_FAST=0 keeps the first kernel)
+    const char* fast_env = getenv("OFC_CELLS_FAST");          // read per call: tests compare both kernels in one process
+    const bool fast_on = !(fast_env && atoi(fast_env) == 0);
+    if (fast_on && kmeans_cells_fast_supported(n, d, k)) {
+        KmCellsFastParams p;
+        memset(&p, 0, sizeof(p));
+        p.X = X; p.n = (int)n; p.k = k; p.init = init; p.seed = seed; p.problem_offset = 0; p.max_iter = max_iter; p.tol = tol;
+        p.labels = labels; p.centres = centres; p.inertia = inertia; p.n_iter = n_iter; p.counts = (long long*)counts;
+        p.closest_ws = (unsigned*)workspace;
+        return launch_kmeans_cells_fast(p, batch, stream);
+    }
     return launch_kmeans_cells(X, batch, n, d, k, init, seed, max_iter, tol, labels, centres, inertia, n_iter,
                                (long long*)counts, (double*)workspace, stream);
+}
+
+size_t ofc_grid_kmeans_cells_workspace_bytes(int n_frames, int height, int width, int rows, int cols, int k) {
+    if (n_frames <= 0 || rows <= 0 || cols <= 0 || height < rows || width < cols) return 0;
+    const int64_t n = (int64_t)(height / rows) * (width / cols);
+    return kmeans_cells_fast_workspace(n_frames * rows * cols, n, k, true);
+}
+
+int ofc_grid_kmeans_cells(const uint8_t* bgr, int n_frames, int height, int width, int rows, int cols, int draw_lines,
+                          int threshold, int swap_rb, int k, uint64_t seed, uint64_t first_frame, int max_iter, double tol,
+                          uint8_t* dom_centre, uint8_t* dom_hue, double* centres, int64_t* counts, int32_t* n_iter,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    OFC_REQUIRE(n_frames >= 0 && height > 0 && width > 0, "bad sizes");
+    OFC_REQUIRE(rows > 0 && cols > 0 && rows <= height && cols <= width, "grid %dx%d does not fit %dx%d", rows, cols, height, width);
+    OFC_REQUIRE(threshold >= 0 && threshold <= 255 && max_iter >= 0, "bad threshold / max_iter");
+    const int64_t n = (int64_t)(height / rows) * (width / cols);
+    OFC_REQUIRE(k >= 1 && n >= k, "n_samples=%lld should be >= n_clusters=%d.", (long long)n, k);
+    if (!kmeans_cells_fast_supported(n, 4, k)) {
+        set_error("per-cell k-means on the frame needs k <= 16 and cells of at most ~40 000 pixels (k=%d, %lld pixels): "
+                  "gather the cells with ofc_grid_extract_cells and call ofc_kmeans_cells", k, (long long)n);
+        return OFC_ERR_UNSUPPORTED;
+    }
+    if (n_frames == 0) return OFC_OK;
+    OFC_REQUIRE(bgr && (dom_centre || dom_hue || centres), "null buffer");
+    const size_t need = ofc_grid_kmeans_cells_workspace_bytes(n_frames, height, width, rows, cols, k);
+    if (need && (!workspace || workspace_bytes < need)) {
+        set_error("k-means++ seeding needs %zu bytes of workspace", need);
+        return OFC_ERR_WORKSPACE;
+    }
+    KmCellsFastParams p;
+    memset(&p, 0, sizeof(p));
+    p.bgr = bgr; p.frame_stride = (int64_t)height * width * 3; p.W = width; p.H = height; p.cols = cols; p.cells = rows * cols;
+    p.x_step = width / cols; p.y_step = height / rows; p.draw_lines = draw_lines; p.threshold = threshold; p.swap_rb = swap_rb;
+    p.n = (int)n; p.k = k; p.init = nullptr; p.seed = seed; p.problem_offset = first_frame * (uint64_t)(rows * cols);
+    p.max_iter = max_iter; p.tol = tol;
+    p.centres = centres; p.counts = (long long*)counts; p.n_iter = n_iter; p.dom_centre = dom_centre; p.dom_hue = dom_hue;
+    p.closest_ws = (unsigned*)workspace;
+    return launch_kmeans_cells_fast(p, n_frames * rows * cols, stream);
 }
 
 int ofc_grid_extract_cells(const uint8_t* bgr, int n_frames, int height, int width, int rows, int cols,

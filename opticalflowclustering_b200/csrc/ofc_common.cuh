@@ -43,6 +43,18 @@ int check_cuda(cudaError_t e, const char* what);
 
 #define OFC_CHECK_LAUNCH(name) OFC_CUDA(cudaGetLastError())
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per device, so the
+// "already done" cache is keyed by (current device, kernel) and guarded by a mutex: one process may
+// drive several GPUs and several host threads may launch (ofc_api.cu).
+int smem_optin(const void* kernel, size_t bytes);
+#define OFC_SMEM_OPTIN(kernel, bytes)                                                   \
+    do {                                                                                \
+        if ((size_t)(bytes) > 48 * 1024) {                                              \
+            int ofc_rc_ = ::ofc::smem_optin(reinterpret_cast<const void*>(kernel), (size_t)(bytes)); \
+            if (ofc_rc_ != OFC_OK) return ofc_rc_;                                      \
+        }                                                                               \
+    } while (0)
+
 #define OFC_REQUIRE(cond, ...)                                      \
     do {                                                            \
         if (!(cond)) {                                              \
@@ -61,7 +73,7 @@ enum ProfKind {
     PK_COUNT = 20
 };
 struct ProfScope {
-    int kind; void* stream; bool on;
+    int kind; void* stream; bool on; int index;
     ProfScope(int kind, void* stream);
     ~ProfScope();
 };
@@ -87,6 +99,15 @@ __host__ __device__ __forceinline__ int reflect101(int i, int n) {
 // same map for -n < i < 2n-1 without the modulo (n >= 2)
 __host__ __device__ __forceinline__ int reflect101_near(int i, int n) {
     return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i);
+}
+
+// byte T of a word as a float without an integer->float conversion: 0x4B0000bb is 2^23 + bb
+template <int T> __device__ __forceinline__ float byte_to_float(unsigned w) {
+#ifndef OFC_EMULATE
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + T)) - 8388608.f;
+#else
+    return (float)((w >> (8 * T)) & 255u);
+#endif
 }
 
 }  // namespace ofc

@@ -821,11 +821,7 @@ template <int BN, bool BRES>
 int launch_tc_form(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh, const CUtensorMap& tmBl, const TcParams& p,
                    void* stream) {
     const size_t smem = (size_t)p.tile_bytes + 1024 + 256 + 128 * 12 * 4;
-    static size_t configured = 0;
-    if (smem > configured) {
-        OFC_CUDA(cudaFuncSetAttribute((kmeans_assign_tc_kernel<BN, BRES>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    OFC_SMEM_OPTIN((kmeans_assign_tc_kernel<BN, BRES>), smem);
     const int64_t mtiles = (p.n + BM - 1) / BM;
     const int grid = (int)(mtiles < sm_count() ? mtiles : sm_count());
     kmeans_assign_tc_kernel<BN, BRES><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmAh, tmAl, tmBh, tmBl, p);
@@ -942,21 +938,13 @@ static int tc_assign_impl(const float* Xh, const float* Xl, const float* xnorm, 
     if (X8) {
         const size_t fix_smem = (size_t)8 * d * 8;
         const int use_smem = fix_smem <= 200 * 1024;
-        static size_t fix_conf8 = 0;
-        if (use_smem && fix_smem > 48 * 1024 && fix_smem > fix_conf8) {
-            OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_fix_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fix_smem));
-            fix_conf8 = fix_smem;
-        }
+        if (use_smem) OFC_SMEM_OPTIN(kmeans_assign_fix_u8_kernel, fix_smem);
         kmeans_assign_fix_u8_kernel<<<fix_ctas, 256, use_smem ? fix_smem : 0, st>>>(X8, mean8, d, k, centres, c2d, (const int4*)(ws + w.off_amb),
                                                                                     count, labels, (double*)(ws + w.off_fixrows), use_smem);
     } else {
         const size_t fix_smem = (size_t)8 * d * 4;
         const int use_smem = fix_smem <= 200 * 1024;
-        static size_t fix_conf = 0;
-        if (use_smem && fix_smem > 48 * 1024 && fix_smem > fix_conf) {
-            OFC_CUDA(cudaFuncSetAttribute(kmeans_assign_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fix_smem));
-            fix_conf = fix_smem;
-        }
+        if (use_smem) OFC_SMEM_OPTIN(kmeans_assign_fix_kernel, fix_smem);
         kmeans_assign_fix_kernel<<<fix_ctas, 256, use_smem ? fix_smem : 0, st>>>(Xh, Xl, d, k, c32, c2, (const int4*)(ws + w.off_amb),
                                                                                  count, labels, (float*)(ws + w.off_fixrows), use_smem);
     }
@@ -1040,20 +1028,12 @@ static int tc_sums_impl(const float* Xh, const float* Xl, const uint8_t* X8, int
     ProfScope prof(PK_KMEANS, stream);
     const int walk_ctas = (int)((w.n_chunks + 7) / 8);
     const size_t walk_smem = (size_t)8 * k * 4;
-    static size_t walk_conf = 0;
-    if (walk_smem > 48 * 1024 && walk_smem > walk_conf) {
-        OFC_CUDA(cudaFuncSetAttribute(csr_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
-        OFC_CUDA(cudaFuncSetAttribute(csr_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
-        walk_conf = walk_smem;
-    }
+    OFC_SMEM_OPTIN(csr_walk_kernel<false>, walk_smem);
+    OFC_SMEM_OPTIN(csr_walk_kernel<true>, walk_smem);
     csr_walk_kernel<false><<<walk_ctas, 256, walk_smem, st>>>(labels, n, k, table, nullptr);
     OFC_CHECK_LAUNCH("csr_hist");
     const size_t scan_smem = ((size_t)(k >= 1024 ? 1 : 1024 / k) * k + 2 * (size_t)k) * 4;
-    static size_t scan_conf = 0;
-    if (scan_smem > 48 * 1024 && scan_smem > scan_conf) {
-        OFC_CUDA(cudaFuncSetAttribute(csr_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
-        scan_conf = scan_smem;
-    }
+    OFC_SMEM_OPTIN(csr_scan_kernel, scan_smem);
     csr_scan_kernel<<<1, 1024, scan_smem, st>>>(table, w.n_chunks, k, (long long*)counts, seg_first, seg_info, n_segs);
     OFC_CHECK_LAUNCH("csr_scan");
     csr_walk_kernel<true><<<walk_ctas, 256, walk_smem, st>>>(labels, n, k, table, order);

@@ -7,6 +7,8 @@
 // restatement of SURVEY.md Appendix A.3; rounding-sensitive steps use explicit
 // round-to-nearest intrinsics so nvcc cannot contract or reassociate them.
 #include "ofc_common.cuh"
+#include "color_math.cuh"
+#include "grid_kernels.cuh"
 #include "viz_kernels.cuh"
 
 namespace ofc {
@@ -99,6 +101,93 @@ __device__ __forceinline__ void encode_pixel(float fxv, float fyv, float fscale,
     Rr = (unsigned char)(ri < 0 ? 0 : (ri > 255 ? 255 : ri));
 }
 
+// ---------------------------------------------------------------------------
+// The same bytes with far fewer instructions (the production path).  encode_pixel above stays as the
+// plain statement of the arithmetic and as the slow path.
+//   * hue: the byte only needs trunc(hv).  hv is evaluated with a fast reciprocal instead of the two IEEE
+//     divisions and without the rad -> deg round trip: |hv' - hv| < 1e-4 (1-2 ulp in the quotient, at most
+//     four roundings of the conversion chain, on values <= 180).  When hv' is further than 2e-3 from an
+//     integer its truncation is hv's; the few pixels nearer than that run the exact chain.
+//   * value: trunc(v) for 0 <= v < 2^23 is the low mantissa of (v + 2^23) rounded toward zero -- FADD.RZ is
+//     a full-rate instruction, float<->int conversions are quarter rate (rint likewise with FADD.RN).
+//   * HSV -> BGR with S = 255: every channel is  trunc(((V / 255) * m) * 255)  with m one of
+//     {1, 1 - s, 1 - s fr, 1 - s (1 - fr)} chosen by the hue sector.  The three multipliers per hue (0..180)
+//     are a 181-entry table built per CTA with the exact operations of encode_pixel.
+// ---------------------------------------------------------------------------
+constexpr int HUE_TAB = 181;
+
+// table entry H -> (m_b, m_g, m_r): multipliers of v in encode_pixel's sector switch
+__device__ __forceinline__ float4 hue_multipliers(int H) {
+    const float h = __fmul_rn((float)H, 0.033333335f);
+    int sec = (int)floorf(h);
+    const float fr = __fsub_rn(h, (float)sec);
+    sec %= 6;
+    if (sec < 0) sec += 6;
+    const float s = __fmul_rn(255.f, 0.003921569f);
+    const float m0 = 1.f;
+    const float m1 = __fsub_rn(1.f, s);
+    const float m2 = __fsub_rn(1.f, __fmul_rn(s, fr));
+    const float m3 = __fsub_rn(1.f, __fmul_rn(s, __fsub_rn(1.f, fr)));
+    switch (sec) {
+        case 0: return make_float4(m1, m3, m0, 0.f);
+        case 1: return make_float4(m1, m0, m2, 0.f);
+        case 2: return make_float4(m3, m0, m1, 0.f);
+        case 3: return make_float4(m0, m2, m1, 0.f);
+        case 4: return make_float4(m0, m1, m3, 0.f);
+        default: return make_float4(m2, m1, m0, 0.f);
+    }
+}
+
+__device__ __forceinline__ void build_hue_table(float4* tab) {
+    for (int i = threadIdx.x; i < HUE_TAB; i += blockDim.x) tab[i] = hue_multipliers(i);
+}
+
+// exact hue byte (the chain of encode_pixel)
+__device__ __forceinline__ float exact_hue(float fxv, float fyv) {
+    const float rad = __fmul_rn(angle_deg(fxv, fyv), 0.017453292f);
+    const float hv = __fmul_rn(__fdiv_rn(__fmul_rn(rad, 180.f), 3.1415927f), 0.5f);
+    return (float)(int)hv;
+}
+
+// low 8 bits: trunc(y) (or rint(y) for the scalar tail of a row), y clamped at 0, y < 256
+__device__ __forceinline__ unsigned to_byte_bits(float y, bool round_tail) {
+    y = fmaxf(y, 0.f);
+    return __float_as_uint(round_tail ? __fadd_rn(y, 8388608.f) : __fadd_rz(y, 8388608.f));
+}
+
+// one pixel: returns B | G << 8 | R << 16 (and H, V bytes through hv_out when asked: H | 255 << 8 | V << 16)
+__device__ __forceinline__ unsigned encode_pixel_fast(float fxv, float fyv, float fscale, float fshift, bool round_tail,
+                                                      const float4* __restrict__ tab, float& mag, unsigned* hv_out) {
+    mag = magnitude(fxv, fyv);
+    // value byte
+    const float vv = __fmaf_rn(mag, fscale, fshift);
+    float Vf = __fadd_rz(fmaxf(vv, 0.f), 8388608.f) - 8388608.f;
+    Vf = fminf(Vf, 255.f);
+    // hue byte
+    const float ax = fabsf(fxv), ay = fabsf(fyv);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float c = __fdividef(mn, __fadd_rn(mx, 2.220446e-16f));
+    const float c2 = c * c;
+    const float p1 = 57.283627f, p3 = -18.667446f, p5 = 8.9140005f, p7 = -2.5397246f;
+    float a = fmaf(fmaf(fmaf(c2, p7, p5), c2, p3), c2, p1) * c;
+    if (ax < ay) a = 90.f - a;
+    if (fxv < 0.f) a = 180.f - a;
+    if (fyv < 0.f) a = 360.f - a;
+    const float hv = a * 0.5f;
+    float Hf = __fadd_rz(hv, 8388608.f) - 8388608.f;
+    const float frac = hv - Hf;
+    if (!(frac > 2e-3f && frac < 1.f - 2e-3f)) Hf = exact_hue(fxv, fyv);
+    const unsigned Hi = __float_as_uint(Hf + 8388608.f) & 255u;
+    // HSV -> BGR
+    const float4 m = tab[Hi < HUE_TAB ? Hi : HUE_TAB - 1];
+    const float v = __fmul_rn(Vf, 0.003921569f);
+    const unsigned b = to_byte_bits(__fmul_rn(__fmul_rn(v, m.x), 255.f), round_tail);
+    const unsigned g = to_byte_bits(__fmul_rn(__fmul_rn(v, m.y), 255.f), round_tail);
+    const unsigned r = to_byte_bits(__fmul_rn(__fmul_rn(v, m.z), 255.f), round_tail);
+    if (hv_out) *hv_out = Hi | (255u << 8) | ((__float_as_uint(Vf + 8388608.f) & 255u) << 16);
+    return (b & 255u) | ((g & 255u) << 8) | ((r & 255u) << 16);
+}
+
 // x may run past the row end inside a quad: wrap to the next row's column
 __device__ __forceinline__ bool is_tail(int x, int width, int tail_from) {
     if (x >= width) x -= width;
@@ -119,6 +208,10 @@ __global__ void __launch_bounds__(256) flow_encode_kernel(VizParams p) {
     const float fscale = (float)scale;
     const float fshift = -__fmul_rn(mn, fscale);
 
+    __shared__ float4 s_tab[HUE_TAB];
+    build_hue_table(s_tab);
+    __syncthreads();
+    unsigned char* hsv = p.hsv ? p.hsv + (int64_t)frame * p.n_px * 3 : nullptr;
     const int tail_from = p.width - (p.width % 32);
     double local = 0.0;
     const int64_t n_quads = (p.n_px + 3) / 4;
@@ -128,24 +221,33 @@ __global__ void __launch_bounds__(256) flow_encode_kernel(VizParams p) {
         if (px + 3 < p.n_px && aligned) {
             const float4* f4 = reinterpret_cast<const float4*>(flow + px);
             float4 a = f4[0], b = f4[1];
-            unsigned char c[12];
             float m0, m1, m2, m3;
+            unsigned h0, h1, h2, h3;
             const int x = (int)((unsigned)px % (unsigned)p.width);          // a frame has < 2^32 pixels
-            encode_pixel(a.x, a.y, fscale, fshift, is_tail(x, p.width, tail_from), c[0], c[1], c[2], m0);
-            encode_pixel(a.z, a.w, fscale, fshift, is_tail(x + 1, p.width, tail_from), c[3], c[4], c[5], m1);
-            encode_pixel(b.x, b.y, fscale, fshift, is_tail(x + 2, p.width, tail_from), c[6], c[7], c[8], m2);
-            encode_pixel(b.z, b.w, fscale, fshift, is_tail(x + 3, p.width, tail_from), c[9], c[10], c[11], m3);
+            const unsigned c0 = encode_pixel_fast(a.x, a.y, fscale, fshift, is_tail(x, p.width, tail_from), s_tab, m0, hsv ? &h0 : nullptr);
+            const unsigned c1 = encode_pixel_fast(a.z, a.w, fscale, fshift, is_tail(x + 1, p.width, tail_from), s_tab, m1, hsv ? &h1 : nullptr);
+            const unsigned c2 = encode_pixel_fast(b.x, b.y, fscale, fshift, is_tail(x + 2, p.width, tail_from), s_tab, m2, hsv ? &h2 : nullptr);
+            const unsigned c3 = encode_pixel_fast(b.z, b.w, fscale, fshift, is_tail(x + 3, p.width, tail_from), s_tab, m3, hsv ? &h3 : nullptr);
             unsigned* o = reinterpret_cast<unsigned*>(out + px * 3);
-            o[0] = c[0] | (c[1] << 8) | (c[2] << 16) | ((unsigned)c[3] << 24);
-            o[1] = c[4] | (c[5] << 8) | (c[6] << 16) | ((unsigned)c[7] << 24);
-            o[2] = c[8] | (c[9] << 8) | (c[10] << 16) | ((unsigned)c[11] << 24);
+            o[0] = c0 | (c1 << 24);
+            o[1] = (c1 >> 8) | (c2 << 16);
+            o[2] = (c2 >> 16) | (c3 << 8);
+            if (hsv) {
+                unsigned* ho = reinterpret_cast<unsigned*>(hsv + px * 3);
+                ho[0] = h0 | (h1 << 24);
+                ho[1] = (h1 >> 8) | (h2 << 16);
+                ho[2] = (h2 >> 16) | (h3 << 8);
+            }
             local += (double)m0 + (double)m1 + (double)m2 + (double)m3;
         } else {
             for (int64_t i = px; i < px + 4 && i < p.n_px; ++i) {
                 float2 f = flow[i];
                 float m;
-                encode_pixel(f.x, f.y, fscale, fshift, (int)((unsigned)i % (unsigned)p.width) >= tail_from, out[i * 3], out[i * 3 + 1],
-                             out[i * 3 + 2], m);
+                unsigned hh;
+                const unsigned c = encode_pixel_fast(f.x, f.y, fscale, fshift, (int)((unsigned)i % (unsigned)p.width) >= tail_from, s_tab, m,
+                                                     hsv ? &hh : nullptr);
+                out[i * 3] = (unsigned char)c; out[i * 3 + 1] = (unsigned char)(c >> 8); out[i * 3 + 2] = (unsigned char)(c >> 16);
+                if (hsv) { hsv[i * 3] = (unsigned char)hh; hsv[i * 3 + 1] = 255; hsv[i * 3 + 2] = (unsigned char)(hh >> 16); }
                 local += (double)m;
             }
         }
@@ -164,6 +266,132 @@ __global__ void __launch_bounds__(256) flow_encode_kernel(VizParams p) {
             // into a double by mag_sum_finalize_kernel.  A frame's sum of |flow| stays far below 2^35.
             atomicAdd(reinterpret_cast<unsigned long long*>(p.mag_sum) + frame,
                       (unsigned long long)(t * 268435456.0 + 0.5));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Visualisation + grid pass fused: one CTA per (grid cell, frame) encodes the cell's pixels (and the frame's
+// right / bottom remainder next to the last column / row of cells), writes the BGR bytes once and keeps the
+// per-cell sums of overlayGridAndComputeAvgColor and of the k = 1 colour cluster in registers -- the
+// visualisation is never read back (grid_cells_kernel's arithmetic, KmeanGrids.py:52-113, 269-339).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flow_encode_grid_kernel(VizParams p, GridParams gp) {
+    const int cell = blockIdx.x, frame = blockIdx.y;
+    const int cy = cell / gp.cols, cx = cell - cy * gp.cols;
+    const int W = gp.W, H = gp.H;
+    const int x1 = cx * gp.x_step, y1 = cy * gp.y_step;
+    const int cw = min(x1 + gp.x_step, W) - x1, chh = min(y1 + gp.y_step, H) - y1;          // the cell proper
+    const int rw = (cx == gp.cols - 1 ? W : x1 + gp.x_step) - x1;                           // region this CTA encodes
+    const int rh = (cy == gp.rows - 1 ? H : y1 + gp.y_step) - y1;
+    const float2* flow = p.flow + (int64_t)frame * p.n_px;
+    unsigned char* out = p.bgr + (int64_t)frame * p.n_px * 3;
+    const float mn = __uint_as_float(p.minmax[2 * frame]), mxv = __uint_as_float(p.minmax[2 * frame + 1]);
+    const double range = (double)mxv - (double)mn;
+    const double scale = 255.0 * (range > 2.220446049250313e-16 ? 1.0 / range : 0.0);
+    const float fscale = (float)scale;
+    const float fshift = -__fmul_rn(mn, fscale);
+    __shared__ float4 s_tab[HUE_TAB];
+    build_hue_table(s_tab);
+    __syncthreads();
+    const int tail_from = W - (W % 32);
+    const bool mean_row = gp.draw_lines && cy > 0, mean_col = gp.draw_lines && cx > 0;
+
+    unsigned sa[3] = {0, 0, 0}, sb[4] = {0, 0, 0, 0};
+    double local = 0.0;
+    auto add_pixel = [&](unsigned c, int ly, int lx) {
+        if (ly >= chh || lx >= cw) return;                       // remainder pixels belong to no cell
+        const unsigned c0 = c & 255u, c1 = (c >> 8) & 255u, c2 = (c >> 16) & 255u;
+        const bool wa = (ly == 0 && mean_row) || (lx == 0 && mean_col);
+        sa[0] += wa ? 255u : c0; sa[1] += wa ? 255u : c1; sa[2] += wa ? 255u : c2;
+        const bool wb = gp.draw_lines && (ly == 0 || lx == 0);
+        unsigned k0 = wb ? 255u : c0, k1 = wb ? 255u : c1, k2 = wb ? 255u : c2;
+        if (gp.threshold) {
+            k0 = k0 < (unsigned)gp.threshold ? 0u : k0;
+            k1 = k1 < (unsigned)gp.threshold ? 0u : k1;
+            k2 = k2 < (unsigned)gp.threshold ? 0u : k2;
+        }
+        const unsigned gray = (3735u * k0 + 19235u * k1 + 9798u * k2 + 16384u) >> 15;
+        sb[0] += k0; sb[1] += k1; sb[2] += k2; sb[3] += gray > 0 ? 1u : 0u;
+    };
+    const bool quads = (rw & 3) == 0 && (x1 & 3) == 0 && (W & 3) == 0 && ((uintptr_t)p.flow & 15) == 0 && ((uintptr_t)p.bgr & 3) == 0 &&
+                       (p.n_px & 3) == 0;
+    if (quads) {
+        const int qpr = rw >> 2;
+        const int rows_per_pass = 256 / qpr > 0 ? 256 / qpr : 1;
+        const int lq = threadIdx.x % qpr, ly0 = threadIdx.x / qpr;
+        if (ly0 < rows_per_pass) {
+            for (int ly = ly0; ly < rh; ly += rows_per_pass) {
+                for (int q = lq; q < qpr; q += 256) {            // one step unless a region row is wider than 1024 px
+                    const int x = x1 + q * 4;
+                    const int64_t px = (int64_t)(y1 + ly) * W + x;
+                    const float4* f4 = reinterpret_cast<const float4*>(flow + px);
+                    const float4 a = f4[0], b = f4[1];
+                    float m0, m1, m2, m3;
+                    const unsigned c0 = encode_pixel_fast(a.x, a.y, fscale, fshift, x >= tail_from, s_tab, m0, nullptr);
+                    const unsigned c1 = encode_pixel_fast(a.z, a.w, fscale, fshift, x + 1 >= tail_from, s_tab, m1, nullptr);
+                    const unsigned c2 = encode_pixel_fast(b.x, b.y, fscale, fshift, x + 2 >= tail_from, s_tab, m2, nullptr);
+                    const unsigned c3 = encode_pixel_fast(b.z, b.w, fscale, fshift, x + 3 >= tail_from, s_tab, m3, nullptr);
+                    unsigned* o = reinterpret_cast<unsigned*>(out + px * 3);
+                    o[0] = c0 | (c1 << 24);
+                    o[1] = (c1 >> 8) | (c2 << 16);
+                    o[2] = (c2 >> 16) | (c3 << 8);
+                    local += (double)m0 + (double)m1 + (double)m2 + (double)m3;
+                    add_pixel(c0, ly, q * 4); add_pixel(c1, ly, q * 4 + 1); add_pixel(c2, ly, q * 4 + 2); add_pixel(c3, ly, q * 4 + 3);
+                }
+            }
+        }
+    } else {
+        const int n_reg = rw * rh;
+        for (int i = threadIdx.x; i < n_reg; i += 256) {
+            const int ly = i / rw, lx = i - ly * rw;
+            const int64_t px = (int64_t)(y1 + ly) * W + x1 + lx;
+            const float2 f = flow[px];
+            float m;
+            const unsigned c = encode_pixel_fast(f.x, f.y, fscale, fshift, x1 + lx >= tail_from, s_tab, m, nullptr);
+            out[px * 3] = (unsigned char)c; out[px * 3 + 1] = (unsigned char)(c >> 8); out[px * 3 + 2] = (unsigned char)(c >> 16);
+            local += (double)m;
+            add_pixel(c, ly, lx);
+        }
+    }
+    // cell results (grid_cells_kernel's tail) and the frame's magnitude sum
+    __shared__ unsigned s_red[8][7];
+    __shared__ double s_part[8];
+    unsigned vals[7] = {sa[0], sa[1], sa[2], sb[0], sb[1], sb[2], sb[3]};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        unsigned v = vals[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        vals[k] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 7; ++k) s_red[threadIdx.x >> 5][k] = vals[k];
+        s_part[threadIdx.x >> 5] = local;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t[7] = {0, 0, 0, 0, 0, 0, 0};
+        double tm = 0.0;
+        for (int wv = 0; wv < 8; ++wv) {
+            for (int k = 0; k < 7; ++k) t[k] += s_red[wv][k];
+            tm += s_part[wv];
+        }
+        if (p.mag_sum)
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.mag_sum) + frame, (unsigned long long)(tm * 268435456.0 + 0.5));
+        const int n = cw * chh;
+        const int64_t o = (int64_t)frame * gridDim.x + cell;
+        if (n > 0) {
+            const unsigned a0 = t[0] / n, a1 = t[1] / n, a2 = t[2] / n;           // floor: .astype(uint8)
+            if (gp.avg_bgr) { gp.avg_bgr[o * 3] = (unsigned char)a0; gp.avg_bgr[o * 3 + 1] = (unsigned char)a1; gp.avg_bgr[o * 3 + 2] = (unsigned char)a2; }
+            if (gp.avg_hue) gp.avg_hue[o] = (unsigned char)hue_of_bgr((int)a0, (int)a1, (int)a2);
+            const unsigned k0 = rint_div(t[3], n), k1 = rint_div(t[4], n), k2 = rint_div(t[5], n);
+            const unsigned k3 = rint_div((unsigned long long)t[6] * 255ull, n);
+            if (gp.km_centre) { gp.km_centre[o * 4] = (unsigned char)k0; gp.km_centre[o * 4 + 1] = (unsigned char)k1; gp.km_centre[o * 4 + 2] = (unsigned char)k2; gp.km_centre[o * 4 + 3] = (unsigned char)k3; }
+            if (gp.km_hue) gp.km_hue[o] = (unsigned char)hue_of_bgr((int)k0, (int)k1, (int)k2);
+            if (gp.km_sums) { gp.km_sums[o * 4] = t[3]; gp.km_sums[o * 4 + 1] = t[4]; gp.km_sums[o * 4 + 2] = t[5]; gp.km_sums[o * 4 + 3] = t[6] * 255u; }
         }
     }
 }
@@ -217,6 +445,18 @@ int launch_flow_encode(const VizParams& p, int n_frames, void* stream) {
     ProfScope prof(PK_ENCODE, stream);
     OFC_LAUNCH(flow_encode_kernel, dim3(bx, n_frames), dim3(256), 0, stream, p);
     OFC_CHECK_LAUNCH("flow_encode");
+    if (p.mag_sum) {
+        OFC_LAUNCH(mag_sum_finalize_kernel, dim3(cdiv(n_frames, 128)), dim3(128), 0, stream, p.mag_sum, n_frames);
+        OFC_CHECK_LAUNCH("mag_sum_finalize");
+    }
+    return OFC_OK;
+}
+
+int launch_flow_encode_grid(const VizParams& p, const GridParams& gp, int n_frames, void* stream) {
+    if (n_frames <= 0 || p.n_px <= 0) return OFC_OK;
+    ProfScope prof(PK_ENCODE, stream);
+    OFC_LAUNCH(flow_encode_grid_kernel, dim3(gp.rows * gp.cols, n_frames), dim3(256), 0, stream, p, gp);
+    OFC_CHECK_LAUNCH("flow_encode_grid");
     if (p.mag_sum) {
         OFC_LAUNCH(mag_sum_finalize_kernel, dim3(cdiv(n_frames, 128)), dim3(128), 0, stream, p.mag_sum, n_frames);
         OFC_CHECK_LAUNCH("mag_sum_finalize");

@@ -206,7 +206,8 @@ def flow_minmax(flow: torch.Tensor) -> torch.Tensor:
     return mm
 
 
-def flow_to_bgr(flow: torch.Tensor, minmax: torch.Tensor | None = None, want_mean_magnitude: bool = False):
+def flow_to_bgr(flow: torch.Tensor, minmax: torch.Tensor | None = None, want_mean_magnitude: bool = False,
+                want_hsv: bool = False):
     """cartToPolar + hue byte + NORM_MINMAX + HSV2BGR (computeOpticalFlowModule.py:25-33).
 
     flow f32 [n,H,W,2] (CUDA) -> BGR u8 [n,H,W,3] (and mean |flow| per frame f64[n]).
@@ -218,6 +219,12 @@ def flow_to_bgr(flow: torch.Tensor, minmax: torch.Tensor | None = None, want_mea
     if minmax is None:
         minmax = flow_minmax(f)
     bgr = torch.empty((n, H, W, 3), dtype=torch.uint8, device=f.device)
+    if want_hsv:
+        # also the HSV `mask` of the reference (H, 255, V): returns (bgr, hsv)
+        hsv = torch.empty_like(bgr)
+        with torch.cuda.device(f.device):
+            _lib.check(_lib.lib().ofc_flow_to_hsv(_ptr(f), n, H, W, _ptr(minmax), _ptr(bgr), _ptr(hsv), _stream_ptr()))
+        return bgr, hsv
     mag = torch.empty(n, dtype=torch.float64, device=f.device) if want_mean_magnitude else None
     with torch.cuda.device(f.device):
         _lib.check(_lib.lib().ofc_flow_to_bgr(_ptr(f), n, H, W, _ptr(minmax), _ptr(bgr), _ptr(mag), _stream_ptr()))

@@ -24,7 +24,14 @@ class ClipPipeline:
     def __init__(self, width: int, height: int, chunk_frames: int = 9, rows: int = 14, cols: int = 25,
                  draw_lines: bool = True, threshold: int = 30, device=None, keep_viz: bool = False,
                  pyr_scale: float = 0.5, levels: int = 3, winsize: int = 15, iterations: int = 3,
-                 poly_n: int = 5, poly_sigma: float = 1.2):
+                 poly_n: int = 5, poly_sigma: float = 1.2, n_clusters: int = 1, kmeans_seed: int = 0,
+                 kmeans_max_iter: int = 300, kmeans_tol: float = 1e-4):
+        """``n_clusters``: the reference's ``-c`` (KmeanGrids.py:248-250).  1 (every documented command): the per-cell
+        k-means centre is the cell mean and rides the grid pass.  k > 1: every cell of every pair gets its own
+        ``KMeans(n_clusters=k)`` fit (k-means++ from ``kmeans_seed`` -- the reference leaves ``random_state`` unset)
+        on the device, straight from the visualisation (``ofc_grid_kmeans_cells``); ``km_centre`` / ``km_hue`` then
+        hold the largest cluster's rounded centre and its hue (KmeanGrids.py:299-339), ``km_n_iter`` the Lloyd
+        iterations per cell."""
         self.W, self.H, self.F = int(width), int(height), int(chunk_frames)
         if self.F < 2:
             raise ValueError("chunk_frames must be >= 2")
@@ -45,6 +52,20 @@ class ClipPipeline:
         self.km_centre = torch.empty((P, self.cells, 4), dtype=torch.uint8, device=dev)
         self.km_hue = torch.empty((P, self.cells), dtype=torch.uint8, device=dev)
         self.keep_viz = keep_viz
+        import os
+        self.fuse_grid = os.environ.get("OFC_FUSE_GRID", "1") != "0"
+        self.n_clusters = int(n_clusters)
+        if self.n_clusters < 1:
+            raise ValueError("n_clusters must be >= 1")
+        self.kmeans_seed, self.kmeans_max_iter, self.kmeans_tol = int(kmeans_seed), int(kmeans_max_iter), float(kmeans_tol)
+        self.km_n_iter = None
+        self._km_ws = None
+        self._pairs_done = 0             # pairs processed so far: the k-means++ stream is indexed by absolute pair number
+        if self.n_clusters > 1:
+            L = _lib.lib()
+            self.km_n_iter = torch.empty((P, self.cells), dtype=torch.int32, device=dev)
+            nb = int(L.ofc_grid_kmeans_cells_workspace_bytes(P, self.H, self.W, self.rows, self.cols, self.n_clusters))
+            self._km_ws = torch.empty(max(nb, 8), dtype=torch.uint8, device=dev)
         self._last_gray_index = None     # where the last processed frame's gray image sits in self.gray
         #: kernels launched by one full-chunk call of :meth:`run_chunk`
         self.launches_per_chunk = 1 + 2 * self.plan.num_levels + 1 + self.plan.num_levels * iterations + 1 + 1
@@ -81,11 +102,27 @@ class ClipPipeline:
             self._last_gray_index = n - 1
             _lib.check(L.ofc_farneback_sequence(self.plan._ptr, _ptr(self.gray), n, _ptr(self.flow), _ptr(self.minmax),
                                                 _ptr(self.plan.workspace), self.plan.workspace_bytes, s))
-            _lib.check(L.ofc_flow_to_bgr(_ptr(self.flow), P, self.H, self.W, _ptr(self.minmax), _ptr(self.viz),
-                                         _ptr(self.mag_sum), s))
-            _lib.check(L.ofc_grid_cells(_ptr(self.viz), P, self.H, self.W, self.rows, self.cols, self.draw_lines,
-                                        self.threshold, _ptr(self.avg_bgr), _ptr(self.avg_hue), _ptr(self.km_centre),
-                                        _ptr(self.km_hue), C.c_void_p(0), s))
+            k1 = self.n_clusters == 1
+            kc = _ptr(self.km_centre) if k1 else C.c_void_p(0)
+            kh = _ptr(self.km_hue) if k1 else C.c_void_p(0)
+            if self.fuse_grid:
+                # visualisation + grid pass in one kernel: the BGR bytes are written once and not read back
+                _lib.check(L.ofc_flow_to_bgr_grid(_ptr(self.flow), P, self.H, self.W, _ptr(self.minmax), _ptr(self.viz),
+                                                  _ptr(self.mag_sum), self.rows, self.cols, self.draw_lines, self.threshold,
+                                                  _ptr(self.avg_bgr), _ptr(self.avg_hue), kc, kh, s))
+            else:
+                _lib.check(L.ofc_flow_to_bgr(_ptr(self.flow), P, self.H, self.W, _ptr(self.minmax), _ptr(self.viz),
+                                             _ptr(self.mag_sum), s))
+                _lib.check(L.ofc_grid_cells(_ptr(self.viz), P, self.H, self.W, self.rows, self.cols, self.draw_lines,
+                                            self.threshold, _ptr(self.avg_bgr), _ptr(self.avg_hue), kc, kh, C.c_void_p(0), s))
+            if not k1:
+                first = 0 if not carry else self._pairs_done
+                _lib.check(L.ofc_grid_kmeans_cells(_ptr(self.viz), P, self.H, self.W, self.rows, self.cols, self.draw_lines,
+                                                   self.threshold, 0, self.n_clusters, C.c_uint64(self.kmeans_seed),
+                                                   C.c_uint64(first), self.kmeans_max_iter, C.c_double(self.kmeans_tol),
+                                                   _ptr(self.km_centre), _ptr(self.km_hue), C.c_void_p(0), C.c_void_p(0),
+                                                   _ptr(self.km_n_iter), _ptr(self._km_ws), C.c_size_t(self._km_ws.numel()), s))
+            self._pairs_done = (self._pairs_done if carry else 0) + P
         return P
 
     def process_clip(self, frames, pinned_out: torch.Tensor | None = None):
@@ -125,6 +162,7 @@ class ClipPipeline:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ofc_bgr2gray(_ptr(f), _ptr(self.gray), self.H * self.W, _stream_ptr()))
         self._last_gray_index = 0
+        self._pairs_done = 0
 
     def process_stream(self, frames, on_pairs=None, want_viz: bool = False, nbuf: int = 3):
         """Streaming ingest: ``frames`` is any iterable of host BGR uint8 frames

@@ -124,3 +124,72 @@ def rint_mean_exact(sum_int: np.ndarray, n: int) -> np.ndarray:
     q, r = np.divmod(s, n)
     up = (2 * r > n) | ((2 * r == n) & (q % 2 == 1))
     return q + up.astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# k-means++ seeding of the DEVICE-RESIDENT per-cell fits (ofc_kmeans_cells / ofc_grid_kmeans_cells with
+# init = NULL).  The procedure is scikit-learn's (sklearn/cluster/_kmeans.py:181-268: first centre uniform,
+# then 2 + int(log k) candidates per step drawn in proportion to the squared distance to the closest chosen
+# centre, keep the candidate with the lowest potential); the RANDOM STREAM is the build's own counter-based
+# one (splitmix64 of (seed, problem index)) because the reference leaves random_state unset,
+# so there is no sklearn output to pin it to: this restatement in numpy integers is the independent check
+# of the CUDA kernels' seeding.  The sklearn-RNG-exact seeding is kmeans.kmeans_plusplus (host loop).
+# ---------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def cells_seed_indices(X: np.ndarray, k: int, seed: int, problem: int) -> np.ndarray:
+    """Row indices the device-resident seeding picks for problem number ``problem`` (uint8 rows [n, d])."""
+    import math
+    Xi = X.astype(np.int64)
+    n = Xi.shape[0]
+    state = [_splitmix64((seed ^ ((0xD1B54A32D192ED03 * (problem + 1)) & _M64)) & _M64)]
+
+    def uniform():
+        state[0] = _splitmix64(state[0])
+        return float(state[0] >> 11) * (1.0 / 9007199254740992.0)
+
+    def dist_to(i):
+        return ((Xi - Xi[i]) ** 2).sum(axis=1)
+
+    trials = 2 + int(math.log(k))
+    first = min(int(uniform() * float(n)), n - 1)
+    idx = [first]
+    closest = dist_to(first)
+    for _ in range(1, k):
+        pot = int(closest.sum())
+        cum = np.cumsum(closest).astype(np.float64)           # exact: < 2^53
+        cands = []
+        for _t in range(trials):
+            r = uniform() * float(pot)
+            cands.append(min(int(np.searchsorted(cum, r, side="right")), n - 1))      # first row with r < running sum
+        pots = [int(np.minimum(closest, dist_to(c)).sum()) for c in cands]
+        best = cands[int(np.argmin(pots))]                    # first lowest
+        idx.append(best)
+        closest = np.minimum(closest, dist_to(best))
+    return np.array(idx, np.int64)
+
+
+def cells_fit(X: np.ndarray, k: int, seed: int, problem: int, max_iter: int = 300, tol: float = 1e-4):
+    """One device-resident per-cell fit: seeding above, then :func:`kmeans_fit`.  Returns
+    ``(labels, centers, inertia, n_iter, seed_indices)``."""
+    idx = cells_seed_indices(X, k, seed, problem)
+    lab, cen, inertia, n_iter = kmeans_fit(X, X[idx].astype(np.float64), max_iter=max_iter, tol=tol)
+    return lab, cen, inertia, n_iter, idx
+
+
+def dominant_centre_hue(X: np.ndarray, labels: np.ndarray, centers: np.ndarray):
+    """Largest cluster (first on equal shares) -> np.rint -> uint8 BGR -> cv2 BGR2HSV hue
+    (reference KmeanGrids.py:304-336)."""
+    from . import viz_np
+    counts = np.bincount(labels, minlength=centers.shape[0])
+    c = np.rint(centers[int(np.argmax(counts))])
+    hue = viz_np.bgr2hsv_u8(c[:3].astype(np.uint8).reshape(1, 1, 3))[0, 0, 0]
+    return c, int(hue)

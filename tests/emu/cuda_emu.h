@@ -283,6 +283,14 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+// round-toward-zero float add: the double sum of two floats is exact here (exponents < 2^29 apart)
+static inline float __fadd_rz(float a, float b) {
+    const double d = (double)a + (double)b;
+    float r = (float)d;
+    if (std::fabs((double)r) > std::fabs(d)) r = std::nextafterf(r, 0.0f);
+    return r;
+}
+static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }

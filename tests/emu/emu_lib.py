@@ -145,3 +145,34 @@ def draw_grid(bgr, rows, cols):
     n, H, W, _ = bgr.shape
     _check(lib().ofc_draw_grid(_p(bgr), n, H, W, rows, cols, C.c_void_p(0)))
     return bgr
+
+
+def flow_to_bgr_grid(flow, rows, cols, minmax=None, draw_lines=1, threshold=30):
+    """the fused visualisation + grid kernel; returns (bgr, mag_sum, grid outputs)"""
+    flow = np.ascontiguousarray(flow, np.float32)
+    n, H, W = flow.shape[:3]
+    if minmax is None:
+        minmax = np.zeros((n, 2), np.uint32)
+        _check(lib().ofc_flow_minmax(_p(flow), n, C.c_int64(H * W), _p(minmax), C.c_void_p(0)))
+    bgr = np.zeros((n, H, W, 3), np.uint8)
+    mag = np.zeros(n, np.float64)
+    cells = rows * cols
+    out = dict(avg_bgr=np.zeros((n, cells, 3), np.uint8), avg_hue=np.zeros((n, cells), np.uint8),
+               km_centre=np.zeros((n, cells, 4), np.uint8), km_hue=np.zeros((n, cells), np.uint8))
+    _check(lib().ofc_flow_to_bgr_grid(_p(flow), n, H, W, _p(minmax), _p(bgr), _p(mag), rows, cols, draw_lines, threshold,
+                                      _p(out["avg_bgr"]), _p(out["avg_hue"]), _p(out["km_centre"]), _p(out["km_hue"]),
+                                      C.c_void_p(0)))
+    return bgr, mag, out
+
+
+def flow_to_hsv(flow, minmax=None):
+    """BGR visualisation + the reference's `mask` (H, 255, V)"""
+    flow = np.ascontiguousarray(flow, np.float32)
+    n, H, W = flow.shape[:3]
+    if minmax is None:
+        minmax = np.zeros((n, 2), np.uint32)
+        _check(lib().ofc_flow_minmax(_p(flow), n, C.c_int64(H * W), _p(minmax), C.c_void_p(0)))
+    bgr = np.zeros((n, H, W, 3), np.uint8)
+    hsv = np.zeros((n, H, W, 3), np.uint8)
+    _check(lib().ofc_flow_to_hsv(_p(flow), n, H, W, _p(minmax), _p(bgr), _p(hsv), C.c_void_p(0)))
+    return bgr, hsv

@@ -133,6 +133,12 @@ for (H, W) in [(61, 250), (101, 150)]:
     ref = FB.calc_optical_flow_farneback(g[0], g[1])
     e = np.linalg.norm(f - ref, axis=-1)
     assert e.mean() < 2e-6 and e.max() < 2e-4, (H, W, e.mean(), e.max())
+    if os.environ.get("OFC_ITER_TMEM") == "1":
+        # the coarse flow up-sampled inside the walk (default) == the separate up-sample launch, bit for bit
+        os.environ["OFC_FUSE_UPSAMPLE"] = "0"
+        f2 = E.Plan(W, H, max_frames=2).sequence(g)[0]
+        del os.environ["OFC_FUSE_UPSAMPLE"]
+        assert (f2 == f).all(), (H, W, np.abs(f2 - f).max())
 print("ok")
 '''
     e = dict(os.environ)
@@ -140,3 +146,70 @@ print("ok")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_emu_pyramid_prefilter_equals_tile_kernel(monkeypatch):
+    """the one-launch pyramid pre-filter (levels that are an exact 1/2, 1/4, 1/8 of the frame) writes the bits of the
+    per-level tile kernel, and both match the oracle's GaussianBlur + resize"""
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    H, W = 256, 328                                     # 328 = 8 * 41: ragged last column block, not a multiple of 16
+    g = E.bgr2gray(synthetic_clip(2, H, W, seed=23).numpy())
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("OFC_PREFILTER_PYR", mode)
+        pl = E.Plan(W, H, max_frames=2, iterations=1)
+        assert pl.n_levels == 4
+        pl.sequence(g)
+        got[mode] = [pl.buffer(l, 0, f)[..., 0].copy() for l in range(pl.n_levels) for f in range(2)]
+    monkeypatch.delenv("OFC_PREFILTER_PYR")
+    for a, b in zip(got["1"], got["0"]):
+        assert a.shape == b.shape and (a == b).all()
+    _, inter = FB.calc_optical_flow_farneback(g[0], g[1], iterations=1, return_intermediates=True)
+    for l, it in enumerate(inter):
+        assert np.abs(got["1"][2 * l] - it["I0"]).max() < 1e-4
+
+
+def test_emu_fast_encode_exhaustive_hue_boundaries():
+    """the fast visualisation arithmetic (approximate hue with exact re-evaluation near byte boundaries, FADD.RZ
+    truncation, per-hue multiplier table) against the oracle's statement of cv2 on flows chosen to sit ON the
+    boundaries: every hue byte edge, axis-aligned and zero vectors, magnitudes at value-byte edges"""
+    rng = np.random.default_rng(5)
+    ang = np.concatenate([np.arange(0, 360, 2.0), np.arange(0, 360, 2.0) + 1e-4, np.arange(0, 360, 2.0) - 1e-4,
+                          rng.uniform(0, 360, 4000)])
+    mag = rng.uniform(0.01, 9.0, ang.size)
+    mag[:97] = np.linspace(0, 9, 97)                               # includes the exact minimum and maximum
+    fx = (mag * np.cos(np.deg2rad(ang))).astype(np.float32)
+    fy = (mag * np.sin(np.deg2rad(ang))).astype(np.float32)
+    fx[100:110] = 0.0
+    fy[110:120] = 0.0
+    fx[120], fy[120] = 0.0, 0.0
+    n = fx.size - fx.size % 33
+    flow = np.stack([fx[:n], fy[:n]], -1).reshape(1, n // 33, 33, 2)           # width 33: one scalar-tail pixel per row
+    bgr, mag_sum, _ = E.flow_to_bgr(flow)
+    want, m = V.flow_to_bgr(flow[0])
+    assert (bgr[0] == want).all()
+    assert abs(mag_sum[0] - m.astype(np.float64).sum()) <= 1e-9 * m.sum()
+    bgr2, hsv = E.flow_to_hsv(flow)
+    assert (bgr2 == bgr).all()
+    mg, an = V.cart_to_polar(flow[0, ..., 0], flow[0, ..., 1])
+    assert (hsv[0, ..., 0] == V.hue_byte(an)).all() and (hsv[0, ..., 1] == 255).all()
+    assert (hsv[0, ..., 2] == V.normalize_minmax_u8(mg)).all()
+
+
+@pytest.mark.parametrize("shape", [(2, 135, 240, 14, 25), (1, 77, 100, 3, 4), (1, 64, 96, 4, 6)])
+def test_emu_fused_encode_grid_equals_separate_kernels(shape):
+    """ofc_flow_to_bgr_grid == ofc_flow_to_bgr followed by ofc_grid_cells: quad path (cells a multiple of 4 wide),
+    scalar path, and grids that leave a right / bottom remainder"""
+    n, H, W, rows, cols = shape
+    if (H, W) == (135, 240):
+        flow = np.load(os.path.join(GOLDEN, "flow_135x240.npz"))["flow"][:n]
+    else:
+        rng = np.random.default_rng(H)
+        flow = rng.normal(0, 2.0, (n, H, W, 2)).astype(np.float32)
+    bgr, mag, mm = E.flow_to_bgr(flow)
+    want = E.grid_cells(bgr, rows, cols)
+    bgr2, mag2, got = E.flow_to_bgr_grid(flow, rows, cols, minmax=mm)
+    assert (bgr2 == bgr).all()
+    assert np.abs(mag2 - mag).max() <= 1e-9 * np.abs(mag).max()
+    for k in got:
+        assert (got[k] == want[k]).all(), k

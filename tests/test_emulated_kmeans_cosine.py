@@ -272,3 +272,105 @@ def test_extract_cells_matches_reference_rois(L):
         for c, roi in enumerate(rois):
             want = G.preprocess_image(roi.copy()).reshape(-1, 4)
             assert (out[f, c] == want).all()
+
+
+def _cells_both(L, X, k, monkeypatch, **kw):
+    """the same problems through the shared-memory / filtered kernel (cells_kmeans.cu) and the first kernel"""
+    monkeypatch.setenv("OFC_CELLS_FAST", "1")
+    fast = km.lloyd_cells(X, k, _lib_override=L, **kw)
+    monkeypatch.setenv("OFC_CELLS_FAST", "0")
+    slow = km.lloyd_cells(X, k, _lib_override=L, **kw)
+    monkeypatch.delenv("OFC_CELLS_FAST")
+    return fast, slow
+
+
+@pytest.mark.parametrize("k", [1, 3, 8, 13])
+def test_cells_fast_kernel_is_bit_identical_to_the_first_kernel(L, k, monkeypatch):
+    """labels, centres, inertia, n_iter, counts: identical bits, with given centres and with k-means++ seeding"""
+    rng = np.random.default_rng(40 + k)
+    B, n = 4, 700
+    cen = rng.uniform(10, 240, (B, max(k, 2), 4))
+    X = np.clip(np.rint(cen[np.arange(B)[:, None], rng.integers(max(k, 2), size=(B, n))] + rng.normal(0, 14, (B, n, 4))), 0, 255).astype(np.uint8)
+    X[3] = rng.integers(0, 256, (n, 4), dtype=np.uint8)            # one unclustered problem: many iterations, near-ties
+    init = X[:, :k].astype(np.float64)
+    for kw in ({"init": init}, {"seed": 5}):
+        fast, slow = _cells_both(L, X, k, monkeypatch, **kw)
+        for u, v in zip(fast, slow):
+            assert torch.equal(u, v)
+    lab, cen_d, inertia, n_iter, counts = fast
+    assert int(n_iter.max()) > 1 or k == 1
+
+
+def test_cells_fast_kernel_degenerate_cells(L, monkeypatch):
+    """fewer distinct colours than clusters (a black cell with its white grid lines): relocation of empty clusters,
+    exact ties between duplicated centres -- still the first kernel's bits, and the oracle's labels for a given init"""
+    n = 26 * 25
+    X = np.zeros((3, n, 4), np.uint8)
+    X[0, :60] = 255                                                 # two colours
+    X[1, :] = (40, 90, 200, 255)                                    # one colour
+    X[2, ::3] = (255, 0, 0, 255); X[2, 1::3] = (0, 255, 0, 255)     # three colours, integer-symmetric (exact ties)
+    for k in (2, 8):
+        for kw in ({"seed": 1}, {"init": X[:, :k].astype(np.float64)}):
+            fast, slow = _cells_both(L, X, k, monkeypatch, **kw)
+            for u, v in zip(fast, slow):
+                assert torch.equal(u, v)
+    init = X[:, :2].astype(np.float64)
+    lab = km.lloyd_cells(X, 2, init=init, _lib_override=L)[0]
+    for b in range(3):
+        assert (lab[b].numpy() == K.kmeans_fit(X[b], init[b])[0]).all()
+
+
+def test_grid_kmeans_cells_fused_equals_gather_then_cluster(L):
+    """ofc_grid_kmeans_cells (cells gathered inside the k-means kernel) == ofc_grid_extract_cells + ofc_kmeans_cells
+    + the host-side dominant-cluster rule, and first_frame shifts the random stream as documented"""
+    import ctypes as C
+    rng = np.random.default_rng(50)
+    F, H, W, rows, cols, k = 2, 50, 66, 3, 4, 3
+    base = rng.integers(0, 256, (F, rows, cols, 1, 1, 3))
+    img = np.clip(np.repeat(np.repeat(base, H // rows, 3), W // cols, 4).transpose(0, 1, 3, 2, 4, 5).reshape(F, rows * (H // rows), cols * (W // cols), 3)
+                  + rng.normal(0, 25, (F, rows * (H // rows), cols * (W // cols), 3)), 0, 255).astype(np.uint8)
+    frames = np.zeros((F, H, W, 3), np.uint8)
+    frames[:, :img.shape[1], :img.shape[2]] = img
+    cells, n = rows * cols, (H // rows) * (W // cols)
+    p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+    def fused(first_frame, fr):
+        nf = fr.shape[0]
+        dc, dh = np.zeros((nf, cells, 4), np.uint8), np.zeros((nf, cells), np.uint8)
+        cen, cnt, nit = np.zeros((nf, cells, k, 4)), np.zeros((nf, cells, k), np.int64), np.zeros((nf, cells), np.int32)
+        L.ofc_grid_kmeans_cells_workspace_bytes.restype = C.c_size_t
+        ws = np.zeros(max(8, L.ofc_grid_kmeans_cells_workspace_bytes(nf, H, W, rows, cols, k)), np.uint8)
+        rc = L.ofc_grid_kmeans_cells(p(fr), nf, H, W, rows, cols, 1, 30, 0, k, C.c_uint64(9), C.c_uint64(first_frame), 300,
+                                     C.c_double(1e-4), p(dc), p(dh), p(cen), p(cnt), p(nit), p(ws), C.c_size_t(ws.size), None)
+        assert rc == 0, L.ofc_last_error()
+        return dc, dh, cen, cnt, nit
+
+    dc, dh, cen, cnt, nit = fused(0, frames)
+    out = np.zeros((F, cells, n, 4), np.uint8)
+    assert L.ofc_grid_extract_cells(p(frames), F, H, W, rows, cols, 1, 30, 0, p(out), None) == 0
+    lab, c2, inertia, n2, counts = km.lloyd_cells(out.reshape(F * cells, n, 4), k, seed=9, _lib_override=L)
+    assert (cen.reshape(-1, k, 4) == c2.numpy()).all() and (cnt.reshape(-1, k) == counts.numpy()).all()
+    assert (nit.reshape(-1) == n2.numpy()).all()
+    top = counts.numpy().argmax(1)                                              # first largest
+    want = np.rint(c2.numpy()[np.arange(F * cells), top])
+    assert (dc.reshape(-1, 4) == want.astype(np.uint8)).all()
+    from oracle import viz_np
+    hues = np.array([viz_np.bgr2hsv_u8(want[i, :3].astype(np.uint8).reshape(1, 1, 3))[0, 0, 0] for i in range(F * cells)])
+    assert (dh.reshape(-1) == hues).all()
+    # frame 1 processed alone with first_frame = 1 reproduces its row of the two-frame call
+    dc1, dh1, cen1, cnt1, nit1 = fused(1, frames[1:])
+    assert (dc1[0] == dc[1]).all() and (dh1[0] == dh[1]).all() and (cen1[0] == cen[1]).all()
+
+
+def test_cells_seeding_and_dominant_hue_vs_numpy_oracle(L):
+    """the device-resident seeding (counter-based stream), the fit and the dominant-cluster hue against the
+    independent numpy restatement (oracle/kmeans_np.py: cells_seed_indices / cells_fit / dominant_centre_hue)"""
+    rng = np.random.default_rng(61)
+    B, n, k = 5, 640, 4
+    cen = rng.uniform(10, 240, (B, k, 4))
+    X = np.clip(np.rint(cen[np.arange(B)[:, None], rng.integers(k, size=(B, n))] + rng.normal(0, 9, (B, n, 4))), 0, 255).astype(np.uint8)
+    lab, cen_d, inertia, n_iter, counts = km.lloyd_cells(X, k, seed=123, _lib_override=L)
+    for b in range(B):
+        wl, wc, wi, wn, idx = K.cells_fit(X[b], k, 123, b)
+        assert (lab[b].numpy() == wl).all() and int(n_iter[b]) == wn
+        assert np.abs(cen_d[b].numpy() - wc).max() <= 1e-9 and abs(float(inertia[b]) - wi) <= 1e-9 * wi

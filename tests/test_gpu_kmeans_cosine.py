@@ -280,3 +280,85 @@ def test_sliding_cosine_large_properties(km):
     best, frame, sims = cosine.sliding_cosine(short, long_, return_sims=True)
     assert frame == 777_000 and abs(best - 1.0) < 1e-15
     assert sims[123_000] == sims[777_000] == sims.max()
+
+
+# ---- per-cell KMeans(k > 1): the shared-memory / filtered kernel and the device-resident pipeline --------------
+def _cells_both(km, X, k, monkeypatch, **kw):
+    monkeypatch.setenv("OFC_CELLS_FAST", "1")
+    fast = km.lloyd_cells(X, k, **kw)
+    monkeypatch.setenv("OFC_CELLS_FAST", "0")
+    slow = km.lloyd_cells(X, k, **kw)
+    monkeypatch.delenv("OFC_CELLS_FAST")
+    return fast, slow
+
+
+@pytest.mark.parametrize("k", [2, 8, 16])
+def test_cells_fast_kernel_bit_identical_to_first_kernel_full_frame(km, k, monkeypatch):
+    """one 1080p frame's worth of cells (350 x 5852 px, the BASELINE shape): float32-filtered E-step with float64
+    re-evaluation + incremental integer M-step == the all-float64 kernel, every output, bit for bit"""
+    g = torch.Generator().manual_seed(k)
+    X = torch.randint(0, 256, (350, 76 * 77, 4), generator=g).to(torch.uint8)
+    X[:40, :, 3] = 255                                               # some cells on a 3-D slice
+    X[40:60] = (X[40:60] // 64) * 64                                  # heavy duplicates: exact ties
+    X = X.cuda()
+    for kw in ({"seed": 11}, {"init": X[:, :k].double()}):
+        fast, slow = _cells_both(km, X, k, monkeypatch, **kw)
+        for name, u, v in zip(("labels", "centres", "inertia", "n_iter", "counts"), fast, slow):
+            assert torch.equal(u, v), name
+
+
+def test_cells_fast_kernel_vs_numpy_oracle_with_seeding(km):
+    """device-resident seeding + fit + dominant hue against oracle/kmeans_np.py (cells_fit, dominant_centre_hue)"""
+    from opticalflowclustering_b200 import grid
+    rng = np.random.default_rng(71)
+    H, W, rows, cols, k = 96, 120, 4, 5, 3
+    frames = np.zeros((2, H, W, 3), np.uint8)
+    for f in range(2):
+        for cy in range(rows):
+            for cx in range(cols):
+                cen = rng.uniform(0, 255, (k, 3))
+                cell = cen[rng.integers(k, size=(H // rows, W // cols))] + rng.normal(0, 12, (H // rows, W // cols, 3))
+                frames[f, cy * 24:(cy + 1) * 24, cx * 24:(cx + 1) * 24] = np.clip(np.rint(cell), 0, 255)
+    out = grid.grid_kmeans_cells(torch.from_numpy(frames).cuda(), k, rows, cols, seed=5, first_frame=7, want_centres=True)
+    for f in range(2):
+        fr = frames[f].copy()
+        _, _, rois = G.grid_mean_hues(fr, rows, cols)                       # ROI views with the white lines drawn
+        for c, roi in enumerate(rois):
+            X = G.preprocess_image(roi.copy()).reshape(-1, 4)
+            lab, cen, inertia, n_iter, idx = K.cells_fit(X, k, 5, (7 + f) * rows * cols + c)
+            assert int(out["n_iter"][f, c]) == n_iter
+            assert np.abs(out["centres"][f, c].cpu().numpy() - cen).max() <= 1e-9
+            assert (out["counts"][f, c].cpu().numpy() == np.bincount(lab, minlength=k)).all()
+            want_c, want_h = K.dominant_centre_hue(X, lab, cen)
+            assert (out["dom_centre"][f, c].cpu().numpy() == want_c.astype(np.uint8)).all()
+            assert int(out["dom_hue"][f, c]) == want_h
+
+
+def test_clip_pipeline_k8_device_resident(km):
+    """ClipPipeline(n_clusters=8): flow -> visualisation -> per-cell KMeans(8) hues without leaving the device;
+    equals the oracle run on the pipeline's own visualisation, and does not depend on the chunking"""
+    from opticalflowclustering_b200.pipeline import ClipPipeline
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    H, W, T, rows, cols, k = 144, 200, 5, 6, 8, 8
+    clip = synthetic_clip(T, H, W, seed=13)
+    pipe = ClipPipeline(W, H, chunk_frames=T, rows=rows, cols=cols, n_clusters=k, kmeans_seed=3)
+    pipe.run_chunk(clip.cuda())
+    viz = pipe.viz.cpu().numpy()
+    hue = pipe.km_hue.cpu().numpy()
+    nit = pipe.km_n_iter.cpu().numpy()
+    for p in (0, T - 2):
+        fr = viz[p].copy()
+        _, _, rois = G.grid_mean_hues(fr, rows, cols)
+        for c in range(0, rows * cols, 5):
+            X = G.preprocess_image(rois[c].copy()).reshape(-1, 4)
+            lab, cen, inertia, n_iter, idx = K.cells_fit(X, k, 3, p * rows * cols + c)
+            assert int(nit[p, c]) == n_iter
+            assert int(hue[p, c]) == K.dominant_centre_hue(X, lab, cen)[1]
+    # two chunks (3 + 2 new frames) give the same rows as one
+    pipe2 = ClipPipeline(W, H, chunk_frames=3, rows=rows, cols=cols, n_clusters=k, kmeans_seed=3)
+    res = pipe2.process_clip(clip)
+    assert (res["km_hue"].numpy() == hue).all()
+    # k = 1 keeps riding the grid pass
+    pipe1 = ClipPipeline(W, H, chunk_frames=T, rows=rows, cols=cols)
+    pipe1.run_chunk(clip.cuda())
+    assert (pipe1.avg_hue.cpu().numpy() == pipe.avg_hue.cpu().numpy()).all()
