@@ -13,6 +13,12 @@ the step's new frames and D2H of its hue rows / magnitudes inside the timed regi
 
 Under torchrun (N > 1) every rank processes its own clip shard (weak scaling, no
 data-path collective); timing is max over ranks, value the aggregate.
+
+`extras` carries the other BASELINE.json configs measured in the same run: the 720p and 4K sizes,
+`-c 8` (per-cell KMeans(8), configs[1]) at 720p and 1080p with the CPU reference at k = 8, the literal
+drop-in calls (numpy in / numpy out, one pair per call), the k-means / cosine sweep of configs[4], and --
+on every N -- the one collective of the path: whole Lloyd fits over row-sharded vectors with the NCCL
+all-reduce (`dist_kmeans`), plus the host-link ceiling with all ranks uploading at once.
 """
 from __future__ import annotations
 
@@ -38,6 +44,7 @@ ROWS, COLS = 14, 25
 # per flow_iter launch per pixel (update-matrices 68 B + blur/solve 28 B)
 ALGO_BYTES_PER_PAIR = 951.4e6
 ITER_BYTES_PER_PX = 96.0
+FUSED_ITER_BYTES_PER_PX = 56.0
 
 
 def parse():
@@ -50,12 +57,14 @@ def parse():
     ap.add_argument("--clip-frames", type=int, default=129)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--size", default="1080p", choices=sorted(SIZES), help="frame size (the metric is quoted on 1080p)")
+    ap.add_argument("--k", type=int, default=1, help="the reference's -c: clusters per grid cell (every documented command uses 1)")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline workload")
     args = ap.parse_args()
     global H, W, LEVELS, ALGO_BYTES_PER_PAIR, SIZE_NAME, METRIC
     H, W, LEVELS, ALGO_BYTES_PER_PAIR = SIZES[args.size]
     SIZE_NAME = args.size
-    if args.size != "1080p":
-        METRIC = f"{args.size} frame-pairs/sec (flow+grid+k-means)"
+    if args.size != "1080p" or args.k != 1:
+        METRIC = f"{args.size} frame-pairs/sec (flow+grid+k-means{'' if args.k == 1 else ', k=%d' % args.k})"
         if args.size == "4k" and args.clip_frames == 129 and args.chunk == 33:
             args.clip_frames, args.chunk = 33, 9           # 25 MB frames: keep the resident and pinned clips small
     return args
@@ -121,9 +130,9 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_reference_throughput(frames_np, workers, pairs_per_worker):
+def cpu_reference_throughput(frames_np, workers, pairs_per_worker, n_clusters=1):
     from oracle import reference_chain
-    return reference_chain.timed_throughput(frames_np, workers, pairs_per_worker, 1, ROWS, COLS)
+    return reference_chain.timed_throughput(frames_np, workers, pairs_per_worker, n_clusters, ROWS, COLS)
 
 
 def run_reference(args):
@@ -137,24 +146,24 @@ def run_reference(args):
     from opticalflowclustering_b200.synthetic import synthetic_clip
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
-    ppw = 2
+    ppw = 2 if args.k == 1 else 1
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     frames = synthetic_clip(min(args.clip_frames, 33), H, W, seed=0, device=dev).cpu().numpy()
     times = []
     for i in range(args.warmup + args.steps):
-        v, wall = cpu_reference_throughput(frames, workers, ppw)
+        v, wall = cpu_reference_throughput(frames, workers, ppw, args.k)
         if i >= args.warmup:
             times.append((v, wall))
         if sum(w for _, w in times) > 150:
             break
     value = sum(workers * ppw for _ in times) / sum(w for _, w in times)
     ms = 1e3 * sum(w for _, w in times) / len(times)
-    sample = f"{workers} processes x {ppw} consecutive 1080p pairs per step, cv2.setNumThreads(1), k=1"
+    sample = f"{workers} processes x {ppw} consecutive {SIZE_NAME} pairs per step, cv2.setNumThreads(1), k={args.k}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic {SIZE_NAME} clip, Farneback levels={LEVELS} winsize=15 iters=3, 14x25 grid, k=1",
+        "config": {"workload": f"synthetic {SIZE_NAME} clip, Farneback levels={LEVELS} winsize=15 iters=3, 14x25 grid, k={args.k}",
                    "impl": "oracle/reference_chain.py: cv2 4.13 calcOpticalFlowFarneback + sklearn KMeans, as the reference calls them"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -302,6 +311,215 @@ def kmeans_cosine_extras(dev, peak):
     return out
 
 
+def _timed_steps(pipe, clip, F, steps, warmup):
+    """device-resident steps over `clip` (walking through it), CUDA-event timed; returns ms per step"""
+    import torch
+    P, T = F - 1, int(clip.shape[0])
+    starts = [(i * P) % (T - F + 1) for i in range(warmup + steps)]
+    for i in range(warmup):
+        pipe.run_chunk(clip[starts[i]:starts[i] + F])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(warmup, warmup + steps):
+        pipe.run_chunk(clip[starts[i]:starts[i] + F])
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _kind_ms(pipe, clip, F, kinds, steps=3):
+    """per-kernel-kind device time (ms per step) of `steps` steps, events around every launch"""
+    import ctypes as C
+    from opticalflowclustering_b200 import _lib
+    L = _lib.lib()
+    _lib.check(L.ofc_profile_begin())
+    for _ in range(steps):
+        pipe.run_chunk(clip[:F])
+    ms_k, n_k = (C.c_float * 20)(), (C.c_int * 20)()
+    _lib.check(L.ofc_profile_end(ms_k, n_k, 20))
+    return {name: ms_k[k] / steps for k, name in kinds.items() if n_k[k]}
+
+
+def other_sizes_leg(dev, peak):
+    """BASELINE configs at 720p (levels=3) and 4K (levels=5), k = 1, device-resident, a few steps each"""
+    import torch
+    from opticalflowclustering_b200.pipeline import ClipPipeline
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    out = {}
+    for name, F, T in (("720p", 33, 65), ("4k", 9, 17)):
+        h, w, levels, algo = SIZES[name]
+        clip = synthetic_clip(T, h, w, seed=7, device=dev)
+        pipe = ClipPipeline(w, h, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=levels)
+        ms = _timed_steps(pipe, clip, F, 6, 3)
+        out[name] = {"value": (F - 1) / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "pairs_per_step": F - 1, "levels": levels,
+                     "step_frac": algo * (F - 1) / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_pair": algo}
+        del pipe, clip
+        torch.cuda.empty_cache()
+    return out
+
+
+def k8_leg(dev, with_cpu):
+    """`-c 8` (BASELINE configs[1]: 720p, k = 8; and the 1080p metric at k = 8): every cell of every pair gets its own
+    KMeans(8) fit on the device (ofc_grid_kmeans_cells), straight from the visualisation"""
+    import torch
+    from opticalflowclustering_b200.pipeline import ClipPipeline
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    out = {}
+    for name, F, T in (("720p", 33, 65), ("1080p", 17, 33)):
+        h, w, levels, _ = SIZES[name]
+        clip = synthetic_clip(T, h, w, seed=5, device=dev)
+        rec = {}
+        for k in (1, 8):
+            pipe = ClipPipeline(w, h, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=levels, n_clusters=k)
+            ms = _timed_steps(pipe, clip, F, 6, 3)
+            rec[f"k{k}"] = {"value": (F - 1) / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "pairs_per_step": F - 1}
+            if k == 8:
+                kinds = _kind_ms(pipe, clip, F, {8: "kmeans_cells"})
+                rec["k8"]["kmeans_ms_per_frame"] = kinds.get("kmeans_cells", 0.0) / (F - 1)
+                rec["k8"]["mean_lloyd_iterations"] = float(pipe.km_n_iter.float().mean().item())
+                rec["k8"]["max_lloyd_iterations"] = int(pipe.km_n_iter.max().item())
+            del pipe
+        rec["k8_over_k1_time"] = rec["k8"]["ms_per_step"] / rec["k1"]["ms_per_step"]
+        if with_cpu and name == "720p":
+            cores = os.cpu_count() or 1
+            workers = max(1, min(cores, 64))
+            v, wall = cpu_reference_throughput(clip[:9].cpu().numpy(), workers, 1, 8)
+            rec["cpu_reference_k8"] = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+                                       "sample": f"{workers} processes x 1 pair of the same 720p clip, cv2 Farneback + grid loop + "
+                                                 f"sklearn KMeans(8) per cell, {wall:.1f} s wall"}
+        out[name] = rec
+        del clip
+        torch.cuda.empty_cache()
+    return out
+
+
+def dropin_leg(host_clip):
+    """The literal drop-in calls, numpy in / numpy out, one pair per call (what a user of the reference types):
+    ComputeOpticalFLow(first).compute(frame) (computeOpticalFlowModule.py:6-36) and the cv2-signature
+    calc_optical_flow_farneback(prev, next, None, 0.5, 3, 15, 3, 5, 1.2, 0).  Wall clock per call, host copies included."""
+    import numpy as np
+    import torch
+    from opticalflowclustering_b200.computeOpticalFlowModule import ComputeOpticalFLow
+    from opticalflowclustering_b200.flow import calc_optical_flow_farneback
+    from oracle import reference_chain
+    frames = host_clip[:8].numpy()
+    cf = ComputeOpticalFLow(frames[0])
+    cf.compute(frames[1])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for f in frames[2:8]:
+        out = cf.compute(f)
+    t_compute = (time.perf_counter() - t0) / 6
+    gray = np.stack([reference_chain._cv2().cvtColor(f, reference_chain._cv2().COLOR_BGR2GRAY) for f in frames[:4]])
+    calc_optical_flow_farneback(gray[0], gray[1], None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    t0 = time.perf_counter()
+    for i in range(1, 3):
+        fl = calc_optical_flow_farneback(gray[i], gray[i + 1], None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    t_flow = (time.perf_counter() - t0) / 2
+    ref = reference_chain.FlowState(frames[0])
+    t0 = time.perf_counter()
+    ref.compute(frames[1])
+    t_cv2 = time.perf_counter() - t0
+    return {"ComputeOpticalFLow.compute_ms_per_call": 1e3 * t_compute, "calc_optical_flow_farneback_ms_per_call": 1e3 * t_flow,
+            "reference_compute_ms_per_call_cv2": 1e3 * t_cv2, "frame": f"{W}x{H} BGR uint8 numpy in, numpy out",
+            "out_shape": list(out.shape), "flow_shape": list(fl.shape)}
+
+
+def dist_kmeans_leg(dev, world, rank):
+    """The one collective of the path (north_star: NCCL all-reduce of k-means centroid sums and counts per iteration):
+    WHOLE Lloyd fits over vectors sharded by row across the ranks (kmeans.lloyd(group=...)), timed on the device
+    (max over ranks).  Total rows are fixed, so across N this leg is strong scaling; `rows_iter_per_s` = rows x
+    iterations / fit time."""
+    import torch
+    import torch.distributed as dist
+    from opticalflowclustering_b200 import kmeans as km
+    from opticalflowclustering_b200.sharding import shard_range
+    out = {}
+    cases = {"u8_8Mx4_k8": (8_000_000, 4, 8, True), "u8_64Mx4_k8": (64_000_000, 4, 8, True), "f32_1Mx128_k1024": (1_000_000, 128, 1024, False)}
+    for name, (N, D, K, is_u8) in cases.items():
+        gd = torch.Generator(device=dev).manual_seed(11)
+        cen = torch.rand((K, D), device=dev, generator=gd) * (200 if is_u8 else 8) + (25 if is_u8 else 0)
+        lo, hi = shard_range(N, rank, world)
+        # every rank draws the whole label / noise stream in blocks and keeps its rows: identical data for every N
+        rows = []
+        init = None
+        blk = 4_000_000 if is_u8 else 250_000
+        for s0 in range(0, N, blk):
+            nb = min(blk, N - s0)
+            lab = torch.randint(0, K, (nb,), device=dev, generator=gd)
+            x = cen[lab] + (12 if is_u8 else 1) * torch.randn((nb, D), device=dev, generator=gd)
+            if s0 == 0:                          # initial centres: the first K rows of the whole set (same on every rank)
+                init = (x[:K].round().clamp(0, 255) if is_u8 else x[:K].float()).double()
+            a, b = max(lo, s0), min(hi, s0 + nb)
+            if a < b:
+                x = x[a - s0:b - s0]
+                rows.append(x.round().clamp(0, 255).to(torch.uint8) if is_u8 else x.float())
+            del lab, x
+        X = torch.cat(rows).contiguous()
+        del rows
+        group = dist.group.WORLD if world > 1 else None
+        km.lloyd(X, init, group=group)           # warm-up fit
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        labels, centres, inertia, n_iter = km.lloyd(X, init, group=group)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        it = int(n_iter)
+        rec = {"rows": N, "d": D, "k": K, "n_iter": it, "fit_ms": ms, "host_wall_ms": 1e3 * wall, "ms_per_iteration": ms / max(it, 1),
+               "rows_iter_per_s": N * it / (ms / 1e3), "inertia": float(inertia)}
+        if world == 1:
+            # same fit with events around every kernel: how much of the fit is kernel time (host-free loop)
+            import ctypes as C
+            from opticalflowclustering_b200 import _lib
+            L = _lib.lib()
+            _lib.check(L.ofc_profile_begin())
+            km.lloyd(X, init)
+            ms_k, n_k = (C.c_float * 20)(), (C.c_int * 20)()
+            _lib.check(L.ofc_profile_end(ms_k, n_k, 20))
+            rec["sum_of_kernel_ms"] = float(sum(ms_k[i] for i in range(20)))
+            rec["kernel_launches"] = int(sum(n_k[i] for i in range(20)))
+            rec["fit_over_kernel_time"] = ms / max(rec["sum_of_kernel_ms"], 1e-9)
+        out[name] = rec
+        del X, labels
+        torch.cuda.empty_cache()
+    return out
+
+
+def h2d_concurrent_leg(dev, world):
+    """Host-link ceiling of the end-to-end number: pinned 50 MB uploads (one step's frames) on EVERY rank at the same
+    time -- what each rank's copy engine gets when all N share the host's memory system / PCIe roots."""
+    import torch
+    import torch.distributed as dist
+    hbuf = torch.empty(50 * 1024 * 1024, dtype=torch.uint8).pin_memory()
+    dbuf = torch.empty_like(hbuf, device=dev)
+    dbuf.copy_(hbuf, non_blocking=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(8):
+        dbuf.copy_(hbuf, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = torch.tensor([8 * hbuf.numel() / (e0.elapsed_time(e1) / 1e3) / 1e9], dtype=torch.float64, device=dev)
+    lo, tot = gbs.clone(), gbs.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    return {"per_rank_min_gb_s": float(lo.item()), "all_ranks_gb_s": float(tot.item()), "ranks": world}
+
+
 _JSON_OUT = None
 
 
@@ -347,7 +565,7 @@ def main():
     P = F - 1
     T = max(args.clip_frames, F)
     clip = synthetic_clip(T, H, W, seed=rank, device=dev)              # resident in HBM, > L2
-    pipe = ClipPipeline(W, H, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=LEVELS)
+    pipe = ClipPipeline(W, H, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=LEVELS, n_clusters=args.k)
     starts = [(i * P) % (T - F + 1) for i in range(args.warmup + args.steps)]
 
     # ---- value: inputs resident in HBM --------------------------------------
@@ -380,8 +598,8 @@ def main():
     ms_k = (C.c_float * 20)()
     n_k = (C.c_int * 20)()
     _lib.check(L.ofc_profile_end(ms_k, n_k, 20))
-    names = {0: "bgr2gray", 1: "prefilter", 2: "polyexp", 3: "minmax_init", 4: "flow_encode", 5: "grid_cells",
-             10: "flow_upsample"}
+    names = {0: "bgr2gray", 1: "prefilter", 2: "polyexp", 3: "minmax_init", 4: "flow_encode_grid" if pipe.fuse_grid else "flow_encode",
+             5: "grid_cells", 8: "kmeans_cells", 10: "flow_upsample"}
     names.update({12 + l: f"flow_iter_L{l}" for l in range(8)})
     kernels = {names[k]: {"ms_per_step": ms_k[k] / prof_steps, "launches_per_step": n_k[k] // prof_steps}
                for k in names if n_k[k]}
@@ -393,21 +611,33 @@ def main():
         per_launch_ms = it0["ms_per_step"] / it0["launches_per_step"]
         algo = ITER_BYTES_PER_PX * H * W * P
         achieved = algo / (per_launch_ms / 1e3) / 1e9
-        traffic = None
+        # DRAM bytes of this launch are not measurable inside the run: the figure comes from the committed ncu capture of
+        # the same launch (profiles/r02_flow_iter_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, --set full),
+        # scaled by the pairs per launch, and is labelled as such
+        traffic, traffic_source = None, None
         try:
             if SIZE_NAME != "1080p":
                 raise KeyError("the ncu capture is of the 1080p launch")
-            with open(os.path.join(ROOT, "profiles", "flow_iter_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_flow_iter_traffic.json")) as f:
                 tj = json.load(f)
-                # the ncu capture is of an 8-pair launch: DRAM bytes scale with the pairs per launch
-                traffic = tj.get("dram_bytes_per_launch") * P / float(tj.get("pairs_per_launch", 8))
+            traffic = tj["dram_bytes_per_launch"] * P / float(tj.get("pairs_per_launch", P))
+            traffic_source = "ncu capture committed as profiles/r02_flow_iter_traffic.json (not measured in this run), scaled by pairs per launch"
         except Exception:
             pass
         total_ms = sum(v["ms_per_step"] for v in kernels.values())
+        # the fused kernel never writes or re-reads the update matrices M that SURVEY 8(d)'s 96 B/px charges: what it must
+        # move is R of both frames (2 x 20 B), the flow in (8 B) and the flow out (8 B) = 56 B/px
+        fused = FUSED_ITER_BYTES_PER_PX * H * W * P / (per_launch_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": f"flow_iter_tmem_kernel<R=7,TW=240> @{W}x{H} (update-matrices + 15x15 box + 2x2 solve fused, "
                               "persistent strip walk, ring in TMEM, cp.async tap landing; 3 launches per step)",
                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "algorithmic_bytes_per_launch": algo, "ms_per_launch": per_launch_ms,
+                    "traffic": traffic, "traffic_source": traffic_source,
+                    "algorithmic_bytes_per_launch": algo, "ms_per_launch": per_launch_ms,
+                    "achieved_fused_model": fused, "frac_fused": fused / peak,
+                    "dram_frac_of_peak": (traffic / (per_launch_ms / 1e3) / 1e9 / peak) if traffic else None,
+                    "note": "`frac` follows SURVEY 8(d)'s unfused dataflow (96 B/px incl. writing and re-reading M); the kernel keeps M "
+                            "on the SM, so `frac_fused` (56 B/px: R0 + R1 + flow in + flow out) and `dram_frac_of_peak` (measured DRAM "
+                            "bytes / time) say how far from the HBM bound it really runs: it is issue / latency bound",
                     "share_of_step": it0["ms_per_step"] / total_ms,
                     "step_achieved_gbs": ALGO_BYTES_PER_PAIR * P / (ms_total / args.steps / 1e3) / 1e9,
                     "step_frac": ALGO_BYTES_PER_PAIR * P / (ms_total / args.steps / 1e3) / 1e9 / peak}
@@ -473,24 +703,36 @@ def main():
            "d2h_bytes_per_step": P * (2 * ROWS * COLS + 8),
            "api": "ClipPipeline.run_chunk(new frames, carry=True) on pinned host frames, triple-buffered upload"}
 
-    extras = kmeans_cosine_extras(dev, peak) if rank == 0 else None
+    extras = None
+    if not args.no_extras:
+        dk = dist_kmeans_leg(dev, world, rank)                 # every rank takes part
+        hl = h2d_concurrent_leg(dev, world)
+        if rank == 0:
+            extras = kmeans_cosine_extras(dev, peak)
+            extras["dist_kmeans"] = dk
+            extras["h2d_pinned_all_ranks"] = hl
+            if SIZE_NAME == "1080p" and args.k == 1:
+                extras["sizes"] = other_sizes_leg(dev, peak)
+                extras["k8"] = k8_leg(dev, with_cpu=(world == 1 and not args.no_cpu_baseline))
+                extras["dropin_latency"] = dropin_leg(host_clip)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and LEVELS == 3:
         cores = os.cpu_count() or 1
         workers = max(1, min(cores, 64))
         frames_np = host_clip[:min(T, 33)].numpy()
-        v, wall = cpu_reference_throughput(frames_np, workers, 2)
+        ppw = 2 if args.k == 1 else 1
+        v, wall = cpu_reference_throughput(frames_np, workers, ppw, args.k)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
-                        "sample": f"{workers} processes x 2 consecutive 1080p pairs of the same clip "
-                                  f"(cv2 Farneback + grid loop + sklearn KMeans(1) per cell), {wall:.1f} s wall"}
+                        "sample": f"{workers} processes x {ppw} consecutive {SIZE_NAME} pairs of the same clip "
+                                  f"(cv2 Farneback + grid loop + sklearn KMeans({args.k}) per cell), {wall:.1f} s wall"}
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic {SIZE_NAME} clip, Farneback levels={LEVELS} winsize=15 iters=3, 14x25 grid, k=1",
+            "config": {"workload": f"synthetic {SIZE_NAME} clip, Farneback levels={LEVELS} winsize=15 iters=3, 14x25 grid, k={args.k}",
                        "frames_per_step": F, "pairs_per_step": P, "clip_frames": T,
                        "l2": f"steps walk a {T}-frame clip ({T * H * W * 3 / 1e6:.0f} MB > L2); intermediates "
                              f"({pipe.plan.workspace_bytes / 1e6:.0f} MB workspace) are rewritten every step"},

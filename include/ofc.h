@@ -213,6 +213,14 @@ int ofc_kmeans_update(int batch, int64_t n, int d, int k, const double* sums, co
                       int32_t* n_active, const int32_t* labels_cur, int32_t* labels_other, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* MiniBatchKMeans centre update, the arithmetic behind the reference's color-quantization/quant.py:18-20
+ * (clt = MiniBatchKMeans(n_clusters); clt.fit_predict(image)) -> scikit-learn 1.9.0 _minibatch_update_dense
+ * (sklearn/cluster/_k_means_minibatch.pyx:60-110): for one mini-batch Xb [batch_rows][d] with labels from
+ * ofc_kmeans_assign,  c_new = (c_old * weight_sum + members in batch order) / (weight_sum + n_members), weight_sums
+ * updated in place; clusters without a member keep their centre.  float32 data is worked in float32. */
+int ofc_minibatch_update(const void* Xb, int dtype, int batch_rows, int d, int k, const int32_t* labels,
+                         const double* centres_old, double* centres_new, double* weight_sums, void* stream);
+
 /* Empty-cluster relocation on the sums/counts (_k_means_common.pyx:167-211): every empty
  * cluster, in index order, takes the point farthest from the (old) centre of its label.
  * Distances use (x - mean) against centres_old; raw_sums says whether `sums` holds sums of

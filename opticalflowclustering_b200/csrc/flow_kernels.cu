@@ -417,18 +417,22 @@ __device__ __forceinline__ void pyr_level(const PyrParams& p, const PyrLevel& L,
     for (int bi = 0; bi < n_batches; ++bi) {
         __syncthreads();                                         // the previous batch has been consumed
         const int r0 = S * m_lo + bi * RB;
-        for (int idx = t; idx < RB * PW; idx += NT) {
-            const int lr = idx / PW, wc = idx - lr * PW;
-            const unsigned char* row = gray + (int64_t)reflect101(r0 + lr, H) * W;
-            const int gc = cb + 4 * wc;
-            unsigned v;
-            if (gc >= 0 && gc + 3 < W) {
-                v = *reinterpret_cast<const unsigned*>(row + gc);
-            } else {
-                v = (unsigned)row[reflect101(gc, W)] | ((unsigned)row[reflect101(gc + 1, W)] << 8) |
-                    ((unsigned)row[reflect101(gc + 2, W)] << 16) | ((unsigned)row[reflect101(gc + 3, W)] << 24);
+        // warp w stages rows w, w + 4, ...; lanes stride over the row's words (no index division; the row reflection
+        // needs no modulo: a batch overshoots the frame by less than a frame height)
+        for (int lr = t >> 5; lr < RB; lr += NT / 32) {
+            const unsigned char* row = gray + (int64_t)reflect101_near(r0 + lr, H) * W;
+            unsigned* dst = srow + lr * PW;
+            for (int wc = t & 31; wc < PW; wc += 32) {
+                const int gc = cb + 4 * wc;
+                unsigned v;
+                if (gc >= 0 && gc + 3 < W) {
+                    v = *reinterpret_cast<const unsigned*>(row + gc);
+                } else {
+                    v = (unsigned)row[reflect101(gc, W)] | ((unsigned)row[reflect101(gc + 1, W)] << 8) |
+                        ((unsigned)row[reflect101(gc + 2, W)] << 16) | ((unsigned)row[reflect101(gc + 3, W)] << 24);
+                }
+                dst[wc] = v;
             }
-            srow[idx] = v;
         }
         __syncthreads();
 #pragma unroll
@@ -719,12 +723,15 @@ __global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const u
 // ---------------------------------------------------------------------------
 // cv::resize(INTER_LINEAR) of the coarser level's flow at one pixel, times 1/pyr_scale: the ONE expression every
 // consumer uses (tile kernel, stand-alone up-sample kernel, fused strip walk), so they agree bit for bit
-__device__ __forceinline__ float2 bilerp_flow(float2 q00, float2 q01, float2 q10, float2 q11, float fx, float fy, double mul) {
+__device__ __forceinline__ float2 bilerp_raw(float2 q00, float2 q01, float2 q10, float2 q11, float fx, float fy) {
     const float ax = 1.f - fx, ay = 1.f - fy;
     const float tx0 = q00.x * ax + q01.x * fx, tx1 = q10.x * ax + q11.x * fx;
     const float ty0 = q00.y * ax + q01.y * fx, ty1 = q10.y * ax + q11.y * fx;
-    const float u = tx0 * ay + tx1 * fy, v = ty0 * ay + ty1 * fy;
-    return make_float2((float)((double)u * mul), (float)((double)v * mul));
+    return make_float2(tx0 * ay + tx1 * fy, ty0 * ay + ty1 * fy);
+}
+__device__ __forceinline__ float2 bilerp_flow(float2 q00, float2 q01, float2 q10, float2 q11, float fx, float fy, double mul) {
+    const float2 r = bilerp_raw(q00, q01, q10, q11, fx, fy);
+    return make_float2((float)((double)r.x * mul), (float)((double)r.y * mul));
 }
 
 __device__ __forceinline__ float2 load_flow(const IterParams& p, const float2* fin, int gx, int gy) {
@@ -1275,9 +1282,9 @@ static inline void tmem_st8(unsigned taddr, const float (&v)[8]) { memcpy(&ofc_e
 static inline void tmem_wait_st() {}
 #endif
 
-// UPS: flow_in is the COARSER level's flow; every flow row is up-sampled on the fly (bilerp_flow, the expression of
+// UPS != 0: flow_in is the COARSER level's flow (1 general ratio, 2 exact x2); every flow row is up-sampled on the fly (bilerp_flow, the expression of
 // flow_upsample_kernel), so the first iteration of a level needs no up-sample launch and no full-size scratch field.
-template <int R, int TW, int NT, int G, bool MINMAX, bool UPS>
+template <int R, int TW, int NT, int G, bool MINMAX, int UPS>
 __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int n_cols, int64_t total_rows) {
     constexpr int K = 2 * R + 1;
     constexpr int CW = TW + 2 * R;
@@ -1378,14 +1385,30 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
         src_coord(gx, p.usx, p.wc, ups_xi, ups_fx);
         ups_xj = min(ups_xi + 1, p.wc - 1);
     }
+    // the level is exactly twice the coarser one and 1/pyr_scale is a power of two (pyr_scale = 0.5 on frames whose
+    // sides divide): the row's resize coordinate is integer arithmetic and the scaling a float multiply -- the same
+    // bits as src_coord / the float64 multiply of bilerp_flow (exact operations), without their conversions
+    constexpr bool ups_fast = UPS == 2;
+    const float ups_mul = (float)p.flow_mul;
     auto flow_at = [&](int row) -> float2 {
         if (!UPS) return fin[row * w + gx];
         int yi;
         float fy;
-        src_coord(row, p.usy, p.hc, yi, fy);
+        if (ups_fast) {
+            yi = (row - 1) >> 1;
+            fy = (row & 1) ? 0.25f : 0.75f;
+            if (row == 0) { yi = 0; fy = 0.f; }
+            if (yi >= p.hc - 1) { yi = p.hc - 1; fy = 0.f; }
+        } else {
+            src_coord(row, p.usy, p.hc, yi, fy);
+        }
         const int yj = min(yi + 1, p.hc - 1);
         const float2* r0p = fin + yi * p.wc;
         const float2* r1p = fin + yj * p.wc;
+        if (ups_fast) {
+            const float2 r = bilerp_raw(r0p[ups_xi], r0p[ups_xj], r1p[ups_xi], r1p[ups_xj], ups_fx, fy);
+            return make_float2(r.x * ups_mul, r.y * ups_mul);
+        }
         return bilerp_flow(r0p[ups_xi], r0p[ups_xj], r1p[ups_xi], r1p[ups_xj], ups_fx, fy, p.flow_mul);
     };
 
@@ -1760,7 +1783,7 @@ int launch_prefilter_pyramid(const PrefilterParams* levels, const size_t* smem_f
             if (S != pass || p.W != p.w * S || p.H != p.h * S) continue;
             const int want_ksz = S == 2 ? 3 : (S == 4 ? 9 : (S == 8 ? 19 : 39));
             if (p.ksz != want_ksz || (p.W & 3) || (p.gray_stride & 3) || ((uintptr_t)p.gray & 3)) continue;
-            if (p.H < 2 * S + p.ksz) continue;
+            if (p.H < 4 * S + p.ksz + 16) continue;        // a staged batch may overshoot the frame by < H rows (single reflection)
             if (pp.n_levels == 0) { pp.gray = p.gray; pp.gray_stride = p.gray_stride; pp.W = p.W; pp.H = p.H; }
             PyrLevel& L = pp.lv[pp.n_levels++];
             L.out = p.out; L.out_stride = p.out_stride; L.taps = p.taps; L.w = p.w; L.h = p.h; L.S = S;
@@ -1882,7 +1905,7 @@ static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
                     : launch_strip_rm<R, TW, NT, G, MINB, false>(p, n_pairs, stream);
 }
 
-template <bool MINMAX, bool UPS>
+template <bool MINMAX, int UPS>
 static int launch_tmem(const IterParams& p, int n_pairs, void* stream) {
     constexpr int R = 7, TW = 240, NT = 256, G = 4;
     constexpr int CW = TW + 2 * R, CP = (CW + 3) / 4 * 4 + 4, S = 3;
@@ -1906,9 +1929,15 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
     IterParams p = p_in;
     const int use_tmem0 = env_int("OFC_ITER_TMEM", 513), any_w0 = env_int("OFC_TMEM_ANYW", 1);
     const bool tmem_path = use_tmem0 && (p.w >= use_tmem0 || p.w % 240 == 0) && (any_w0 || p.w % 240 == 0);
-    // the tensor-memory walk up-samples the coarser flow itself (OFC_FUSE_UPSAMPLE=0: separate launch as before)
-    if (p.upsample && tmem_path && env_int("OFC_FUSE_UPSAMPLE", 1) && (int64_t)p.wc * p.hc < ((int64_t)1 << 30))
-        return p.minmax ? launch_tmem<true, true>(p, n_pairs, stream) : launch_tmem<false, true>(p, n_pairs, stream);
+    // OFC_FUSE_UPSAMPLE=1: the tensor-memory walk up-samples the coarser flow itself (bit-identical).  Measured SLOWER
+    // than the separate up-sample launch (r02c: +0.29 ms on the level-0 launch against 0.26 ms of up-sample kernels per
+    // 32 pairs: the four coarse loads sit on the walk's critical path, two rows before the tap addresses they feed),
+    // so it is off by default
+    if (p.upsample && tmem_path && env_int("OFC_FUSE_UPSAMPLE", 0) && (int64_t)p.wc * p.hc < ((int64_t)1 << 30))
+    {
+        if (p.ups_fast) return p.minmax ? launch_tmem<true, 2>(p, n_pairs, stream) : launch_tmem<false, 2>(p, n_pairs, stream);
+        return p.minmax ? launch_tmem<true, 1>(p, n_pairs, stream) : launch_tmem<false, 1>(p, n_pairs, stream);
+    }
     if (p.upsample) {
         dim3 g(cdiv(p.w, 64), cdiv(p.h, 16), n_pairs);
         {
@@ -1923,7 +1952,7 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
     static const int use_tmem = env_int("OFC_ITER_TMEM", 513);      // minimum level width; 0 = off
     // (OFC_TMEM_ANYW=0 restricts it to widths that are a multiple of its 240-column strips)
     static const int any_w = env_int("OFC_TMEM_ANYW", 1);
-    if (use_tmem && (p.w >= use_tmem || p.w % 240 == 0) && (any_w || p.w % 240 == 0)) return p.minmax ? launch_tmem<true, false>(p, n_pairs, stream) : launch_tmem<false, false>(p, n_pairs, stream);
+    if (use_tmem && (p.w >= use_tmem || p.w % 240 == 0) && (any_w || p.w % 240 == 0)) return p.minmax ? launch_tmem<true, 0>(p, n_pairs, stream) : launch_tmem<false, 0>(p, n_pairs, stream);
     static const int minb4 = env_int("OFC_STRIP_MINB4", 1);
     if (p.w > 512 && minb4) return launch_strip_r<7, 128, 160, 4, 4>(p, n_pairs, stream);
     if (p.w > 512) return launch_strip_r<7, 128, 160, 4, 3>(p, n_pairs, stream);

@@ -40,6 +40,7 @@ struct IterParams {
     int upsample;                // flow_in is the coarser level: bilinear resize * flow_mul
     int wc, hc;
     double usx, usy, flow_mul;
+    int ups_fast;                // w == 2 wc, h == 2 hc and flow_mul a power of two: integer resize coordinates, float scaling
     float2* flow_out;
     int64_t flow_out_stride;
     int w, h;

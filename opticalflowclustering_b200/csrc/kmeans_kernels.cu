@@ -26,6 +26,15 @@ template <typename W> __device__ __forceinline__ W fma_w(W a, W b, W c);
 template <> __device__ __forceinline__ double fma_w<double>(double a, double b, double c) { return fma(a, b, c); }
 template <> __device__ __forceinline__ float fma_w<float>(float a, float b, float c) { return fmaf(a, b, c); }
 
+// ||c||^2 of one centre in the working type: float64 in numpy's einsum order (norm_sq_numpy_f64), float32 as a
+// sequential fma chain
+__device__ __forceinline__ double centre_norm_sq(const double* c, int d) { return norm_sq_numpy_f64(c, d); }
+__device__ __forceinline__ float centre_norm_sq(const float* c, int d) {
+    float s = 0.f;
+    for (int t = 0; t < d; ++t) s = fmaf(c[t], c[t], s);
+    return s;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -61,11 +70,7 @@ __global__ void __launch_bounds__(256) kmeans_assign_small_kernel(KmAssignParams
     for (int i = tid; i < k * d; i += 256) sc[i] = (W)cen[i];
     for (int i = tid; i < d; i += 256) smean[i] = p.mean ? (W)p.mean[(int64_t)b * d + i] : (W)0;
     __syncthreads();
-    for (int j = tid; j < k; j += 256) {
-        W s = (W)0;
-        for (int t = 0; t < d; ++t) s = fma_w<W>(sc[j * d + t], sc[j * d + t], s);
-        sc2[j] = s;
-    }
+    for (int j = tid; j < k; j += 256) sc2[j] = centre_norm_sq(sc + j * d, d);
     __syncthreads();
 
     const T* X = reinterpret_cast<const T*>(p.X) + (int64_t)b * p.n * d;
@@ -261,9 +266,7 @@ __global__ void kmeans_c2_kernel(const double* centres, double* c2, int d, int k
         for (int t = 0; t < d; ++t) s = fmaf((float)c[t], (float)c[t], s);
         c2[(int64_t)b * k + j] = (double)s;
     } else {
-        double s = 0.0;
-        for (int t = 0; t < d; ++t) s = fma(c[t], c[t], s);
-        c2[(int64_t)b * k + j] = s;
+        c2[(int64_t)b * k + j] = norm_sq_numpy_f64(c, d);
     }
 }
 
@@ -365,11 +368,7 @@ __global__ void __launch_bounds__(256) kmeans_step_u8_kernel(KmAssignParams p, d
     for (int i = tid; i < d; i += 256) smean[i] = p.mean ? p.mean[(int64_t)b * d + i] : 0.0;
     for (int s = 0; s < slots; ++s) acc[s * 256 + tid] = 0u;
     __syncthreads();
-    for (int j = tid; j < k; j += 256) {
-        double s = 0.0;
-        for (int t = 0; t < d; ++t) s = fma(sc[j * d + t], sc[j * d + t], s);
-        sc2[j] = s;
-    }
+    for (int j = tid; j < k; j += 256) sc2[j] = norm_sq_numpy_f64(sc + j * d, d);
     __syncthreads();
     const unsigned char* X = reinterpret_cast<const unsigned char*>(p.X) + (int64_t)b * p.n * d;
     int32_t* labels = p.labels + (int64_t)b * p.n;
@@ -582,6 +581,48 @@ __global__ void __launch_bounds__(256) kmeans_update_kernel(int d, int k, const 
         } else if (n_active) {
             atomicAdd(n_active, 1);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// MiniBatchKMeans centre update (reference color-quantization/quant.py:18-20 -> scikit-learn 1.9.0
+// sklearn/cluster/_k_means_minibatch.pyx:60-110, update_center_dense): per cluster, in the mini-batch's sample
+// order,  c_new = (c_old * weight_sum + sum of the members) / (weight_sum + n_members);  clusters without a member keep
+// their centre.  One thread per (cluster, feature) walks the batch sequentially -- the reference's accumulation
+// order, so the float result is the same; float32 data is worked in float32 like sklearn (W = float).
+// ---------------------------------------------------------------------------
+template <typename T, typename W>
+__global__ void __launch_bounds__(256) minibatch_update_kernel(const T* __restrict__ Xb, int bs, int d, int k,
+                                                               const int32_t* __restrict__ labels, const double* __restrict__ centres_old,
+                                                               double* __restrict__ centres_new, double* __restrict__ weight_sums) {
+    OFC_DYN_SMEM(int, s_lab);                            // [bs]
+    __shared__ int s_any;
+    for (int i = threadIdx.x; i < bs; i += 256) s_lab[i] = labels[i];
+    __syncthreads();
+    for (int e0 = 0; e0 < k * d; e0 += 256) {
+        const int e = e0 + threadIdx.x;
+        int cnt = 0, j = 0;
+        if (e < k * d) {
+            j = e / d;
+            const int t = e - j * d;
+            for (int i = 0; i < bs; ++i) cnt += s_lab[i] == j ? 1 : 0;
+            const W c_old = (W)centres_old[e];
+            W out = c_old;
+            if (cnt > 0) {
+                const W ws = (W)weight_sums[j];
+                W acc = c_old * ws;
+                for (int i = 0; i < bs; ++i)
+                    if (s_lab[i] == j) acc += (W)Xb[(int64_t)i * d + t];
+                const W ws_new = ws + (W)cnt;
+                const W alpha = (W)1 / ws_new;
+                out = acc * alpha;
+            }
+            centres_new[e] = (double)out;
+        }
+        __syncthreads();                                  // every feature of a cluster has read its old weight
+        if (e < k * d && e - j * d == 0 && cnt > 0) weight_sums[j] = (double)((W)weight_sums[j] + (W)cnt);
+        if (threadIdx.x == 0) s_any = 0;
+        __syncthreads();
     }
 }
 
@@ -930,9 +971,7 @@ __global__ void __launch_bounds__(256) kmeans_cells_kernel(KmCellsParams p) {
     int iters = 0;
     for (int it = 0; it < p.max_iter; ++it) {
         for (int j = tid; j < k; j += 256) {
-            double sq = 0.0;
-            for (int t = 0; t < d; ++t) sq = fma(cc[j * d + t], cc[j * d + t], sq);
-            c2[j] = sq;
+            c2[j] = norm_sq_numpy_f64(cc + j * d, d);
             s_cnt[j] = 0;
         }
         for (int e = tid; e < k * d; e += 256) s_sum[e] = 0u;
@@ -1049,9 +1088,7 @@ __global__ void __launch_bounds__(256) kmeans_cells_kernel(KmCellsParams p) {
 
     // ---- closing E-step on the final centres, inertia, member counts ------------------------------
     for (int j = tid; j < k; j += 256) {
-        double sq = 0.0;
-        for (int t = 0; t < d; ++t) sq = fma(cc[j * d + t], cc[j * d + t], sq);
-        c2[j] = sq;
+        c2[j] = norm_sq_numpy_f64(cc + j * d, d);
         s_cnt[j] = 0;
     }
     __syncthreads();
@@ -1320,6 +1357,25 @@ int launch_kmeans_update(int batch, int d, int k, const double* sums, const long
         OFC_LAUNCH(kmeans_freeze_labels_kernel, dim3((unsigned)bx, batch), dim3(256), 0, stream, n, just_done, labels_cur, labels_other);
         OFC_CHECK_LAUNCH("kmeans_freeze_labels");
     }
+    return OFC_OK;
+}
+
+int launch_minibatch_update(const void* Xb, int dtype, int bs, int d, int k, const int32_t* labels, const double* centres_old,
+                            double* centres_new, double* weight_sums, void* stream) {
+    const size_t smem = (size_t)bs * sizeof(int);
+    if (smem > 200 * 1024) { set_error("mini-batch of %d rows is too large (<= 51200)", bs); return OFC_ERR_UNSUPPORTED; }
+    ProfScope prof(PK_KMEANS, stream);
+#define OFC_MB(TT, WW)                                                                                               \
+    {                                                                                                                \
+        OFC_SMEM_OPTIN((minibatch_update_kernel<TT, WW>), smem);                                                     \
+        OFC_LAUNCH((minibatch_update_kernel<TT, WW>), dim3(1), dim3(256), smem, stream, (const TT*)Xb, bs, d, k, labels, \
+                   centres_old, centres_new, weight_sums);                                                           \
+    }
+    if (dtype == DT_U8) OFC_MB(unsigned char, double)
+    else if (dtype == DT_F32) OFC_MB(float, float)
+    else OFC_MB(double, double)
+#undef OFC_MB
+    OFC_CHECK_LAUNCH("minibatch_update");
     return OFC_OK;
 }
 

@@ -55,6 +55,8 @@ int launch_kmeans_update(int batch, int d, int k, const double* sums, const long
                          const unsigned long long* n_changed, const double* tol, int it, unsigned char* active,
                          unsigned char* just_done, int* n_iter, int* n_active, int64_t n, const int32_t* labels_cur,
                          int32_t* labels_other, void* stream);
+int launch_minibatch_update(const void* Xb, int dtype, int bs, int d, int k, const int32_t* labels, const double* centres_old,
+                            double* centres_new, double* weight_sums, void* stream);
 int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                            const int32_t* labels, const double* centres_old, double* sums, long long* counts,
                            int raw_sums, const unsigned char* active, void* stream);
@@ -85,6 +87,7 @@ struct KmCellsFastParams {
     unsigned char* dom_hue;        // [batch]    BGR2HSV hue of its first three channels, or null
     unsigned* closest_ws;          // [batch][n] k-means++ scratch when it does not fit shared memory
     int closest_in_smem;           // set by the launcher
+    int mstep_mode;                // set by the launcher (OFC_CELLS_MSTEP)
 };
 bool kmeans_cells_fast_supported(int64_t n, int d, int k);
 size_t kmeans_cells_fast_workspace(int batch, int64_t n, int k, bool seeding);

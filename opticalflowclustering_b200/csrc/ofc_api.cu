@@ -266,7 +266,7 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
             ip.w = L.w; ip.h = L.h;
             ip.border[0] = 0.14f; ip.border[1] = 0.14f; ip.border[2] = 0.4472f; ip.border[3] = 0.4472f; ip.border[4] = 0.4472f;
             ip.blur_scale = 1.0 / ((double)pl->winsize * pl->winsize);
-            ip.upsample = 0; ip.wc = ip.hc = 0; ip.usx = ip.usy = 1.0; ip.flow_mul = 1.0;
+            ip.upsample = 0; ip.wc = ip.hc = 0; ip.usx = ip.usy = 1.0; ip.flow_mul = 1.0; ip.ups_fast = 0;
             if (it == 0 && l == 0 && init_flow) {
                 // cv2 flag 4: resize(flow0, INTER_AREA) * scale seeds the coarsest level (other ping-pong buffer)
                 double scale = 1.0;
@@ -285,6 +285,9 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
                     ip.usx = 1.0 / ((double)L.w / prev_w);
                     ip.usy = 1.0 / ((double)L.h / prev_h);
                     ip.flow_mul = 1.0 / pl->pyr_scale;
+                    int e2 = 0;
+                    const bool pow2 = frexp(ip.flow_mul, &e2) == 0.5 && ip.flow_mul >= 1.0 && ip.flow_mul <= 16.0;
+                    ip.ups_fast = (pow2 && L.w == 2 * prev_w && L.h == 2 * prev_h) ? 1 : 0;
                 }
             } else {
                 ip.flow_in = (const float2*)(ws + L.off_flow[(it - 1) & 1]);
@@ -768,6 +771,14 @@ int ofc_kmeans_update(int batch, int64_t n, int d, int k, const double* sums, co
     return launch_kmeans_update(batch, d, k, sums, (const long long*)counts, mean_sub, use_reciprocal, round_f32, centres, shift_tot,
                                 (double*)workspace, (const unsigned long long*)n_changed, tol, iteration, active, just_done, n_iter,
                                 n_active, n, labels_cur, labels_other, stream);
+}
+
+int ofc_minibatch_update(const void* Xb, int dtype, int batch_rows, int d, int k, const int32_t* labels, const double* centres_old,
+                         double* centres_new, double* weight_sums, void* stream) {
+    OFC_REQUIRE(dtype == OFC_U8 || dtype == OFC_F32 || dtype == OFC_F64, "bad dtype %d", dtype);
+    OFC_REQUIRE(batch_rows >= 1 && d >= 1 && k >= 1, "bad shape");
+    OFC_REQUIRE(Xb && labels && centres_old && centres_new && weight_sums, "null buffer");
+    return launch_minibatch_update(Xb, dtype, batch_rows, d, k, labels, centres_old, centres_new, weight_sums, stream);
 }
 
 int ofc_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,

@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(256) kmeans_assign_fix_u8_kernel(const unsigne
     }
 }
 
-// c2 in float64 in the order of kmeans_c2_kernel (sequential fma chain) for the re-evaluation, and its float32
+// c2 in float64 in the order of kmeans_c2_kernel (numpy's einsum order, norm_sq_numpy_f64) for the re-evaluation, and its float32
 // image (padded with +inf) for the tensor-core epilogue
 __global__ void centres_c2_f64_kernel(const double* __restrict__ c, double* __restrict__ c2d, float* __restrict__ c2f, int d, int k,
                                       int k_pad) {
@@ -470,8 +470,7 @@ __global__ void centres_c2_f64_kernel(const double* __restrict__ c, double* __re
         return;
     }
     const double* r = c + (int64_t)j * d;
-    double s = 0.0;
-    for (int t = 0; t < d; ++t) s = fma(r[t], r[t], s);
+    const double s = norm_sq_numpy_f64(r, d);
     c2d[j] = s;
     c2f[j] = (float)s;
 }

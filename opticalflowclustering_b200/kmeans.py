@@ -26,7 +26,6 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
-from fractions import Fraction
 
 import numpy as np
 import torch
@@ -37,12 +36,24 @@ _vp = C.c_void_p
 _DT = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}
 
 
+#: set by tests only (tests/emu: the same .cu sources compiled for the host): the library every entry point of this
+#: module and of cosine.py uses instead of libofc.so.  The product never sets it; there is no CPU fallback.
+_TEST_LIBRARY = None
+
+
+def _use_test_library(lib):
+    """Private test hook: route this module through the host-side debug emulation (``None`` restores libofc.so)."""
+    global _TEST_LIBRARY
+    _TEST_LIBRARY = lib
+
+
 class _Ctx:
-    """Library handle + device.  The product path is always libofc.so on a CUDA device;
-    tests pass the host-side debug emulation of the same kernels explicitly."""
+    """Library handle + device.  The product path is always libofc.so on a CUDA device."""
 
     def __init__(self, device, lib=None):
         self.device = torch.device(device)
+        if lib is None:
+            lib = _TEST_LIBRARY
         if lib is None:
             if self.device.type != "cuda":
                 raise _lib.OfcError("a CUDA device is required: this package has no CPU fallback")
@@ -65,9 +76,10 @@ def _ptr(t):
     return _vp(t.data_ptr()) if t is not None else _vp(0)
 
 
-def _target_device(X, lib_override):
-    """Where host inputs go: the current CUDA device (product) -- or the host when a test passes
+def _target_device(X, lib_override=None):
+    """Where host inputs go: the current CUDA device (product) -- or the host when a test has installed
     the emulated library.  Fails loudly when neither the GPU nor the CUDA library is there."""
+    lib_override = lib_override if lib_override is not None else _TEST_LIBRARY
     if lib_override is not None:
         return None if (isinstance(X, torch.Tensor) and X.is_cuda) else "cpu"
     if isinstance(X, torch.Tensor) and X.is_cuda:
@@ -117,14 +129,18 @@ class LloydState:
             self.ws_bytes = max(self.ws_bytes, int(lib.ofc_kmeans_assign_workspace_bytes(self.B, self.n, self.d, max(self.k, 1))))
         self.ws = torch.empty(max(self.ws_bytes, 256), dtype=torch.uint8, device=dev)
         self.labels = [torch.full((self.B, self.n), -1, dtype=torch.int32, device=dev) for _ in range(2)]
-        # one flat fp64 buffer so a single all-reduce moves sums, counts and n_changed together
-        kd = self.k * self.d
-        self.red = torch.zeros((self.B, kd + self.k + 1), dtype=torch.float64, device=dev)
-        self.sums = torch.empty((self.B, self.k, self.d), dtype=torch.float64, device=dev)
-        self.counts = torch.empty((self.B, self.k), dtype=torch.int64, device=dev)
-        self.n_changed = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        # the kernels write straight into the buffers the all-reduces move: float64 sums, and ONE int64 buffer holding
+        # the member counts followed by the label-change counts (two collectives per iteration, no staging copies)
+        self.sums = torch.zeros((self.B, self.k, self.d), dtype=torch.float64, device=dev)
+        self.icnt = torch.zeros(self.B * self.k + self.B, dtype=torch.int64, device=dev)
+        self.counts = self.icnt[:self.B * self.k].view(self.B, self.k)
+        self.n_changed = self.icnt[self.B * self.k:]
         self.shift = torch.zeros(self.B, dtype=torch.float64, device=dev)
         self.inertia = torch.zeros(self.B, dtype=torch.float64, device=dev)
+        # device-side loop control (ofc_kmeans_update): which problems still run, who just stopped, iterations done
+        self.active = torch.ones(self.B, dtype=torch.uint8, device=dev)
+        self.just_done = torch.zeros(self.B, dtype=torch.uint8, device=dev)
+        self.n_iter = torch.zeros(self.B, dtype=torch.int32, device=dev)
 
     # -- thin wrappers over the C-ABI -----------------------------------------------------
     def assign(self, mean, centres, labels, prev=None, n_changed=None, inertia=None, min_dist=None, active=None):
@@ -158,6 +174,15 @@ class LloydState:
                                          int(use_reciprocal), _ptr(centres), _ptr(shift), _ptr(active), _ptr(self.ws),
                                          C.c_size_t(self.ws.numel()), c.stream()))
 
+    def update_(self, sums, counts, mean_sub, use_reciprocal, round_f32, centres, n_changed, tol, it, n_active, lab, lab_other):
+        """new centres + sklearn's stopping rule on the device (no read-back): see ofc_kmeans_update"""
+        c = self.ctx
+        c.check(c.lib.ofc_kmeans_update(self.B, C.c_int64(self.n), self.d, int(centres.shape[1]), _ptr(sums), _ptr(counts),
+                                        _ptr(mean_sub), int(use_reciprocal), int(round_f32), _ptr(centres), _ptr(self.shift),
+                                        _ptr(n_changed), _ptr(tol), int(it), _ptr(self.active), _ptr(self.just_done),
+                                        _ptr(self.n_iter), _ptr(n_active), _ptr(lab), _ptr(lab_other), _ptr(self.ws),
+                                        C.c_size_t(self.ws.numel()), c.stream()))
+
     def relocate(self, mean, labels, centres_old, sums, counts, raw_sums, active=None):
         c = self.ctx
         c.check(c.lib.ofc_kmeans_relocate(_ptr(self.X), self.dtype, self.B, C.c_int64(self.n), self.d, self.k, _ptr(mean),
@@ -173,8 +198,8 @@ class TensorCoreSteps:
     of the CUDA-core E-step; the M-step walks a label-sorted member list (uint8: exact integer sums)."""
 
     @staticmethod
-    def usable(st: "LloydState", lib_override) -> bool:
-        return (lib_override is None and st.X.is_cuda and st.dtype in (0, 1) and st.B == 1 and st.d > 32 and st.d % 4 == 0
+    def usable(st: "LloydState") -> bool:
+        return (_TEST_LIBRARY is None and st.X.is_cuda and st.dtype in (0, 1) and st.B == 1 and st.d > 32 and st.d % 4 == 0
                 and 2 <= st.k <= 4096 and st.n < 2 ** 31 and _tc_worth_it(st.dtype, st.d, st.k)
                 and os.environ.get("OFC_KMEANS_TC", "1") != "0")
 
@@ -225,8 +250,8 @@ def _tc_worth_it(dtype: int, d: int, k: int) -> bool:
     return dtype == 1 or k * d >= 4096
 
 
-def _tc_wanted(Xb, k, lib_override) -> bool:
-    return (lib_override is None and Xb.is_cuda and Xb.dtype in (torch.float32, torch.uint8) and Xb.shape[0] == 1
+def _tc_wanted(Xb, k) -> bool:
+    return (_TEST_LIBRARY is None and Xb.is_cuda and Xb.dtype in (torch.float32, torch.uint8) and Xb.shape[0] == 1
             and Xb.shape[2] > 32 and Xb.shape[2] % 4 == 0 and 2 <= k <= 4096
             and _tc_worth_it(_DT[Xb.dtype], int(Xb.shape[2]), k) and os.environ.get("OFC_KMEANS_TC", "1") != "0")
 
@@ -302,14 +327,12 @@ def column_mean_var(st: LloydState, group=None):
         sq = s2.view(B, d).clone()
         if group is not None:
             _all_reduce(sq, group)
-        sx = red[:, :d].cpu().numpy()
-        sxx = sq.cpu().numpy()
-        nn = n_tot.cpu().numpy().reshape(-1)
+        # one read-back per fit (set-up, not the iteration loop); int / int is correctly rounded in Python
+        host = torch.cat([red[:, :d], sq, n_tot], dim=1).cpu().numpy()
         var = np.empty((B, d))
         for b in range(B):
-            N = int(nn[b])
-            for t in range(d):
-                var[b, t] = float((Fraction(int(sxx[b, t])) - Fraction(int(sx[b, t])) ** 2 / N) / N)
+            N = int(host[b, 2 * d])
+            var[b] = [(int(host[b, d + t]) * N - int(host[b, t]) ** 2) / (N * N) for t in range(d)]
         var = torch.from_numpy(var).to(dev)
     else:
         st.sums_(mean.contiguous(), None, s2, None, 1, square=1)
@@ -320,18 +343,30 @@ def column_mean_var(st: LloydState, group=None):
     return mean.contiguous(), var, n_tot.view(-1)
 
 
-def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_override=None):
+#: how many iterations the host may run ahead of the device's "everybody has stopped" signal
+_POLL_LAG = 4
+
+
+def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None):
     """Batched ``KMeans(n_clusters=k, init=init, n_init=1, max_iter=max_iter, tol=tol).fit(X)``.
 
     X ``[n,d]`` or ``[B,n,d]`` (uint8 / float32 / float64; torch on the compute device, or numpy);
     init ``[k,d]`` or ``[B,k,d]``.  With ``group`` every rank passes its own rows (same B, d, k)
     and receives the global centres / inertia and the labels of its rows.
 
+    The loop keeps the host out of the data path: every iteration is a handful of kernel launches (E-step +
+    M-step sums, empty-cluster relocation, ``ofc_kmeans_update`` = new centres + stopping rule on the device);
+    the only thing the host reads is the "problems still running" counter, asynchronously and ``_POLL_LAG``
+    iterations late -- the iterations enqueued past the stop are skipped by every kernel.  With ``group`` the
+    kernels write into the buffers the two all-reduces move (float64 sums; int64 counts + label changes), and
+    one 1-byte flag per iteration tells the host whether a cluster is empty anywhere (the cross-rank relocation
+    is host-orchestrated).
+
     Returns ``(labels int32, centres float64, inertia float64, n_iter int64)`` as torch
     tensors on X's device, squeezed when X was ``[n,d]``.
     """
-    Xb, single = _as_batch(X, _target_device(X, _lib_override))
-    ctx = _Ctx(Xb.device, _lib_override)
+    Xb, single = _as_batch(X, _target_device(X))
+    ctx = _Ctx(Xb.device)
     init = torch.as_tensor(np.asarray(init) if not isinstance(init, torch.Tensor) else init)
     init = init.to(device=Xb.device, dtype=torch.float64)
     if init.dim() == 2:
@@ -341,36 +376,40 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
     k = int(init.shape[1])
     if init.shape[0] != B or init.shape[2] != d:
         raise ValueError(f"init shape {tuple(init.shape)} does not match X {tuple(Xb.shape)}")
-    st = LloydState(ctx, Xb, k, ws_k=1 if _tc_wanted(Xb, k, _lib_override) else None)
-    row_offset = 0
+    st = LloydState(ctx, Xb, k, ws_k=1 if _tc_wanted(Xb, k) else None)
+    dev = Xb.device
+    row_offset, n_total = 0, n
     if group is not None:
         # global index of this rank's first row (ranks hold consecutive row ranges): the tie rule of the relocation
         import torch.distributed as dist
-        ns = [torch.zeros(1, dtype=torch.int64, device=Xb.device) for _ in range(dist.get_world_size(group))]
-        dist.all_gather(ns, torch.tensor([n], dtype=torch.int64, device=Xb.device), group=group)
-        row_offset = sum(int(t.item()) for t in ns[:dist.get_rank(group)])
-    mean, var, n_tot = column_mean_var(st, group)
-    if int(n_tot.min().item()) < k:
-        raise ValueError(f"n_samples={int(n_tot.min().item())} should be >= n_clusters={k}.")   # _kmeans.py:876-879
-    tol_ = (var.mean(dim=1) * tol).cpu().numpy()
+        ns = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(ns, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
+        ns = [int(t.item()) for t in ns]
+        row_offset, n_total = sum(ns[:dist.get_rank(group)]), sum(ns)
+    if n_total < k:
+        raise ValueError(f"n_samples={n_total} should be >= n_clusters={k}.")   # _kmeans.py:876-879
+    mean, var, _ = column_mean_var(st, group)
+    tol_ = (var.mean(dim=1) * tol).contiguous()                  # stays on the device
     is_u8 = st.dtype == 0
-    if st.dtype == 1:
+    is_f32 = st.dtype == 1
+    if is_f32:
         # sklearn keeps float32 data in float32: centre with the float32 mean
         mean = mean.to(torch.float32).to(torch.float64).contiguous()
     centres = (init - mean.unsqueeze(1)).contiguous()            # centred
-    if st.dtype == 1:
+    if is_f32:
         centres = centres.to(torch.float32).to(torch.float64).contiguous()
-    centres_old = torch.empty_like(centres)
     # dense float32 corner (d > 32): E/M steps on the tensor-core path, same labels as the float32 kernels
-    tc = TensorCoreSteps(st, mean[0].contiguous()) if TensorCoreSteps.usable(st, _lib_override) else None
-
+    tc = TensorCoreSteps(st, mean[0].contiguous()) if TensorCoreSteps.usable(st) else None
     fused = tc is None and is_u8 and st.step_supported()
 
-    active = torch.ones(B, dtype=torch.uint8, device=Xb.device)
-    active_h = np.ones(B, bool)
-    strict = np.zeros(B, bool)
-    n_iter = np.zeros(B, np.int64)
-    kd = k * d
+    active = st.active
+    n_active = torch.zeros(max(max_iter, 1), dtype=torch.int32, device=dev)        # problems still running after iteration i
+    is_cuda = dev.type == "cuda"
+    seen = torch.empty(max(max_iter, 1), dtype=torch.int32, pin_memory=is_cuda)
+    events = []
+    flag_dev = flag_host = None
+    if group is not None:
+        flag_host = torch.empty(1, dtype=torch.uint8, pin_memory=is_cuda)
     cur = 0
     for it in range(max_iter):
         lab, lab_old = st.labels[cur], st.labels[cur ^ 1]
@@ -384,45 +423,37 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
             # uint8: raw (exact integer) sums; floats: sums of the centred rows like sklearn
             st.sums_(None if is_u8 else mean, lab, st.sums, st.counts, k, active=active)
         if group is not None:
-            st.red[:, :kd] = st.sums.view(B, kd)
-            st.red[:, kd:kd + k] = st.counts.to(torch.float64)
-            st.red[:, kd + k] = st.n_changed.to(torch.float64)
-            _all_reduce(st.red, group)
-            st.sums.view(B, kd).copy_(st.red[:, :kd])
-            st.counts.copy_(st.red[:, kd:kd + k].to(torch.int64))
-            st.n_changed.copy_(st.red[:, kd + k].to(torch.int64))
-            if bool((st.counts == 0).any().item()):
+            if B > 1:
+                # stopped problems contribute nothing (their buffers hold already-reduced values)
+                off = (active == 0)
+                st.sums.masked_fill_(off.view(B, 1, 1), 0.0)
+                st.counts.masked_fill_(off.view(B, 1), 0)
+                st.n_changed.masked_fill_(off, 0)
+            _all_reduce(st.sums, group)
+            _all_reduce(st.icnt, group)
+            flag_dev = ((st.counts == 0) & (active != 0).view(B, 1)).any().to(torch.uint8).view(1)
+            flag_host.copy_(flag_dev, non_blocking=True)
+            if is_cuda:
+                torch.cuda.current_stream(dev).synchronize()
+            if int(flag_host[0]):
                 _relocate_across_ranks(st, mean, lab, centres, st.sums, st.counts, is_u8, group, row_offset)
         else:
             st.relocate(mean, lab, centres, st.sums, st.counts, is_u8, active=active)
-        centres_old.copy_(centres)
-        st.centres_(st.sums, st.counts, mean if is_u8 else None, 0 if is_u8 else 1, centres, st.shift, active=active)
-        if st.dtype == 1:
-            centres.copy_(centres.to(torch.float32).to(torch.float64))
-        host = torch.stack([st.n_changed.to(torch.float64), st.shift]).cpu().numpy()
-        changed, shift = host[0], host[1]
-        done_now = np.zeros(B, bool)
-        for b in range(B):
-            if not active_h[b]:
-                continue
-            n_iter[b] = it + 1
-            if changed[b] == 0:
-                strict[b] = True
-                done_now[b] = True
-            elif shift[b] <= tol_[b]:
-                done_now[b] = True
-        if done_now.any():
-            active_h &= ~done_now
-            active.copy_(torch.from_numpy(active_h.astype(np.uint8)))
-        # frozen problems must keep the labels they stopped with: both label buffers
-        # get them, so swapping buffers never resurrects stale labels
-        if done_now.any():
-            idx = torch.from_numpy(np.nonzero(done_now)[0]).to(Xb.device)
-            lab_old[idx] = lab[idx]
-        if not active_h.any():
-            break
+        st.update_(st.sums, st.counts, mean if is_u8 else None, 0 if is_u8 else 1, 1 if is_f32 else 0, centres, st.n_changed,
+                   tol_, it, n_active[it:it + 1], lab, lab_old)
+        seen[it:it + 1].copy_(n_active[it:it + 1], non_blocking=True)
+        if is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            events.append(ev)
+        back = it - (_POLL_LAG if is_cuda and group is None else 0)
+        if back >= 0:
+            if is_cuda:
+                events[back].synchronize()
+            if int(seen[back]) == 0:
+                break
         cur ^= 1
-    final = st.labels[cur]
+    final = st.labels[0]
     # strict stops already hold the labels of the final centres; the rest get one more E-step
     # (_kmeans.py:745-755).  Re-running it for everyone is idempotent for the strict ones and
     # yields the inertia of the final (centres, labels) in the same pass.
@@ -434,14 +465,13 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _lib_over
     if group is not None:
         _all_reduce(inertia, group)
     out_centres = centres + mean.unsqueeze(1)
-    n_iter_t = torch.from_numpy(n_iter).to(Xb.device)
+    n_iter_t = st.n_iter.to(torch.int64)
     if single:
         return final[0], out_centres[0], inertia[0], n_iter_t[0]
     return final, out_centres, inertia, n_iter_t
 
 
-def lloyd_cells(X, n_clusters: int, init=None, seed: int = 0, max_iter: int = 300, tol: float = 1e-4,
-                _lib_override=None):
+def lloyd_cells(X, n_clusters: int, init=None, seed: int = 0, max_iter: int = 300, tol: float = 1e-4):
     """All Lloyd runs of a batch of small uint8 problems in ONE kernel launch (one CTA per problem): the
     reference's per-cell ``KMeans(n_clusters=k).fit`` loop over a frame's grid cells
     (KmeanGrids.py:376-392).  X uint8 ``[B, n, d]`` (d <= 8, k <= 64).  ``init`` ``[B,k,d]`` / ``[k,d]``
@@ -449,10 +479,10 @@ def lloyd_cells(X, n_clusters: int, init=None, seed: int = 0, max_iter: int = 30
 
     Returns ``(labels int32 [B,n], centres float64 [B,k,d], inertia [B], n_iter int32 [B], counts int64 [B,k])``
     on X's device; ``counts`` are the member counts of the final labels."""
-    Xb, single = _as_batch(X, _target_device(X, _lib_override))
+    Xb, single = _as_batch(X, _target_device(X))
     if Xb.dtype != torch.uint8:
         raise TypeError("lloyd_cells takes uint8 rows (the reference's pixels)")
-    ctx = _Ctx(Xb.device, _lib_override)
+    ctx = _Ctx(Xb.device)
     B, n, d = (int(v) for v in Xb.shape)
     k = int(n_clusters)
     dev = Xb.device
@@ -479,10 +509,10 @@ def lloyd_cells(X, n_clusters: int, init=None, seed: int = 0, max_iter: int = 30
     return labels, centres, inertia, n_iter, counts
 
 
-def predict(X, centres, _lib_override=None):
+def predict(X, centres):
     """``KMeans.predict``: E-step on the un-centred rows (_kmeans.py:1075-1107)."""
-    Xb, single = _as_batch(X, _target_device(X, _lib_override))
-    ctx = _Ctx(Xb.device, _lib_override)
+    Xb, single = _as_batch(X, _target_device(X))
+    ctx = _Ctx(Xb.device)
     c = torch.as_tensor(np.asarray(centres) if not isinstance(centres, torch.Tensor) else centres)
     c = c.to(device=Xb.device, dtype=torch.float64)
     if c.dim() == 2:
@@ -493,7 +523,7 @@ def predict(X, centres, _lib_override=None):
     return st.labels[0][0] if single else st.labels[0]
 
 
-def kmeans_plusplus(X, n_clusters: int, random_state=None, _lib_override=None):
+def kmeans_plusplus(X, n_clusters: int, random_state=None):
     """k-means++ seeding with sklearn's procedure and RNG call sequence
     (sklearn/cluster/_kmeans.py:181-268): first centre by ``random_state.choice``, then
     ``2 + int(log(k))`` candidates per step sampled in proportion to the squared distance to
@@ -503,10 +533,10 @@ def kmeans_plusplus(X, n_clusters: int, random_state=None, _lib_override=None):
 
     The reference leaves ``random_state`` unset (KmeanGrids.py:300), so this seeding is not
     pinned by any reference output."""
-    Xb, single = _as_batch(X, _target_device(X, _lib_override))
+    Xb, single = _as_batch(X, _target_device(X))
     if not single:
         raise ValueError("kmeans_plusplus takes one problem [n, d]")
-    ctx = _Ctx(Xb.device, _lib_override)
+    ctx = _Ctx(Xb.device)
     rs = random_state if isinstance(random_state, np.random.RandomState) else np.random.RandomState(random_state)
     n, d = int(Xb.shape[1]), int(Xb.shape[2])
     k = int(n_clusters)
@@ -545,11 +575,9 @@ class KMeans:
     ``.cluster_centers_``, ``.labels_``, ``.inertia_``, ``.n_iter_``.  ``init`` may be
     ``'k-means++'`` (default, see :func:`kmeans_plusplus`) or an array ``[k, d]``."""
 
-    def __init__(self, n_clusters=8, *, init="k-means++", n_init="auto", max_iter=300, tol=1e-4, random_state=None,
-                 _lib_override=None):
+    def __init__(self, n_clusters=8, *, init="k-means++", n_init="auto", max_iter=300, tol=1e-4, random_state=None):
         self.n_clusters, self.init, self.n_init = int(n_clusters), init, n_init
         self.max_iter, self.tol, self.random_state = int(max_iter), float(tol), random_state
-        self._lo = _lib_override
 
     def fit(self, X, y=None):
         Xa = X if isinstance(X, torch.Tensor) else np.asarray(X)
@@ -563,10 +591,10 @@ class KMeans:
             if self.n_clusters == 1:
                 init = (Xa[:1].to(torch.float64) if isinstance(Xa, torch.Tensor) else Xa[:1].astype(np.float64))
             else:
-                init, _ = kmeans_plusplus(Xa, self.n_clusters, self.random_state, _lib_override=self._lo)
+                init, _ = kmeans_plusplus(Xa, self.n_clusters, self.random_state)
         else:
             init = self.init
-        labels, centres, inertia, n_iter = lloyd(Xa, init, self.max_iter, self.tol, _lib_override=self._lo)
+        labels, centres, inertia, n_iter = lloyd(Xa, init, self.max_iter, self.tol)
         self._centres_t = centres
         self.cluster_centers_ = centres.cpu().numpy()
         if not isinstance(X, torch.Tensor) and np.asarray(X).dtype == np.float32:
@@ -577,7 +605,7 @@ class KMeans:
         return self
 
     def predict(self, X):
-        return predict(X, self._centres_t, _lib_override=self._lo).cpu().numpy()
+        return predict(X, self._centres_t).cpu().numpy()
 
     def fit_predict(self, X, y=None):
         return self.fit(X).labels_

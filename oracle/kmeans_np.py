@@ -28,7 +28,10 @@ def _work_dtype(X: np.ndarray):
 
 def _e_step(X, centers):
     """labels = first strict minimum of ||c||^2 - 2 x.c  (ties -> lowest index)."""
-    c2 = (centers * centers).sum(axis=1)
+    # sklearn: row_norms(centers, squared=True) == np.einsum("ij,ij->i", ...) -- its summation order (two interleaved
+    # partial sums, no fma) differs from .sum(axis=1) in the last bit, which decides labels of rows that sit exactly on
+    # a bisector (uint8 lattice data)
+    c2 = np.einsum("ij,ij->i", centers, centers)
     n = X.shape[0]
     labels = np.empty(n, np.int32)
     chunk = 1 << 16

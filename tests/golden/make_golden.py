@@ -163,6 +163,8 @@ def main():
     print("kmeans goldens ok")
     make_dense_kmeans_golden()
     make_seeded_kmeans_golden()
+    make_sweep_kmeans_golden()
+    make_minibatch_golden()
 
 
 def make_dense_kmeans_golden():
@@ -185,8 +187,6 @@ def make_dense_kmeans_golden():
     print("dense kmeans goldens ok")
 
 
-if __name__ == "__main__":
-    main()
 
 
 def make_seeded_kmeans_golden():
@@ -210,3 +210,72 @@ def make_seeded_kmeans_golden():
         cases[name + "_niter"] = np.int64(km.n_iter_)
     np.savez_compressed(f"{HERE}/kmeans_sklearn_seeded.npz", **cases)
     print("seeded kmeans goldens ok")
+
+
+SWEEP_CASES = {   # name: (N, D, k, seed, dtype) -- the ends of BASELINE.json configs[4]'s sweep (D = 2 .. 5000)
+    "u8_d2_k8": (20000, 2, 8, 21, "u8"), "f32_d2_k8": (20000, 2, 8, 22, "f32"),
+    "f32_d2048_k16": (3000, 2048, 16, 23, "f32"), "f32_d5000_k8": (2000, 5000, 8, 24, "f32"),
+    "u8_d5000_k8": (1500, 5000, 8, 25, "u8"), "f32_d2050_k12": (2500, 2050, 12, 26, "f32"),
+}
+
+
+def sweep_case(name):
+    """regenerate the rows of a sweep case from its seed (the fixture stores only the sklearn results)"""
+    N, D, k, seed, kind = SWEEP_CASES[name]
+    rng = np.random.default_rng(seed)
+    if kind == "u8":
+        cen = rng.uniform(20, 230, (k, D))
+        X = np.clip(np.rint(cen[rng.integers(k, size=N)] + rng.normal(0, 12, (N, D))), 0, 255).astype(np.uint8)
+        init = X[:k].astype(np.float64)
+    else:
+        cen = rng.uniform(0, 8, (k, D))
+        X = (cen[rng.integers(k, size=N)] + rng.normal(0, 1, (N, D))).astype(np.float32)
+        init = X[:k].copy()
+    return X, init
+
+
+def make_sweep_kmeans_golden():
+    """sklearn 1.9.0 KMeans(init=first k rows, n_init=1) at D = 2, 2048, 2050 (not a multiple of 4), 5000"""
+    from sklearn.cluster import KMeans
+    cases = {}
+    for name in SWEEP_CASES:
+        X, init = sweep_case(name)
+        km = KMeans(n_clusters=init.shape[0], init=init, n_init=1).fit(X)
+        cases[name + "_labels"] = km.labels_.astype(np.int32)
+        cases[name + "_center_sums"] = km.cluster_centers_.astype(np.float64).sum(axis=1)     # [k]: keeps the fixture small
+        cases[name + "_inertia"] = np.float64(km.inertia_)
+        cases[name + "_niter"] = np.int64(km.n_iter_)
+    np.savez_compressed(f"{HERE}/kmeans_sklearn_sweep.npz", **cases)
+    print("sweep kmeans goldens ok")
+
+
+MINIBATCH_CASES = {"lab_k8_rs0": (30000, 8, 0, 31), "lab_k4_rs7": (9000, 4, 7, 32), "lab_k16_rs3": (50000, 16, 3, 33)}
+
+
+def minibatch_case(name):
+    """LAB-like uint8 pixels: a few colour blobs on a smooth background (regenerated from the seed)"""
+    n, k, rs, seed = MINIBATCH_CASES[name]
+    rng = np.random.default_rng(seed)
+    cen = rng.uniform(30, 220, (k + 2, 3))
+    X = np.clip(np.rint(cen[rng.integers(k + 2, size=n)] + rng.normal(0, 9, (n, 3))), 0, 255).astype(np.uint8)
+    return X, k, rs
+
+
+def make_minibatch_golden():
+    """SURVEY section 8f-4 (color-quantization/quant.py:18-19): sklearn 1.9.0 MiniBatchKMeans(n_clusters=k,
+    random_state=rs).fit on uint8 pixels -- centres, labels, number of mini-batch steps, inertia"""
+    from sklearn.cluster import MiniBatchKMeans
+    cases = {}
+    for name in MINIBATCH_CASES:
+        X, k, rs = minibatch_case(name)
+        clt = MiniBatchKMeans(n_clusters=k, random_state=rs).fit(X)
+        cases[name + "_labels"] = clt.labels_.astype(np.int32)
+        cases[name + "_centers"] = clt.cluster_centers_
+        cases[name + "_inertia"] = np.float64(clt.inertia_)
+        cases[name + "_nsteps"] = np.int64(clt.n_steps_)
+    np.savez_compressed(f"{HERE}/minibatch_sklearn.npz", **cases)
+    print("minibatch goldens ok")
+
+
+if __name__ == "__main__":
+    main()

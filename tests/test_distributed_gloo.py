@@ -49,9 +49,10 @@ def _worker(rank, world, port, out_dir, case="plain"):
     from opticalflowclustering_b200 import kmeans as km
     from opticalflowclustering_b200.sharding import shard_range
     from tests.emu import emu_lib as E
+    km._use_test_library(E.lib())
     X, init = _case() if case == "plain" else _case_empty()
     lo, hi = shard_range(len(X), rank, world)
-    labels, centres, inertia, n_iter = km.lloyd(X[lo:hi], init, group=dist.group.WORLD, _lib_override=E.lib())
+    labels, centres, inertia, n_iter = km.lloyd(X[lo:hi], init, group=dist.group.WORLD)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), labels=labels.numpy(), centres=centres.numpy(),
              inertia=float(inertia), n_iter=int(n_iter), lo=lo, hi=hi)
     dist.destroy_process_group()
@@ -61,8 +62,10 @@ def test_sharded_lloyd_equals_single_rank(tmp_path):
     from tests.emu import emu_lib as E
     E.build()
     from opticalflowclustering_b200 import kmeans as km
+    km._use_test_library(E.lib())
     X, init = _case()
-    l1, c1, i1, n1 = km.lloyd(X, init, _lib_override=E.lib())
+    l1, c1, i1, n1 = km.lloyd(X, init)
+    km._use_test_library(None)
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     got = [np.load(tmp_path / f"r{r}.npz") for r in range(2)]
@@ -81,8 +84,10 @@ def test_sharded_lloyd_relocates_empty_clusters_like_single_rank(tmp_path):
     E.build()
     from opticalflowclustering_b200 import kmeans as km
     from oracle import kmeans_np as K
+    km._use_test_library(E.lib())
     X, init = _case_empty()
-    l1, c1, i1, n1 = km.lloyd(X, init, _lib_override=E.lib())
+    l1, c1, i1, n1 = km.lloyd(X, init)
+    km._use_test_library(None)
     ref = K.kmeans_fit(X, init)                              # the relocation really happens and matches sklearn's rule
     assert (l1.numpy() == ref[0]).all() and int(n1) == ref[3]
     port = _free_port()

@@ -134,8 +134,8 @@ for (H, W) in [(61, 250), (101, 150)]:
     e = np.linalg.norm(f - ref, axis=-1)
     assert e.mean() < 2e-6 and e.max() < 2e-4, (H, W, e.mean(), e.max())
     if os.environ.get("OFC_ITER_TMEM") == "1":
-        # the coarse flow up-sampled inside the walk (default) == the separate up-sample launch, bit for bit
-        os.environ["OFC_FUSE_UPSAMPLE"] = "0"
+        # the coarse flow up-sampled inside the walk (OFC_FUSE_UPSAMPLE=1) == the separate up-sample launch, bit for bit
+        os.environ["OFC_FUSE_UPSAMPLE"] = "1"
         f2 = E.Plan(W, H, max_frames=2).sequence(g)[0]
         del os.environ["OFC_FUSE_UPSAMPLE"]
         assert (f2 == f).all(), (H, W, np.abs(f2 - f).max())

@@ -26,6 +26,19 @@ def _epe(a, b):
     return np.linalg.norm(a - b, axis=-1)
 
 
+def _record_parity(key, stats):
+    """the measured distributions also go to gpurun_out/flow_parity.json (copied to profiles/ as evidence)"""
+    import json
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "flow_parity.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur[key] = stats
+        json.dump(cur, open(path, "w"), indent=1)
+    except OSError:
+        pass
+
+
 @pytest.fixture(scope="module")
 def ofc():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
@@ -287,12 +300,20 @@ def test_full_size_properties(ofc, size):
     inner = (slice(40, H - 40), slice(40, W - 40))
     err = (f1[0][inner] - truth[inner]).norm(dim=-1)
     assert err.mean().item() < 0.1, err.mean().item()
-    if have_cv2() and size == (720, 1280):
+    if have_cv2():
+        # the direct comparison at BOTH BASELINE sizes (1080p is the headline config and the one width whose strips
+        # are never ragged), with the distribution BASELINE.md section 5 asks for
         import cv2
+        from tests.conftest import flow_parity_stats
         g = gray.cpu().numpy()
         ref = cv2.calcOpticalFlowFarneback(g[0], g[1], None, 0.5, 3, 15, 3, 5, 1.2, 0)
-        e = _epe(f1[0].cpu().numpy(), ref)
-        assert e.mean() <= MEAN_EPE and e.max() <= MAX_EPE, (e.mean(), e.max())
+        top = plan.num_levels - 1
+        st = flow_parity_stats(f1[0].cpu().numpy(), ref, plan.buffer(top, 1, 0).cpu().numpy(), plan.buffer(top, 2, 0).cpu().numpy()[..., 0])
+        print(f"\nflow parity vs cv2 {W}x{H}: {st}")
+        _record_parity(f"{W}x{H}_L3", st)
+        assert st["mean"] <= MEAN_EPE and st["max"] <= MAX_EPE, st
+        assert st["p99"] <= 1e-4 and st["p99.9"] <= 5e-4 and st["max_well_conditioned"] <= MAX_EPE, st
+        assert st["well_conditioned_share"] > 0.5
 
 
 def test_4k_five_level_pyramid_properties(ofc):
@@ -318,5 +339,97 @@ def test_4k_five_level_pyramid_properties(ofc):
         import cv2
         g = gray.cpu().numpy()
         ref = cv2.calcOpticalFlowFarneback(g[0], g[1], None, 0.5, 5, 15, 3, 5, 1.2, 0)
-        e = _epe(f1[0].cpu().numpy(), ref)
-        assert e.mean() <= MEAN_EPE and e.max() <= 5 * MAX_EPE, (e.mean(), e.max())
+        from tests.conftest import flow_parity_stats
+        top = plan.num_levels - 1
+        st = flow_parity_stats(f1[0].cpu().numpy(), ref, plan.buffer(top, 1, 0).cpu().numpy(), plan.buffer(top, 2, 0).cpu().numpy()[..., 0])
+        print(f"\nflow parity vs cv2 {W}x{H} levels=5: {st}")
+        _record_parity(f"{W}x{H}_L5", st)
+        assert st["mean"] <= MEAN_EPE and st["max"] <= 5 * MAX_EPE, st
+        assert st["p99"] <= 1e-4 and st["max_well_conditioned"] <= 5 * MAX_EPE, st
+
+
+# ---- round-2 kernels: every fused / fast form against the form it replaces, at the BASELINE sizes -------------------
+def _flow_with_env(monkeypatch, env, W, H, gray, levels=3):
+    from opticalflowclustering_b200.flow import FarnebackPlan
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    plan = FarnebackPlan(W, H, max_frames=int(gray.shape[0]), levels=levels).keep_intermediates()
+    out = plan.sequence(gray).clone()
+    inter = [plan.buffer(l, 0, 1).clone() for l in range(plan.num_levels)]
+    for k in env:
+        monkeypatch.delenv(k)
+    return out, inter
+
+
+@pytest.mark.parametrize("size,levels", [((1080, 1920), 3), ((720, 1280), 3), ((2160, 3840), 5)])
+def test_pyramid_prefilter_and_fused_upsample_bit_identical(ofc, size, levels, monkeypatch):
+    """one-launch pyramid pre-filter == per-level tile kernels (I of every level, bit for bit), and the coarse flow
+    up-sampled inside the TMEM walk == the separate up-sample launch (final flow, bit for bit)"""
+    from opticalflowclustering_b200.flow import bgr2gray
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    H, W = size
+    gray = bgr2gray(synthetic_clip(2, H, W, seed=31, device="cuda"))
+    new, inew = _flow_with_env(monkeypatch, {"OFC_PREFILTER_PYR": "1", "OFC_FUSE_UPSAMPLE": "1"}, W, H, gray, levels)
+    old, iold = _flow_with_env(monkeypatch, {"OFC_PREFILTER_PYR": "0", "OFC_FUSE_UPSAMPLE": "0"}, W, H, gray, levels)
+    for a, b in zip(inew, iold):
+        assert torch.equal(a, b)
+    assert torch.equal(new, old)
+
+
+@pytest.mark.parametrize("size,grid", [((1080, 1920), (14, 25)), ((720, 1280), (14, 25)), ((270, 484), (5, 7))])
+def test_fused_encode_grid_equals_separate_kernels(ofc, size, grid):
+    """ofc_flow_to_bgr_grid == ofc_flow_to_bgr + ofc_grid_cells on real flow fields: word path (1080p cells are 76 px
+    wide), scalar path (720p: 51 px), ragged remainder; and both equal the oracle's statement of cv2"""
+    from opticalflowclustering_b200.pipeline import ClipPipeline
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    H, W = size
+    rows, cols = grid
+    clip = synthetic_clip(3, H, W, seed=41, device="cuda")
+    a = ClipPipeline(W, H, chunk_frames=3, rows=rows, cols=cols)
+    assert a.fuse_grid
+    a.run_chunk(clip)
+    b = ClipPipeline(W, H, chunk_frames=3, rows=rows, cols=cols)
+    b.fuse_grid = False
+    b.run_chunk(clip)
+    for name in ("viz", "avg_bgr", "avg_hue", "km_centre", "km_hue"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert (a.mag_sum - b.mag_sum).abs().max().item() <= 1e-9 * b.mag_sum.abs().max().item()
+    want, _ = V.flow_to_bgr(a.flow[0].cpu().numpy())
+    assert (a.viz[0].cpu().numpy() == want).all()
+
+
+def test_compute_optical_flow_mask_attribute(ofc):
+    """ComputeOpticalFLow.mask follows the reference (computeOpticalFlowModule.py:14-15, 28-31): S = 255 always, H and V
+    bytes of the latest pair after compute()"""
+    from opticalflowclustering_b200.computeOpticalFlowModule import ComputeOpticalFLow
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    clip = synthetic_clip(3, 120, 168, seed=3).numpy()
+    cf = ComputeOpticalFLow(clip[0])
+    m0 = cf.mask
+    assert m0.shape == clip[0].shape and (m0[..., 1] == 255).all() and (m0[..., 0] == 0).all() and (m0[..., 2] == 0).all()
+    for f in clip[1:]:
+        out = cf.compute(f)
+        fl = cf.last_flow.cpu().numpy()
+        mag, ang = V.cart_to_polar(fl[..., 0], fl[..., 1])
+        m = cf.mask
+        assert (m[..., 0] == V.hue_byte(ang)).all() and (m[..., 1] == 255).all() and (m[..., 2] == V.normalize_minmax_u8(mag)).all()
+        assert (out == V.flow_to_bgr(fl)[0]).all()
+
+
+def test_one_process_two_devices(ofc):
+    """the > 48 KB shared-memory opt-in of every kernel is recorded per device: the same process runs the pipeline on
+    cuda:0 and then on cuda:1 (skipped on a one-GPU box)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from opticalflowclustering_b200.pipeline import ClipPipeline
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    clip = synthetic_clip(3, 288, 720, seed=2)
+    res = []
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            pipe = ClipPipeline(720, 288, chunk_frames=3, rows=6, cols=8, device=f"cuda:{d}", n_clusters=2)
+            pipe.run_chunk(clip.to(f"cuda:{d}"))
+            torch.cuda.synchronize(d)
+            res.append((pipe.avg_hue.cpu(), pipe.km_hue.cpu(), pipe.flow.cpu()))
+    for u, v in zip(res[0], res[1]):
+        assert torch.equal(u, v)

@@ -77,8 +77,10 @@ def test_lloyd_dense_float32_vs_sklearn_golden(name):
     cen = rng.uniform(0, 8, (k, D))
     X = (cen[rng.integers(k, size=N)] + rng.normal(0, 1, (N, D))).astype(np.float32)
     labels, centres, inertia, n_iter = kmeans.kmeans_fit(X, X[:k].copy())
-    assert (labels == z[name + "_labels"]).mean() > 0.9995
-    assert np.abs(centres - z[name + "_centers"]).max() < 1e-2
+    bad = int((labels != z[name + "_labels"]).sum())
+    print(f"\n{name} (tensor-core path): {bad} of {labels.size} labels differ from sklearn")
+    assert bad == 0
+    assert np.abs(centres - z[name + "_centers"]).max() < 1e-4
     assert abs(inertia - float(z[name + "_inertia"])) <= 1e-5 * float(z[name + "_inertia"])
     assert n_iter == int(z[name + "_niter"])
 

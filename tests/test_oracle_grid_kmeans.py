@@ -106,3 +106,21 @@ def test_rint_mean_exact_matches_sklearn_k1():
         want = np.rint(km.cluster_centers_[0])
         got = K.rint_mean_exact(X.astype(np.int64).sum(0), n)
         assert (want == got).all(), (want, got)
+
+
+def test_oracle_kmeans_sweep_ends_vs_sklearn_golden():
+    """the oracle against the committed sklearn results at D = 2 / 2048 / 2050 / 5000 (tests/golden/make_golden.py:
+    make_sweep_kmeans_golden): labels bit-exact, same n_iter"""
+    import os
+    import sys
+    import numpy as np
+    from oracle import kmeans_np as K
+    from tests.conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_golden as MG
+    z = np.load(os.path.join(GOLDEN, "kmeans_sklearn_sweep.npz"))
+    for name in MG.SWEEP_CASES:
+        X, init = MG.sweep_case(name)
+        w = K.kmeans_fit(X, init)
+        assert (w[0] == z[name + "_labels"]).all() and w[3] == int(z[name + "_niter"]), name
+        assert abs(w[2] - float(z[name + "_inertia"])) <= 1e-5 * float(z[name + "_inertia"])
