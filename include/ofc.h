@@ -226,18 +226,20 @@ int ofc_minibatch_update(const void* Xb, int dtype, int batch_rows, int d, int k
  * Distances use (x - mean) against centres_old; raw_sums says whether `sums` holds sums of
  * the raw rows (uint8 path) or of the centred rows.  Returns immediately on the device for
  * problems without an empty cluster, so it can be launched every iteration; call it
- * between ofc_kmeans_sums and ofc_kmeans_centres. */
+ * between ofc_kmeans_sums and ofc_kmeans_centres.  scratch (f64 [batch][n], may be NULL): with it the row
+ * distances are computed once by the whole grid and the picks read them (same result; without it one CTA per
+ * problem re-reads X once per empty cluster, which is only tolerable for small problems). */
 int ofc_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                         const int32_t* labels, const double* centres_old, double* sums, int64_t* counts,
-                        int raw_sums, const uint8_t* active, void* stream);
+                        int raw_sums, const uint8_t* active, double* scratch, void* stream);
 
 /* Row-sharded data (one shard per GPU): the search half of that relocation.  out_val / out_idx [batch][n_far] =
  * this shard's n_far farthest rows (squared distance to the old centre of their label; largest first, lowest
  * index on ties; idx -1 past the shard's size).  The host merges the ranks' lists and applies the moves to the
- * all-reduced sums (opticalflowclustering_b200/kmeans.py, _relocate_across_ranks). */
+ * all-reduced sums (opticalflowclustering_b200/kmeans.py, _relocate_across_ranks).  scratch: as above. */
 int ofc_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                           const int32_t* labels, const double* centres_old, int n_far,
-                          double* out_val, int64_t* out_idx, void* stream);
+                          double* out_val, int64_t* out_idx, double* scratch, void* stream);
 
 /* Whole Lloyd runs on the device, one CTA per problem: the reference's per-cell fits
  * (KMeans(n_clusters=k).fit on every grid cell of a frame, KmeanGrids.py:376-392) in ONE launch --

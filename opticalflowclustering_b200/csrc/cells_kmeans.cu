@@ -88,7 +88,7 @@ template <int SEL> __device__ __forceinline__ unsigned spread2(unsigned w) {
 
 }  // namespace
 
-template <int KP>
+template <int KP, int RU, bool PACK>
 __global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kernel(KmCellsFastParams p) {
     constexpr int D = 4;
     OFC_DYN_SMEM(unsigned char, smraw);
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kern
     // product adds <= 4 u * 260100; rounding ||c'||^2 adds <= 260100 u; the closing fma adds <= 780300 u; with the
     // factor 2 on the dot product the total is < 3.7e6 u = 0.22 < E = 0.25.  ||x - c'||^2 and the centred float64
     // chain differ by a per-row constant (||x||^2 - ||x - mean||^2 terms cancel between clusters), and the float64
-    // chain's own rounding (< 1e-9) is far inside the margin, so a filtered gap > 4 E = 1.0 fixes the arg-min.
+    // chain's own rounding (< 1e-9) is far inside the margin, so a filtered gap > MARGIN (below) fixes the arg-min.
     // Four rows per thread step and no serial best/second chain: the distances of a row are independent, the
     // minimum is a tree, the label the lowest index that attains it, and "near tie" = more than one distance within
     // 1.0 of the minimum -- so a thread always has four rows' worth of independent arithmetic in flight.
@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kern
         for (int j = 0; j < KP; ++j) {
             fx[j] = s_cf[j * 5 + 0]; fy[j] = s_cf[j * 5 + 1]; fz[j] = s_cf[j * 5 + 2]; fw[j] = s_cf[j * 5 + 3]; fq[j] = s_cf[j * 5 + 4];
         }
-        constexpr int RU = 4;
+        // filtered values carry: the float32 evaluation error E < 0.25, the rounding of the shifted norm (< 0.07) and the
+        // index bits (< KP ulp of values below 2^21 = KP / 8); twice their sum, rounded up, separates "unique minimum"
+        constexpr float MARGIN = !PACK ? 1.5f : (KP <= 4 ? 2.f : (KP <= 8 ? 3.f : 5.f));
         for (int i0 = tid; i0 < n; i0 += 256 * RU) {
             unsigned w[RU];
             int label[RU];
@@ -315,7 +317,10 @@ __global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kern
                     dot = fmaf(x1, fy[j], dot);
                     dot = fmaf(x2, fz[j], dot);
                     dot = fmaf(x3, fw[j], dot);
-                    dj[j] = fmaf(-2.f, dot, fq[j]);
+                    // the cluster index rides in the low mantissa bits (distances are positive, see prepare_centres): the
+                    // minimum of the packed values is the arg-min, lowest index first among equal distances
+                    const float dv = fmaf(-2.f, dot, fq[j]);
+                    dj[j] = PACK ? __uint_as_float((__float_as_uint(dv) & ~(unsigned)(KP - 1)) | (unsigned)j) : dv;
                 }
                 float m[KP];
 #pragma unroll
@@ -324,11 +329,12 @@ __global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kern
                 for (int st = KP / 2; st > 0; st >>= 1)
 #pragma unroll
                     for (int j = 0; j < st; ++j) m[j] = fminf(m[j], m[j + st]);
-                const float best = m[0], lim = best + 1.0f;
-                int lb = KP - 1, cnt = 0;
+                const float best = m[0], lim = best + MARGIN;
+                int lb = PACK ? (int)(__float_as_uint(best) & (unsigned)(KP - 1)) : KP - 1;
+                int cnt = 0;
 #pragma unroll
                 for (int j = KP - 1; j >= 0; --j) {
-                    lb = dj[j] == best ? j : lb;
+                    if (!PACK) lb = dj[j] == best ? j : lb;
                     cnt += dj[j] <= lim ? 1 : 0;
                 }
                 label[r] = lb;
@@ -355,7 +361,8 @@ __global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kern
                     s_cf[j * 5 + t] = (float)u;
                 }
                 c2[j] = sq;
-                s_cf[j * 5 + 4] = (float)squ;
+                // + 2^18: ||c'||^2 - 2 x.c' >= -||x||^2 >= -260100, so every filtered distance is a positive float below 2^21
+                s_cf[j * 5 + 4] = (float)(squ + 262144.0);
             } else {
                 for (int t = 0; t < D; ++t) s_cf[j * 5 + t] = 0.f;
                 s_cf[j * 5 + 4] = 3.0e38f;
@@ -366,6 +373,7 @@ __global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kern
     for (int e = tid; e < KP * D; e += 256) s_sum[e] = 0u;
     for (int j = tid; j < KP; j += 256) s_cnt[j] = 0;
     int iters = 0;
+    bool strict = false;
     int prev_changed = n;                                  // the first E-step labels every row
     for (int it = 0; it < p.max_iter; ++it) {
         prepare_centres();
@@ -538,17 +546,22 @@ __global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kern
         }
         __syncthreads();
         iters = it + 1;
-        if (s_stop) break;
+        if (s_stop) { strict = s_stop == 2; break; }
     }
 
     // ---- closing E-step on the final centres: labels, member counts, inertia -----------------------------
-    prepare_centres();
-    for (int j = tid; j < KP; j += 256) s_cnt[j] = 0;
-    __syncthreads();
+    // After a strict stop the labels are already those of the final centres and s_cnt their member counts
+    // (_kmeans.py:745-755 skips the extra E-step too), so the pass only runs when its by-products are wanted.
     int32_t* labels_out = p.labels ? p.labels + b * n : nullptr;
     double inert = 0.0;
     const bool want_inertia = p.inertia != nullptr;
-    e_step([&](int i, unsigned w, int label) {
+    const bool closing = !strict || want_inertia || labels_out != nullptr;
+    if (closing) {
+        prepare_centres();
+        for (int j = tid; j < KP; j += 256) s_cnt[j] = 0;
+    }
+    __syncthreads();
+    if (closing) e_step([&](int i, unsigned w, int label) {
         lab[i] = (unsigned char)label;
         if (labels_out) labels_out[i] = label;
         atomicAdd(&s_cnt[label], 1);
@@ -594,6 +607,198 @@ __global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kern
     }
 }
 
+// ---------------------------------------------------------------------------
+// One stepwise Lloyd iteration (E-step + exact integer M-step sums) for the reference's pixel shape -- uint8 rows
+// with 4 channels, k <= 8 -- as ONE pass: kmeans_step_u8_kernel's results (labels, n_changed, per-CTA integer
+// partial sums, bit for bit) with the float32-filtered E-step of the per-cell kernel above and the M-step in packed
+// 16-bit register fields (flushed through warp reductions every 256 rows of a thread).  Four rows per thread step
+// (one 16-byte load, one 16-byte label store).  The centres of the stepwise API are arbitrary (any initial centres),
+// so the filter margin is computed from them:  |filtered - exact| <= 2^-24 (3060 ||c'||_1 + 2 ||c'||^2) per cluster
+// (derivation at e_step() above, with |x_t| <= 255); rows whose two best filtered distances are closer than 8x the
+// largest such bound are re-evaluated with the float64 chain.
+// ---------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(256, 2) kmeans_step_u8d4_kernel(KmAssignParams p, double* __restrict__ partial,
+                                                                  long long* __restrict__ cnt_partial) {
+    constexpr int D = 4;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, k = p.k;
+    if (p.active && !p.active[b]) return;
+    __shared__ double s_c[KP * D], s_c2[KP], s_mean[D];
+    __shared__ float s_cf[KP * 5], s_bound[KP];
+    __shared__ unsigned s_acc[KP * 5];
+    const double* cen = p.centres + (int64_t)b * k * D;
+    for (int i = tid; i < KP * D; i += 256) s_c[i] = i < k * D ? cen[i] : 0.0;
+    if (tid < D) s_mean[tid] = p.mean ? p.mean[(int64_t)b * D + tid] : 0.0;
+    for (int i = tid; i < KP * 5; i += 256) s_acc[i] = 0u;
+    __syncthreads();
+    if (tid < KP) {
+        const int j = tid;
+        if (j < k) {
+            s_c2[j] = norm_sq_numpy_f64(s_c + j * D, D);
+            double l1 = 0.0, l2 = 0.0;
+            for (int t = 0; t < D; ++t) {
+                const double u = s_c[j * D + t] + s_mean[t];
+                l1 += fabs(u); l2 += u * u;
+                s_cf[j * 5 + t] = (float)u;
+            }
+            s_cf[j * 5 + 4] = (float)l2;
+            s_bound[j] = (float)((3060.0 * l1 + 2.0 * l2) * (1.0 / 16777216.0));
+        } else {
+            s_c2[j] = 0.0;
+            for (int t = 0; t < D; ++t) s_cf[j * 5 + t] = 0.f;
+            s_cf[j * 5 + 4] = 3.0e38f;
+            s_bound[j] = 0.f;
+        }
+    }
+    __syncthreads();
+    float margin = 0.f;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) margin = fmaxf(margin, s_bound[j]);
+    margin = 8.f * margin + 1e-6f;
+    float fx[KP], fy[KP], fz[KP], fw[KP], fq[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        fx[j] = s_cf[j * 5 + 0]; fy[j] = s_cf[j * 5 + 1]; fz[j] = s_cf[j * 5 + 2]; fw[j] = s_cf[j * 5 + 3]; fq[j] = s_cf[j * 5 + 4];
+    }
+    auto exact_label = [&](unsigned w) -> int {            // kmeans_step_u8_kernel's float64 chain
+        double xc[D];
+#pragma unroll
+        for (int t = 0; t < D; ++t) xc[t] = (double)((w >> (8 * t)) & 255u) - s_mean[t];
+        double bestd = 0.0;
+        int label = 0;
+        for (int j = 0; j < k; ++j) {
+            double dot = 0.0;
+#pragma unroll
+            for (int t = 0; t < D; ++t) dot = fma(xc[t], s_c[j * D + t], dot);
+            const double dist = fma(-2.0, dot, s_c2[j]);
+            if (j == 0 || dist < bestd) { bestd = dist; label = j; }
+        }
+        return label;
+    };
+    auto filter_label = [&](unsigned w, bool& near) -> int {
+        const float x0 = byte_as_float<0>(w), x1 = byte_as_float<1>(w), x2 = byte_as_float<2>(w), x3 = byte_as_float<3>(w);
+        float dj[KP], m[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            float dot = x0 * fx[j];
+            dot = fmaf(x1, fy[j], dot);
+            dot = fmaf(x2, fz[j], dot);
+            dot = fmaf(x3, fw[j], dot);
+            dj[j] = fmaf(-2.f, dot, fq[j]);
+            m[j] = dj[j];
+        }
+#pragma unroll
+        for (int st = KP / 2; st > 0; st >>= 1)
+#pragma unroll
+            for (int j = 0; j < st; ++j) m[j] = fminf(m[j], m[j + st]);
+        const float best = m[0], lim = best + margin;
+        int lb = KP - 1, cnt = 0;
+#pragma unroll
+        for (int j = KP - 1; j >= 0; --j) {
+            lb = dj[j] == best ? j : lb;
+            cnt += dj[j] <= lim ? 1 : 0;
+        }
+        near = cnt > 1;
+        return lb;
+    };
+
+    const int64_t n = p.n, n4 = n >> 2;
+    const uint4* X4 = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.X) + (int64_t)b * n * D);
+    int4* L4 = reinterpret_cast<int4*>(p.labels + (int64_t)b * n);
+    const int4* P4 = p.prev_labels ? reinterpret_cast<const int4*>(p.prev_labels + (int64_t)b * n) : nullptr;
+    unsigned a0[KP], a1[KP], ac[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) { a0[j] = 0u; a1[j] = 0u; ac[j] = 0u; }
+    auto flush = [&]() {                                   // warp-collective: every thread of the CTA calls it together
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            if (j < k) {
+                const unsigned s0 = warp_sum_u32(a0[j] & 0xFFFFu), s1 = warp_sum_u32(a0[j] >> 16);
+                const unsigned s2 = warp_sum_u32(a1[j] & 0xFFFFu), s3 = warp_sum_u32(a1[j] >> 16);
+                const unsigned sc = warp_sum_u32(ac[j]);
+                if (lane == 0 && sc) {
+                    atomicAdd(&s_acc[j * 5 + 0], s0); atomicAdd(&s_acc[j * 5 + 1], s1);
+                    atomicAdd(&s_acc[j * 5 + 2], s2); atomicAdd(&s_acc[j * 5 + 3], s3);
+                    atomicAdd(&s_acc[j * 5 + 4], sc);
+                }
+            }
+            a0[j] = 0u; a1[j] = 0u; ac[j] = 0u;
+        }
+    };
+    unsigned changed = 0;
+    int since_flush = 0;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < n4; base += (int64_t)gridDim.x * 256) {
+        const int64_t g = base + tid;
+        if (g < n4) {
+            const uint4 q = X4[g];
+            const unsigned w[4] = {q.x, q.y, q.z, q.w};
+            int lab[4];
+            bool near[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) lab[r] = filter_label(w[r], near[r]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (near[r]) lab[r] = exact_label(w[r]);
+            L4[g] = make_int4(lab[0], lab[1], lab[2], lab[3]);
+            if (P4) {
+                const int4 pl = P4[g];
+                changed += (pl.x != lab[0]) + (pl.y != lab[1]) + (pl.z != lab[2]) + (pl.w != lab[3]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const unsigned p0 = spread2<0x4140>(w[r]), p1 = spread2<0x4342>(w[r]);
+#pragma unroll
+                for (int j = 0; j < KP; ++j) {
+                    const bool mine = lab[r] == j;
+                    a0[j] += mine ? p0 : 0u;
+                    a1[j] += mine ? p1 : 0u;
+                    ac[j] += mine ? 1u : 0u;
+                }
+            }
+        }
+        since_flush += 4;
+        if (since_flush >= 256) { flush(); since_flush = 0; }
+    }
+    flush();
+    // the n % 4 last rows: scalar, exact chain
+    if (blockIdx.x == 0 && tid < (int)(n & 3)) {
+        const int64_t i = (n4 << 2) + tid;
+        const unsigned w = reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(p.X) + (int64_t)b * n * D)[i];
+        const int label = exact_label(w);
+        p.labels[(int64_t)b * n + i] = label;
+        if (p.prev_labels && p.prev_labels[(int64_t)b * n + i] != label) ++changed;
+        for (int t = 0; t < D; ++t) atomicAdd(&s_acc[label * 5 + t], (w >> (8 * t)) & 255u);
+        atomicAdd(&s_acc[label * 5 + 4], 1u);
+    }
+    __syncthreads();
+    for (int e = tid; e < k * D; e += 256)
+        partial[((int64_t)b * gridDim.x + blockIdx.x) * k * D + e] = (double)s_acc[(e >> 2) * 5 + (e & 3)];
+    for (int j = tid; j < k; j += 256) cnt_partial[((int64_t)b * gridDim.x + blockIdx.x) * k + j] = (long long)s_acc[j * 5 + 4];
+    if (p.n_changed && p.prev_labels) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+        if (lane == 0 && changed) atomicAdd(p.n_changed + b, (unsigned long long)changed);
+    }
+}
+
+bool kmeans_step_u8d4_usable(const KmAssignParams& p, int batch) {
+    if (p.dtype != DT_U8 || p.d != 4 || p.k < 1 || p.k > 8) return false;
+    if (((uintptr_t)p.X & 15) || ((uintptr_t)p.labels & 15) || (p.prev_labels && ((uintptr_t)p.prev_labels & 15))) return false;
+    if (batch > 1 && (p.n & 3)) return false;                      // the next problem's rows would be misaligned
+    const char* e = getenv("OFC_KMEANS_STEP_FAST");
+    return !(e && atoi(e) == 0);
+}
+
+int launch_kmeans_step_u8d4(const KmAssignParams& p, int batch, int grid, double* partial, long long* cnt_partial, void* stream) {
+    if (p.k <= 4) {
+        OFC_LAUNCH(kmeans_step_u8d4_kernel<4>, dim3(grid, batch), dim3(256), 0, stream, p, partial, cnt_partial);
+    } else {
+        OFC_LAUNCH(kmeans_step_u8d4_kernel<8>, dim3(grid, batch), dim3(256), 0, stream, p, partial, cnt_partial);
+    }
+    OFC_CHECK_LAUNCH("kmeans_step_u8d4");
+    return OFC_OK;
+}
+
 static int env_int_cells(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -637,14 +842,20 @@ int launch_kmeans_cells_fast(KmCellsFastParams p, int batch, void* stream) {
         return OFC_ERR_WORKSPACE;
     }
     ProfScope prof(PK_KMEANS, stream);
-#define OFC_CELLS_FAST(KPV)                                                                   \
-    {                                                                                         \
-        OFC_SMEM_OPTIN(kmeans_cells_fast_kernel<KPV>, smem);                                  \
-        OFC_LAUNCH(kmeans_cells_fast_kernel<KPV>, dim3(batch), dim3(256), smem, stream, p);   \
+#define OFC_CELLS_FAST(KPV, RUV, PK)                                                                        \
+    {                                                                                                       \
+        OFC_SMEM_OPTIN((kmeans_cells_fast_kernel<KPV, RUV, PK>), smem);                                     \
+        OFC_LAUNCH((kmeans_cells_fast_kernel<KPV, RUV, PK>), dim3(batch), dim3(256), smem, stream, p);      \
     }
-    if (kp == 4) OFC_CELLS_FAST(4)
-    else if (kp == 8) OFC_CELLS_FAST(8)
-    else OFC_CELLS_FAST(16)
+    // tuning switches for the k <= 8 form (rows per thread step, index-in-mantissa arg-min)
+    const int ru = env_int_cells("OFC_CELLS_RU", 4), pack = env_int_cells("OFC_CELLS_PACK", 1);
+    if (kp == 4) OFC_CELLS_FAST(4, 4, true)
+    else if (kp == 8) {
+        if (ru == 2 && pack) OFC_CELLS_FAST(8, 2, true)
+        else if (ru == 2) OFC_CELLS_FAST(8, 2, false)
+        else if (pack) OFC_CELLS_FAST(8, 4, true)
+        else OFC_CELLS_FAST(8, 4, false)
+    } else OFC_CELLS_FAST(16, 4, true)
 #undef OFC_CELLS_FAST
     OFC_CHECK_LAUNCH("kmeans_cells_fast");
     return OFC_OK;

@@ -719,6 +719,146 @@ __global__ void __launch_bounds__(1024) kmeans_relocate_kernel(const T* Xall, in
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same relocation in two kernels for large problems: (1) every row's squared distance to the old centre of its
+// label, written to a scratch array by the whole grid (the arithmetic of kmeans_relocate_kernel: sequential fma over
+// the features) -- skipped at once when no cluster is empty, unless `force`; (2) one CTA per problem picks, per empty
+// cluster in index order, the farthest remaining row from the scratch (ties: lowest index), marks it taken and moves
+// it in the sums.  kmeans_relocate_kernel re-reads all of X once per empty cluster through ONE CTA: 369 ms per
+// launch on 1 M x 128 float32 rows with a handful of empty clusters (ncu r02e) against ~1 ms this way.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) kmeans_rowdist_kernel(const T* Xall, int64_t n, int d, int k, const double* mean_all,
+                                                             const int32_t* labels_all, const double* centres_all,
+                                                             const long long* counts_all, double* scratch_all, int force,
+                                                             const unsigned char* active) {
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (active && !active[b]) return;
+    __shared__ int s_any;
+    if (!force) {
+        if (tid == 0) s_any = 0;
+        __syncthreads();
+        const long long* counts = counts_all + (int64_t)b * k;
+        int any = 0;
+        for (int j = tid; j < k; j += 256) any |= counts[j] == 0;
+        if (any) s_any = 1;
+        __syncthreads();
+        if (!s_any) return;
+    }
+    const T* X = Xall + (int64_t)b * n * d;
+    const int32_t* labels = labels_all + (int64_t)b * n;
+    const double* cen = centres_all + (int64_t)b * k * d;
+    const double* mean = mean_all ? mean_all + (int64_t)b * d : nullptr;
+    double* scratch = scratch_all + (int64_t)b * n;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < n; i += (int64_t)gridDim.x * 256) {
+        const double* c = cen + (int64_t)labels[i] * d;
+        const T* row = X + i * d;
+        double v = 0.0;
+        for (int t = 0; t < d; ++t) {
+            const double df = ((double)row[t] - (mean ? mean[t] : 0.0)) - c[t];
+            v = fma(df, df, v);
+        }
+        scratch[i] = v;
+    }
+}
+
+// block-wide arg-max over scratch[0..n): largest value, lowest index among equals; -1 when nothing is left
+__device__ __forceinline__ void block_argmax_1024(const double* scratch, int64_t n, double* s_val, long long* s_idx, double& out_v,
+                                                  long long& out_i) {
+    const int tid = threadIdx.x;
+    double bv = -1.0;
+    long long bi = -1;
+    for (int64_t i = tid; i < n; i += 1024) {
+        const double v = scratch[i];
+        if (v > bv) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    double v = -1.0;
+    long long idx = -1;
+    for (int w = 0; w < 32; ++w)
+        if (s_idx[w] >= 0 && (idx < 0 || s_val[w] > v || (s_val[w] == v && s_idx[w] < idx))) { v = s_val[w]; idx = s_idx[w]; }
+    __syncthreads();
+    out_v = v;
+    out_i = idx;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) kmeans_relocate_apply_kernel(const T* Xall, int64_t n, int d, int k, const double* mean_all,
+                                                                      const int32_t* labels_all, double* scratch_all, double* sums_all,
+                                                                      long long* counts_all, int raw_sums, const unsigned char* active) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (active && !active[b]) return;
+    long long* counts = counts_all + (int64_t)b * k;
+    __shared__ int s_any;
+    __shared__ double s_val[32];
+    __shared__ long long s_idx[32];
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    {
+        int any = 0;
+        for (int j = tid; j < k; j += 1024) any |= counts[j] == 0;
+        if (any) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) return;
+    const T* X = Xall + (int64_t)b * n * d;
+    const int32_t* labels = labels_all + (int64_t)b * n;
+    const double* mean = mean_all ? mean_all + (int64_t)b * d : nullptr;
+    double* sums = sums_all + (int64_t)b * k * d;
+    double* scratch = scratch_all + (int64_t)b * n;
+    int n_taken = 0;
+    for (int e = 0; e < k; ++e) {
+        if (counts[e] != 0) continue;                  // uniform: written only behind a barrier
+        double v;
+        long long fi;
+        block_argmax_1024(scratch, n, s_val, s_idx, v, fi);
+        if (n_taken == 0 && !(v > 0.0)) return;        // np.max(distances) == 0: nothing to do
+        if (fi < 0) return;
+        ++n_taken;
+        const int old = labels[fi];
+        for (int t = tid; t < d; t += 1024) {
+            const double x = (double)X[fi * d + t] - ((mean && !raw_sums) ? mean[t] : 0.0);
+            sums[(int64_t)old * d + t] -= x;
+            sums[(int64_t)e * d + t] = x;
+        }
+        if (tid == 0) {
+            counts[e] = 1;
+            counts[old] -= 1;
+            scratch[fi] = -1.0;                        // taken
+        }
+        __syncthreads();
+        __threadfence_block();
+    }
+}
+
+// the listing form for row-sharded data: the n_far farthest rows of this shard from the scratch distances
+__global__ void __launch_bounds__(1024) kmeans_far_list_kernel(int64_t n, double* scratch_all, int n_far, double* out_val,
+                                                               long long* out_idx) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ double s_val[32];
+    __shared__ long long s_idx[32];
+    double* scratch = scratch_all + (int64_t)b * n;
+    for (int e = 0; e < n_far; ++e) {
+        double v;
+        long long idx;
+        block_argmax_1024(scratch, n, s_val, s_idx, v, idx);
+        if (tid == 0) {
+            out_val[(int64_t)b * n_far + e] = v;
+            out_idx[(int64_t)b * n_far + e] = idx;
+            if (idx >= 0) scratch[idx] = -1.0;
+        }
+        __syncthreads();
+        __threadfence_block();
+    }
+}
+
 // The search half of the relocation for row-sharded data: this rank's n_far farthest rows
 // (squared distance to the old centre of their label, same arithmetic and tie rule as kmeans_relocate_kernel:
 // largest first, lowest index on ties).  The host merges the ranks' lists and applies the moves to the
@@ -1285,7 +1425,11 @@ int launch_kmeans_step_u8(KmAssignParams p, int batch, double* partial, long lon
     // (register-resident centres, KREG = 8, measured slower at d = 4, k = 8: 1.15 vs 0.75 ms per 64 M rows -- the
     // 64 extra registers cost more occupancy than the shared-memory broadcasts they save)
     static const int kreg = getenv("OFC_KMEANS_STEP_KREG") ? atoi(getenv("OFC_KMEANS_STEP_KREG")) : 0;
-    if (kreg && p.d == 4 && p.k <= 8) OFC_KM_STEP(4, 8)
+    if (kmeans_step_u8d4_usable(p, batch)) {
+        // the reference's pixel shape: float32-filtered E-step + packed register M-step, same bits (cells_kmeans.cu)
+        int rc = launch_kmeans_step_u8d4(p, batch, grid, partial, cnt_partial, stream);
+        if (rc != OFC_OK) return rc;
+    } else if (kreg && p.d == 4 && p.k <= 8) OFC_KM_STEP(4, 8)
     else if (p.d <= 4) OFC_KM_STEP(4, 0)
     else if (p.d <= 8) OFC_KM_STEP(8, 0)
     else if (p.d <= 16) OFC_KM_STEP(16, 0)
@@ -1379,11 +1523,48 @@ int launch_minibatch_update(const void* Xb, int dtype, int bs, int d, int k, con
     return OFC_OK;
 }
 
+static int rowdist_grid(int64_t n, int batch) {
+    int64_t g = (n + 255) / 256;
+    int64_t cap = (148 * 8 + batch - 1) / batch;
+    if (cap < 1) cap = 1;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+template <typename T>
+static int launch_rowdist(const void* X, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
+                          const double* centres_old, const long long* counts, double* scratch, int force,
+                          const unsigned char* active, void* stream) {
+    OFC_LAUNCH(kmeans_rowdist_kernel<T>, dim3(rowdist_grid(n, batch), batch), dim3(256), 0, stream, (const T*)X, n, d, k, mean, labels,
+               centres_old, counts, scratch, force, active);
+    OFC_CHECK_LAUNCH("kmeans_rowdist");
+    return OFC_OK;
+}
+
 int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                            const int32_t* labels, const double* centres_old, double* sums, long long* counts,
-                           int raw_sums, const unsigned char* active, void* stream) {
+                           int raw_sums, const unsigned char* active, double* scratch, void* stream) {
     if (batch <= 0) return OFC_OK;
+    if (batch > 65535) { set_error("batch=%d exceeds 65535", batch); return OFC_ERR_UNSUPPORTED; }
     ProfScope prof(PK_KMEANS, stream);
+    if (scratch) {
+        // two kernels: distances by the whole grid, then the pick loop (see kmeans_rowdist_kernel)
+        int rc;
+        if (dtype == DT_U8) rc = launch_rowdist<unsigned char>(X, batch, n, d, k, mean, labels, centres_old, counts, scratch, 0, active, stream);
+        else if (dtype == DT_F32) rc = launch_rowdist<float>(X, batch, n, d, k, mean, labels, centres_old, counts, scratch, 0, active, stream);
+        else rc = launch_rowdist<double>(X, batch, n, d, k, mean, labels, centres_old, counts, scratch, 0, active, stream);
+        if (rc != OFC_OK) return rc;
+        if (dtype == DT_U8)
+            OFC_LAUNCH(kmeans_relocate_apply_kernel<unsigned char>, dim3(batch), dim3(1024), 0, stream, (const unsigned char*)X, n, d, k, mean,
+                       labels, scratch, sums, counts, raw_sums, active);
+        else if (dtype == DT_F32)
+            OFC_LAUNCH(kmeans_relocate_apply_kernel<float>, dim3(batch), dim3(1024), 0, stream, (const float*)X, n, d, k, mean, labels,
+                       scratch, sums, counts, raw_sums, active);
+        else
+            OFC_LAUNCH(kmeans_relocate_apply_kernel<double>, dim3(batch), dim3(1024), 0, stream, (const double*)X, n, d, k, mean, labels,
+                       scratch, sums, counts, raw_sums, active);
+        OFC_CHECK_LAUNCH("kmeans_relocate_apply");
+        return OFC_OK;
+    }
     const size_t smem = (size_t)k * sizeof(long long);
     // the list of rows already given away is k words of shared memory: opt in past 48 KB (k <= 25 600)
     if (smem > 200 * 1024) { set_error("k=%d too large for the relocation kernel (k <= 25600)", k); return OFC_ERR_UNSUPPORTED; }
@@ -1404,9 +1585,19 @@ int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d
 }
 
 int launch_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
-                             const double* centres_old, int n_far, double* out_val, long long* out_idx, void* stream) {
+                             const double* centres_old, int n_far, double* out_val, long long* out_idx, double* scratch, void* stream) {
     if (batch <= 0 || n_far <= 0) return OFC_OK;
     ProfScope prof(PK_KMEANS, stream);
+    if (scratch) {
+        int rc;
+        if (dtype == DT_U8) rc = launch_rowdist<unsigned char>(X, batch, n, d, k, mean, labels, centres_old, nullptr, scratch, 1, nullptr, stream);
+        else if (dtype == DT_F32) rc = launch_rowdist<float>(X, batch, n, d, k, mean, labels, centres_old, nullptr, scratch, 1, nullptr, stream);
+        else rc = launch_rowdist<double>(X, batch, n, d, k, mean, labels, centres_old, nullptr, scratch, 1, nullptr, stream);
+        if (rc != OFC_OK) return rc;
+        OFC_LAUNCH(kmeans_far_list_kernel, dim3(batch), dim3(1024), 0, stream, n, scratch, n_far, out_val, out_idx);
+        OFC_CHECK_LAUNCH("kmeans_far_list");
+        return OFC_OK;
+    }
     const size_t smem = (size_t)n_far * sizeof(long long);
     if (smem > 40 * 1024) { set_error("n_far=%d too large", n_far); return OFC_ERR_UNSUPPORTED; }
     if (dtype == DT_U8)

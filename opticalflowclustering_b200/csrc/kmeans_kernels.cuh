@@ -59,9 +59,9 @@ int launch_minibatch_update(const void* Xb, int dtype, int bs, int d, int k, con
                             double* centres_new, double* weight_sums, void* stream);
 int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                            const int32_t* labels, const double* centres_old, double* sums, long long* counts,
-                           int raw_sums, const unsigned char* active, void* stream);
+                           int raw_sums, const unsigned char* active, double* scratch, void* stream);
 int launch_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
-                             const double* centres_old, int n_far, double* out_val, long long* out_idx, void* stream);
+                             const double* centres_old, int n_far, double* out_val, long long* out_idx, double* scratch, void* stream);
 int launch_inertia_reduce(const double* partial, int parts, int batch, double* inertia, const unsigned char* active,
                           void* stream);
 int launch_kmeans_cells(const unsigned char* X, int batch, int64_t n, int d, int k, const double* init,
@@ -92,6 +92,9 @@ struct KmCellsFastParams {
 bool kmeans_cells_fast_supported(int64_t n, int d, int k);
 size_t kmeans_cells_fast_workspace(int batch, int64_t n, int k, bool seeding);
 int launch_kmeans_cells_fast(KmCellsFastParams p, int batch, void* stream);
+// fused uint8 step for 4-channel rows, k <= 8 (cells_kmeans.cu): float32-filtered E-step + packed register M-step
+bool kmeans_step_u8d4_usable(const KmAssignParams& p, int batch);
+int launch_kmeans_step_u8d4(const KmAssignParams& p, int batch, int grid, double* partial, long long* cnt_partial, void* stream);
 int kmeans_assign_grid(int64_t n);
 int kmeans_sums_splits(int64_t n, int batch);
 

@@ -783,22 +783,24 @@ int ofc_minibatch_update(const void* Xb, int dtype, int batch_rows, int d, int k
 
 int ofc_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                         const int32_t* labels, const double* centres_old, double* sums, int64_t* counts,
-                        int raw_sums, const uint8_t* active, void* stream) {
+                        int raw_sums, const uint8_t* active, double* scratch, void* stream) {
     int rc = km_check(X, dtype, batch, n, d, k);
     if (rc != OFC_OK) return rc;
     if (batch == 0 || n == 0) return OFC_OK;
     OFC_REQUIRE(labels && centres_old && sums && counts, "null buffer");
-    return launch_kmeans_relocate(X, dtype, batch, n, d, k, mean, labels, centres_old, sums, (long long*)counts, raw_sums, active, stream);
+    return launch_kmeans_relocate(X, dtype, batch, n, d, k, mean, labels, centres_old, sums, (long long*)counts, raw_sums, active, scratch,
+                                  stream);
 }
 
 int ofc_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
-                          const double* centres_old, int n_far, double* out_val, int64_t* out_idx, void* stream) {
+                          const double* centres_old, int n_far, double* out_val, int64_t* out_idx, double* scratch, void* stream) {
     int rc = km_check(X, dtype, batch, n, d, k);
     if (rc != OFC_OK) return rc;
     OFC_REQUIRE(n_far >= 1 && n_far <= k, "n_far=%d outside [1, k]", n_far);
     if (batch == 0) return OFC_OK;
     OFC_REQUIRE(n > 0 && labels && centres_old && out_val && out_idx, "null buffer / empty shard");
-    return launch_kmeans_far_points(X, dtype, batch, n, d, k, mean, labels, centres_old, n_far, out_val, (long long*)out_idx, stream);
+    return launch_kmeans_far_points(X, dtype, batch, n, d, k, mean, labels, centres_old, n_far, out_val, (long long*)out_idx, scratch,
+                                    stream);
 }
 
 int ofc_kmeans_cells(const uint8_t* X, int batch, int64_t n, int d, int k, const double* init, uint64_t seed, int max_iter,

@@ -187,7 +187,13 @@ class LloydState:
         c = self.ctx
         c.check(c.lib.ofc_kmeans_relocate(_ptr(self.X), self.dtype, self.B, C.c_int64(self.n), self.d, self.k, _ptr(mean),
                                           _ptr(labels), _ptr(centres_old), _ptr(sums), _ptr(counts), int(raw_sums),
-                                          _ptr(active), c.stream()))
+                                          _ptr(active), _ptr(self.row_scratch()), c.stream()))
+
+    def row_scratch(self):
+        """float64 [B, n]: the row distances of the empty-cluster relocation (allocated on first use)"""
+        if getattr(self, "_row_scratch", None) is None:
+            self._row_scratch = torch.empty((self.B, max(self.n, 1)), dtype=torch.float64, device=self.X.device)
+        return self._row_scratch
 
 
 class TensorCoreSteps:
@@ -272,12 +278,16 @@ def _relocate_across_ranks(st: "LloydState", mean, labels, centres_old, sums, co
     idx = torch.full((B, n_far), -1, dtype=torch.int64, device=dev)
     if st.n > 0:
         c.check(c.lib.ofc_kmeans_far_points(_ptr(st.X), st.dtype, B, C.c_int64(st.n), d, k, _ptr(mean), _ptr(labels), _ptr(centres_old),
-                                            n_far, _ptr(val), _ptr(idx), c.stream()))
-    safe = idx.clamp(min=0)
-    rows = torch.gather(st.X, 1, safe.unsqueeze(-1).expand(B, n_far, d)).to(torch.float64)
-    if not raw_sums and mean is not None:
-        rows = rows - mean.unsqueeze(1)
-    lab = torch.gather(labels, 1, safe).to(torch.float64)
+                                            n_far, _ptr(val), _ptr(idx), _ptr(st.row_scratch()), c.stream()))
+    if st.n > 0:
+        safe = idx.clamp(min=0)
+        rows = torch.gather(st.X, 1, safe.unsqueeze(-1).expand(B, n_far, d)).to(torch.float64)
+        if not raw_sums and mean is not None:
+            rows = rows - mean.unsqueeze(1)
+        lab = torch.gather(labels, 1, safe).to(torch.float64)
+    else:                                                    # a rank without rows offers no candidate (idx stays -1)
+        rows = torch.zeros((B, n_far, d), dtype=torch.float64, device=dev)
+        lab = torch.zeros((B, n_far), dtype=torch.float64, device=dev)
     gidx = torch.where(idx >= 0, idx + row_offset, idx).to(torch.float64)
     pay = torch.cat([val.unsqueeze(-1), gidx.unsqueeze(-1), lab.unsqueeze(-1), rows], dim=-1).contiguous()   # [B, n_far, 3 + d]
     allpay = [torch.empty_like(pay) for _ in range(world)]
