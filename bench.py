@@ -130,6 +130,26 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, BEFORE the pinned staging buffers are allocated: first
+    touch then places them on the GPU's NUMA node and the copy-issuing thread runs next to it (with 8 ranks uploading
+    ~27 GB/s each, remote-node staging is what the host memory system cannot sustain).  Returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        cpus = [c for c in cpus if c < (os.cpu_count() or 0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_throughput(frames_np, workers, pairs_per_worker, n_clusters=1):
     from oracle import reference_chain
     return reference_chain.timed_throughput(frames_np, workers, pairs_per_worker, n_clusters, ROWS, COLS)
@@ -553,7 +573,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
     if world > 1:
+        if os.environ.get("OFC_BENCH_NUMA", "1") != "0":
+            numa_cpus = bind_to_gpu_numa(local)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -733,7 +756,7 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"synthetic {SIZE_NAME} clip, Farneback levels={LEVELS} winsize=15 iters=3, 14x25 grid, k={args.k}",
-                       "frames_per_step": F, "pairs_per_step": P, "clip_frames": T,
+                       "frames_per_step": F, "pairs_per_step": P, "clip_frames": T, "rank_cpu_affinity": numa_cpus,
                        "l2": f"steps walk a {T}-frame clip ({T * H * W * 3 / 1e6:.0f} MB > L2); intermediates "
                              f"({pipe.plan.workspace_bytes / 1e6:.0f} MB workspace) are rewritten every step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

@@ -99,6 +99,16 @@ int ofc_farneback_pair_init(const ofc_flow_plan* plan, const uint8_t* prev, cons
                             const float* init_flow, float* flow, uint32_t* minmax,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Streaming form of ofc_farneback_pair for the reference's per-frame loop (ComputeOpticalFLow keeps prev_gray and is
+ * called once per decoded frame, computeOpticalFlowModule.py:18-36): the plan keeps the previous frame's pre-filtered
+ * image and polynomial expansion in its workspace (two frame slots used alternately), so every call expands ONE
+ * frame instead of two.  begin(first frame) primes slot 0; next(frame) returns the flow previous -> frame.  Same bits as
+ * ofc_farneback_pair(previous, frame).  The plan needs max_frames >= 2; the same workspace must be passed every call. */
+int ofc_farneback_stream_begin(ofc_flow_plan* plan, const uint8_t* first_gray, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int ofc_farneback_stream_next(ofc_flow_plan* plan, const uint8_t* gray, float* flow, uint32_t* minmax, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ---- 8-bit colour ---------------------------------------------------------
  * cv.cvtColor(frame, COLOR_BGR2GRAY)        computeOpticalFlowModule.py:16,19 */
 int ofc_bgr2gray(const uint8_t* bgr, uint8_t* gray, int64_t n_pixels, void* stream);

@@ -31,6 +31,8 @@ SIGNATURES = {
     "ofc_farneback_sequence": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "ofc_farneback_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_farneback_pair_init": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ofc_farneback_stream_begin": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "ofc_farneback_stream_next": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_bgr2gray": (_i, [_vp, _vp, _i64, _vp]),
     "ofc_bgr2hsv": (_i, [_vp, _vp, _i64, _vp]),
     "ofc_flow_minmax": (_i, [_vp, _i, _i64, _vp, _vp]),

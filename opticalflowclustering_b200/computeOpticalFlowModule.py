@@ -31,6 +31,8 @@ class ComputeOpticalFLow:
         dev_frame = _flow.to_device_u8(firstframe)
         self._plan = _flow.FarnebackPlan(self.width, self.height, 2, 0.5, 3, 15, 3, 5, 1.2, 0, device=dev_frame.device)
         self._prev_gray = _flow.bgr2gray(dev_frame)
+        # the previous frame's pre-filtered image and polynomial expansion stay on the device: compute() expands one frame
+        self._plan.stream_begin(self._prev_gray)
         self._minmax = torch.empty((1, 2), dtype=torch.int32, device=dev_frame.device)
         self.last_flow = None            # CUDA float32 [H,W,2] of the latest pair
 
@@ -53,7 +55,7 @@ class ComputeOpticalFLow:
     def compute(self, frame):
         dev_frame = _flow.to_device_u8(frame, self._prev_gray.device)
         gray = _flow.bgr2gray(dev_frame)
-        fl = self._plan.pair(self._prev_gray, gray, minmax=self._minmax)
+        fl = self._plan.stream_next(gray, minmax=self._minmax)
         bgr = _flow.flow_to_bgr(fl.unsqueeze(0), self._minmax)[0]
         self._prev_gray = gray
         self.last_flow = fl

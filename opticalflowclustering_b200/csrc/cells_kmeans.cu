@@ -89,7 +89,7 @@ template <int SEL> __device__ __forceinline__ unsigned spread2(unsigned w) {
 }  // namespace
 
 template <int KP, int RU, bool PACK>
-__global__ void __launch_bounds__(256, (KP <= 4 ? 3 : 2)) kmeans_cells_fast_kernel(KmCellsFastParams p) {
+__global__ void __launch_bounds__(256, ((KP <= 4 || RU == 2) ? 3 : 2)) kmeans_cells_fast_kernel(KmCellsFastParams p) {
     constexpr int D = 4;
     OFC_DYN_SMEM(unsigned char, smraw);
     const int n = p.n, k = p.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -848,7 +848,10 @@ int launch_kmeans_cells_fast(KmCellsFastParams p, int batch, void* stream) {
         OFC_LAUNCH((kmeans_cells_fast_kernel<KPV, RUV, PK>), dim3(batch), dim3(256), smem, stream, p);      \
     }
     // tuning switches for the k <= 8 form (rows per thread step, index-in-mantissa arg-min)
-    const int ru = env_int_cells("OFC_CELLS_RU", 4), pack = env_int_cells("OFC_CELLS_PACK", 1);
+    // measured on 1080p visualisation cells, k = 8 (r02f / r02g): 0.264 ms per frame with 4 rows per step and the plain
+    // label chain, 0.285 with the index packed into the mantissa (one more ALU-pipe op per distance); 2 rows per step
+    // fit 80 registers = 3 CTAs per SM: 0.241 ms (default)
+    const int ru = env_int_cells("OFC_CELLS_RU", 2), pack = env_int_cells("OFC_CELLS_PACK", 0);
     if (kp == 4) OFC_CELLS_FAST(4, 4, true)
     else if (kp == 8) {
         if (ru == 2 && pack) OFC_CELLS_FAST(8, 2, true)

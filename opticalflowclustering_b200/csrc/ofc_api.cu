@@ -110,6 +110,9 @@ struct ofc_flow_plan {
     size_t workspace_bytes;
     float* d_taps;
     ofc::PolyParams poly;            // taps / inverse-Gram constants filled in
+    // streaming use (ofc_farneback_stream_*): which of the two frame slots holds the previous frame's I / R
+    int stream_slot;
+    int stream_primed;
 };
 
 namespace ofc {
@@ -173,9 +176,13 @@ static int prepare_poly(int n, double sigma, PolyParams& pp) {
     return OFC_OK;
 }
 
+// stage1_frames / slot_first: the frames at `gray` are expanded into frame slots slot_first, slot_first + 1, ...;
+// iterate: run the coarse-to-fine iterations for n_frames - 1 pairs whose "prev" frame sits in slot prev_slot and whose
+// "next" frame is next_delta slots further (+1 for a batch; -1 / +1 alternating in streaming use).
 static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t gray_stride, int n_frames,
                          float* flow, uint32_t* minmax, void* workspace, size_t workspace_bytes, void* stream,
-                         const float* init_flow = nullptr) {
+                         const float* init_flow = nullptr, int stage1_frames = -1, int slot_first = 0, bool iterate = true,
+                         int prev_slot = 0, int next_delta = 1) {
     OFC_REQUIRE(pl != nullptr, "null plan");
     if ((pl->flags & OFC_FLOW_USE_INITIAL_FLOW) && !init_flow) {
         set_error("the plan was created with OPTFLOW_USE_INITIAL_FLOW: call ofc_farneback_pair_init with the initial flow");
@@ -183,7 +190,8 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
     }
     if (!(pl->flags & OFC_FLOW_USE_INITIAL_FLOW)) init_flow = nullptr;
     OFC_REQUIRE(n_frames >= 2 && n_frames <= pl->max_frames, "n_frames=%d outside [2, %d]", n_frames, pl->max_frames);
-    OFC_REQUIRE(gray && flow && workspace, "null buffer");
+    OFC_REQUIRE(gray && (flow || !iterate) && workspace, "null buffer");
+    if (stage1_frames < 0) stage1_frames = n_frames;
     if (workspace_bytes < pl->workspace_bytes) {
         set_error("workspace too small: %zu < %zu", workspace_bytes, pl->workspace_bytes);
         return OFC_ERR_WORKSPACE;
@@ -218,7 +226,7 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         const Level& L = pl->lv[l];
         PrefilterParams& pf = pfs[l];
         pf.gray = gray; pf.gray_stride = gray_stride;
-        pf.out = (float*)(ws + L.off_I); pf.out_stride = (int64_t)L.w * L.h;
+        pf.out = (float*)(ws + L.off_I) + (int64_t)slot_first * L.w * L.h; pf.out_stride = (int64_t)L.w * L.h;
         pf.W = pl->W; pf.H = pl->H; pf.w = L.w; pf.h = L.h;
         pf.ksz = L.ksz; pf.sx = L.sx; pf.sy = L.sy;
         pf.taps = pl->d_taps + L.taps_off;
@@ -227,25 +235,37 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         pf_smem[l] = L.prefilter_smem;
     }
     {
-        int rc = launch_prefilter_pyramid(pfs.data(), pf_smem.data(), nl, n_frames, reinterpret_cast<bool*>(pf_done.data()), stream1);
+        int rc = stage1_frames > 0 ? launch_prefilter_pyramid(pfs.data(), pf_smem.data(), nl, stage1_frames,
+                                                             reinterpret_cast<bool*>(pf_done.data()), stream1)
+                                   : OFC_OK;
         if (rc != OFC_OK) return rc;
     }
     for (int l = 0; l < nl; ++l) {
         const Level& L = pl->lv[l];
         const PrefilterParams& pf = pfs[l];
         int rc = OFC_OK;
+        if (stage1_frames <= 0) {
+            if (fork) OFC_CUDA(cudaEventRecord(pl->ev_level[l], pl->side));
+            continue;
+        }
         if (!pf.identity3 && !pf_done[l]) {
-            rc = launch_prefilter(pf, n_frames, L.prefilter_smem, stream1);
+            rc = launch_prefilter(pf, stage1_frames, L.prefilter_smem, stream1);
             if (rc != OFC_OK) return rc;
         }
         PolyParams pp = pl->poly;
         pp.I = pf.out; pp.in_stride = pf.out_stride;
-        pp.RA = (float4*)(ws + L.off_RA); pp.RB = (float*)(ws + L.off_RB);
+        pp.RA = (float4*)(ws + L.off_RA) + (int64_t)slot_first * L.w * L.h; pp.RB = (float*)(ws + L.off_RB) + (int64_t)slot_first * L.w * L.h;
         pp.out_stride = (int64_t)L.w * L.h; pp.w = L.w; pp.h = L.h;
-        rc = launch_polyexp(pp, pl->poly_n, n_frames, pf.identity3 ? gray : nullptr, gray_stride,
+        rc = launch_polyexp(pp, pl->poly_n, stage1_frames, pf.identity3 ? gray : nullptr, gray_stride,
                             (pl->keep_level0_I || pl->poly_n != 5) ? pf.out : nullptr, stream1);
         if (rc != OFC_OK) return rc;
         if (fork) OFC_CUDA(cudaEventRecord(pl->ev_level[l], pl->side));
+    }
+    if (!iterate) {
+        // stage 1 only (priming a stream): join the side stream and leave
+        if (fork) OFC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, pl->ev_level[nl - 1], 0));
+        side_join.armed = false;
+        return OFC_OK;
     }
     if (minmax) {
         int rc = launch_minmax_init(minmax, n_pairs, stream);
@@ -261,8 +281,8 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
         if (fork) OFC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, pl->ev_level[l], 0));
         for (int it = 0; it < pl->iterations; ++it) {
             IterParams ip;
-            ip.RA = (const float4*)(ws + L.off_RA); ip.RB = (const float*)(ws + L.off_RB);
-            ip.r_stride = npx; ip.r_next = npx;
+            ip.RA = (const float4*)(ws + L.off_RA) + (int64_t)prev_slot * npx; ip.RB = (const float*)(ws + L.off_RB) + (int64_t)prev_slot * npx;
+            ip.r_stride = npx; ip.r_next = (int64_t)next_delta * npx;
             ip.w = L.w; ip.h = L.h;
             ip.border[0] = 0.14f; ip.border[1] = 0.14f; ip.border[2] = 0.4472f; ip.border[3] = 0.4472f; ip.border[4] = 0.4472f;
             ip.blur_scale = 1.0 / ((double)pl->winsize * pl->winsize);
@@ -367,6 +387,8 @@ int ofc_flow_plan_create(ofc_flow_plan** out, int width, int height, int max_fra
     memset(&pl->gauss, 0, sizeof(pl->gauss));
     pl->d_taps = nullptr;
     pl->keep_level0_I = 0;
+    pl->stream_slot = 0;
+    pl->stream_primed = 0;
     pl->side = nullptr;
     pl->ev_fork = cudaEvent_t();
     memset(&pl->poly, 0, sizeof(pl->poly));
@@ -535,6 +557,31 @@ int ofc_farneback_pair_init(const ofc_flow_plan* plan, const uint8_t* prev, cons
     OFC_REQUIRE(plan->flags & OFC_FLOW_USE_INITIAL_FLOW, "the plan was created without OPTFLOW_USE_INITIAL_FLOW");
     OFC_REQUIRE(((uintptr_t)init_flow & 7) == 0, "initial flow must be 8-byte aligned");
     return run_farneback(plan, prev, (int64_t)(next - prev), 2, flow, minmax, workspace, workspace_bytes, stream, init_flow);
+}
+
+int ofc_farneback_stream_begin(ofc_flow_plan* plan, const uint8_t* first_gray, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!plan) { set_error("null plan"); return OFC_ERR_INVALID; }
+    OFC_REQUIRE(first_gray != nullptr, "null frame");
+    OFC_REQUIRE(!(plan->flags & OFC_FLOW_USE_INITIAL_FLOW), "streaming use does not take an initial flow");
+    int rc = run_farneback(plan, first_gray, (int64_t)plan->W * plan->H, 2, nullptr, nullptr, workspace, workspace_bytes, stream, nullptr,
+                           /*stage1_frames=*/1, /*slot_first=*/0, /*iterate=*/false);
+    if (rc != OFC_OK) return rc;
+    plan->stream_slot = 0;
+    plan->stream_primed = 1;
+    return OFC_OK;
+}
+
+int ofc_farneback_stream_next(ofc_flow_plan* plan, const uint8_t* gray, float* flow, uint32_t* minmax, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (!plan) { set_error("null plan"); return OFC_ERR_INVALID; }
+    OFC_REQUIRE(gray && flow, "null buffer");
+    OFC_REQUIRE(plan->stream_primed, "call ofc_farneback_stream_begin with the first frame");
+    const int prev = plan->stream_slot, cur = prev ^ 1;
+    int rc = run_farneback(plan, gray, (int64_t)plan->W * plan->H, 2, flow, minmax, workspace, workspace_bytes, stream, nullptr,
+                           /*stage1_frames=*/1, /*slot_first=*/cur, /*iterate=*/true, /*prev_slot=*/prev, /*next_delta=*/cur - prev);
+    if (rc != OFC_OK) return rc;
+    plan->stream_slot = cur;
+    return OFC_OK;
 }
 
 int ofc_bgr2gray(const uint8_t* bgr, uint8_t* gray, int64_t n_pixels, void* stream) {

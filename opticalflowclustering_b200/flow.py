@@ -129,6 +129,28 @@ class FarnebackPlan:
                                                      _ptr(self.workspace), self.workspace_bytes, _stream_ptr()))
         return flow
 
+    def stream_begin(self, first_gray: torch.Tensor):
+        """Prime the streaming form with the first frame (CUDA uint8 [H,W]): its pre-filtered image and polynomial expansion
+        stay in the workspace, so :meth:`stream_next` expands one frame per call (the reference's per-frame loop)."""
+        g = first_gray.contiguous()
+        if tuple(g.shape) != (self.height, self.width) or g.dtype != torch.uint8 or not g.is_cuda:
+            raise ValueError("frame must be CUDA uint8 [H,W] of the plan's size")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ofc_farneback_stream_begin(self._ptr, _ptr(g), _ptr(self.workspace), self.workspace_bytes,
+                                                             _stream_ptr()))
+
+    def stream_next(self, gray: torch.Tensor, flow: torch.Tensor | None = None, minmax: torch.Tensor | None = None):
+        """Flow from the previous frame of the stream to ``gray`` (same bits as :meth:`pair`)."""
+        g = gray.contiguous()
+        if tuple(g.shape) != (self.height, self.width) or g.dtype != torch.uint8 or not g.is_cuda:
+            raise ValueError("frame must be CUDA uint8 [H,W] of the plan's size")
+        if flow is None:
+            flow = torch.empty((self.height, self.width, 2), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ofc_farneback_stream_next(self._ptr, _ptr(g), _ptr(flow), _ptr(minmax), _ptr(self.workspace),
+                                                            self.workspace_bytes, _stream_ptr()))
+        return flow
+
     def __del__(self):
         try:
             if self._ptr:

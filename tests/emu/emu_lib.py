@@ -100,6 +100,17 @@ class Plan:
                                              C.c_size_t(self.ws_bytes), C.c_void_p(0)))
         return flow
 
+    def stream_begin(self, gray0):
+        g = np.ascontiguousarray(gray0, np.uint8)
+        _check(lib().ofc_farneback_stream_begin(self.ptr, _p(g), _p(self.ws), C.c_size_t(self.ws_bytes), C.c_void_p(0)))
+
+    def stream_next(self, gray):
+        g = np.ascontiguousarray(gray, np.uint8)
+        flow = np.zeros((self.H, self.W, 2), np.float32)
+        _check(lib().ofc_farneback_stream_next(self.ptr, _p(g), _p(flow), C.c_void_p(0), _p(self.ws), C.c_size_t(self.ws_bytes),
+                                               C.c_void_p(0)))
+        return flow
+
     def __del__(self):
         try:
             lib().ofc_flow_plan_destroy(self.ptr)

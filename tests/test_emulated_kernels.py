@@ -213,3 +213,18 @@ def test_emu_fused_encode_grid_equals_separate_kernels(shape):
     assert np.abs(mag2 - mag).max() <= 1e-9 * np.abs(mag).max()
     for k in got:
         assert (got[k] == want[k]).all(), k
+
+
+def test_emu_streaming_form_equals_pairs():
+    """ofc_farneback_stream_begin / _next (the previous frame's expansion stays in the workspace, two frame slots used
+    alternately) gives the bits of ofc_farneback_sequence on the same frames"""
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    H, W = 64, 96
+    g = E.bgr2gray(synthetic_clip(4, H, W, seed=6).numpy())
+    want = E.Plan(W, H, max_frames=4).sequence(g)
+    pl = E.Plan(W, H, max_frames=2)
+    pl.stream_begin(g[0])
+    for t in range(1, 4):
+        assert (pl.stream_next(g[t]) == want[t - 1]).all(), t
+    with pytest.raises(RuntimeError, match="stream_begin"):
+        E.Plan(W, H, max_frames=2).stream_next(g[1])

@@ -28,7 +28,8 @@ def timed(fn, reps=3):
 def main():
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(0)
-    for k in (3, 8, 16):
+    only_k8 = len(sys.argv) > 1 and sys.argv[1] == "k8"
+    for k in ((8,) if only_k8 else (3, 8, 16)):
         cells = torch.randint(0, 256, (350, 76 * 77, 4), generator=g).to(torch.uint8).to(dev)
         os.environ["OFC_CELLS_FAST"] = "1"
         t_fast, a = timed(lambda: km.lloyd_cells(cells, k, seed=1))
@@ -39,6 +40,15 @@ def main():
         print(json.dumps({"case": f"random 350x5852x4 k={k}", "fast_ms": t_fast, "first_kernel_ms": t_slow, "identical": same,
                           "mean_iters": float(a[3].float().mean())}), flush=True)
     if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        return
+    if only_k8:
+        H, W, F = 1080, 1920, 9
+        clip = synthetic_clip(F, H, W, seed=3, device=dev)
+        pipe = ClipPipeline(W, H, chunk_frames=F, device=dev)
+        pipe.run_chunk(clip)
+        viz = pipe.viz.clone()
+        t, out = timed(lambda: grid.grid_kmeans_cells(viz, 8, seed=0))
+        print(json.dumps({"case": "1080p viz k=8", "fused_ms_per_frame": t / (F - 1), "mean_iters": float(out["n_iter"].float().mean())}), flush=True)
         return
     for name, (H, W) in {"720p": (720, 1280), "1080p": (1080, 1920)}.items():
         F = 9

@@ -97,8 +97,10 @@ def main():
         for k, (n, t) in sorted(by.items(), key=lambda kv: -kv[1][1]):
             md.append(f"| `{k}` | {n} | {t:.1f} | {100 * t / total:.1f} % |")
         md.append("")
-    for rep in sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep"))):
-        name = os.path.basename(rep)[5:-8]
+    reps = sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep")) + glob.glob(os.path.join(OUT, f"{tag}_*.ncu-rep")))
+    for rep in reps:
+        base = os.path.basename(rep)
+        name = base[5:-8] if base.startswith("prof_") else base[len(tag) + 1:-8]
         rows = raw_rows(rep)
         with open(os.path.join(PROF, f"{tag}_{name}.json"), "w") as f:
             json.dump(rows, f, indent=1)
@@ -117,9 +119,10 @@ def main():
                    + (f", tensor pipe active {d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']:.1f} %"
                       if 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active' in d else "")]
         md.append("")
-        if name.startswith("flow_iter") and rows:
-            d = max(rows, key=lambda r: r.get("gpu__time_duration.sum", 0.0))     # the full-resolution launch
-            with open(os.path.join(PROF, "flow_iter_traffic.json"), "w") as f:
+        iters = [r for r in rows if "flow_iter_tmem" in r["kernel"]]
+        if iters:
+            d = max(iters, key=lambda r: r.get("gpu__time_duration.sum", 0.0))     # the full-resolution launch
+            with open(os.path.join(PROF, f"{tag[:3]}_flow_iter_traffic.json"), "w") as f:
                 json.dump({"source": f"profiles/{tag}_{name}.json", "kernel": d["kernel"], "grid": d["grid"],
                            "pairs_per_launch": int(os.environ.get("OFC_CHUNK", "9")) - 1,
                            "dram_bytes_per_launch": d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0),
