@@ -251,6 +251,20 @@ int ofc_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d,
                           const int32_t* labels, const double* centres_old, int n_far,
                           double* out_val, int64_t* out_idx, double* scratch, void* stream);
 
+/* The same relocation for row-sharded data WITHOUT a host round trip: after the all-reduce of sums / counts every rank
+ * calls ofc_kmeans_far_payload (payload f64 [batch][n_far][3 + d] = value, global row index, label, row -- all -1 when
+ * no cluster is empty, in which case the row pass is skipped on the device), all-gathers the payloads into
+ * all_payload [world][batch][n_far][3 + d] and calls ofc_kmeans_relocate_merge, which applies the same moves on every
+ * rank: each empty cluster, in index order, takes the globally farthest remaining row (ties: lowest global index).
+ * More than n_far clusters empty at once sets *overflow (sticky, may be NULL); the caller then falls back to
+ * ofc_kmeans_far_points with a larger list. */
+int ofc_kmeans_far_payload(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
+                           const int32_t* labels, const double* centres_old, const int64_t* counts, int raw_sums,
+                           int n_far, int64_t row_offset, double* payload, double* scratch, const uint8_t* active,
+                           void* stream);
+int ofc_kmeans_relocate_merge(int batch, int d, int k, int world, int n_far, const double* all_payload, double* sums,
+                              int64_t* counts, int32_t* overflow, const uint8_t* active, void* stream);
+
 /* Whole Lloyd runs on the device, one CTA per problem: the reference's per-cell fits
  * (KMeans(n_clusters=k).fit on every grid cell of a frame, KmeanGrids.py:376-392) in ONE launch --
  * column statistics, seeding, all iterations, relocation, sklearn's stopping rule, closing E-step.

@@ -859,6 +859,126 @@ __global__ void __launch_bounds__(1024) kmeans_far_list_kernel(int64_t n, double
     }
 }
 
+// ---------------------------------------------------------------------------
+// Empty-cluster relocation for ROW-SHARDED data without a host round trip.  Per iteration,
+// after the all-reduce of sums / counts, every rank launches
+//   kmeans_rowdist_kernel        row distances of its shard (returns at once when no cluster is empty),
+//   kmeans_far_payload_kernel    its n_far farthest rows as [value, global row index, label, row...] records
+//                                (value -1 = no candidate; all -1 when no cluster is empty),
+//   [all-gather of the records],
+//   kmeans_relocate_merge_kernel every rank applies the same moves to the all-reduced sums: each empty cluster, in index
+//                                order, takes the globally farthest remaining row (ties: lowest global index).
+// Same result as kmeans_relocate_kernel on the whole set.  More empty clusters than n_far at once raise *overflow
+// (sticky); the host, which polls it a few iterations late, then redoes the fit with the host-merged path.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) kmeans_far_payload_kernel(const T* Xall, int64_t n, int d, int k, const double* mean_all,
+                                                                   const int32_t* labels_all, const long long* counts_all,
+                                                                   double* scratch_all, int raw_sums, int n_far, long long row_offset,
+                                                                   double* payload_all, const unsigned char* active) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int rec = 3 + d;
+    double* payload = payload_all + (int64_t)b * n_far * rec;
+    __shared__ int s_any;
+    __shared__ double s_val[32];
+    __shared__ long long s_idx[32];
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    if (!(active && !active[b])) {
+        const long long* counts = counts_all + (int64_t)b * k;
+        int any = 0;
+        for (int j = tid; j < k; j += 1024) any |= counts[j] == 0;
+        if (any) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any || n <= 0) {
+        for (int e = tid; e < n_far; e += 1024) { payload[(int64_t)e * rec] = -1.0; payload[(int64_t)e * rec + 1] = -1.0; }
+        return;
+    }
+    const T* X = Xall + (int64_t)b * n * d;
+    const int32_t* labels = labels_all + (int64_t)b * n;
+    const double* mean = mean_all ? mean_all + (int64_t)b * d : nullptr;
+    double* scratch = scratch_all + (int64_t)b * n;
+    for (int e = 0; e < n_far; ++e) {
+        double v;
+        long long idx;
+        block_argmax_1024(scratch, n, s_val, s_idx, v, idx);
+        double* r = payload + (int64_t)e * rec;
+        if (idx < 0) {
+            if (tid == 0) { r[0] = -1.0; r[1] = -1.0; }
+        } else {
+            if (tid == 0) {
+                r[0] = v; r[1] = (double)(idx + row_offset); r[2] = (double)labels[idx];
+                scratch[idx] = -1.0;
+            }
+            for (int t = tid; t < d; t += 1024) r[3 + t] = (double)X[idx * d + t] - ((mean && !raw_sums) ? mean[t] : 0.0);
+        }
+        __syncthreads();
+        __threadfence_block();
+    }
+}
+
+// allpay [world][batch][n_far][3 + d]; one CTA per problem
+__global__ void __launch_bounds__(256) kmeans_relocate_merge_kernel(int batch, int d, int k, int world, int n_far, const double* allpay,
+                                                                    double* sums_all, long long* counts_all, int* overflow,
+                                                                    const unsigned char* active) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (active && !active[b]) return;
+    const int rec = 3 + d, ncand = world * n_far;
+    long long* counts = counts_all + (int64_t)b * k;
+    double* sums = sums_all + (int64_t)b * k * d;
+    OFC_DYN_SMEM(unsigned char, s_used);                  // [ncand]
+    __shared__ int s_pick, s_empty, s_state;
+    if (tid == 0) {
+        int ne = 0;
+        for (int j = 0; j < k; ++j) ne += counts[j] == 0;
+        s_state = ne == 0 ? 0 : (ne > n_far ? 2 : 1);
+        if (ne > n_far && overflow) atomicExch(overflow, 1);
+    }
+    for (int c = tid; c < ncand; c += 256) s_used[c] = 0;
+    __syncthreads();
+    if (s_state != 1) return;
+    auto cand = [&](int c) -> const double* {
+        const int r = c / n_far, e = c - r * n_far;
+        return allpay + (((int64_t)r * batch + b) * n_far + e) * rec;
+    };
+    int e_next = 0;
+    for (int round = 0;; ++round) {
+        if (tid == 0) {
+            int e = e_next;
+            while (e < k && counts[e] != 0) ++e;
+            s_empty = e;
+            int best = -1;
+            if (e < k) {
+                for (int c = 0; c < ncand; ++c) {
+                    if (s_used[c]) continue;
+                    const double* r = cand(c);
+                    if (r[1] < 0.0) continue;
+                    if (best < 0) { best = c; continue; }
+                    const double* q = cand(best);
+                    if (r[0] > q[0] || (r[0] == q[0] && r[1] < q[1])) best = c;
+                }
+                if (best >= 0 && round == 0 && !(cand(best)[0] > 0.0)) best = -1;      // np.max(distances) == 0: nothing to do
+            }
+            s_pick = best;
+            if (best >= 0) s_used[best] = 1;
+        }
+        __syncthreads();
+        const int e = s_empty, best = s_pick;
+        if (e >= k || best < 0) return;
+        const double* r = cand(best);
+        const int old = (int)r[2];
+        for (int t = tid; t < d; t += 256) {
+            sums[(int64_t)old * d + t] -= r[3 + t];
+            sums[(int64_t)e * d + t] = r[3 + t];
+        }
+        __syncthreads();
+        if (tid == 0) { counts[e] = 1; counts[old] -= 1; }
+        e_next = e + 1;
+        __syncthreads();
+    }
+}
+
 // The search half of the relocation for row-sharded data: this rank's n_far farthest rows
 // (squared distance to the old centre of their label, same arithmetic and tie rule as kmeans_relocate_kernel:
 // largest first, lowest index on ties).  The host merges the ranks' lists and applies the moves to the
@@ -1581,6 +1701,43 @@ int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d
         OFC_LAUNCH(kmeans_relocate_kernel<double>, dim3(batch), dim3(1024), smem, stream, (const double*)X, n, d, k, mean, labels,
                    centres_old, sums, counts, raw_sums, active);
     OFC_CHECK_LAUNCH("kmeans_relocate");
+    return OFC_OK;
+}
+
+int launch_kmeans_far_payload(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
+                              const double* centres_old, const long long* counts, int raw_sums, int n_far, long long row_offset,
+                              double* payload, double* scratch, const unsigned char* active, void* stream) {
+    if (batch <= 0 || n_far <= 0) return OFC_OK;
+    ProfScope prof(PK_KMEANS, stream);
+    int rc = OFC_OK;
+    if (n > 0) {
+        if (dtype == DT_U8) rc = launch_rowdist<unsigned char>(X, batch, n, d, k, mean, labels, centres_old, counts, scratch, 0, active, stream);
+        else if (dtype == DT_F32) rc = launch_rowdist<float>(X, batch, n, d, k, mean, labels, centres_old, counts, scratch, 0, active, stream);
+        else rc = launch_rowdist<double>(X, batch, n, d, k, mean, labels, centres_old, counts, scratch, 0, active, stream);
+        if (rc != OFC_OK) return rc;
+    }
+    if (dtype == DT_U8)
+        OFC_LAUNCH(kmeans_far_payload_kernel<unsigned char>, dim3(batch), dim3(1024), 0, stream, (const unsigned char*)X, n, d, k, mean, labels,
+                   counts, scratch, raw_sums, n_far, row_offset, payload, active);
+    else if (dtype == DT_F32)
+        OFC_LAUNCH(kmeans_far_payload_kernel<float>, dim3(batch), dim3(1024), 0, stream, (const float*)X, n, d, k, mean, labels, counts,
+                   scratch, raw_sums, n_far, row_offset, payload, active);
+    else
+        OFC_LAUNCH(kmeans_far_payload_kernel<double>, dim3(batch), dim3(1024), 0, stream, (const double*)X, n, d, k, mean, labels, counts,
+                   scratch, raw_sums, n_far, row_offset, payload, active);
+    OFC_CHECK_LAUNCH("kmeans_far_payload");
+    return OFC_OK;
+}
+
+int launch_kmeans_relocate_merge(int batch, int d, int k, int world, int n_far, const double* allpay, double* sums, long long* counts,
+                                 int* overflow, const unsigned char* active, void* stream) {
+    if (batch <= 0) return OFC_OK;
+    ProfScope prof(PK_KMEANS, stream);
+    const size_t smem = (size_t)world * n_far;
+    OFC_SMEM_OPTIN(kmeans_relocate_merge_kernel, smem);
+    OFC_LAUNCH(kmeans_relocate_merge_kernel, dim3(batch), dim3(256), smem, stream, batch, d, k, world, n_far, allpay, sums, counts, overflow,
+               active);
+    OFC_CHECK_LAUNCH("kmeans_relocate_merge");
     return OFC_OK;
 }
 

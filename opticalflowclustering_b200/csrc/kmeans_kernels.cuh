@@ -60,6 +60,11 @@ int launch_minibatch_update(const void* Xb, int dtype, int bs, int d, int k, con
 int launch_kmeans_relocate(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean,
                            const int32_t* labels, const double* centres_old, double* sums, long long* counts,
                            int raw_sums, const unsigned char* active, double* scratch, void* stream);
+int launch_kmeans_far_payload(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
+                              const double* centres_old, const long long* counts, int raw_sums, int n_far, long long row_offset,
+                              double* payload, double* scratch, const unsigned char* active, void* stream);
+int launch_kmeans_relocate_merge(int batch, int d, int k, int world, int n_far, const double* allpay, double* sums, long long* counts,
+                                 int* overflow, const unsigned char* active, void* stream);
 int launch_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
                              const double* centres_old, int n_far, double* out_val, long long* out_idx, double* scratch, void* stream);
 int launch_inertia_reduce(const double* partial, int parts, int batch, double* inertia, const unsigned char* active,

@@ -850,6 +850,27 @@ int ofc_kmeans_far_points(const void* X, int dtype, int batch, int64_t n, int d,
                                     stream);
 }
 
+int ofc_kmeans_far_payload(const void* X, int dtype, int batch, int64_t n, int d, int k, const double* mean, const int32_t* labels,
+                           const double* centres_old, const int64_t* counts, int raw_sums, int n_far, int64_t row_offset,
+                           double* payload, double* scratch, const uint8_t* active, void* stream) {
+    OFC_REQUIRE(dtype == OFC_U8 || dtype == OFC_F32 || dtype == OFC_F64, "bad dtype %d", dtype);
+    OFC_REQUIRE(batch >= 0 && n >= 0 && d >= 1 && k >= 1, "bad shape");
+    OFC_REQUIRE(n_far >= 1 && n_far <= k, "n_far=%d outside [1, k]", n_far);
+    if (batch == 0) return OFC_OK;
+    OFC_REQUIRE(counts && payload && (n == 0 || (X && labels && centres_old && scratch)), "null buffer");
+    return launch_kmeans_far_payload(X, dtype, batch, n, d, k, mean, labels, centres_old, (const long long*)counts, raw_sums, n_far,
+                                     (long long)row_offset, payload, scratch, active, stream);
+}
+
+int ofc_kmeans_relocate_merge(int batch, int d, int k, int world, int n_far, const double* all_payload, double* sums, int64_t* counts,
+                              int32_t* overflow, const uint8_t* active, void* stream) {
+    OFC_REQUIRE(batch >= 0 && d >= 1 && k >= 1 && world >= 1 && n_far >= 1, "bad shape");
+    if (batch == 0) return OFC_OK;
+    OFC_REQUIRE(all_payload && sums && counts, "null buffer");
+    OFC_REQUIRE((size_t)world * n_far <= 200 * 1024, "too many candidates");
+    return launch_kmeans_relocate_merge(batch, d, k, world, n_far, all_payload, sums, (long long*)counts, overflow, active, stream);
+}
+
 int ofc_kmeans_cells(const uint8_t* X, int batch, int64_t n, int d, int k, const double* init, uint64_t seed, int max_iter,
                      double tol, int32_t* labels, double* centres, double* inertia, int32_t* n_iter, int64_t* counts,
                      void* workspace, size_t workspace_bytes, void* stream) {

@@ -357,7 +357,7 @@ def column_mean_var(st: LloydState, group=None):
 _POLL_LAG = 4
 
 
-def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None):
+def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_relocation: bool = False):
     """Batched ``KMeans(n_clusters=k, init=init, n_init=1, max_iter=max_iter, tol=tol).fit(X)``.
 
     X ``[n,d]`` or ``[B,n,d]`` (uint8 / float32 / float64; torch on the compute device, or numpy);
@@ -368,9 +368,11 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None):
     M-step sums, empty-cluster relocation, ``ofc_kmeans_update`` = new centres + stopping rule on the device);
     the only thing the host reads is the "problems still running" counter, asynchronously and ``_POLL_LAG``
     iterations late -- the iterations enqueued past the stop are skipped by every kernel.  With ``group`` the
-    kernels write into the buffers the two all-reduces move (float64 sums; int64 counts + label changes), and
-    one 1-byte flag per iteration tells the host whether a cluster is empty anywhere (the cross-rank relocation
-    is host-orchestrated).
+    kernels write into the buffers the two all-reduces move (float64 sums; int64 counts + label changes), and the
+    relocation of empty clusters across ranks runs on the device as well: every rank lists its farthest rows
+    (``ofc_kmeans_far_payload``, skipped on the device when no cluster is empty), the lists are all-gathered and every
+    rank applies the same moves (``ofc_kmeans_relocate_merge``).  Should more clusters be empty at once than the
+    list holds (16), the fit is redone with the host-merged relocation (``_relocate_across_ranks``).
 
     Returns ``(labels int32, centres float64, inertia float64, n_iter int64)`` as torch
     tensors on X's device, squeezed when X was ``[n,d]``.
@@ -417,9 +419,20 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None):
     is_cuda = dev.type == "cuda"
     seen = torch.empty(max(max_iter, 1), dtype=torch.int32, pin_memory=is_cuda)
     events = []
-    flag_dev = flag_host = None
+    flag_host = None
+    n_far = min(k, 16)
+    payload = allpay = overflow = None
+    world = 1
     if group is not None:
-        flag_host = torch.empty(1, dtype=torch.uint8, pin_memory=is_cuda)
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        if _host_relocation:
+            flag_host = torch.empty(1, dtype=torch.uint8, pin_memory=is_cuda)
+        else:
+            payload = torch.empty((B, n_far, 3 + d), dtype=torch.float64, device=dev)
+            allpay = torch.empty((world, B, n_far, 3 + d), dtype=torch.float64, device=dev)
+            overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    overflow_seen = torch.zeros(max(max_iter, 1), dtype=torch.int32, pin_memory=is_cuda) if overflow is not None else None
     cur = 0
     for it in range(max_iter):
         lab, lab_old = st.labels[cur], st.labels[cur ^ 1]
@@ -441,28 +454,47 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None):
                 st.n_changed.masked_fill_(off, 0)
             _all_reduce(st.sums, group)
             _all_reduce(st.icnt, group)
-            flag_dev = ((st.counts == 0) & (active != 0).view(B, 1)).any().to(torch.uint8).view(1)
-            flag_host.copy_(flag_dev, non_blocking=True)
-            if is_cuda:
-                torch.cuda.current_stream(dev).synchronize()
-            if int(flag_host[0]):
-                _relocate_across_ranks(st, mean, lab, centres, st.sums, st.counts, is_u8, group, row_offset)
+            if _host_relocation:
+                flag_dev = ((st.counts == 0) & (active != 0).view(B, 1)).any().to(torch.uint8).view(1)
+                flag_host.copy_(flag_dev, non_blocking=True)
+                if is_cuda:
+                    torch.cuda.current_stream(dev).synchronize()
+                if int(flag_host[0]):
+                    _relocate_across_ranks(st, mean, lab, centres, st.sums, st.counts, is_u8, group, row_offset)
+            else:
+                ctx.check(ctx.lib.ofc_kmeans_far_payload(_ptr(st.X), st.dtype, B, C.c_int64(n), d, k, _ptr(mean), _ptr(lab), _ptr(centres),
+                                                         _ptr(st.counts), int(is_u8), n_far, C.c_int64(row_offset), _ptr(payload),
+                                                         _ptr(st.row_scratch()), _ptr(active), ctx.stream()))
+                dist.all_gather(list(allpay.unbind(0)), payload, group=group)
+                ctx.check(ctx.lib.ofc_kmeans_relocate_merge(B, d, k, world, n_far, _ptr(allpay), _ptr(st.sums), _ptr(st.counts),
+                                                            _ptr(overflow), _ptr(active), ctx.stream()))
         else:
             st.relocate(mean, lab, centres, st.sums, st.counts, is_u8, active=active)
         st.update_(st.sums, st.counts, mean if is_u8 else None, 0 if is_u8 else 1, 1 if is_f32 else 0, centres, st.n_changed,
                    tol_, it, n_active[it:it + 1], lab, lab_old)
         seen[it:it + 1].copy_(n_active[it:it + 1], non_blocking=True)
+        if overflow is not None:
+            overflow_seen[it:it + 1].copy_(overflow, non_blocking=True)
         if is_cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             events.append(ev)
-        back = it - (_POLL_LAG if is_cuda and group is None else 0)
+        back = it - (_POLL_LAG if is_cuda and not _host_relocation else 0)
         if back >= 0:
             if is_cuda:
                 events[back].synchronize()
+            if overflow is not None and int(overflow_seen[back]):
+                break
             if int(seen[back]) == 0:
                 break
         cur ^= 1
+    if overflow is not None:
+        if is_cuda:
+            torch.cuda.current_stream(dev).synchronize()
+        if int(overflow.item()):
+            # more clusters empty at once than the device-side candidate list holds: redo the fit with the host-merged
+            # relocation (every rank takes this branch: the all-reduced counts are the same everywhere)
+            return lloyd(X, init, max_iter, tol, group, _host_relocation=True)
     final = st.labels[0]
     # strict stops already hold the labels of the final centres; the rest get one more E-step
     # (_kmeans.py:745-755).  Re-running it for everyone is idempotent for the strict ones and

@@ -41,6 +41,17 @@ def _case_empty():
     return X, init
 
 
+def _case_many_empty():
+    """20 clusters empty at once: more than the device-side candidate list (16) holds -> the fit is redone with the
+    host-merged relocation"""
+    rng = np.random.default_rng(23)
+    n, d, k = 2200, 4, 26
+    cen = rng.uniform(60, 120, (6, d))
+    X = np.clip(np.rint(cen[rng.integers(6, size=n)] + rng.normal(0, 9, (n, d))), 0, 255).astype(np.uint8)
+    init = np.concatenate([X[:6].astype(np.float64), np.full((20, d), 235.0) + np.arange(20)[:, None]])
+    return X, init
+
+
 def _worker(rank, world, port, out_dir, case="plain"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -50,7 +61,7 @@ def _worker(rank, world, port, out_dir, case="plain"):
     from opticalflowclustering_b200.sharding import shard_range
     from tests.emu import emu_lib as E
     km._use_test_library(E.lib())
-    X, init = _case() if case == "plain" else _case_empty()
+    X, init = {"plain": _case, "empty": _case_empty, "many": _case_many_empty}[case]()
     lo, hi = shard_range(len(X), rank, world)
     labels, centres, inertia, n_iter = km.lloyd(X[lo:hi], init, group=dist.group.WORLD)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), labels=labels.numpy(), centres=centres.numpy(),
@@ -92,6 +103,22 @@ def test_sharded_lloyd_relocates_empty_clusters_like_single_rank(tmp_path):
     assert (l1.numpy() == ref[0]).all() and int(n1) == ref[3]
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path), "empty"), nprocs=2, join=True)
+    got = [np.load(tmp_path / f"r{r}.npz") for r in range(2)]
+    assert (np.concatenate([g["labels"] for g in got]) == l1.numpy()).all()
+    for g in got:
+        assert (g["centres"] == c1.numpy()).all() and int(g["n_iter"]) == int(n1)
+
+
+def test_sharded_lloyd_many_empty_clusters_falls_back(tmp_path):
+    from tests.emu import emu_lib as E
+    E.build()
+    from opticalflowclustering_b200 import kmeans as km
+    km._use_test_library(E.lib())
+    X, init = _case_many_empty()
+    l1, c1, i1, n1 = km.lloyd(X, init)
+    km._use_test_library(None)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path), "many"), nprocs=2, join=True)
     got = [np.load(tmp_path / f"r{r}.npz") for r in range(2)]
     assert (np.concatenate([g["labels"] for g in got]) == l1.numpy()).all()
     for g in got:
