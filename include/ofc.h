@@ -216,12 +216,14 @@ int ofc_kmeans_centres(int batch, int d, int k, const double* sums, const int64_
  * labels_other so both ping-pong buffers hold them).  n_iter[b] = iteration + 1 for every problem still running;
  * *n_active += number of problems that continue (the host polls it asynchronously).  round_f32: store the
  * centres rounded to float32 (float32 data).  NULL tol / n_changed / active / just_done / n_iter / n_active /
- * labels_* skip the corresponding part. */
+ * labels_* skip the corresponding part.  it_counter (may be NULL): the iteration number is read from the device
+ * (and incremented afterwards) instead of `iteration`, and the running count goes to n_active[*it_counter] -- so one
+ * iteration can be captured in a CUDA graph and replayed. */
 int ofc_kmeans_update(int batch, int64_t n, int d, int k, const double* sums, const int64_t* counts, const double* mean_sub,
                       int use_reciprocal, int round_f32, double* centres, double* shift_tot, const uint64_t* n_changed,
                       const double* tol, int iteration, uint8_t* active, uint8_t* just_done, int32_t* n_iter,
-                      int32_t* n_active, const int32_t* labels_cur, int32_t* labels_other, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      int32_t* n_active, const int32_t* labels_cur, int32_t* labels_other, int32_t* it_counter,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* MiniBatchKMeans centre update, the arithmetic behind the reference's color-quantization/quant.py:18-20
  * (clt = MiniBatchKMeans(n_clusters); clt.fit_predict(image)) -> scikit-learn 1.9.0 _minibatch_update_dense

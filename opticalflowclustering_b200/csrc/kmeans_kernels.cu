@@ -532,10 +532,14 @@ __global__ void __launch_bounds__(256) kmeans_centres_kernel(int d, int k, const
 __global__ void __launch_bounds__(256) kmeans_update_kernel(int d, int k, const double* sums, const long long* counts,
                                                             const double* mean_sub, int use_reciprocal, int round_f32,
                                                             double* centres, double* shift_tot, double* shift_ws,
-                                                            const unsigned long long* n_changed, const double* tol, int it,
+                                                            const unsigned long long* n_changed, const double* tol, int it_arg,
                                                             unsigned char* active, unsigned char* just_done, int* n_iter,
-                                                            int* n_active) {
+                                                            int* n_active_base, const int* it_counter) {
     const int b = blockIdx.x, tid = threadIdx.x;
+    // it_counter: the iteration number lives on the device (the loop body is replayed from a CUDA graph, so it cannot be a
+    // launch argument); the "still running" count then goes to slot [it] of n_active_base
+    const int it = it_counter ? *it_counter : it_arg;
+    int* n_active = n_active_base ? n_active_base + (it_counter ? it : 0) : nullptr;
     if (just_done && tid == 0) just_done[b] = 0;
     if (active && !active[b]) return;
     const double* S = sums + (int64_t)b * k * d;
@@ -625,6 +629,8 @@ __global__ void __launch_bounds__(256) minibatch_update_kernel(const T* __restri
         __syncthreads();
     }
 }
+
+__global__ void kmeans_counter_inc_kernel(int* counter) { *counter += 1; }
 
 // problems that stopped in this iteration keep the labels they stopped with in BOTH ping-pong buffers
 __global__ void __launch_bounds__(256) kmeans_freeze_labels_kernel(int64_t n, const unsigned char* just_done, const int32_t* cur,
@@ -1609,12 +1615,16 @@ int launch_kmeans_update(int batch, int d, int k, const double* sums, const long
                          int use_reciprocal, int round_f32, double* centres, double* shift_tot, double* shift_ws,
                          const unsigned long long* n_changed, const double* tol, int it, unsigned char* active,
                          unsigned char* just_done, int* n_iter, int* n_active, int64_t n, const int32_t* labels_cur,
-                         int32_t* labels_other, void* stream) {
+                         int32_t* labels_other, int* it_counter, void* stream) {
     if (batch <= 0) return OFC_OK;
     ProfScope prof(PK_KMEANS, stream);
     OFC_LAUNCH(kmeans_update_kernel, dim3(batch), dim3(256), 0, stream, d, k, sums, counts, mean_sub, use_reciprocal, round_f32,
-               centres, shift_tot, shift_ws, n_changed, tol, it, active, just_done, n_iter, n_active);
+               centres, shift_tot, shift_ws, n_changed, tol, it, active, just_done, n_iter, n_active, it_counter);
     OFC_CHECK_LAUNCH("kmeans_update");
+    if (it_counter) {
+        OFC_LAUNCH(kmeans_counter_inc_kernel, dim3(1), dim3(1), 0, stream, it_counter);
+        OFC_CHECK_LAUNCH("kmeans_counter_inc");
+    }
     if (batch > 1 && just_done && labels_cur && labels_other && n > 0) {
         int64_t bx = (n + 255) / 256;
         if (bx > 64) bx = 64;

@@ -810,14 +810,15 @@ int ofc_kmeans_centres(int batch, int d, int k, const double* sums, const int64_
 int ofc_kmeans_update(int batch, int64_t n, int d, int k, const double* sums, const int64_t* counts, const double* mean_sub,
                       int use_reciprocal, int round_f32, double* centres, double* shift_tot, const uint64_t* n_changed,
                       const double* tol, int iteration, uint8_t* active, uint8_t* just_done, int32_t* n_iter, int32_t* n_active,
-                      const int32_t* labels_cur, int32_t* labels_other, void* workspace, size_t workspace_bytes, void* stream) {
+                      const int32_t* labels_cur, int32_t* labels_other, int32_t* it_counter, void* workspace, size_t workspace_bytes,
+                      void* stream) {
     OFC_REQUIRE(batch >= 0 && d >= 1 && k >= 1 && n >= 0, "bad shape");
     if (batch == 0) return OFC_OK;
     OFC_REQUIRE(sums && counts && centres, "null buffer");
     OFC_REQUIRE(workspace && workspace_bytes >= align_up((size_t)batch * k * 8, 256), "k-means workspace too small");
     return launch_kmeans_update(batch, d, k, sums, (const long long*)counts, mean_sub, use_reciprocal, round_f32, centres, shift_tot,
                                 (double*)workspace, (const unsigned long long*)n_changed, tol, iteration, active, just_done, n_iter,
-                                n_active, n, labels_cur, labels_other, stream);
+                                n_active, n, labels_cur, labels_other, it_counter, stream);
 }
 
 int ofc_minibatch_update(const void* Xb, int dtype, int batch_rows, int d, int k, const int32_t* labels, const double* centres_old,

@@ -174,14 +174,15 @@ class LloydState:
                                          int(use_reciprocal), _ptr(centres), _ptr(shift), _ptr(active), _ptr(self.ws),
                                          C.c_size_t(self.ws.numel()), c.stream()))
 
-    def update_(self, sums, counts, mean_sub, use_reciprocal, round_f32, centres, n_changed, tol, it, n_active, lab, lab_other):
+    def update_(self, sums, counts, mean_sub, use_reciprocal, round_f32, centres, n_changed, tol, it, n_active, lab, lab_other,
+                it_counter=None):
         """new centres + sklearn's stopping rule on the device (no read-back): see ofc_kmeans_update"""
         c = self.ctx
         c.check(c.lib.ofc_kmeans_update(self.B, C.c_int64(self.n), self.d, int(centres.shape[1]), _ptr(sums), _ptr(counts),
                                         _ptr(mean_sub), int(use_reciprocal), int(round_f32), _ptr(centres), _ptr(self.shift),
                                         _ptr(n_changed), _ptr(tol), int(it), _ptr(self.active), _ptr(self.just_done),
-                                        _ptr(self.n_iter), _ptr(n_active), _ptr(lab), _ptr(lab_other), _ptr(self.ws),
-                                        C.c_size_t(self.ws.numel()), c.stream()))
+                                        _ptr(self.n_iter), _ptr(n_active), _ptr(lab), _ptr(lab_other), _ptr(it_counter),
+                                        _ptr(self.ws), C.c_size_t(self.ws.numel()), c.stream()))
 
     def relocate(self, mean, labels, centres_old, sums, counts, raw_sums, active=None):
         c = self.ctx
@@ -433,8 +434,11 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
             allpay = torch.empty((world, B, n_far, 3 + d), dtype=torch.float64, device=dev)
             overflow = torch.zeros(1, dtype=torch.int32, device=dev)
     overflow_seen = torch.zeros(max(max_iter, 1), dtype=torch.int32, pin_memory=is_cuda) if overflow is not None else None
-    cur = 0
-    for it in range(max_iter):
+    it_counter = torch.zeros(1, dtype=torch.int32, device=dev)       # iteration number, kept on the device
+
+    def iteration(cur):
+        """one Lloyd iteration, enqueued on the current stream; nothing in it depends on host-side values, so on one GPU it
+        can be captured in a CUDA graph (the iteration number is `it_counter`)"""
         lab, lab_old = st.labels[cur], st.labels[cur ^ 1]
         if tc is not None:
             tc.assign(centres, lab, prev=lab_old, n_changed=st.n_changed)
@@ -465,13 +469,33 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
                 ctx.check(ctx.lib.ofc_kmeans_far_payload(_ptr(st.X), st.dtype, B, C.c_int64(n), d, k, _ptr(mean), _ptr(lab), _ptr(centres),
                                                          _ptr(st.counts), int(is_u8), n_far, C.c_int64(row_offset), _ptr(payload),
                                                          _ptr(st.row_scratch()), _ptr(active), ctx.stream()))
-                dist.all_gather(list(allpay.unbind(0)), payload, group=group)
+                if is_cuda:
+                    dist.all_gather_into_tensor(allpay, payload, group=group)
+                else:
+                    dist.all_gather(list(allpay.unbind(0)), payload, group=group)
                 ctx.check(ctx.lib.ofc_kmeans_relocate_merge(B, d, k, world, n_far, _ptr(allpay), _ptr(st.sums), _ptr(st.counts),
                                                             _ptr(overflow), _ptr(active), ctx.stream()))
         else:
             st.relocate(mean, lab, centres, st.sums, st.counts, is_u8, active=active)
         st.update_(st.sums, st.counts, mean if is_u8 else None, 0 if is_u8 else 1, 1 if is_f32 else 0, centres, st.n_changed,
-                   tol_, it, n_active[it:it + 1], lab, lab_old)
+                   tol_, 0, n_active, lab, lab_old, it_counter=it_counter)
+
+    def stopped(upto):
+        """have all problems stopped by iteration `upto` (as far as the host has seen)?  None = keep going"""
+        if overflow is not None and int(overflow_seen[upto]):
+            return True
+        return int(seen[upto]) == 0
+
+    lag = _POLL_LAG if is_cuda and not _host_relocation else 0
+    use_graph = (is_cuda and group is None and _TEST_LIBRARY is None and max_iter >= 8
+                 and os.environ.get("OFC_KMEANS_GRAPH", "1") != "0")
+    it = 0
+    done = False
+    n_eager = min(max_iter, 2) if use_graph else max_iter
+    # eager iterations (all of them without a graph; the first two otherwise: they also do the lazy allocations and
+    # the shared-memory opt-ins a capture must not contain)
+    while it < n_eager and not done:
+        iteration(it & 1)
         seen[it:it + 1].copy_(n_active[it:it + 1], non_blocking=True)
         if overflow is not None:
             overflow_seen[it:it + 1].copy_(overflow, non_blocking=True)
@@ -479,15 +503,40 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             events.append(ev)
-        back = it - (_POLL_LAG if is_cuda and not _host_relocation else 0)
+        back = it - lag
         if back >= 0:
             if is_cuda:
                 events[back].synchronize()
-            if overflow is not None and int(overflow_seen[back]):
-                break
-            if int(seen[back]) == 0:
-                break
-        cur ^= 1
+            done = stopped(back)
+        it += 1
+    if use_graph and not done and it < max_iter:
+        # one GPU: two iterations (one per label buffer) captured once and replayed -- a fit is then a handful of graph
+        # launches instead of ~10 kernel launches and ctypes calls per iteration
+        torch.cuda.current_stream(dev).synchronize()
+        if int(seen[it - 1]) != 0:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                iteration(0)
+                iteration(1)
+            replays = []
+            while it + 2 <= max_iter:
+                graph.replay()
+                seen.copy_(n_active, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                replays.append((ev, it + 1))
+                it += 2
+                if len(replays) > 2:
+                    ev_b, upto = replays[-3]
+                    ev_b.synchronize()
+                    if int(seen[upto]) == 0:
+                        done = True
+                        break
+            if not done and it < max_iter:                     # odd max_iter: the last iteration
+                torch.cuda.current_stream(dev).synchronize()
+                if int(seen[it - 1]) != 0:
+                    iteration(it & 1)
+                    it += 1
     if overflow is not None:
         if is_cuda:
             torch.cuda.current_stream(dev).synchronize()

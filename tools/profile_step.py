@@ -10,7 +10,7 @@ from opticalflowclustering_b200.synthetic import synthetic_clip
 H, W = {"720p": (720, 1280), "1080p": (1080, 1920), "4k": (2160, 3840)}[os.environ.get("OFC_SIZE", "1080p")]
 F = int(os.environ.get("OFC_CHUNK", "9"))
 clip = synthetic_clip(F, H, W, seed=0, device="cuda")
-pipe = ClipPipeline(W, H, chunk_frames=F)
+pipe = ClipPipeline(W, H, chunk_frames=F, n_clusters=int(os.environ.get("OFC_K", "1")))
 for _ in range(3):
     pipe.run_chunk(clip)
 torch.cuda.synchronize()
