@@ -356,6 +356,8 @@ def column_mean_var(st: LloydState, group=None):
 
 #: how many iterations the host may run ahead of the device's "everybody has stopped" signal
 _POLL_LAG = 4
+#: iterations enqueued one by one before the loop body is captured in a CUDA graph (even)
+_EAGER_ITERATIONS = 8
 
 
 def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_relocation: bool = False):
@@ -487,13 +489,18 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
         return int(seen[upto]) == 0
 
     lag = _POLL_LAG if is_cuda and not _host_relocation else 0
-    use_graph = (is_cuda and group is None and _TEST_LIBRARY is None and max_iter >= 8
-                 and os.environ.get("OFC_KMEANS_GRAPH", "1") != "0")
+    # under a process group the captured iteration contains the NCCL collectives as well (torch.distributed's NCCL ops
+    # are capturable once the communicator is warm -- the two eager iterations); OFC_KMEANS_GRAPH_NCCL=0 keeps that
+    # path eager
+    use_graph = (is_cuda and _TEST_LIBRARY is None and max_iter >= 8 and os.environ.get("OFC_KMEANS_GRAPH", "1") != "0"
+                 and (group is None or (not _host_relocation and os.environ.get("OFC_KMEANS_GRAPH_NCCL", "0") == "1")))
     it = 0
     done = False
-    n_eager = min(max_iter, 2) if use_graph else max_iter
-    # eager iterations (all of them without a graph; the first two otherwise: they also do the lazy allocations and
-    # the shared-memory opt-ins a capture must not contain)
+    n_eager = min(max_iter, _EAGER_ITERATIONS) if use_graph else max_iter
+    # eager iterations: all of them without a graph; otherwise the first _EAGER_ITERATIONS (an even number: the graph
+    # starts on label buffer 0).  They do the lazy allocations and shared-memory opt-ins a capture must not contain,
+    # and short fits never pay for a capture: measured (r02i) a 5-iteration fit of 8 M x 4 rows takes 1.4 ms eagerly
+    # and 2.4 ms when a graph is captured after two iterations
     while it < n_eager and not done:
         iteration(it & 1)
         seen[it:it + 1].copy_(n_active[it:it + 1], non_blocking=True)
@@ -522,6 +529,8 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
             while it + 2 <= max_iter:
                 graph.replay()
                 seen.copy_(n_active, non_blocking=True)
+                if overflow is not None:
+                    overflow_seen[:1].copy_(overflow, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
                 replays.append((ev, it + 1))
@@ -529,7 +538,7 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
                 if len(replays) > 2:
                     ev_b, upto = replays[-3]
                     ev_b.synchronize()
-                    if int(seen[upto]) == 0:
+                    if int(seen[upto]) == 0 or (overflow is not None and int(overflow_seen[0])):
                         done = True
                         break
             if not done and it < max_iter:                     # odd max_iter: the last iteration
