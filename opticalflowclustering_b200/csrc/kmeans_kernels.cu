@@ -893,19 +893,22 @@ __global__ void __launch_bounds__(1024) kmeans_far_payload_kernel(const T* Xall,
     if (!(active && !active[b])) {
         const long long* counts = counts_all + (int64_t)b * k;
         int any = 0;
-        for (int j = tid; j < k; j += 1024) any |= counts[j] == 0;
-        if (any) s_any = 1;
+        for (int j = tid; j < k; j += 1024) any += counts[j] == 0 ? 1 : 0;
+        if (any) atomicAdd(&s_any, any);
     }
     __syncthreads();
+    // only as many candidates as there are empty clusters can ever be used (every rank sees the same all-reduced counts)
+    const int wanted = min(s_any, n_far);
+    for (int e = wanted + tid; e < n_far; e += 1024) { payload[(int64_t)e * rec] = -1.0; payload[(int64_t)e * rec + 1] = -1.0; }
     if (!s_any || n <= 0) {
-        for (int e = tid; e < n_far; e += 1024) { payload[(int64_t)e * rec] = -1.0; payload[(int64_t)e * rec + 1] = -1.0; }
+        for (int e = tid; e < wanted; e += 1024) { payload[(int64_t)e * rec] = -1.0; payload[(int64_t)e * rec + 1] = -1.0; }
         return;
     }
     const T* X = Xall + (int64_t)b * n * d;
     const int32_t* labels = labels_all + (int64_t)b * n;
     const double* mean = mean_all ? mean_all + (int64_t)b * d : nullptr;
     double* scratch = scratch_all + (int64_t)b * n;
-    for (int e = 0; e < n_far; ++e) {
+    for (int e = 0; e < wanted; ++e) {
         double v;
         long long idx;
         block_argmax_1024(scratch, n, s_val, s_idx, v, idx);
