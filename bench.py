@@ -497,6 +497,26 @@ def dist_kmeans_leg(dev, world, rank):
         it = int(n_iter)
         rec = {"rows": N, "d": D, "k": K, "n_iter": it, "fit_ms": ms, "host_wall_ms": 1e3 * wall, "ms_per_iteration": ms / max(it, 1),
                "rows_iter_per_s": N * it / (ms / 1e3), "inertia": float(inertia)}
+        if world > 1:
+            # which exchange the fit above used, and the same fit with the library collectives (NCCL all-reduce x 2 +
+            # all-gather per iteration) for comparison
+            from opticalflowclustering_b200.peer import PeerExchange
+            peer = any(v not in (None, False) for v in PeerExchange._cache.values())
+            rec["exchange"] = "one peer-memory kernel per iteration over NVLink (csrc/peer_exchange.cu)" if peer else "NCCL collectives"
+            if peer:
+                os.environ["OFC_KMEANS_PEER"] = "0"
+                km.lloyd(X, init, group=group)
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0.record()
+                _, c_n, _, it_n = km.lloyd(X, init, group=group)
+                e1.record()
+                torch.cuda.synchronize()
+                os.environ.pop("OFC_KMEANS_PEER")
+                tn = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+                dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+                rec["fit_ms_nccl"] = float(tn.item())
+                rec["same_result_as_nccl"] = bool(torch.equal(c_n, centres) and int(it_n) == it)
         if world == 1:
             # same fit with events around every kernel: how much of the fit is kernel time (host-free loop)
             import ctypes as C
@@ -600,10 +620,13 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # profiler range = the timed steps: `ncu --profile-from-start off` then lists exactly these launches (no-ops otherwise)
+    torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for i in range(args.warmup, args.warmup + args.steps):
         pipe.run_chunk(clip[starts[i]:starts[i] + F])
     e1.record()
+    torch.cuda.cudart().cudaProfilerStop()
     sampler.sample_now()        # after the last enqueue: the GPU is still working, and a slow NVML call cannot stall the timed steps
     barrier()
     clocks = sampler.stop()

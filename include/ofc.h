@@ -267,6 +267,30 @@ int ofc_kmeans_far_payload(const void* X, int dtype, int batch, int64_t n, int d
 int ofc_kmeans_relocate_merge(int batch, int d, int k, int world, int n_far, const double* all_payload, double* sums,
                               int64_t* counts, int32_t* overflow, const uint8_t* active, void* stream);
 
+/* The exchange step of the row-sharded fit over NVLink peer memory, one kernel per rank and exchange instead of one
+ * library collective per buffer (replaces, for ranks on one node, the all-reduce of sums / counts / label changes and the
+ * all-gather of the far-point payloads above; what a multi-worker KMeans.fit of KmeanGrids.py:299-304 has to exchange
+ * per Lloyd iteration).  Each rank owns one buffer: ofc_peer_alloc (cudaMalloc, zeroed; `handle64` = its 64-byte CUDA
+ * IPC handle, to be sent to the other ranks by whatever transport the host has), ofc_peer_open maps a peer's buffer
+ * into this process.  Layout: ofc_peer_header_bytes() of flags, then regions the caller lays out (offsets multiple of
+ * 16).  `bufs` = DEVICE array of `world` pointers (own buffer at [rank]).
+ * ofc_peer_exchange, enqueued by every rank on its own stream after the kernels that filled its region:
+ *   mode 0: out_f64[i] = sum over ranks (in rank order: bit-identical on every rank) of the region's first n_f64 doubles,
+ *           out_i64[i] = the same for the n_i64 int64 that follow;
+ *   mode 1: out_f64[src][i] = rank src's n_f64 doubles (all-gather).
+ * gate (device int64[gate_n], identical on all ranks, may be NULL): the exchange is skipped unless one entry is zero
+ * ("some cluster is empty").  A region may be rewritten once ANOTHER exchange has completed after the one that read it
+ * (alternate two regions).  A rank that waits longer than timeout_s (<= 0: 10 s) for a peer sets the error word that
+ * ofc_peer_error reads back (after a stream synchronise) instead of hanging the device. */
+size_t ofc_peer_header_bytes(void);
+int ofc_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int ofc_peer_open(const unsigned char* handle64, void** ptr);
+int ofc_peer_close(void* ptr);
+int ofc_peer_free(void* ptr);
+int ofc_peer_exchange(const void* bufs, int world, int rank, size_t region_offset, int mode, int64_t n_f64, int64_t n_i64,
+                      double* out_f64, int64_t* out_i64, const int64_t* gate, int gate_n, double timeout_s, void* stream);
+int ofc_peer_error(const void* own_buffer, int* err);
+
 /* Whole Lloyd runs on the device, one CTA per problem: the reference's per-cell fits
  * (KMeans(n_clusters=k).fit on every grid cell of a frame, KmeanGrids.py:376-392) in ONE launch --
  * column statistics, seeding, all iterations, relocation, sklearn's stopping rule, closing E-step.

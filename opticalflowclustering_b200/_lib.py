@@ -55,6 +55,13 @@ SIGNATURES = {
     "ofc_kmeans_far_points": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "ofc_kmeans_far_payload": (_i, [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
     "ofc_kmeans_relocate_merge": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ofc_peer_header_bytes": (_sz, []),
+    "ofc_peer_alloc": (_i, [_sz, _vp, _vp]),
+    "ofc_peer_open": (_i, [_vp, _vp]),
+    "ofc_peer_close": (_i, [_vp]),
+    "ofc_peer_free": (_i, [_vp]),
+    "ofc_peer_exchange": (_i, [_vp, _i, _i, _sz, _i, _i64, _i64, _vp, _vp, _vp, _i, _d, _vp]),
+    "ofc_peer_error": (_i, [_vp, _vp]),
     "ofc_kmeans_cells": (_i, [_vp, _i, _i64, _i, _i, _vp, C.c_uint64, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ofc_grid_kmeans_cells_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "ofc_grid_kmeans_cells": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.c_uint64, C.c_uint64, _i, _d, _vp, _vp, _vp, _vp,

@@ -436,30 +436,50 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
             allpay = torch.empty((world, B, n_far, 3 + d), dtype=torch.float64, device=dev)
             overflow = torch.zeros(1, dtype=torch.int32, device=dev)
     overflow_seen = torch.zeros(max(max_iter, 1), dtype=torch.int32, pin_memory=is_cuda) if overflow is not None else None
+    # ranks on one node exchange through NVLink peer memory (peer.py): the E/M kernels write this rank's sums / counts /
+    # label changes into its shared buffer (two slots, alternating per iteration) and ONE kernel pulls and adds every
+    # rank's copy; the far-point lists of the relocation travel the same way.  None -> the NCCL collectives.
+    px = None
+    local = [(st.sums, st.counts, st.n_changed)] * 2
+    n_f64, n_i64 = B * k * d, B * k + B
+    if payload is not None and is_cuda and _TEST_LIBRARY is None:
+        from .peer import PeerExchange
+        px = PeerExchange.create(group, dev, (n_f64 + n_i64) * 8, payload.numel() * 8)
+    if px is not None:
+        local = []
+        for s in (0, 1):
+            r = px.region(px.slot_offset(s), (n_f64 + n_i64) * 8)
+            ic = r[n_f64 * 8:].view(torch.int64)
+            local.append((r[:n_f64 * 8].view(torch.float64).view(B, k, d), ic[:B * k].view(B, k), ic[B * k:]))
+        payload = px.region(px.gather_offset(), payload.numel() * 8).view(torch.float64).view(B, n_far, 3 + d)
     it_counter = torch.zeros(1, dtype=torch.int32, device=dev)       # iteration number, kept on the device
 
     def iteration(cur):
         """one Lloyd iteration, enqueued on the current stream; nothing in it depends on host-side values, so on one GPU it
         can be captured in a CUDA graph (the iteration number is `it_counter`)"""
         lab, lab_old = st.labels[cur], st.labels[cur ^ 1]
+        sums_w, counts_w, changed_w = local[cur]                 # where this rank's partial results go
         if tc is not None:
-            tc.assign(centres, lab, prev=lab_old, n_changed=st.n_changed)
-            tc.sums_(lab, st.sums, st.counts)
+            tc.assign(centres, lab, prev=lab_old, n_changed=changed_w)
+            tc.sums_(lab, sums_w, counts_w)
         elif fused:
-            st.step(mean, centres, lab, lab_old, st.n_changed, st.sums, st.counts, active=active)
+            st.step(mean, centres, lab, lab_old, changed_w, sums_w, counts_w, active=active)
         else:
-            st.assign(mean, centres, lab, prev=lab_old, n_changed=st.n_changed, active=active)
+            st.assign(mean, centres, lab, prev=lab_old, n_changed=changed_w, active=active)
             # uint8: raw (exact integer) sums; floats: sums of the centred rows like sklearn
-            st.sums_(None if is_u8 else mean, lab, st.sums, st.counts, k, active=active)
+            st.sums_(None if is_u8 else mean, lab, sums_w, counts_w, k, active=active)
         if group is not None:
             if B > 1:
                 # stopped problems contribute nothing (their buffers hold already-reduced values)
                 off = (active == 0)
-                st.sums.masked_fill_(off.view(B, 1, 1), 0.0)
-                st.counts.masked_fill_(off.view(B, 1), 0)
-                st.n_changed.masked_fill_(off, 0)
-            _all_reduce(st.sums, group)
-            _all_reduce(st.icnt, group)
+                sums_w.masked_fill_(off.view(B, 1, 1), 0.0)
+                counts_w.masked_fill_(off.view(B, 1), 0)
+                changed_w.masked_fill_(off, 0)
+            if px is not None:
+                px.exchange(px.slot_offset(cur), 0, n_f64, n_i64, st.sums, st.icnt, None, ctx.stream())
+            else:
+                _all_reduce(st.sums, group)
+                _all_reduce(st.icnt, group)
             if _host_relocation:
                 flag_dev = ((st.counts == 0) & (active != 0).view(B, 1)).any().to(torch.uint8).view(1)
                 flag_host.copy_(flag_dev, non_blocking=True)
@@ -471,7 +491,10 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
                 ctx.check(ctx.lib.ofc_kmeans_far_payload(_ptr(st.X), st.dtype, B, C.c_int64(n), d, k, _ptr(mean), _ptr(lab), _ptr(centres),
                                                          _ptr(st.counts), int(is_u8), n_far, C.c_int64(row_offset), _ptr(payload),
                                                          _ptr(st.row_scratch()), _ptr(active), ctx.stream()))
-                if is_cuda:
+                if px is not None:
+                    # only when some cluster is empty (the all-reduced counts say so on every rank alike)
+                    px.exchange(px.gather_offset(), 1, payload.numel(), 0, allpay, None, st.counts.view(-1), ctx.stream())
+                elif is_cuda:
                     dist.all_gather_into_tensor(allpay, payload, group=group)
                 else:
                     dist.all_gather(list(allpay.unbind(0)), payload, group=group)
@@ -489,11 +512,19 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
         return int(seen[upto]) == 0
 
     lag = _POLL_LAG if is_cuda and not _host_relocation else 0
+    # tensor-core fits with long iterations (>= ~0.3 ms of kernels): the tensor-core kernels do not look at the stop flag,
+    # so every iteration enqueued past the stop costs its full time (measured r02k: 1 M x 128, k = 1024 on 2 GPUs, 81 ms
+    # with six iterations of overshoot against 69 ms with four).  One iteration of look-ahead hides the host's poll there,
+    # and launch overhead is noise next to the kernels, so no graph either.
+    heavy = tc is not None and float(n) * k * d >= 1e9
+    if heavy and lag:
+        lag = 1
     # under a process group the captured iteration contains the NCCL collectives as well (torch.distributed's NCCL ops
     # are capturable once the communicator is warm -- the two eager iterations); OFC_KMEANS_GRAPH_NCCL=0 keeps that
     # path eager
-    use_graph = (is_cuda and _TEST_LIBRARY is None and max_iter >= 8 and os.environ.get("OFC_KMEANS_GRAPH", "1") != "0"
-                 and (group is None or (not _host_relocation and os.environ.get("OFC_KMEANS_GRAPH_NCCL", "0") == "1")))
+    use_graph = (is_cuda and _TEST_LIBRARY is None and max_iter >= 8 and not heavy and os.environ.get("OFC_KMEANS_GRAPH", "1") != "0"
+                 and (group is None or px is not None
+                      or (not _host_relocation and os.environ.get("OFC_KMEANS_GRAPH_NCCL", "0") == "1")))
     it = 0
     done = False
     n_eager = min(max_iter, _EAGER_ITERATIONS) if use_graph else max_iter
@@ -549,6 +580,8 @@ def lloyd(X, init, max_iter: int = 300, tol: float = 1e-4, group=None, _host_rel
     if overflow is not None:
         if is_cuda:
             torch.cuda.current_stream(dev).synchronize()
+        if px is not None:
+            px.check()
         if int(overflow.item()):
             # more clusters empty at once than the device-side candidate list holds: redo the fit with the host-merged
             # relocation (every rank takes this branch: the all-reduced counts are the same everywhere)

@@ -23,19 +23,45 @@ X = (cen[torch.randint(0, K, (N,), generator=g)] + 12 * torch.randn(N, D, genera
 init = X[:K].double()
 lo, hi = shard_range(N, rank, world)
 Xs = X[lo:hi].cuda()
-km.lloyd(Xs, init, group=dist.group.WORLD)                   # warm-up
-torch.cuda.synchronize(); dist.barrier()
-t0 = time.perf_counter()
-labels, centres, inertia, n_iter = km.lloyd(Xs, init, group=dist.group.WORLD)
-torch.cuda.synchronize(); dist.barrier()
-dt = time.perf_counter() - t0
-ok = True
+from opticalflowclustering_b200.peer import PeerExchange
+
+
+def timed_fit(Xr, init_, peer):
+    """one warm-up fit + one timed fit; peer=False forces the NCCL collectives, True the NVLink peer-memory kernel"""
+    os.environ["OFC_KMEANS_PEER"] = "1" if peer else "0"
+    km.lloyd(Xr, init_, group=dist.group.WORLD)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    out = km.lloyd(Xr, init_, group=dist.group.WORLD)
+    torch.cuda.synchronize(); dist.barrier()
+    return out, time.perf_counter() - t0
+
+
+(labels_n, centres_n, inertia_n, n_iter_n), dt_nccl = timed_fit(Xs, init, False)
+(labels, centres, inertia, n_iter), dt = timed_fit(Xs, init, True)
+peer_used = any(v not in (None, False) for v in PeerExchange._cache.values())
+ok = torch.equal(centres, centres_n) and torch.equal(labels, labels_n) and int(n_iter) == int(n_iter_n)
 if rank == 0:
     l1, c1, i1, n1 = km.lloyd(X.cuda(), init)
-    ok = torch.equal(c1, centres) and int(n1) == int(n_iter) and torch.equal(l1[lo:hi], labels) and \
+    ok = ok and torch.equal(c1, centres) and int(n1) == int(n_iter) and torch.equal(l1[lo:hi], labels) and \
         abs(float(i1) - float(inertia)) <= 1e-12 * float(i1)
-    print(f"world={world} N={N} D={D} k={K} n_iter={int(n_iter)} sharded {dt * 1e3:.1f} ms "
-          f"({N * int(n_iter) / dt / 1e9:.2f} G rows/s)  centres bit-identical to 1 GPU: {ok}")
+    print(f"world={world} N={N} D={D} k={K} n_iter={int(n_iter)} sharded: NCCL collectives {dt_nccl * 1e3:.2f} ms, "
+          f"peer-memory exchange kernel {dt * 1e3:.2f} ms (used: {peer_used}; {N * int(n_iter) / dt / 1e9:.2f} G rows/s)  "
+          f"centres bit-identical to 1 GPU and between the two exchanges: {ok}")
+# empty clusters: two of the initial centres sit far outside the data, so the relocation (far-point lists gathered
+# across the ranks) runs in the first iterations; both exchanges against one GPU
+init_e = init.clone()
+init_e[1] = 255.0 * 40
+init_e[5] = -255.0 * 40
+(lab_en, cen_en, _, it_en), _ = timed_fit(Xs, init_e, False)
+(lab_e, cen_e, _, it_e), _ = timed_fit(Xs, init_e, True)
+ok_e = torch.equal(cen_e, cen_en) and torch.equal(lab_e, lab_en) and int(it_e) == int(it_en)
+if rank == 0:
+    l1, c1, i1, n1 = km.lloyd(X.cuda(), init_e)
+    ok_e = ok_e and torch.equal(c1, cen_e) and int(n1) == int(it_e) and torch.equal(l1[lo:hi], lab_e)
+    print(f"world={world} two empty clusters at the start: n_iter={int(it_e)}, relocation across ranks bit-identical to 1 GPU "
+          f"(NCCL gather and peer gather): {ok_e}")
+ok = ok and ok_e
 # dense float32 rows (d = 128, k = 64): every rank runs the tensor-core E-step / CSR M-step on its shard, the
 # all-reduce moves the float64 sums.  The cross-rank reduction order differs from the single-GPU fold, so the bar
 # is the float32 one: same n_iter, >= 99.95 % labels, centres to 1e-5, inertia to 1e-6 relative.
@@ -46,19 +72,17 @@ X2 = (cen2[torch.randint(0, K2, (N2,), generator=g2)] + torch.randn((N2, D2), ge
 init2 = X2[:K2].double()
 lo2, hi2 = shard_range(N2, rank, world)
 X2s = X2[lo2:hi2].cuda()
-km.lloyd(X2s, init2, group=dist.group.WORLD)
-torch.cuda.synchronize(); dist.barrier()
-t0 = time.perf_counter()
-lab2, c2, in2, it2 = km.lloyd(X2s, init2, group=dist.group.WORLD)
-torch.cuda.synchronize(); dist.barrier()
-dt2 = time.perf_counter() - t0
+(_, c2n, _, it2n), dt2_nccl = timed_fit(X2s, init2, False)
+(lab2, c2, in2, it2), dt2 = timed_fit(X2s, init2, True)
 ok2 = True
 if rank == 0:
     l1, c1, i1, n1 = km.lloyd(X2.cuda(), init2)
     agree = (l1[lo2:hi2] == lab2).float().mean().item()
     ok2 = int(n1) == int(it2) and agree > 0.9995 and (c1 - c2).abs().max().item() < 1e-5 and \
         abs(float(i1) - float(in2)) <= 1e-6 * float(i1)
-    print(f"world={world} dense float32 N={N2} D={D2} k={K2} n_iter={int(it2)} sharded {dt2 * 1e3:.1f} ms: labels agree "
+    ok2 = ok2 and int(it2n) == int(it2) and (c2n - c2).abs().max().item() < 1e-5
+    print(f"world={world} dense float32 N={N2} D={D2} k={K2} n_iter={int(it2)} sharded: NCCL {dt2_nccl * 1e3:.1f} ms, peer "
+          f"{dt2 * 1e3:.1f} ms: labels agree "
           f"{100 * agree:.4f} %, max |centre diff| {(c1 - c2).abs().max().item():.2e}, ok: {ok2}")
 dist.destroy_process_group()
 sys.exit(0 if (ok and ok2) else 1)

@@ -11,7 +11,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log
 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_1gpu.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/${TAG}_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err; echo "reference rc=$?"
 SHORT="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline"
-$SHORT > gpurun_out/${TAG}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $SHORT > gpurun_out/${TAG}_ncu_list.log 2>&1
+$SHORT > gpurun_out/${TAG}_plain.log 2>&1 && ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $SHORT > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "ncu list rc=$?"
 export OFC_CHUNK=33
 P="python tools/profile_step.py"
