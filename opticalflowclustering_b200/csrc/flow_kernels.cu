@@ -710,6 +710,47 @@ __global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const u
     }   // segments of this CTA's row range
 }
 
+// The 2x2 solve of one pixel from the five window sums S (box window): OpenCV evaluates, in float64,
+//     g = S * scale,  idet = 1 / (g11 g22 - g12^2 + 1e-3),  flow = ((g11 h2 - g12 h1) idet, (g22 h1 - g12 h2) idet)
+// and rounds to float32.  The scale cancels: flow = N / (D + 1e-3 / scale^2) with N, D the same 2x2 determinants of the
+// raw sums.  Both determinants are evaluated in float32 with error-free products (a b = p + e exactly, e from one fma),
+// so the cancellation in D and N costs nothing: the results are within about one float32 ulp of the float64 evaluation
+// (tests: same bars against cv2 as before; measured r02l: emulated mean end-point error against cv2 1.69e-7 -> 1.74e-7 px),
+// at a fifth of the float64-pipe and conversion work: the three level-0 launches 3.62 -> 3.43 ms per 32 pairs (r02n).  `c_hi + c_lo` is
+// 1e-3 / scale^2 split into two floats on the host.
+__device__ __forceinline__ float det_eft(float a, float b, float c, float d, float& lo) {
+    // a b - c d = (p - q) + (e - f) with p + e = a b and q + f = c d exactly
+    const float p = __fmul_rn(a, b), q = __fmul_rn(c, d);
+    const float e = __fmaf_rn(a, b, -p), f = __fmaf_rn(c, d, -q);
+    lo = __fsub_rn(e, f);
+    return __fsub_rn(p, q);
+}
+
+__device__ __forceinline__ float rcp_seed(float x) {
+#ifndef OFC_EMULATE
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
+__device__ __forceinline__ float2 solve2x2(const IterParams& p, float s11, float s12, float s22, float sh1, float sh2) {
+    float dl, n1l, n2l;
+    const float dh = det_eft(s11, s22, s12, s12, dl);
+    const float n1h = det_eft(s11, sh2, s12, sh1, n1l);
+    const float n2h = det_eft(s22, sh1, s12, sh2, n2l);
+    // D + c > 0: D >= 0 up to rounding (a sum of positive semi-definite matrices), c = 50.625 for winsize 15
+    const float den = __fadd_rn(__fadd_rn(dh, p.solve_c_hi), __fadd_rn(dl, p.solve_c_lo));
+    const float n1 = __fadd_rn(n1h, n1l), n2 = __fadd_rn(n2h, n2l);
+    const float r0 = rcp_seed(den);
+    const float r = __fmaf_rn(__fmaf_rn(-den, r0, 1.f), r0, r0);               // one Newton step: ~1 ulp
+    const float q1 = __fmul_rn(n1, r), q2 = __fmul_rn(n2, r);
+    // residual correction: the quotient is correctly rounded except in rare half-way cases
+    return make_float2(__fmaf_rn(__fmaf_rn(-q1, den, n1), r, q1), __fmaf_rn(__fmaf_rn(-q2, den, n2), r, q2));
+}
+
 // ---------------------------------------------------------------------------
 // K4+K5+K6 fused: one Farneback iteration.
 //   phase 1  M(y,x) for the tile + box-filter halo, straight from R0, warped R1
@@ -860,12 +901,7 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_kernel(IterParams p) {
         float2 res[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            double g11 = (double)S[0][j] * p.blur_scale, g12 = (double)S[1][j] * p.blur_scale;
-            double g22 = (double)S[2][j] * p.blur_scale;
-            double h1 = (double)S[3][j] * p.blur_scale, h2 = (double)S[4][j] * p.blur_scale;
-            double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-            res[j].x = (float)((g11 * h2 - g12 * h1) * idet);
-            res[j].y = (float)((g22 * h1 - g12 * h2) * idet);
+            res[j] = solve2x2(p, S[0][j], S[1][j], S[2][j], S[3][j], S[4][j]);
         }
         float2* out = p.flow_out + (int64_t)pair * p.flow_out_stride + (int64_t)gy * w + gx0;
         if (gx0 + 7 < w && (w & 1) == 0) {
@@ -996,12 +1032,7 @@ __device__ __forceinline__ void solve_rows(const IterParams& p, const float* han
         float2 res[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const double g11 = (double)S[0][j] * p.blur_scale, g12 = (double)S[1][j] * p.blur_scale;
-            const double g22 = (double)S[2][j] * p.blur_scale;
-            const double h1 = (double)S[3][j] * p.blur_scale, h2 = (double)S[4][j] * p.blur_scale;
-            const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-            res[j].x = (float)((g11 * h2 - g12 * h1) * idet);
-            res[j].y = (float)((g22 * h1 - g12 * h2) * idet);
+            res[j] = solve2x2(p, S[0][j], S[1][j], S[2][j], S[3][j], S[4][j]);
         }
         float2* out = fout + (int64_t)gy * w + gx0;
         if (gx0 + 3 < w && (w & 1) == 0) {
@@ -1475,19 +1506,18 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
             m[0] = r4 * r4 + r6 * r6; m[1] = (r4 + r5) * r6; m[2] = r5 * r5 + r6 * r6;
             m[3] = r4 * r2 + r6 * r3; m[4] = r6 * r2 + r5 * r3;
             m[5] = m[6] = m[7] = 0.f;
-            if (ri < nrows) {
+            {
                 // float64 sums of <= 2R+1 float32 terms are exact: the result does not depend on
-                // where the walk started (see flow_iter_strip_kernel)
+                // where the walk started (see flow_iter_strip_kernel).  No row tests here: rows before the window is
+                // full (ri < 2R) and rows past the end of the segment hand over values that solve_rows skips, and the
+                // sums are re-initialised with the next segment -- straight-line code schedules better than two branches
                 cs0 -= (double)old[0]; cs1 -= (double)old[1]; cs2 -= (double)old[2]; cs3 -= (double)old[3]; cs4 -= (double)old[4];
                 cs0 += (double)m[0]; cs1 += (double)m[1]; cs2 += (double)m[2]; cs3 += (double)m[3]; cs4 += (double)m[4];
-                if (ri >= 2 * R) {
-                    float* hd = hand + i * (5 * CP) + t;
-                    hd[0 * CP] = (float)cs0; hd[1 * CP] = (float)cs1; hd[2 * CP] = (float)cs2;
-                    hd[3 * CP] = (float)cs3; hd[4 * CP] = (float)cs4;
-                }
+                float* hd = hand + i * (5 * CP) + t;
+                hd[0 * CP] = (float)cs0; hd[1 * CP] = (float)cs1; hd[2 * CP] = (float)cs2;
+                hd[3 * CP] = (float)cs3; hd[4 * CP] = (float)cs4;
             }
-            // the store is warp-collective: issued on every path (rows past the end rewrite the slot
-            // with values nobody reads)
+            // the store is warp-collective (rows past the end rewrite the slot with values nobody reads)
             tmem_st8(ring_base + slot * 8, m);
             slot = slot + 1 == K ? 0 : slot + 1;
             ls = ls + 1 == S ? 0 : ls + 1;

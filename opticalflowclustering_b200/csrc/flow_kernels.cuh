@@ -47,6 +47,7 @@ struct IterParams {
     unsigned* minmax;            // [n_pairs][2] float bits (min, max) of |flow|, or null
     float border[5];
     double blur_scale;           // 1 / winsize^2
+    float solve_c_hi, solve_c_lo; // 1e-3 / blur_scale^2 as two floats (solve2x2)
 };
 
 // OPTFLOW_FARNEBACK_GAUSSIAN window: k[0] centre tap, k[i] the tap at distance i (2r+1 taps)

@@ -286,6 +286,12 @@ static int run_farneback(const ofc_flow_plan* pl, const uint8_t* gray, int64_t g
             ip.w = L.w; ip.h = L.h;
             ip.border[0] = 0.14f; ip.border[1] = 0.14f; ip.border[2] = 0.4472f; ip.border[3] = 0.4472f; ip.border[4] = 0.4472f;
             ip.blur_scale = 1.0 / ((double)pl->winsize * pl->winsize);
+            {
+                // float32 solve (solve2x2): the regulariser 1e-3 in units of the raw window sums, as two floats
+                const double c = 1e-3 / (ip.blur_scale * ip.blur_scale);
+                ip.solve_c_hi = (float)c;
+                ip.solve_c_lo = (float)(c - (double)ip.solve_c_hi);
+            }
             ip.upsample = 0; ip.wc = ip.hc = 0; ip.usx = ip.usy = 1.0; ip.flow_mul = 1.0; ip.ups_fast = 0;
             if (it == 0 && l == 0 && init_flow) {
                 // cv2 flag 4: resize(flow0, INTER_AREA) * scale seeds the coarsest level (other ping-pong buffer)

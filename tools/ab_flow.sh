@@ -1,0 +1,20 @@
+#!/bin/bash
+# A/B of kernel switches on one B200: each line "NAME VAR=VAL ..." runs the short bench in a fresh process and prints
+# pairs/s plus the per-kernel times.  Usage: bash tools/ab_flow.sh <tag> "base" "f64 OFC_SOLVE_F64=1" ...
+TAG=$1; shift
+export PYTHONPATH=.
+mkdir -p gpurun_out
+for spec in "$@"; do
+  name=${spec%% *}; envs=""
+  [ "$spec" != "$name" ] && envs=${spec#* }
+  env $envs python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline ${OFC_AB_ARGS} > gpurun_out/${TAG}_ab_${name}.json 2> gpurun_out/${TAG}_ab_${name}.err
+  python - "$name" gpurun_out/${TAG}_ab_${name}.json <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    k = d["kernels"]
+    print(f"{sys.argv[1]:14s} {d['value']:8.1f} pairs/s  step {d['ms_per_step']:.3f} ms | " + "  ".join(f"{n.replace('flow_','')} {v['ms_per_step']:.3f}" for n, v in k.items()))
+except Exception as e:
+    print(sys.argv[1], "FAILED", e)
+PY
+done
