@@ -1001,50 +1001,56 @@ __device__ __forceinline__ void solve_rows(const IterParams& p, const float* han
     constexpr int K = 2 * R + 1;
     constexpr int CW = TW + 2 * R;
     constexpr int CP = (CW + 3) / 4 * 4 + 4;
-    constexpr int SEG = TW / 4;
+    // 4 pixels per task: 8 (fewer shared loads, half the threads busy) and a balanced-tree form of the sums both measured
+    // slower (r02o: 3.62 / 3.54 against 3.50 ms)
+    constexpr int PX = 4;
+    constexpr int SEG = TW / PX;
+    static_assert(TW % PX == 0, "whole tasks per row");
     for (int task = t; task < G * SEG; task += NT) {
         const int i = task / SEG, seg = task - i * SEG;
         const int ri = g0 + i;
-        const int gx0 = x0 + seg * 4;
+        const int gx0 = x0 + seg * PX;
         if (ri < 2 * R || ri >= nrows || gx0 >= w) continue;
         const int gy = ys + ri - 2 * R;
-        constexpr int NV = (4 + 2 * R + 3) / 4 * 4;
-        float S[5][4];
+        constexpr int NV = (PX + 2 * R + 3) / 4 * 4;
+        float S[5][PX];
 #pragma unroll
         for (int ch = 0; ch < 5; ++ch) {
-            const float* src = hand + i * (5 * CP) + ch * CP + seg * 4;
+            const float* src = hand + i * (5 * CP) + ch * CP + seg * PX;
             float v[NV];
 #pragma unroll
             for (int j = 0; j < NV / 4; ++j) {
                 const float4 q = *reinterpret_cast<const float4*>(src + j * 4);
                 v[j * 4 + 0] = q.x; v[j * 4 + 1] = q.y; v[j * 4 + 2] = q.z; v[j * 4 + 3] = q.w;
             }
-            float sum = 0.f;
+            {
+                float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < K; ++j) sum += v[j];
-            S[ch][0] = sum;
+                for (int j = 0; j < K; ++j) sum += v[j];
+                S[ch][0] = sum;
 #pragma unroll
-            for (int j = 1; j < 4; ++j) {
-                sum += v[j + 2 * R] - v[j - 1];
-                S[ch][j] = sum;
+                for (int j = 1; j < PX; ++j) {
+                    sum += v[j + 2 * R] - v[j - 1];
+                    S[ch][j] = sum;
+                }
             }
         }
-        float2 res[4];
+        float2 res[PX];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < PX; ++j) {
             res[j] = solve2x2(p, S[0][j], S[1][j], S[2][j], S[3][j], S[4][j]);
         }
         float2* out = fout + (int64_t)gy * w + gx0;
-        if (gx0 + 3 < w && (w & 1) == 0) {
+        if (gx0 + PX - 1 < w && (w & 1) == 0) {
             float4* o4 = reinterpret_cast<float4*>(out);
-            o4[0] = make_float4(res[0].x, res[0].y, res[1].x, res[1].y);
-            o4[1] = make_float4(res[2].x, res[2].y, res[3].x, res[3].y);
+#pragma unroll
+            for (int j = 0; j < PX / 2; ++j) o4[j] = make_float4(res[2 * j].x, res[2 * j].y, res[2 * j + 1].x, res[2 * j + 1].y);
         } else {
-            for (int j = 0; j < 4 && gx0 + j < w; ++j) out[j] = res[j];
+            for (int j = 0; j < PX && gx0 + j < w; ++j) out[j] = res[j];
         }
         if (MINMAX) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < PX; ++j) {
                 if (gx0 + j < w) {
                     const float m = sqrtf(__fmaf_rn(res[j].x, res[j].x, __fmul_rn(res[j].y, res[j].y)));
                     lmin = fminf(lmin, m);
@@ -1269,6 +1275,9 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16_cg(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 // dst / src byte offsets as immediates: one address register serves several copies
 template <int DOFF, int SOFF> __device__ __forceinline__ void cp_async16_o(unsigned dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
@@ -1299,6 +1308,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 static float ofc_emu_tmem[1024][128];
 static inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
 static inline void cp_async4(void* dst, const void* src) { memcpy(dst, src, 4); }
+static inline void cp_async16_cg(void* dst, const void* src) { memcpy(dst, src, 16); }
 static inline unsigned long long smem_u32(const void* p) { return (unsigned long long)p; }
 template <int DOFF, int SOFF> static inline void cp_async16_o(unsigned long long dst, const void* src) {
     memcpy((char*)dst + DOFF, (const char*)src + SOFF, 16);
@@ -1404,7 +1414,9 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
         cp_async4_o<0, 0>(lsb, pb); cp_async4_o<NT * 4, 4>(lsb, pb);
         cp_async4_o<2 * NT * 4, 0>(lsb, pb + w); cp_async4_o<3 * NT * 4, 4>(lsb, pb + w);
         const int o0 = row * w + gx;
-        cp_async16(land_a + dst_slot * NT + t, RA0 + o0);
+        // R0 is read once per column: past L1 (.cg), which the taps of R1 need for their four-fold reuse
+        // (measured r02o: 3.50 -> 3.42 ms for the three level-0 launches of 32 pairs)
+        cp_async16_cg(land_a + dst_slot * NT + t, RA0 + o0);
         cp_async4(land_b + dst_slot * NT + t, RB0 + o0);
         cp_async_commit();
     };
@@ -1945,6 +1957,19 @@ static int launch_tmem(const IterParams& p, int n_pairs, void* stream) {
     const int cols = cdiv(p.w, TW);
     const int64_t total_rows = (int64_t)n_pairs * cols * p.h;
     int64_t ctas = (int64_t)num_sms() * 2;              // 2 CTAs per SM: 2 x 256 TMEM columns
+    // Frame f's expansion is read twice per launch: as R0 by pair f and through the warped taps by pair f-1.  With a
+    // grid that is a multiple of the pair count every pair is cut into ranges at the same rows, so the CTAs of
+    // neighbouring pairs walk the same rows at the same time and the second read hits L2 instead of DRAM (measured r02q,
+    // 32 pairs at 1080p: 288 CTAs 3.30 ms against 296 CTAs 3.34 ms for the three level-0 launches, although eight CTA
+    // slots stay empty).  Taken when it costs at most 1/16 of the slots.
+    if (n_pairs > 1 && n_pairs <= ctas) {
+        const int64_t aligned = ctas / n_pairs * n_pairs;
+        if (aligned * 16 >= ctas * 15) ctas = aligned;
+    }
+    {
+        static const int force = env_int("OFC_TMEM_CTAS", 0);          // tuning override: grid size
+        if (force > 0) ctas = force;
+    }
     const int64_t max_ctas = (total_rows + 15) / 16;
     if (ctas > max_ctas) ctas = max_ctas;
     ProfScope prof(PK_ITER_L0 + (g_prof_level < 8 ? g_prof_level : 7), stream);
@@ -1982,7 +2007,9 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
     static const int use_tmem = env_int("OFC_ITER_TMEM", 513);      // minimum level width; 0 = off
     // (OFC_TMEM_ANYW=0 restricts it to widths that are a multiple of its 240-column strips)
     static const int any_w = env_int("OFC_TMEM_ANYW", 1);
-    if (use_tmem && (p.w >= use_tmem || p.w % 240 == 0) && (any_w || p.w % 240 == 0)) return p.minmax ? launch_tmem<true, 0>(p, n_pairs, stream) : launch_tmem<false, 0>(p, n_pairs, stream);
+    if (use_tmem && (p.w >= use_tmem || p.w % 240 == 0) && (any_w || p.w % 240 == 0)) {
+        return p.minmax ? launch_tmem<true, 0>(p, n_pairs, stream) : launch_tmem<false, 0>(p, n_pairs, stream);
+    }
     static const int minb4 = env_int("OFC_STRIP_MINB4", 1);
     if (p.w > 512 && minb4) return launch_strip_r<7, 128, 160, 4, 4>(p, n_pairs, stream);
     if (p.w > 512) return launch_strip_r<7, 128, 160, 4, 3>(p, n_pairs, stream);
