@@ -969,6 +969,60 @@ __global__ void __launch_bounds__(256) flow_upsample_kernel(IterParams p, float2
     }
 }
 
+// The same resize when the level is exactly twice the coarser one (w = 2 wc, h = 2 hc, w % 4 == 0: every level of the
+// reference's 1080p / 720p pyramids): cv::resize's taps are then fixed -- output column c reads source columns
+// ((c - 1) >> 1, +1) with weights (0.75, 0.25) for even c and (0.25, 0.75) for odd c, rows alike, the frame border
+// clamped with weight 0 -- so a thread produces a 4 x 2 output block from a 4 x 3 source block (nine loads for eight
+// pixels instead of 32) without any coordinate arithmetic.  Same expressions (bilerp_flow) and therefore the same bits
+// as flow_upsample_kernel.
+__global__ void __launch_bounds__(256) flow_upsample_x2_kernel(IterParams p, float2* dst, int64_t dst_stride) {
+    const int k = blockIdx.x * 64 + (threadIdx.x & 63);           // output columns 4k .. 4k+3
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);            // output rows 2j, 2j+1
+    if (4 * k >= p.w || 2 * j >= p.h) return;
+    const float2* fin = p.flow_in + (int64_t)blockIdx.z * p.flow_in_stride;
+    float2* out = dst + (int64_t)blockIdx.z * dst_stride;
+    const int wc = p.wc, hc = p.hc;
+    // source block: columns 2k-1 .. 2k+2 and rows j-1 .. j+1, clamped to the frame
+    const int cl = max(2 * k - 1, 0), cr = min(2 * k + 2, wc - 1);
+    float2 q[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float2* row = fin + (int64_t)clampi(j - 1 + r, 0, hc - 1) * wc;
+        const float4 mid = *reinterpret_cast<const float4*>(row + 2 * k);     // columns 2k, 2k+1 (wc is even: 16-byte aligned)
+        q[r][0] = row[cl];
+        q[r][1] = make_float2(mid.x, mid.y);
+        q[r][2] = make_float2(mid.z, mid.w);
+        q[r][3] = row[cr];
+    }
+    // src_coord at scale 0.5: (c + 0.5) / 2 - 0.5 = c / 2 - 0.25 -> tap (c - 1) >> 1 with fraction 0.75 (even c) or 0.25 (odd c);
+    // c = 0 reads taps (0, 1) with fraction 0 and the last column / row its clamped tap twice with fraction 0
+    const bool first_col = k == 0, last_col = 2 * k + 1 >= wc - 1;
+    const bool first_row = j == 0, last_row = j >= hc - 1;
+    const float fx0 = first_col ? 0.f : 0.75f, fx3 = last_col ? 0.f : 0.25f;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        float2 a[4], b[4];                                         // the two source rows of this output row
+        float fy;
+        if (rr == 0) {
+            fy = first_row ? 0.f : 0.75f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { a[c] = first_row ? q[1][c] : q[0][c]; b[c] = first_row ? q[2][c] : q[1][c]; }
+        } else {
+            fy = last_row ? 0.f : 0.25f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { a[c] = q[1][c]; b[c] = q[2][c]; }
+        }
+        float2 res[4];
+        res[0] = bilerp_flow(first_col ? a[1] : a[0], first_col ? a[2] : a[1], first_col ? b[1] : b[0], first_col ? b[2] : b[1], fx0, fy, p.flow_mul);
+        res[1] = bilerp_flow(a[1], a[2], b[1], b[2], 0.25f, fy, p.flow_mul);
+        res[2] = bilerp_flow(a[1], a[2], b[1], b[2], 0.75f, fy, p.flow_mul);
+        res[3] = bilerp_flow(a[2], a[3], b[2], b[3], fx3, fy, p.flow_mul);
+        float4* o4 = reinterpret_cast<float4*>(out + (int64_t)(2 * j + rr) * p.w + 4 * k);
+        o4[0] = make_float4(res[0].x, res[0].y, res[1].x, res[1].y);
+        o4[1] = make_float4(res[2].x, res[2].y, res[3].x, res[3].y);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K5+K6 fused, strip-walk form (the production iteration kernel, winsize 15).
 //
@@ -1994,10 +2048,18 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
         return p.minmax ? launch_tmem<true, 1>(p, n_pairs, stream) : launch_tmem<false, 1>(p, n_pairs, stream);
     }
     if (p.upsample) {
-        dim3 g(cdiv(p.w, 64), cdiv(p.h, 16), n_pairs);
+        static const int x2 = env_int("OFC_UPSAMPLE_X2", 1);
+        const bool exact2 = x2 && p.w == 2 * p.wc && p.h == 2 * p.hc && p.w % 4 == 0 && p.usx == 0.5 && p.usy == 0.5 &&
+                            p.flow_in_stride % 2 == 0 && ((uintptr_t)p.flow_in & 15) == 0;
         {
             ProfScope prof(PK_UPSAMPLE, stream);
-            OFC_LAUNCH(flow_upsample_kernel, g, dim3(256), 0, stream, p, scratch, (int64_t)p.w * p.h);
+            if (exact2) {
+                OFC_LAUNCH(flow_upsample_x2_kernel, dim3(cdiv(p.w / 4, 64), cdiv(p.h / 2, 4), n_pairs), dim3(256), 0, stream, p, scratch,
+                           (int64_t)p.w * p.h);
+            } else {
+                OFC_LAUNCH(flow_upsample_kernel, dim3(cdiv(p.w, 64), cdiv(p.h, 16), n_pairs), dim3(256), 0, stream, p, scratch,
+                           (int64_t)p.w * p.h);
+            }
             OFC_CHECK_LAUNCH("flow_upsample");
         }
         p.flow_in = scratch;
@@ -2044,10 +2106,10 @@ int launch_flow_iter(const IterParams& p, int winsize, int n_pairs, float2* scra
     // pyramid levels (too few rows per SM for a column walk to hide latency) and other window sizes
     // run the square-tile kernel
     static const int strip_min_w = env_int("OFC_STRIP_MIN_W", 513);
-    // (opt-in, OFC_STRIP_SMALL_ROWS=48: measured neutral) a narrower level also walks strips when the batch
-    // gives every persistent CTA a long enough range
-    // (>= 48 rows per CTA of 2 x 148) and its width is a whole number of 240-column strips
-    static const int small_rows = env_int("OFC_STRIP_SMALL_ROWS", 0);
+    // a narrower level also walks strips when the batch gives every persistent CTA a long enough range (>= 48 rows per
+    // CTA of 2 x 148) and its width is a whole number of 240-column strips: the 480 x 270 level of a 32-pair 1080p chunk,
+    // 0.38 -> 0.30 ms for its three launches (r02r; neutral before the float32 solve, r02c).  OFC_STRIP_SMALL_ROWS=0: off
+    static const int small_rows = env_int("OFC_STRIP_SMALL_ROWS", 48);
     const bool wide = p.w >= strip_min_w;
     const bool batched = small_rows > 0 && p.w % 240 == 0 &&
                          (int64_t)n_pairs * (p.w / 240) * p.h >= (int64_t)2 * num_sms() * small_rows;
