@@ -16,8 +16,14 @@
 // 128-bit and one 32-bit load per tap instead of five scalar loads.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "ofc_common.cuh"
 #include "flow_kernels.cuh"
+
+#ifndef OFC_EXP
+#define OFC_EXP 0                // experimental variants (tools/build_variant.sh); 0 = production
+#endif
 
 namespace ofc {
 
@@ -32,6 +38,63 @@ __device__ __forceinline__ void src_coord(int d, double scale, int n_src, int& i
     if (ii >= n_src - 1) { ii = n_src - 1; fr = 0.f; }
     i = ii;
 }
+
+// asynchronous copies into shared memory (LDGSTS) and tensor-memory loads / stores, with their host-emulation forms
+#ifndef OFC_EMULATE
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// dst / src byte offsets as immediates: one address register serves several copies
+template <int DOFF, int SOFF> __device__ __forceinline__ void cp_async16_o(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
+}
+template <int DOFF, int SOFF> __device__ __forceinline__ void cp_async4_o(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 4;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
+    unsigned r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#else
+// host-side debug emulation: copies are immediate, the "tensor memory" is a per-thread array
+static float ofc_emu_tmem[1024][128];
+static inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+static inline void cp_async4(void* dst, const void* src) { memcpy(dst, src, 4); }
+static inline void cp_async16_cg(void* dst, const void* src) { memcpy(dst, src, 16); }
+static inline unsigned long long smem_u32(const void* p) { return (unsigned long long)p; }
+template <int DOFF, int SOFF> static inline void cp_async16_o(unsigned long long dst, const void* src) {
+    memcpy((char*)dst + DOFF, (const char*)src + SOFF, 16);
+}
+template <int DOFF, int SOFF> static inline void cp_async4_o(unsigned long long dst, const void* src) {
+    memcpy((char*)dst + DOFF, (const char*)src + SOFF, 4);
+}
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+static inline void tmem_ld8(unsigned taddr, float (&v)[8]) { memcpy(v, &ofc_emu_tmem[threadIdx.x][taddr & 127u], 32); }
+static inline void tmem_st8(unsigned taddr, const float (&v)[8]) { memcpy(&ofc_emu_tmem[threadIdx.x][taddr & 127u], v, 32); }
+static inline void tmem_wait_st() {}
+#endif
 
 // ---------------------------------------------------------------------------
 // K2: Gaussian pre-filter at full resolution fused with the bilinear
@@ -525,8 +588,15 @@ __global__ void __launch_bounds__(PYR_NT) prefilter_pyr_kernel(PyrParams p) {
 // 8-bit frame (exact in integers): it is produced on the fly from `gray` and
 // written to p.I only as a by-product.
 // ---------------------------------------------------------------------------
-template <int N, int TW, int NT, bool FUSE3>
-__global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const unsigned char* __restrict__ gray_all,
+// STAGE (FUSE3 only, frame width and base address multiples of 16): the 8-bit rows the next group's I needs are copied
+// into a small shared-memory ring with cp.async one group ahead, instead of 18 byte loads per thread whose first use
+// stalled the walk (ncu r02h: 27 % of the stall samples on the [1 2 1] sums right behind those loads).
+template <int N, int TW, int NT, bool FUSE3, bool STAGE = false>
+// (minimum CTAs per SM: the staged form needs ~100 registers for its 18 shared-memory bytes in flight; at 5 CTAs of 160
+// threads it spills and runs slower than unstaged, at 3 it loses occupancy: 1.02 / 0.69 / 0.73 ms per 33 frames at 5 / 4 / 3
+// against 0.755 ms unstaged, r02t-r02u)
+__global__ void __launch_bounds__(NT, STAGE ? (NT >= 160 ? 4 : 6) : 0) polyexp_strip_kernel(
+    PolyParams p, const unsigned char* __restrict__ gray_all,
                                                            int64_t gray_stride, float* __restrict__ I_out, int n_cols,
                                                            int64_t total_rows) {
     constexpr int G = 4;
@@ -535,7 +605,13 @@ __global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const u
     constexpr int SEG = TW / 4;
     constexpr int NV = (4 + 2 * N + 3) / 4 * 4;
     static_assert(NT >= CW && NT >= G * SEG, "thread count");
+    static_assert(!STAGE || FUSE3, "staging is for the 8-bit frame");
     __shared__ __align__(16) float vbuf[G][3][CP];
+    // staged 8-bit rows: ring of 32 rows (virtual row number & 31), GPB bytes of columns [a0, a0 + GPB) each
+    constexpr int GCH = (CW + 2 + 15 + 15) / 16;         // 16-byte chunks that cover CW + 2 columns from any alignment
+    constexpr int GPB = GCH * 16;
+    static_assert(!STAGE || NT >= (G + 2) * GCH, "one chunk per thread");
+    __shared__ __align__(16) unsigned char gring[STAGE ? 32 : 1][STAGE ? GPB : 16];
 
     const int t = threadIdx.x;
     const int w = p.w, h = p.h;
@@ -570,10 +646,35 @@ __global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const u
         const int acc = hsum(rc - 1) + 2 * hsum(rc) + hsum(rc + 1);
         return (float)acc * 0.0625f;                   // exact: acc <= 4080
     };
+    // staged rows: columns from a0 (a multiple of 16) on; rows first .. first + n - 1 (virtual numbers, reflected here)
+    const int a0 = STAGE ? (max(x0 - N - 1, 0) & ~15) : 0;
+    auto stage_rows = [&](int first, int n) {
+        if constexpr (STAGE) {
+            if (t < n * GCH) {
+                const int rr = t / GCH, ch = t - rr * GCH;
+                const int col = a0 + ch * 16;
+                if (col < w)                             // w is a multiple of 16: the chunk is inside the row
+                    cp_async16(&gring[(first + rr + 32) & 31][ch * 16], gray + (int64_t)reflect101_near(first + rr, h) * w + col);
+            }
+            cp_async_commit();
+        }
+    };
+    auto hsum_staged = [&](int vrow) -> int {
+        const unsigned char* r = gring[(vrow + 32) & 31];
+        return (int)r[xl - a0] + 2 * (int)r[gx - a0] + (int)r[xr - a0];
+    };
     // G consecutive un-clamped rows starting at `first`: each row needs only one new horizontal sum
-    auto load_I_run = [&](int first, float* dst) {
+    auto load_I_run = [&](int first, float* dst, auto staged) {
         if constexpr (FUSE3) {
             if (first >= 0 && first + G <= h) {
+                if constexpr (STAGE && decltype(staged)::value) {
+                    int hs[G + 2];
+#pragma unroll
+                    for (int i = 0; i < G + 2; ++i) hs[i] = hsum_staged(first - 1 + i);
+#pragma unroll
+                    for (int i = 0; i < G; ++i) dst[i] = (float)(hs[i] + 2 * hs[i + 1] + hs[i + 2]) * 0.0625f;
+                    return;
+                }
                 int hs[G + 2];
 #pragma unroll
                 for (int i = 0; i < G + 2; ++i) hs[i] = hsum(first - 1 + i);
@@ -591,7 +692,15 @@ __global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const u
     if (col_thread) {
 #pragma unroll
         for (int j = 0; j < 2 * N; ++j) v[G + j] = load_I(ys - N + j);      // becomes v[0..2N) after the first shift
-        load_I_run(ys + N, nxt);
+        load_I_run(ys + N, nxt, std::false_type{});
+    }
+    if (STAGE) {
+        // the 8-bit rows group 0 turns into the I rows of group 1 (the ring may still be read by a slower warp of the
+        // previous segment: barrier first)
+        __syncthreads();
+        stage_rows(ys + G + N - 1, G + 2);
+        cp_async_wait<0>();
+        __syncthreads();
     }
     for (int g0 = 0; g0 < ye - ys; g0 += G) {
         if (col_thread) {
@@ -599,8 +708,12 @@ __global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const u
             for (int j = 0; j < 2 * N; ++j) v[j] = v[j + G];
 #pragma unroll
             for (int i = 0; i < G; ++i) v[2 * N + i] = nxt[i];
-            // rows of the next group: in flight while this group is processed
-            load_I_run(ys + g0 + G + N, nxt);
+            // rows of the next group: staged one group ago (STAGE), else in flight while this group is processed
+            load_I_run(ys + g0 + G + N, nxt, std::true_type{});
+        }
+        // 8-bit rows the NEXT group converts: G new rows (the two before them are in the ring already)
+        if (STAGE) stage_rows(ys + g0 + 2 * G + N + 1, G);
+        if (col_thread) {
             if (FUSE3 && Iw && t >= N && t < N + TW && x0 + t - N < w) {
 #pragma unroll
                 for (int i = 0; i < G; ++i)
@@ -705,6 +818,7 @@ __global__ void __launch_bounds__(NT) polyexp_strip_kernel(PolyParams p, const u
                 }
             }
         }
+        if (STAGE) cp_async_wait<0>();                   // this thread's staged chunk has landed; the barrier publishes it
         __syncthreads();
     }
     }   // segments of this CTA's row range
@@ -1321,61 +1435,6 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
 // Geometry: 256 threads = 254 halo columns of a 240-column strip (1920 = 8 x 240, halo
 // 1.06x); 2 CTAs per SM x 256 TMEM columns = all 512 columns.
 // ---------------------------------------------------------------------------
-#ifndef OFC_EMULATE
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16_cg(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-// dst / src byte offsets as immediates: one address register serves several copies
-template <int DOFF, int SOFF> __device__ __forceinline__ void cp_async16_o(unsigned dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
-}
-template <int DOFF, int SOFF> __device__ __forceinline__ void cp_async4_o(unsigned dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 4;" ::"r"(dst), "l"(src), "n"(DOFF), "n"(SOFF) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
-    unsigned r0, r1, r2, r3, r4, r5, r6, r7;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
-    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
-}
-__device__ __forceinline__ void tmem_st8(unsigned taddr, const float (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-#else
-// host-side debug emulation: copies are immediate, the "tensor memory" is a per-thread array
-static float ofc_emu_tmem[1024][128];
-static inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
-static inline void cp_async4(void* dst, const void* src) { memcpy(dst, src, 4); }
-static inline void cp_async16_cg(void* dst, const void* src) { memcpy(dst, src, 16); }
-static inline unsigned long long smem_u32(const void* p) { return (unsigned long long)p; }
-template <int DOFF, int SOFF> static inline void cp_async16_o(unsigned long long dst, const void* src) {
-    memcpy((char*)dst + DOFF, (const char*)src + SOFF, 16);
-}
-template <int DOFF, int SOFF> static inline void cp_async4_o(unsigned long long dst, const void* src) {
-    memcpy((char*)dst + DOFF, (const char*)src + SOFF, 4);
-}
-static inline void cp_async_commit() {}
-template <int N> static inline void cp_async_wait() {}
-static inline void tmem_ld8(unsigned taddr, float (&v)[8]) { memcpy(v, &ofc_emu_tmem[threadIdx.x][taddr & 127u], 32); }
-static inline void tmem_st8(unsigned taddr, const float (&v)[8]) { memcpy(&ofc_emu_tmem[threadIdx.x][taddr & 127u], v, 32); }
-static inline void tmem_wait_st() {}
-#endif
 
 // UPS != 0: flow_in is the COARSER level's flow (1 general ratio, 2 exact x2); every flow row is up-sampled on the fly (bilerp_flow, the expression of
 // flow_upsample_kernel), so the first iteration of a level needs no up-sample launch and no full-size scratch field.
@@ -1531,6 +1590,7 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
             if (fin && live) fl[i] = flow_at(clampi(row0 + ri + 4, 0, h - 1));
             // old ring row (leaves the window) -- TMEM read overlaps the wait for the landing zone
             float old[8];
+            // (issuing this load before the row's requests and waiting for it here measured slower, r02s)
             tmem_wait_st();                              // last row's ring store
             tmem_ld8(ring_base + slot * 8, old);
             cp_async_wait<2>();                          // everything but the two newest requests has landed
@@ -1901,12 +1961,12 @@ int launch_prefilter_pyramid(const PrefilterParams* levels, const size_t* smem_f
     return OFC_OK;
 }
 
-template <int N, int TW, int NT, bool FUSE3>
+template <int N, int TW, int NT, bool FUSE3, bool STAGE = false>
 static int launch_polyexp_strip(const PolyParams& p, const unsigned char* gray, int64_t gray_stride, float* I_out,
                                 int n_frames, void* stream) {
     static int resident = 0;
     if (!resident) {
-        OFC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, polyexp_strip_kernel<N, TW, NT, FUSE3>, NT, 0));
+        OFC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, polyexp_strip_kernel<N, TW, NT, FUSE3, STAGE>, NT, 0));
         if (resident < 1) resident = 1;
     }
     const int cols = cdiv(p.w, TW);
@@ -1919,7 +1979,7 @@ static int launch_polyexp_strip(const PolyParams& p, const unsigned char* gray, 
     const int64_t max_ctas = (total_rows + 23) / 24;     // keep ranges >= 24 rows (vertical halo 2N per segment)
     if (ctas > max_ctas) ctas = max_ctas;
     ProfScope prof(PK_POLYEXP, stream);
-    OFC_LAUNCH((polyexp_strip_kernel<N, TW, NT, FUSE3>), dim3((unsigned)ctas), dim3(NT), 0, stream, p, gray, gray_stride, I_out,
+    OFC_LAUNCH((polyexp_strip_kernel<N, TW, NT, FUSE3, STAGE>), dim3((unsigned)ctas), dim3(NT), 0, stream, p, gray, gray_stride, I_out,
                cols, total_rows);
     OFC_CHECK_LAUNCH("polyexp_strip");
     return OFC_OK;
@@ -1931,7 +1991,13 @@ int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, const unsigned
     static const int legacy = env_int("OFC_POLYEXP_LEGACY", 0);
     if (!legacy && poly_n == 5) {
         if (gray) {
-            if (p.w > 512) return launch_polyexp_strip<5, 128, 160, true>(p, gray, gray_stride, I_out, n_frames, stream);
+            static const int stage = env_int("OFC_POLY_STAGE", 1);
+            const bool aligned = p.w % 16 == 0 && gray_stride % 16 == 0 && ((uintptr_t)gray & 15) == 0 && p.h > 16;
+            if (p.w > 512) {
+                if (stage && aligned) return launch_polyexp_strip<5, 128, 160, true, true>(p, gray, gray_stride, I_out, n_frames, stream);
+                return launch_polyexp_strip<5, 128, 160, true>(p, gray, gray_stride, I_out, n_frames, stream);
+            }
+            if (stage && aligned) return launch_polyexp_strip<5, 64, 96, true, true>(p, gray, gray_stride, I_out, n_frames, stream);
             return launch_polyexp_strip<5, 64, 96, true>(p, gray, gray_stride, I_out, n_frames, stream);
         }
         if (p.w > 512) return launch_polyexp_strip<5, 128, 160, false>(p, nullptr, 0, nullptr, n_frames, stream);

@@ -6,7 +6,15 @@ export PYTHONPATH=.
 mkdir -p gpurun_out
 for spec in "$@"; do
   name=${spec%% *}; envs=""
-  [ "$spec" != "$name" ] && envs=${spec#* }
+  # "name@expN ..." runs with build_variants/libofc_expN.so swapped in (the box's copy of the tree is scratch)
+  if [[ "$name" == *@* ]]; then
+    var=${name#*@}; name=${name%@*}
+    [ -f opticalflowclustering_b200/libofc.so.orig ] || cp opticalflowclustering_b200/libofc.so opticalflowclustering_b200/libofc.so.orig
+    cp build_variants/libofc_$var.so opticalflowclustering_b200/libofc.so
+  elif [ -f opticalflowclustering_b200/libofc.so.orig ]; then
+    cp opticalflowclustering_b200/libofc.so.orig opticalflowclustering_b200/libofc.so
+  fi
+  [[ "$spec" == *" "* ]] && envs=${spec#* }
   env $envs python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline ${OFC_AB_ARGS} > gpurun_out/${TAG}_ab_${name}.json 2> gpurun_out/${TAG}_ab_${name}.err
   python - "$name" gpurun_out/${TAG}_ab_${name}.json <<'PY'
 import json, sys
