@@ -606,7 +606,8 @@ __global__ void __launch_bounds__(NT, STAGE ? (NT >= 160 ? 4 : 6) : 0) polyexp_s
     constexpr int NV = (4 + 2 * N + 3) / 4 * 4;
     static_assert(NT >= CW && NT >= G * SEG, "thread count");
     static_assert(!STAGE || FUSE3, "staging is for the 8-bit frame");
-    __shared__ __align__(16) float vbuf[G][3][CP];
+    // two hand-over buffers, alternating per group: one barrier per group (between the vertical and the horizontal pass)
+    __shared__ __align__(16) float vbuf2[2][G][3][CP];
     // staged 8-bit rows: ring of 32 rows (virtual row number & 31), GPB bytes of columns [a0, a0 + GPB) each
     constexpr int GCH = (CW + 2 + 15 + 15) / 16;         // 16-byte chunks that cover CW + 2 columns from any alignment
     constexpr int GPB = GCH * 16;
@@ -699,10 +700,12 @@ __global__ void __launch_bounds__(NT, STAGE ? (NT >= 160 ? 4 : 6) : 0) polyexp_s
         // previous segment: barrier first)
         __syncthreads();
         stage_rows(ys + G + N - 1, G + 2);
+        stage_rows(ys + 2 * G + N + 1, G);               // and the new rows of the group after
         cp_async_wait<0>();
-        __syncthreads();
     }
+    __syncthreads();                                     // staged rows visible; hand-over buffers of the previous segment free
     for (int g0 = 0; g0 < ye - ys; g0 += G) {
+        float (*vbuf)[3][CP] = vbuf2[(g0 / G) & 1];
         if (col_thread) {
 #pragma unroll
             for (int j = 0; j < 2 * N; ++j) v[j] = v[j + G];
@@ -711,8 +714,9 @@ __global__ void __launch_bounds__(NT, STAGE ? (NT >= 160 ? 4 : 6) : 0) polyexp_s
             // rows of the next group: staged one group ago (STAGE), else in flight while this group is processed
             load_I_run(ys + g0 + G + N, nxt, std::true_type{});
         }
-        // 8-bit rows the NEXT group converts: G new rows (the two before them are in the ring already)
-        if (STAGE) stage_rows(ys + g0 + 2 * G + N + 1, G);
+        // 8-bit rows the group after the next converts: G new rows, two groups ahead (the copies of the previous group are
+        // waited for before this group's barrier, which publishes them)
+        if (STAGE) stage_rows(ys + g0 + 3 * G + N + 1, G);
         if (col_thread) {
             if (FUSE3 && Iw && t >= N && t < N + TW && x0 + t - N < w) {
 #pragma unroll
@@ -736,6 +740,7 @@ __global__ void __launch_bounds__(NT, STAGE ? (NT >= 160 ? 4 : 6) : 0) polyexp_s
                 vbuf[o][2][t] = r2;
             }
         }
+        if (STAGE) cp_async_wait<1>();                   // all but this group's copies have landed
         __syncthreads();
         if (t < G * SEG) {
             const int o = t / SEG, seg = t - o * SEG;
@@ -818,9 +823,8 @@ __global__ void __launch_bounds__(NT, STAGE ? (NT >= 160 ? 4 : 6) : 0) polyexp_s
                 }
             }
         }
-        if (STAGE) cp_async_wait<0>();                   // this thread's staged chunk has landed; the barrier publishes it
-        __syncthreads();
     }
+    if (STAGE) cp_async_wait<0>();
     }   // segments of this CTA's row range
 }
 
