@@ -677,7 +677,8 @@ def main():
         # move is R of both frames (2 x 20 B), the flow in (8 B) and the flow out (8 B) = 56 B/px
         fused = FUSED_ITER_BYTES_PER_PX * H * W * P / (per_launch_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": f"flow_iter_tmem_kernel<R=7,TW=240> @{W}x{H} (update-matrices + 15x15 box + 2x2 solve fused, "
-                              "persistent strip walk, ring in TMEM, cp.async tap landing; 3 launches per step)",
+                              "persistent strip walk, ring in TMEM, cp.async tap landing, float32 error-free solve, pair-aligned grid for L2 "
+                              "sharing of the expansions; 3 launches per step)",
                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_source,
                     "algorithmic_bytes_per_launch": algo, "ms_per_launch": per_launch_ms,

@@ -15,13 +15,19 @@ $SHORT > gpurun_out/${TAG}_plain.log 2>&1 && ncu --profile-from-start off --metr
 echo "ncu list rc=$?"
 export OFC_CHUNK=33
 P="python tools/profile_step.py"
-$P > gpurun_out/${TAG}_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'flow_iter_tmem|prefilter_pyr|flow_encode_grid|polyexp_strip|flow_upsample|flow_iter_kernel' -s 36 -c 18 -o gpurun_out/${TAG}_flow -f $P > gpurun_out/${TAG}_ncu_flow.log 2>&1
+$P > gpurun_out/${TAG}_plain2.log 2>&1 && ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'flow_iter|prefilter|flow_encode|polyexp|flow_upsample|bgr2gray' -c 24 -o gpurun_out/${TAG}_flow -f $P > gpurun_out/${TAG}_ncu_flow.log 2>&1
 echo "ncu flow rc=$?"
 export OFC_CHUNK=9 OFC_K=8
-$P > gpurun_out/${TAG}_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'kmeans_cells_fast' -s 2 -c 1 -o gpurun_out/${TAG}_cells -f $P > gpurun_out/${TAG}_ncu_cells.log 2>&1
+$P > gpurun_out/${TAG}_plain3.log 2>&1 && ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'kmeans_cells_fast' -c 1 -o gpurun_out/${TAG}_cells -f $P > gpurun_out/${TAG}_ncu_cells.log 2>&1
 echo "ncu cells rc=$?"
 unset OFC_K
 S="python tools/step_check.py"
 $S > gpurun_out/${TAG}_plain4.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'kmeans_step_u8d4' -s 2 -c 2 -o gpurun_out/${TAG}_step -f $S > gpurun_out/${TAG}_ncu_step.log 2>&1
 echo "ncu step rc=$?"
-ls -la gpurun_out/*.ncu-rep
+# gpurun returns at most 64 MiB: the raw pages travel as CSV, only the flow report itself is kept (source view of the top kernel)
+for n in flow cells step; do
+  ncu -i gpurun_out/${TAG}_${n}.ncu-rep --page raw --csv > gpurun_out/${TAG}_${n}_raw.csv 2>/dev/null
+done
+ncu -i gpurun_out/${TAG}_flow.ncu-rep --page source --csv --kernel-name regex:flow_iter_tmem --launch-count 1 > gpurun_out/${TAG}_flow_iter_source.csv 2>/dev/null
+rm -f gpurun_out/${TAG}_cells.ncu-rep gpurun_out/${TAG}_step.ncu-rep
+ls -la gpurun_out/ | tail -30; du -sm gpurun_out

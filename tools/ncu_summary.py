@@ -40,7 +40,11 @@ UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e-6,
 
 
 def raw_rows(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a capture may travel as its raw-page CSV (exported on the GPU box: gpurun returns at most 64 MiB) instead of the report
+    if rep.endswith("_raw.csv"):
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     if len(rows) < 3:
         return []
@@ -98,6 +102,8 @@ def main():
             md.append(f"| `{k}` | {n} | {t:.1f} | {100 * t / total:.1f} % |")
         md.append("")
     reps = sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep")) + glob.glob(os.path.join(OUT, f"{tag}_*.ncu-rep")))
+    have = {os.path.basename(r)[:-8] for r in reps}
+    reps += [c for c in sorted(glob.glob(os.path.join(OUT, f"{tag}_*_raw.csv"))) if os.path.basename(c)[:-8] not in have]
     for rep in reps:
         base = os.path.basename(rep)
         name = base[5:-8] if base.startswith("prof_") else base[len(tag) + 1:-8]
