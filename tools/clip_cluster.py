@@ -58,11 +58,18 @@ def main():
     torch.cuda.synchronize()
     t_flow = time.perf_counter() - t0
     # identical initial centres on every rank: the first k hue rows of the clip (rank 0's), broadcast
-    init = torch.zeros((args.k, rows.shape[1]), dtype=torch.float64, device="cuda")
-    if rank == 0:
-        init.copy_(rows[:args.k].double())
+    # (a rank may hold fewer than k rows: every rank offers its first k, the first k in rank order are taken)
+    head = torch.zeros((args.k, rows.shape[1]), dtype=torch.float64, device="cuda")
+    n_head = min(args.k, rows.shape[0])
+    head[:n_head] = rows[:n_head].double()
     if world > 1:
-        dist.broadcast(init, 0)
+        heads = torch.empty((world,) + tuple(head.shape), dtype=torch.float64, device="cuda")
+        counts = torch.empty(world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(heads, head)
+        dist.all_gather_into_tensor(counts, torch.tensor([n_head], dtype=torch.int64, device="cuda"))
+        init = torch.cat([heads[r, :int(counts[r])] for r in range(world)])[:args.k].contiguous()
+    else:
+        init = head
     group = dist.group.WORLD if world > 1 else None
     t0 = time.perf_counter()
     labels, centres, inertia, n_iter = km.lloyd(rows, init, group=group)
