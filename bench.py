@@ -709,17 +709,32 @@ def main():
     freed = [torch.cuda.Event() for _ in range(NBUF)]
     n_chunks = host.shape[0] // P               # consecutive P-frame chunks of the there-and-back walk
 
+    d2h_stream = torch.cuda.Stream(device=dev)
+    done_ev = [torch.cuda.Event() for _ in range(2)]
+    read_ev = [torch.cuda.Event() for _ in range(2)]
+    # the result rows of a step are read back on a side stream (into alternating pinned buffers), so the next step's
+    # kernels never queue behind three small device->host copies; OFC_E2E_D2H_INLINE=1 restores the in-line copies
+    d2h_inline = os.environ.get("OFC_E2E_D2H_INLINE", "0") == "1"
+    no_upload = os.environ.get("OFC_E2E_NO_UPLOAD", "0") == "1"        # diagnostic only: what the uploads cost the kernels
+    res2 = [(res_avg, res_km, res_mag), (torch.empty_like(res_avg).pin_memory(), torch.empty_like(res_km).pin_memory(),
+                                         torch.empty_like(res_mag).pin_memory())]
+    dev_res = [(torch.empty((P, ROWS * COLS), dtype=torch.uint8, device=dev), torch.empty((P, ROWS * COLS), dtype=torch.uint8, device=dev),
+                torch.empty(P, dtype=torch.float64, device=dev)) for _ in range(2)]
+
     def e2e_loop(lo, hi):
         main = torch.cuda.current_stream()
         for b in range(NBUF):
             freed[b].record(main)
+        for j in range(2):
+            read_ev[j].record(d2h_stream)
 
         def upload(i):
             b = i % NBUF
             c = i % n_chunks
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[b])
-                stage[b].copy_(host[c * P:(c + 1) * P], non_blocking=True)
+                if not no_upload:
+                    stage[b].copy_(host[c * P:(c + 1) * P], non_blocking=True)
                 ready[b].record(copy_stream)
         # frame 0 of the clip seeds prev_gray (outside the steady state, like the reference's first cap.read())
         pipe.run_chunk(clip[0:2])
@@ -731,10 +746,26 @@ def main():
             main.wait_event(ready[b])
             pipe.run_chunk(stage[b], carry=True)
             freed[b].record(main)
-            res_avg.copy_(pipe.avg_hue[:P], non_blocking=True)
-            res_km.copy_(pipe.km_hue[:P], non_blocking=True)
-            res_mag.copy_(pipe.mag_sum[:P], non_blocking=True)
+            if d2h_inline:
+                res_avg.copy_(pipe.avg_hue[:P], non_blocking=True)
+                res_km.copy_(pipe.km_hue[:P], non_blocking=True)
+                res_mag.copy_(pipe.mag_sum[:P], non_blocking=True)
+            else:
+                # snapshot the step's rows on the device (the pipeline's buffers are rewritten by the next step), then
+                # read the snapshot back beside the next step's kernels
+                j = i & 1
+                main.wait_event(read_ev[j])
+                dev_res[j][0].copy_(pipe.avg_hue[:P], non_blocking=True)
+                dev_res[j][1].copy_(pipe.km_hue[:P], non_blocking=True)
+                dev_res[j][2].copy_(pipe.mag_sum[:P], non_blocking=True)
+                done_ev[j].record(main)
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(done_ev[j])
+                    for k in range(3):
+                        res2[j][k].copy_(dev_res[j][k], non_blocking=True)
+                    read_ev[j].record(d2h_stream)
         main.synchronize()
+        d2h_stream.synchronize()
 
     e2e_loop(0, args.warmup)
     barrier()

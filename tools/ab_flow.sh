@@ -21,7 +21,7 @@ import json, sys
 try:
     d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
     k = d["kernels"]
-    print(f"{sys.argv[1]:14s} {d['value']:8.1f} pairs/s  step {d['ms_per_step']:.3f} ms | " + "  ".join(f"{n.replace('flow_','')} {v['ms_per_step']:.3f}" for n, v in k.items()))
+    print(f"{sys.argv[1]:14s} {d['value']:8.1f} pairs/s  e2e {d['e2e']['value']:8.1f}  step {d['ms_per_step']:.3f} ms | " + "  ".join(f"{n.replace('flow_','')} {v['ms_per_step']:.3f}" for n, v in k.items()))
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
