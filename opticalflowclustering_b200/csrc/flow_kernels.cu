@@ -1450,7 +1450,9 @@ __global__ void __launch_bounds__(NT, MINB) flow_iter_strip_kernel(IterParams p,
 // Six cp.async per row instead of ten, 40 % fewer tap requests to L1 -- same bytes, same arithmetic, same results
 // (bit-identical in the emulated and GPU tests); measured r02z: the three level-0 launches of 32 pairs 3.30 -> 3.15 ms,
 // level 1 0.894 -> 0.859 ms.  OFC_TMEM_SHARE=0 selects the form without sharing.
-template <int R, int TW, int NT, int G, bool MINMAX, int UPS, bool SHARE = false>
+// (Sharing in the x direction as well -- the right taps read from the right neighbour's slots after a shuffle of the tap
+// addresses, two __syncwarp per row -- measured slower: 3.21 against 3.05 ms, r03a.)
+template <int R, int TW, int NT, int G, bool MINMAX, int UPS, int SHARE = 0>
 __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int n_cols, int64_t total_rows) {
     constexpr int K = 2 * R + 1;
     constexpr int CW = TW + 2 * R;
@@ -1533,12 +1535,12 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
     int o1_last = -0x40000000;                           // SHARE: tap address of the previous request (none yet)
     unsigned shq = 0;                                    // SHARE: "upper taps shared" flags of the last requests, newest in bit 0
     auto request_row = [&](int row, float dx, float dy, int dst_slot, int bslot) {
-        if (!live) { cp_async_commit(); return; }
         int x1, y1;
         float fx, fy;
         bool inb;
         warp_point(fgx, row, dx, dy, w, h, x1, y1, fx, fy, inb);
         const int o1 = clampi(y1, 0, h - 2) * w + clampi(x1, 0, w - 2) + r_next;
+        if (!live) { cp_async_commit(); return; }
         const float4* pa = RA0 + o1;
         const float* pb = RB0 + o1;
         if (SHARE) {
@@ -1547,8 +1549,10 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
             shq = (shq << 1) | (sh ? 1u : 0u);
             const auto lqb = smem_u32(land_q + (bslot * 2) * NT + t);
             const auto lsb = smem_u32(land_s + (bslot * 2) * NT + t);
-            cp_async16_o<0, 0>(lqb, pa + w); cp_async16_o<NT * 16, 16>(lqb, pa + w);
-            cp_async4_o<0, 0>(lsb, pb + w); cp_async4_o<NT * 4, 4>(lsb, pb + w);
+            cp_async16_o<0, 0>(lqb, pa + w);
+            cp_async4_o<0, 0>(lsb, pb + w);
+            cp_async16_o<NT * 16, 16>(lqb, pa + w);
+            cp_async4_o<NT * 4, 4>(lsb, pb + w);
             if (!sh) {
                 const auto lqt = smem_u32(land_qt + (dst_slot * 2) * NT + t);
                 const auto lst = smem_u32(land_st + (dst_slot * 2) * NT + t);
@@ -1637,10 +1641,11 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
                 // this row's flag went in two requests ago (rows ri + 1 and ri + 2 followed)
                 const bool sh = (shq >> 2) & 1u;
                 const int top = sh ? (((i + 3) & 3) * 2) * NT + t : (SB * 2 + ls * 2) * NT + t;       // previous row's lower taps, or its own upper ones
+                const int low = ((i & 3) * 2) * NT + t;
                 q00 = land_q[top]; q01 = land_q[top + NT];
                 s00 = land_s[top]; s01 = land_s[top + NT];
-                q10 = land_q[((i & 3) * 2 + 0) * NT + t]; q11 = land_q[((i & 3) * 2 + 1) * NT + t];
-                s10 = land_s[((i & 3) * 2 + 0) * NT + t]; s11 = land_s[((i & 3) * 2 + 1) * NT + t];
+                q10 = land_q[low]; q11 = land_q[low + NT];
+                s10 = land_s[low]; s11 = land_s[low + NT];
             } else {
                 q00 = land_q[(ls * 4 + 0) * NT + t]; q01 = land_q[(ls * 4 + 1) * NT + t];
                 q10 = land_q[(ls * 4 + 2) * NT + t]; q11 = land_q[(ls * 4 + 3) * NT + t];
@@ -2040,7 +2045,7 @@ int launch_polyexp(const PolyParams& p, int poly_n, int n_frames, const unsigned
     static const int legacy = env_int("OFC_POLYEXP_LEGACY", 0);
     if (!legacy && poly_n == 5) {
         if (gray) {
-            static const int stage = env_int("OFC_POLY_STAGE", 1);
+            const int stage = env_int("OFC_POLY_STAGE", 1);
             const bool aligned = p.w % 16 == 0 && gray_stride % 16 == 0 && ((uintptr_t)gray & 15) == 0 && p.h > 16;
             if (p.w > 512) {
                 if (stage && aligned) return launch_polyexp_strip<5, 128, 160, true, true>(p, gray, gray_stride, I_out, n_frames, stream);
@@ -2116,7 +2121,7 @@ static int launch_strip_r(const IterParams& p, int n_pairs, void* stream) {
                     : launch_strip_rm<R, TW, NT, G, MINB, false>(p, n_pairs, stream);
 }
 
-template <bool MINMAX, int UPS, bool SHARE = false>
+template <bool MINMAX, int UPS, int SHARE = 0>
 static int launch_tmem(const IterParams& p, int n_pairs, void* stream) {
     constexpr int R = 7, TW = 240, NT = 256, G = 4;
     constexpr int CW = TW + 2 * R, CP = (CW + 3) / 4 * 4 + 4, S = 3;
@@ -2163,7 +2168,7 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
         return p.minmax ? launch_tmem<true, 1>(p, n_pairs, stream) : launch_tmem<false, 1>(p, n_pairs, stream);
     }
     if (p.upsample) {
-        static const int x2 = env_int("OFC_UPSAMPLE_X2", 1);
+        const int x2 = env_int("OFC_UPSAMPLE_X2", 1);
         const bool exact2 = x2 && p.w == 2 * p.wc && p.h == 2 * p.hc && p.w % 4 == 0 && p.usx == 0.5 && p.usy == 0.5 &&
                             p.flow_in_stride % 2 == 0 && ((uintptr_t)p.flow_in & 15) == 0;
         {
@@ -2185,8 +2190,8 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
     // (OFC_TMEM_ANYW=0 restricts it to widths that are a multiple of its 240-column strips)
     static const int any_w = env_int("OFC_TMEM_ANYW", 1);
     if (use_tmem && (p.w >= use_tmem || p.w % 240 == 0) && (any_w || p.w % 240 == 0)) {
-        static const int share = env_int("OFC_TMEM_SHARE", 1);
-        if (share) return p.minmax ? launch_tmem<true, 0, true>(p, n_pairs, stream) : launch_tmem<false, 0, true>(p, n_pairs, stream);
+        const int share = env_int("OFC_TMEM_SHARE", 1);
+        if (share) return p.minmax ? launch_tmem<true, 0, 1>(p, n_pairs, stream) : launch_tmem<false, 0, 1>(p, n_pairs, stream);
         return p.minmax ? launch_tmem<true, 0>(p, n_pairs, stream) : launch_tmem<false, 0>(p, n_pairs, stream);
     }
     static const int minb4 = env_int("OFC_STRIP_MINB4", 1);

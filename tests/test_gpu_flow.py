@@ -376,6 +376,23 @@ def test_pyramid_prefilter_and_fused_upsample_bit_identical(ofc, size, levels, m
     assert torch.equal(new, old)
 
 
+@pytest.mark.parametrize("size,levels", [((1080, 1920), 3), ((720, 1280), 3), ((2160, 3840), 5)])
+def test_round2b_fast_forms_bit_identical(ofc, size, levels, monkeypatch):
+    """the forms added late in round 2 against the ones they replace, final flow and I of every level bit for bit: lower
+    taps shared between rows (OFC_TMEM_SHARE), exact x2 up-sample kernel (OFC_UPSAMPLE_X2), staged 8-bit rows in the
+    full-resolution polynomial expansion (OFC_POLY_STAGE)"""
+    from opticalflowclustering_b200.flow import bgr2gray
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    H, W = size
+    gray = bgr2gray(synthetic_clip(3, H, W, seed=37, device="cuda"))
+    new, inew = _flow_with_env(monkeypatch, {"OFC_TMEM_SHARE": "1", "OFC_UPSAMPLE_X2": "1", "OFC_POLY_STAGE": "1"}, W, H, gray, levels)
+    for off in ("OFC_TMEM_SHARE", "OFC_UPSAMPLE_X2", "OFC_POLY_STAGE"):
+        old, iold = _flow_with_env(monkeypatch, {off: "0"}, W, H, gray, levels)
+        for a, b in zip(inew, iold):
+            assert torch.equal(a, b), off
+        assert torch.equal(new, old), off
+
+
 @pytest.mark.parametrize("size,grid", [((1080, 1920), (14, 25)), ((720, 1280), (14, 25)), ((270, 484), (5, 7))])
 def test_fused_encode_grid_equals_separate_kernels(ofc, size, grid):
     """ofc_flow_to_bgr_grid == ofc_flow_to_bgr + ofc_grid_cells on real flow fields: word path (1080p cells are 76 px
