@@ -1543,6 +1543,11 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
         if (!live) { cp_async_commit(); return; }
         const float4* pa = RA0 + o1;
         const float* pb = RB0 + o1;
+        // R0 first (it never depends on the flow: 3.06 -> 3.03 ms, r03c), past L1 (.cg: it is read once per column and
+        // L1 is needed for the four-fold reuse of the taps of R1; 3.50 -> 3.42 ms, r02o)
+        const int o0 = row * w + gx;
+        cp_async16_cg(land_a + dst_slot * NT + t, RA0 + o0);
+        cp_async4(land_b + dst_slot * NT + t, RB0 + o0);
         if (SHARE) {
             const bool sh = o1 == o1_last + w;
             o1_last = o1;
@@ -1567,11 +1572,6 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
             cp_async4_o<0, 0>(lsb, pb); cp_async4_o<NT * 4, 4>(lsb, pb);
             cp_async4_o<2 * NT * 4, 0>(lsb, pb + w); cp_async4_o<3 * NT * 4, 4>(lsb, pb + w);
         }
-        const int o0 = row * w + gx;
-        // R0 is read once per column: past L1 (.cg), which the taps of R1 need for their four-fold reuse
-        // (measured r02o: 3.50 -> 3.42 ms for the three level-0 launches of 32 pairs)
-        cp_async16_cg(land_a + dst_slot * NT + t, RA0 + o0);
-        cp_async4(land_b + dst_slot * NT + t, RB0 + o0);
         cp_async_commit();
     };
 
@@ -1628,7 +1628,7 @@ __global__ void __launch_bounds__(NT, 2) flow_iter_tmem_kernel(IterParams p, int
                 request_row(clampi(row0 + ri + 2, 0, h - 1), fl[(i + 2) & 3].x, fl[(i + 2) & 3].y, l2, (i + 2) & 3);
             }
             const float dx = fl[i].x, dy = fl[i].y;
-            if (fin && live) fl[i] = flow_at(clampi(row0 + ri + 4, 0, h - 1));
+            if (fin && live) fl[i] = flow_at(clampi(row0 + ri + 4, 0, h - 1));        // (ahead of the requests: slower, r03c)
             // old ring row (leaves the window) -- TMEM read overlaps the wait for the landing zone
             float old[8];
             // (issuing this load before the row's requests and waiting for it here measured slower, r02s)
