@@ -40,6 +40,16 @@ pipe.run_chunk(clip[0:2])
 timed("carry, 32 new resident frames", lambda i: pipe.run_chunk(clip[starts[i] + 1:starts[i] + F], carry=True))
 
 
+def carry_nocopy(i):
+    pipe._last_gray_index = 0                  # timing only: skips the device copy of the carried gray frame (wrong pairs 0)
+    pipe.run_chunk(clip[starts[i] + 1:starts[i] + F], carry=True)
+
+
+timed("carry without the gray-frame copy (timing only)", carry_nocopy)
+timed("resident chunk of 33 frames (again)", lambda i: pipe.run_chunk(clip[starts[i]:starts[i] + F]))
+pipe.run_chunk(clip[0:2])
+
+
 def with_d2h(i):
     pipe.run_chunk(clip[starts[i] + 1:starts[i] + F], carry=True)
     res[0].copy_(pipe.avg_hue[:P], non_blocking=True)
