@@ -88,8 +88,11 @@ template <int SEL> __device__ __forceinline__ unsigned spread2(unsigned w) {
 
 }  // namespace
 
+#ifndef OFC_CELLS_MINB
+#define OFC_CELLS_MINB 3         // CTAs per SM the compiler must allow for (80 registers at 3; 64 at 4 spills 316 bytes)
+#endif
 template <int KP, int RU, bool PACK>
-__global__ void __launch_bounds__(256, ((KP <= 4 || RU == 2) ? 3 : 2)) kmeans_cells_fast_kernel(KmCellsFastParams p) {
+__global__ void __launch_bounds__(256, ((KP <= 4 || RU == 2) ? OFC_CELLS_MINB : 2)) kmeans_cells_fast_kernel(KmCellsFastParams p) {
     constexpr int D = 4;
     OFC_DYN_SMEM(unsigned char, smraw);
     const int n = p.n, k = p.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

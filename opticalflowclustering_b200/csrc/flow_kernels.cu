@@ -675,13 +675,14 @@ __global__ void __launch_bounds__(NT, STAGE ? (NT >= 160 ? 4 : 6) : 0) polyexp_s
 #pragma unroll
                     for (int i = 0; i < G; ++i) dst[i] = (float)(hs[i] + 2 * hs[i + 1] + hs[i + 2]) * 0.0625f;
                     return;
+                } else {
+                    int hs[G + 2];
+#pragma unroll
+                    for (int i = 0; i < G + 2; ++i) hs[i] = hsum(first - 1 + i);
+#pragma unroll
+                    for (int i = 0; i < G; ++i) dst[i] = (float)(hs[i] + 2 * hs[i + 1] + hs[i + 2]) * 0.0625f;
+                    return;
                 }
-                int hs[G + 2];
-#pragma unroll
-                for (int i = 0; i < G + 2; ++i) hs[i] = hsum(first - 1 + i);
-#pragma unroll
-                for (int i = 0; i < G; ++i) dst[i] = (float)(hs[i] + 2 * hs[i + 1] + hs[i + 2]) * 0.0625f;
-                return;
             }
         }
 #pragma unroll
