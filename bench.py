@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--size", default="1080p", choices=sorted(SIZES), help="frame size (the metric is quoted on 1080p)")
     ap.add_argument("--k", type=int, default=1, help="the reference's -c: clusters per grid cell (every documented command uses 1)")
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload")
+    ap.add_argument("--lanes", type=int, default=3, help="chunks in flight on separate streams (LanedPipeline); 1 = one chain of kernels")
     args = ap.parse_args()
     global H, W, LEVELS, ALGO_BYTES_PER_PAIR, SIZE_NAME, METRIC
     H, W, LEVELS, ALGO_BYTES_PER_PAIR = SIZES[args.size]
@@ -611,11 +612,17 @@ def main():
     T = max(args.clip_frames, F)
     clip = synthetic_clip(T, H, W, seed=rank, device=dev)              # resident in HBM, > L2
     pipe = ClipPipeline(W, H, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=LEVELS, n_clusters=args.k)
+    # the timed loops deal their chunks over `lanes` pipelines on their own streams (one chunk's gaps and tails are
+    # filled by another's CTAs); `pipe` alone serves the per-kernel breakdown, which wants one chain of kernels
+    from opticalflowclustering_b200.pipeline import LanedPipeline
+    n_lanes = max(1, args.lanes)
+    lp = LanedPipeline(W, H, lanes=n_lanes, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=LEVELS, n_clusters=args.k)
     starts = [(i * P) % (T - F + 1) for i in range(args.warmup + args.steps)]
+    main_stream = torch.cuda.current_stream()
 
     # ---- value: inputs resident in HBM --------------------------------------
     for i in range(args.warmup):
-        pipe.run_chunk(clip[starts[i]:starts[i] + F])
+        lp.submit(clip[starts[i]:starts[i] + F])
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -624,7 +631,9 @@ def main():
     torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for i in range(args.warmup, args.warmup + args.steps):
-        pipe.run_chunk(clip[starts[i]:starts[i] + F])
+        lp.submit(clip[starts[i]:starts[i] + F])            # each lane's stream waits for e0 through the current stream
+    for l in range(n_lanes):
+        main_stream.wait_event(lp.done_event(l))
     e1.record()
     torch.cuda.cudart().cudaProfilerStop()
     sampler.sample_now()        # after the last enqueue: the GPU is still working, and a slow NVML call cannot stall the timed steps
@@ -702,7 +711,8 @@ def main():
     res_avg = torch.empty((P, ROWS * COLS), dtype=torch.uint8).pin_memory()
     res_km = torch.empty((P, ROWS * COLS), dtype=torch.uint8).pin_memory()
     res_mag = torch.empty(P, dtype=torch.float64).pin_memory()
-    NBUF = 3        # the upload of step i+1 must not wait for step i-1's kernels to drain: three staging buffers
+    NBUF = n_lanes + 2   # a staging buffer is busy until its chunk has run; `lanes` chunks are in flight and one upload ahead
+    NRES = n_lanes + 1   # result snapshots on the device / pinned read-back buffers
     stage = [torch.empty((P, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(NBUF)]
     copy_stream = torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in range(NBUF)]
@@ -710,22 +720,22 @@ def main():
     n_chunks = host.shape[0] // P               # consecutive P-frame chunks of the there-and-back walk
 
     d2h_stream = torch.cuda.Stream(device=dev)
-    done_ev = [torch.cuda.Event() for _ in range(2)]
-    read_ev = [torch.cuda.Event() for _ in range(2)]
-    # the result rows of a step are read back on a side stream (into alternating pinned buffers), so the next step's
-    # kernels never queue behind three small device->host copies; OFC_E2E_D2H_INLINE=1 restores the in-line copies
-    d2h_inline = os.environ.get("OFC_E2E_D2H_INLINE", "0") == "1"
+    done_ev = [torch.cuda.Event() for _ in range(NRES)]
+    read_ev = [torch.cuda.Event() for _ in range(NRES)]
     no_upload = os.environ.get("OFC_E2E_NO_UPLOAD", "0") == "1"        # diagnostic only: what the uploads cost the kernels
-    res2 = [(res_avg, res_km, res_mag), (torch.empty_like(res_avg).pin_memory(), torch.empty_like(res_km).pin_memory(),
-                                         torch.empty_like(res_mag).pin_memory())]
+    res_pin = [(torch.empty_like(res_avg).pin_memory(), torch.empty_like(res_km).pin_memory(), torch.empty_like(res_mag).pin_memory())
+               for _ in range(NRES)]
     dev_res = [(torch.empty((P, ROWS * COLS), dtype=torch.uint8, device=dev), torch.empty((P, ROWS * COLS), dtype=torch.uint8, device=dev),
-                torch.empty(P, dtype=torch.float64, device=dev)) for _ in range(2)]
+                torch.empty(P, dtype=torch.float64, device=dev)) for _ in range(NRES)]
 
     def e2e_loop(lo, hi):
+        """every step: upload the P new frames of the chunk from pinned host memory (copy stream), run the chunk on the
+        next lane (carry: the frame shared with the previous chunk stays on the device), snapshot its hue rows and
+        magnitudes on the lane's stream and read the snapshot back to pinned host memory on a third stream"""
         main = torch.cuda.current_stream()
         for b in range(NBUF):
             freed[b].record(main)
-        for j in range(2):
+        for j in range(NRES):
             read_ev[j].record(d2h_stream)
 
         def upload(i):
@@ -737,35 +747,32 @@ def main():
                     stage[b].copy_(host[c * P:(c + 1) * P], non_blocking=True)
                 ready[b].record(copy_stream)
         # frame 0 of the clip seeds prev_gray (outside the steady state, like the reference's first cap.read())
-        pipe.run_chunk(clip[0:2])
+        lp.submit(clip[0:2])
         upload(lo)
         for i in range(lo, hi):
             b = i % NBUF
             if i + 1 < hi:
                 upload(i + 1)
-            main.wait_event(ready[b])
-            pipe.run_chunk(stage[b], carry=True)
-            freed[b].record(main)
-            if d2h_inline:
-                res_avg.copy_(pipe.avg_hue[:P], non_blocking=True)
-                res_km.copy_(pipe.km_hue[:P], non_blocking=True)
-                res_mag.copy_(pipe.mag_sum[:P], non_blocking=True)
-            else:
-                # snapshot the step's rows on the device (the pipeline's buffers are rewritten by the next step), then
-                # read the snapshot back beside the next step's kernels
-                j = i & 1
-                main.wait_event(read_ev[j])
-                dev_res[j][0].copy_(pipe.avg_hue[:P], non_blocking=True)
-                dev_res[j][1].copy_(pipe.km_hue[:P], non_blocking=True)
-                dev_res[j][2].copy_(pipe.mag_sum[:P], non_blocking=True)
-                done_ev[j].record(main)
-                with torch.cuda.stream(d2h_stream):
-                    d2h_stream.wait_event(done_ev[j])
-                    for k in range(3):
-                        res2[j][k].copy_(dev_res[j][k], non_blocking=True)
-                    read_ev[j].record(d2h_stream)
-        main.synchronize()
-        d2h_stream.synchronize()
+            l, _ = lp.submit(stage[b], carry=True, wait=ready[b])
+            s, lane = lp.lane_stream(l), lp.lane(l)
+            freed[b].record(s)
+            # snapshot the step's rows on the device (the lane's buffers are rewritten by its next chunk), then read the
+            # snapshot back beside the following kernels
+            j = i % NRES
+            with torch.cuda.stream(s):
+                s.wait_event(read_ev[j])
+                dev_res[j][0].copy_(lane.avg_hue[:P], non_blocking=True)
+                dev_res[j][1].copy_(lane.km_hue[:P], non_blocking=True)
+                dev_res[j][2].copy_(lane.mag_sum[:P], non_blocking=True)
+                done_ev[j].record(s)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done_ev[j])
+                for k in range(3):
+                    res_pin[j][k].copy_(dev_res[j][k], non_blocking=True)
+                read_ev[j].record(d2h_stream)
+        for l in range(n_lanes):
+            main.wait_event(lp.done_event(l))
+        main.wait_stream(d2h_stream)
 
     e2e_loop(0, args.warmup)
     barrier()
@@ -781,7 +788,8 @@ def main():
     e2e_value = world * args.steps * P / (float(t.item()) / 1e3)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": P * H * W * 3,
            "d2h_bytes_per_step": P * (2 * ROWS * COLS + 8),
-           "api": "ClipPipeline.run_chunk(new frames, carry=True) on pinned host frames, triple-buffered upload"}
+           "api": f"LanedPipeline.submit(new frames, carry=True) on pinned host frames, {n_lanes} lanes, staged upload on a copy "
+                  "stream, result rows read back to pinned host memory every step"}
 
     extras = None
     if not args.no_extras:
@@ -814,6 +822,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"synthetic {SIZE_NAME} clip, Farneback levels={LEVELS} winsize=15 iters=3, 14x25 grid, k={args.k}",
                        "frames_per_step": F, "pairs_per_step": P, "clip_frames": T, "rank_cpu_affinity": numa_cpus,
+                       "lanes": n_lanes,
                        "l2": f"steps walk a {T}-frame clip ({T * H * W * 3 / 1e6:.0f} MB > L2); intermediates "
                              f"({pipe.plan.workspace_bytes / 1e6:.0f} MB workspace) are rewritten every step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

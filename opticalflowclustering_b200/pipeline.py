@@ -67,6 +67,7 @@ class ClipPipeline:
             nb = int(L.ofc_grid_kmeans_cells_workspace_bytes(P, self.H, self.W, self.rows, self.cols, self.n_clusters))
             self._km_ws = torch.empty(max(nb, 8), dtype=torch.uint8, device=dev)
         self._last_gray_index = None     # where the last processed frame's gray image sits in self.gray
+        self._gray_event = None          # LanedPipeline: recorded once the chunk's gray frames exist (another lane carries the last)
         #: kernels launched by one full-chunk call of :meth:`run_chunk`
         self.launches_per_chunk = 1 + 2 * self.plan.num_levels + 1 + self.plan.num_levels * iterations + 1 + 1
 
@@ -100,6 +101,8 @@ class ClipPipeline:
             else:
                 _lib.check(L.ofc_bgr2gray(_ptr(frames), _ptr(self.gray), n * self.H * self.W, s))
             self._last_gray_index = n - 1
+            if self._gray_event is not None:
+                self._gray_event.record(torch.cuda.current_stream(self.device))
             _lib.check(L.ofc_farneback_sequence(self.plan._ptr, _ptr(self.gray), n, _ptr(self.flow), _ptr(self.minmax),
                                                 _ptr(self.plan.workspace), self.plan.workspace_bytes, s))
             k1 = self.n_clusters == 1
@@ -243,3 +246,122 @@ class ClipPipeline:
                     "km_hue": torch.empty((0, self.cells), dtype=torch.uint8),
                     "mean_magnitude": torch.empty(0, dtype=torch.float64)}
         return {k: torch.cat([c[k] for c in collected]) for k in collected[0]}
+
+
+class LanedPipeline:
+    """Several :class:`ClipPipeline` lanes on their own streams, chunks dealt to them in turn.
+
+    A chunk is a chain of kernels of very different character -- the level-0 / level-1 walks own every register and
+    tensor-memory column of an SM and are latency-bound, the stage-1 kernels are issue-bound, the coarse levels and the
+    tails of every launch leave SMs idle.  With two or three independent chunks in flight the hardware fills one chain's
+    gaps with another's CTAs: 5 570 -> 5 995 pairs/s with two lanes, 6 087 with three (1080p, chunks of 33 frames,
+    ``tools/two_lane.py``, r03h).  Every lane has its own plan workspace and result buffers (4.5 GB per lane at 1080p).
+
+    ``submit`` enqueues one chunk and returns ``(lane, n_pairs)``; the lane's buffers (``lane.avg_hue`` ...) hold the chunk's
+    results once ``lane_stream(lane)`` has run that far.  Work that reads them belongs on that stream (or behind
+    ``done_event(lane)``) and must be enqueued before the lane's next ``submit`` -- ``lanes`` chunks later -- overwrites them.
+    With ``carry=True`` the chunk's first pair starts at the previous chunk's last frame, whose gray image is taken over
+    from the lane that converted it (the reference's ``prev_gray``, computeOpticalFlowModule.py:34)."""
+
+    def __init__(self, width: int, height: int, lanes: int = 2, device=None, **kw):
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
+        self.pipes = [ClipPipeline(width, height, device=device, **kw) for _ in range(int(lanes))]
+        self.device = self.pipes[0].device
+        self.W, self.H, self.F = self.pipes[0].W, self.pipes[0].H, self.pipes[0].F
+        self.cells = self.pipes[0].cells
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.pipes]
+        self._done = [torch.cuda.Event() for _ in self.pipes]
+        self._taken = [None for _ in self.pipes]        # event: the next lane has copied this lane's last gray frame
+        for p in self.pipes:
+            p._gray_event = torch.cuda.Event()
+        self._next = 0
+        self._last = None                                # lane of the previous chunk
+
+    @property
+    def n_lanes(self) -> int:
+        return len(self.pipes)
+
+    def lane_stream(self, lane: int):
+        return self.streams[lane]
+
+    def done_event(self, lane: int):
+        return self._done[lane]
+
+    def lane(self, lane: int) -> ClipPipeline:
+        return self.pipes[lane]
+
+    def submit(self, frames: torch.Tensor, carry: bool = False, wait=None):
+        """Enqueue one chunk on the next lane.  ``wait``: an event after which ``frames`` are complete (default: whatever
+        the caller's current stream has enqueued so far).  Returns ``(lane, n_pairs)``."""
+        l = self._next
+        pipe, s = self.pipes[l], self.streams[l]
+        if wait is None:
+            s.wait_stream(torch.cuda.current_stream(self.device))
+        else:
+            s.wait_event(wait)
+        if self._taken[l] is not None:                   # the lane's gray buffer is about to be rewritten
+            s.wait_event(self._taken[l])
+            self._taken[l] = None
+        with torch.cuda.stream(s):
+            if carry:
+                if self._last is None:
+                    raise ValueError("carry=True needs a previous chunk")
+                prev = self.pipes[self._last]
+                if self._last != l:
+                    s.wait_event(prev._gray_event)
+                    pipe.gray[0].copy_(prev.gray[prev._last_gray_index])
+                    pipe._last_gray_index = 0
+                    pipe._pairs_done = prev._pairs_done
+                    ev = torch.cuda.Event()
+                    ev.record(s)
+                    self._taken[self._last] = ev
+            P = pipe.run_chunk(frames, carry=carry)
+            self._done[l].record(s)
+        self._last = l
+        self._next = (l + 1) % len(self.pipes)
+        return l, P
+
+    def seed(self, first_frame):
+        """Start a stream of ``carry=True`` chunks: ``first_frame`` becomes ``prev_gray`` (see ClipPipeline.seed)."""
+        with torch.cuda.stream(self.streams[0]):
+            self.pipes[0].seed(first_frame)
+            self.pipes[0]._gray_event.record(self.streams[0])
+        self._last, self._next = 0, (1 % len(self.pipes))
+
+    def synchronize(self):
+        for s in self.streams:
+            s.synchronize()
+
+    def process_clip(self, frames):
+        """Whole clip ``[T,H,W,3]`` uint8 on the device -> dict of host tensors like :meth:`ClipPipeline.process_clip`,
+        with the chunks dealt over the lanes (results are read back one round of lanes late)."""
+        T = int(frames.shape[0])
+        avg = torch.empty((T - 1, self.cells), dtype=torch.uint8)
+        km = torch.empty((T - 1, self.cells), dtype=torch.uint8)
+        mag = torch.empty(T - 1, dtype=torch.float64)
+        pending = []                                     # (lane, first_pair, n_pairs)
+
+        def collect():
+            l, t0, P = pending.pop(0)
+            self._done[l].synchronize()
+            pipe = self.pipes[l]
+            avg[t0:t0 + P] = pipe.avg_hue[:P].cpu()
+            km[t0:t0 + P] = pipe.km_hue[:P].cpu()
+            mag[t0:t0 + P] = pipe.mag_sum[:P].cpu() / float(self.H * self.W)
+
+        t = 0
+        while t < T - 1:
+            first = t == 0
+            n = min(self.F, T - t) if first else min(self.F - 1, T - 1 - t)
+            chunk = frames[t:t + n] if first else frames[t + 1:t + 1 + n]
+            if not chunk.is_cuda:
+                chunk = chunk.to(self.device, non_blocking=True)
+            if len(pending) == len(self.pipes):          # the lane about to be reused still holds unread results
+                collect()
+            l, P = self.submit(chunk, carry=not first)
+            pending.append((l, t, P))
+            t += P
+        while pending:
+            collect()
+        return {"avg_hue": avg, "km_hue": km, "mean_magnitude": mag}

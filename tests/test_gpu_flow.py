@@ -450,3 +450,23 @@ def test_one_process_two_devices(ofc):
             res.append((pipe.avg_hue.cpu(), pipe.km_hue.cpu(), pipe.flow.cpu()))
     for u, v in zip(res[0], res[1]):
         assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("lanes,n_clusters", [(2, 1), (3, 1), (2, 3)])
+def test_laned_pipeline_equals_single_pipeline(ofc, lanes, n_clusters):
+    """LanedPipeline (chunks dealt over pipelines on their own streams, the shared frame's gray image handed from lane to
+    lane) gives the hue rows, k-means hues and magnitudes of one ClipPipeline walking the same clip"""
+    from opticalflowclustering_b200.pipeline import ClipPipeline, LanedPipeline
+    from opticalflowclustering_b200.synthetic import synthetic_clip
+    H, W, T, F = 144, 200, 14, 4
+    clip = synthetic_clip(T, H, W, seed=23, device="cuda")
+    one = ClipPipeline(W, H, chunk_frames=F, rows=6, cols=8, n_clusters=n_clusters, kmeans_seed=9).process_clip(clip)
+    many = LanedPipeline(W, H, lanes=lanes, chunk_frames=F, rows=6, cols=8, n_clusters=n_clusters, kmeans_seed=9).process_clip(clip)
+    for key in ("avg_hue", "km_hue", "mean_magnitude"):
+        assert torch.equal(one[key], many[key]), key
+    # and twice on the same object (events and the lane order are reused)
+    lp = LanedPipeline(W, H, lanes=lanes, chunk_frames=F, rows=6, cols=8, n_clusters=n_clusters, kmeans_seed=9)
+    a = lp.process_clip(clip)
+    b = lp.process_clip(clip)
+    for key in ("avg_hue", "km_hue", "mean_magnitude"):
+        assert torch.equal(a[key], b[key]) and torch.equal(a[key], one[key]), key
