@@ -40,6 +40,7 @@ SIZE_NAME = "1080p"
 # other BASELINE.json configs (parity-test / documentation runs, not the headline): --size 720p | 4k
 SIZES = {"720p": (720, 1280, 3, 422.8e6), "1080p": (1080, 1920, 3, 951.4e6), "4k": (2160, 3840, 5, 3836.6e6)}
 ROWS, COLS = 14, 25
+LANES = 3                        # chunks in flight in the timed loops (--lanes)
 # algorithmic bytes per 1080p pair (levels=3) for flow+viz+grid, and
 # per flow_iter launch per pixel (update-matrices 68 B + blur/solve 28 B)
 ALGO_BYTES_PER_PAIR = 951.4e6
@@ -349,6 +350,26 @@ def _timed_steps(pipe, clip, F, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
+def _timed_steps_laned(lp, clip, F, steps, warmup):
+    """the same over a LanedPipeline (chunks in flight on several streams)"""
+    import torch
+    P, T = F - 1, int(clip.shape[0])
+    starts = [(i * P) % (T - F + 1) for i in range(warmup + steps)]
+    for i in range(warmup):
+        lp.submit(clip[starts[i]:starts[i] + F])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    main = torch.cuda.current_stream()
+    e0.record()
+    for i in range(warmup, warmup + steps):
+        lp.submit(clip[starts[i]:starts[i] + F])
+    for l in range(lp.n_lanes):
+        main.wait_event(lp.done_event(l))
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
 def _kind_ms(pipe, clip, F, kinds, steps=3):
     """per-kernel-kind device time (ms per step) of `steps` steps, events around every launch"""
     import ctypes as C
@@ -365,16 +386,16 @@ def _kind_ms(pipe, clip, F, kinds, steps=3):
 def other_sizes_leg(dev, peak):
     """BASELINE configs at 720p (levels=3) and 4K (levels=5), k = 1, device-resident, a few steps each"""
     import torch
-    from opticalflowclustering_b200.pipeline import ClipPipeline
+    from opticalflowclustering_b200.pipeline import LanedPipeline
     from opticalflowclustering_b200.synthetic import synthetic_clip
     out = {}
     for name, F, T in (("720p", 33, 65), ("4k", 9, 17)):
         h, w, levels, algo = SIZES[name]
         clip = synthetic_clip(T, h, w, seed=7, device=dev)
-        pipe = ClipPipeline(w, h, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=levels)
-        ms = _timed_steps(pipe, clip, F, 6, 3)
+        pipe = LanedPipeline(w, h, lanes=LANES, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=levels)
+        ms = _timed_steps_laned(pipe, clip, F, 9, 3)
         out[name] = {"value": (F - 1) / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "pairs_per_step": F - 1, "levels": levels,
-                     "step_frac": algo * (F - 1) / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_pair": algo}
+                     "lanes": LANES, "step_frac": algo * (F - 1) / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_pair": algo}
         del pipe, clip
         torch.cuda.empty_cache()
     return out
@@ -384,7 +405,7 @@ def k8_leg(dev, with_cpu):
     """`-c 8` (BASELINE configs[1]: 720p, k = 8; and the 1080p metric at k = 8): every cell of every pair gets its own
     KMeans(8) fit on the device (ofc_grid_kmeans_cells), straight from the visualisation"""
     import torch
-    from opticalflowclustering_b200.pipeline import ClipPipeline
+    from opticalflowclustering_b200.pipeline import LanedPipeline
     from opticalflowclustering_b200.synthetic import synthetic_clip
     out = {}
     for name, F, T in (("720p", 33, 65), ("1080p", 17, 33)):
@@ -392,15 +413,16 @@ def k8_leg(dev, with_cpu):
         clip = synthetic_clip(T, h, w, seed=5, device=dev)
         rec = {}
         for k in (1, 8):
-            pipe = ClipPipeline(w, h, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=levels, n_clusters=k)
-            ms = _timed_steps(pipe, clip, F, 6, 3)
-            rec[f"k{k}"] = {"value": (F - 1) / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "pairs_per_step": F - 1}
+            lp = LanedPipeline(w, h, lanes=LANES, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=levels, n_clusters=k)
+            ms = _timed_steps_laned(lp, clip, F, 9, 3)
+            pipe = lp.lane(0)
+            rec[f"k{k}"] = {"value": (F - 1) / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "pairs_per_step": F - 1, "lanes": LANES}
             if k == 8:
                 kinds = _kind_ms(pipe, clip, F, {8: "kmeans_cells"})
                 rec["k8"]["kmeans_ms_per_frame"] = kinds.get("kmeans_cells", 0.0) / (F - 1)
                 rec["k8"]["mean_lloyd_iterations"] = float(pipe.km_n_iter.float().mean().item())
                 rec["k8"]["max_lloyd_iterations"] = int(pipe.km_n_iter.max().item())
-            del pipe
+            del pipe, lp
         rec["k8_over_k1_time"] = rec["k8"]["ms_per_step"] / rec["k1"]["ms_per_step"]
         if with_cpu and name == "720p":
             cores = os.cpu_count() or 1
@@ -615,7 +637,8 @@ def main():
     # the timed loops deal their chunks over `lanes` pipelines on their own streams (one chunk's gaps and tails are
     # filled by another's CTAs); `pipe` alone serves the per-kernel breakdown, which wants one chain of kernels
     from opticalflowclustering_b200.pipeline import LanedPipeline
-    n_lanes = max(1, args.lanes)
+    global LANES
+    n_lanes = LANES = max(1, args.lanes)
     lp = LanedPipeline(W, H, lanes=n_lanes, chunk_frames=F, rows=ROWS, cols=COLS, device=dev, levels=LEVELS, n_clusters=args.k)
     starts = [(i * P) % (T - F + 1) for i in range(args.warmup + args.steps)]
     main_stream = torch.cuda.current_stream()
