@@ -644,6 +644,8 @@ def main():
     main_stream = torch.cuda.current_stream()
 
     # ---- value: inputs resident in HBM --------------------------------------
+    for _ in range(n_lanes):                                   # every lane's buffers touched once, whatever --warmup is
+        lp.submit(clip[0:F])
     for i in range(args.warmup):
         lp.submit(clip[starts[i]:starts[i] + F])
     barrier()
