@@ -2165,8 +2165,8 @@ static int launch_strip(const IterParams& p_in, int n_pairs, float2* scratch, vo
     // so it is off by default
     if (p.upsample && tmem_path && env_int("OFC_FUSE_UPSAMPLE", 0) && (int64_t)p.wc * p.hc < ((int64_t)1 << 30))
     {
-        if (p.ups_fast) return p.minmax ? launch_tmem<true, 2>(p, n_pairs, stream) : launch_tmem<false, 2>(p, n_pairs, stream);
-        return p.minmax ? launch_tmem<true, 1>(p, n_pairs, stream) : launch_tmem<false, 1>(p, n_pairs, stream);
+        if (p.ups_fast) return p.minmax ? launch_tmem<true, 2, 1>(p, n_pairs, stream) : launch_tmem<false, 2, 1>(p, n_pairs, stream);
+        return p.minmax ? launch_tmem<true, 1, 1>(p, n_pairs, stream) : launch_tmem<false, 1, 1>(p, n_pairs, stream);
     }
     if (p.upsample) {
         const int x2 = env_int("OFC_UPSAMPLE_X2", 1);
