@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256, ((KP <= 4 || RU == 2) ? OFC_CELLS_MINB : 
     __shared__ double s_tol;
     __shared__ double s_val[8];
     __shared__ int s_idx[8];
-    __shared__ int s_pick, s_any, s_heavy, s_stop, s_changed, s_nmoves;
+    __shared__ int s_pick, s_stop, s_changed, s_nmoves;
     __shared__ int s_cand[8];
     if (!p.closest_in_smem) closest = p.closest_ws + b * n;
 
@@ -446,14 +446,11 @@ __global__ void __launch_bounds__(256, ((KP <= 4 || RU == 2) ? OFC_CELLS_MINB : 
         __syncthreads();
         prev_changed = s_changed;
         // empty clusters take the farthest points (squared distance to the old centre of their label); the labels
-        // stay as they are (_k_means_common.pyx:167-211), so the moves are undone on the running sums below
-        if (tid == 0) {
-            int any = 0;
-            for (int j = 0; j < k; ++j) any |= s_cnt[j] == 0;
-            s_any = any;
-        }
-        __syncthreads();
-        if (s_any) {
+        // stay as they are (_k_means_common.pyx:167-211), so the moves are undone on the running sums below.
+        // The member counts are final behind the barrier above: every thread tests them itself (no flag, no barrier)
+        int any_empty = 0;
+        for (int j = 0; j < k; ++j) any_empty |= s_cnt[j] == 0;
+        if (any_empty) {
             for (int e = 0; e < k; ++e) {
                 if (s_cnt[e] != 0) continue;
                 const int n_taken = s_nmoves;
@@ -504,29 +501,29 @@ __global__ void __launch_bounds__(256, ((KP <= 4 || RU == 2) ? OFC_CELLS_MINB : 
             }
             __syncthreads();
         }
-        // centres, shift
-        if (tid == 0) {
+        // centres, shift, stopping rule: all of it by warp 0 (k <= 16 <= 32 lanes) between two __syncwarp, while the
+        // other warps go straight to the barrier at the end of the iteration -- three CTA-wide barriers per iteration
+        // instead of six (ncu r03q: barrier waits were 28 % of the stall samples at ~10 pixels per thread)
+        if (warp == 0) {
             int heavy = 0;
             for (int j = 1; j < k; ++j) if (s_cnt[j] > s_cnt[heavy]) heavy = j;
-            s_heavy = heavy;
-        }
-        __syncthreads();
-        for (int j = tid; j < k; j += 256) {
-            const int srcj = s_cnt[j] > 0 ? j : s_heavy;
-            const double wgt = (double)s_cnt[srcj];
-            double ss = 0.0;
-            for (int t = 0; t < D; ++t) {
-                double v = (double)s_sum[srcj * D + t] / wgt;
-                v -= mean[t];
-                const double df = v - cc[j * D + t];
-                ss = fma(df, df, ss);
-                cnew[j * D + t] = v;
+            for (int j = lane; j < k; j += 32) {
+                const int srcj = s_cnt[j] > 0 ? j : heavy;
+                const double wgt = (double)s_cnt[srcj];
+                double ss = 0.0;
+                for (int t = 0; t < D; ++t) {
+                    double v = (double)s_sum[srcj * D + t] / wgt;
+                    v -= mean[t];
+                    const double df = v - cc[j * D + t];
+                    ss = fma(df, df, ss);
+                    cnew[j * D + t] = v;
+                }
+                const double sr = sqrt(ss);
+                shift[j] = sr * sr;
             }
-            const double sr = sqrt(ss);
-            shift[j] = sr * sr;
+            __syncwarp();
+            for (int e = lane; e < k * D; e += 32) cc[e] = cnew[e];
         }
-        __syncthreads();
-        for (int e = tid; e < k * D; e += 256) cc[e] = cnew[e];
         if (tid == 0) {
             double tot = 0.0;
             for (int j = 0; j < k; ++j) tot += shift[j];
