@@ -21,10 +21,6 @@
 #include "ofc_common.cuh"
 #include "flow_kernels.cuh"
 
-#ifndef OFC_EXP
-#define OFC_EXP 0                // experimental variants (tools/build_variant.sh); 0 = production
-#endif
-
 namespace ofc {
 
 // ---------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Build an experimental variant of libofc.so (flow_kernels.cu compiled with -DOFC_EXP=<n>) into build_variants/libofc_exp<n>.so;
 # tools/ab_flow.sh swaps it in on the GPU box ("name@exp<n>" specs).  Other sources are compiled once and cached as objects.
+# (Wrap the code under test in `#if OFC_EXP == <n>` in flow_kernels.cu; nothing in the tree uses the macro between experiments.)
 set -e
 N=$1
 cd "$(dirname "$0")/.."
